@@ -1,0 +1,110 @@
+// jrc_common.cuh -- device helpers shared by the staged and the fused kernels.
+//
+// Arithmetic rule for the whole library: every float operation whose rounding
+// matters for parity is written with an explicit _rn intrinsic, so nvcc can
+// neither contract (a*b+c -> fma) nor re-associate it.  That makes
+//   - the staged kernels bit-identical to the CPU oracle's float pipeline, and
+//   - the fused kernel's re-evaluation of a peak bit-identical to its main loop.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace jrc {
+
+typedef float2 c32;
+
+__device__ __forceinline__ c32 mk(float x, float y) { c32 r; r.x = x; r.y = y; return r; }
+
+// std::complex<float> product with every product and sum rounded separately
+// (what the reference's generic x86-64 build does, lib/mimo_ofdm_radar_impl.cc:273)
+__device__ __forceinline__ c32 cmul_exact(c32 a, c32 b)
+{
+    return mk(__fsub_rn(__fmul_rn(a.x, b.x), __fmul_rn(a.y, b.y)),
+              __fadd_rn(__fmul_rn(a.x, b.y), __fmul_rn(a.y, b.x)));
+}
+__device__ __forceinline__ c32 cadd_exact(c32 a, c32 b) { return mk(__fadd_rn(a.x, b.x), __fadd_rn(a.y, b.y)); }
+__device__ __forceinline__ c32 csub_exact(c32 a, c32 b) { return mk(__fsub_rn(a.x, b.x), __fsub_rn(a.y, b.y)); }
+
+// fast complex product for the fused kernel: 2 FMUL + 2 FFMA, pinned with intrinsics
+__device__ __forceinline__ c32 cmul_fma(c32 a, c32 w)
+{
+    return mk(__fmaf_rn(-a.y, w.y, __fmul_rn(a.x, w.x)),
+              __fmaf_rn(a.y, w.x, __fmul_rn(a.x, w.y)));
+}
+
+// std::pow(std::abs(z), 2) exactly as the reference evaluates it
+// (lib/range_angle_estimator_impl.cc:141,217): hypotf -> float, squared in double.
+// glibc's hypotf is (float)sqrt((double)x*x + (double)y*y); both products are exact
+// in double so fma() vs mul+add round identically.
+__device__ __forceinline__ float ref_abs(c32 z)
+{
+    double s = fma((double)z.x, (double)z.x, (double)z.y * (double)z.y);
+    return (float)sqrt(s);
+}
+__device__ __forceinline__ double ref_pow_abs2(c32 z)
+{
+    double a = (double)ref_abs(z);
+    return a * a;
+}
+
+// 8-point DFT, DIR = -1 forward (e^{-j2pi/8}), +1 backward; natural order in and out.
+// 52 FP32 instructions: 40 FADD + 4 FADD (twiddle pre-sums) + 8 FFMA.
+template <int DIR>
+__device__ __forceinline__ void fft8(c32 (&u)[8])
+{
+    const float C = 0.70710678118654752440f;
+    c32 a0 = mk(__fadd_rn(u[0].x, u[4].x), __fadd_rn(u[0].y, u[4].y));
+    c32 a1 = mk(__fsub_rn(u[0].x, u[4].x), __fsub_rn(u[0].y, u[4].y));
+    c32 a2 = mk(__fadd_rn(u[2].x, u[6].x), __fadd_rn(u[2].y, u[6].y));
+    c32 a3 = mk(__fsub_rn(u[2].x, u[6].x), __fsub_rn(u[2].y, u[6].y));
+    c32 a4 = mk(__fadd_rn(u[1].x, u[5].x), __fadd_rn(u[1].y, u[5].y));
+    c32 a5 = mk(__fsub_rn(u[1].x, u[5].x), __fsub_rn(u[1].y, u[5].y));
+    c32 a6 = mk(__fadd_rn(u[3].x, u[7].x), __fadd_rn(u[3].y, u[7].y));
+    c32 a7 = mk(__fsub_rn(u[3].x, u[7].x), __fsub_rn(u[3].y, u[7].y));
+    c32 E0 = mk(__fadd_rn(a0.x, a2.x), __fadd_rn(a0.y, a2.y));
+    c32 E2 = mk(__fsub_rn(a0.x, a2.x), __fsub_rn(a0.y, a2.y));
+    c32 O0 = mk(__fadd_rn(a4.x, a6.x), __fadd_rn(a4.y, a6.y));
+    c32 O2 = mk(__fsub_rn(a4.x, a6.x), __fsub_rn(a4.y, a6.y));
+    c32 E1, E3, O1, O3, t1, t3;
+    if (DIR < 0) {   // multiply by -j: (x,y) -> (y,-x)
+        E1 = mk(__fadd_rn(a1.x, a3.y), __fsub_rn(a1.y, a3.x));
+        E3 = mk(__fsub_rn(a1.x, a3.y), __fadd_rn(a1.y, a3.x));
+        O1 = mk(__fadd_rn(a5.x, a7.y), __fsub_rn(a5.y, a7.x));
+        O3 = mk(__fsub_rn(a5.x, a7.y), __fadd_rn(a5.y, a7.x));
+        t1 = mk(__fadd_rn(O1.x, O1.y), __fsub_rn(O1.y, O1.x));      // O1*(1-j)
+        t3 = mk(__fsub_rn(O3.y, O3.x), __fsub_rn(-O3.x, O3.y));     // O3*(-1-j)
+        u[2] = mk(__fadd_rn(E2.x, O2.y), __fsub_rn(E2.y, O2.x));
+        u[6] = mk(__fsub_rn(E2.x, O2.y), __fadd_rn(E2.y, O2.x));
+    } else {         // multiply by +j: (x,y) -> (-y,x)
+        E1 = mk(__fsub_rn(a1.x, a3.y), __fadd_rn(a1.y, a3.x));
+        E3 = mk(__fadd_rn(a1.x, a3.y), __fsub_rn(a1.y, a3.x));
+        O1 = mk(__fsub_rn(a5.x, a7.y), __fadd_rn(a5.y, a7.x));
+        O3 = mk(__fadd_rn(a5.x, a7.y), __fsub_rn(a5.y, a7.x));
+        t1 = mk(__fsub_rn(O1.x, O1.y), __fadd_rn(O1.x, O1.y));      // O1*(1+j)
+        t3 = mk(__fsub_rn(-O3.x, O3.y), __fsub_rn(O3.x, O3.y));     // O3*(-1+j)
+        u[2] = mk(__fsub_rn(E2.x, O2.y), __fadd_rn(E2.y, O2.x));
+        u[6] = mk(__fadd_rn(E2.x, O2.y), __fsub_rn(E2.y, O2.x));
+    }
+    u[0] = mk(__fadd_rn(E0.x, O0.x), __fadd_rn(E0.y, O0.y));
+    u[4] = mk(__fsub_rn(E0.x, O0.x), __fsub_rn(E0.y, O0.y));
+    u[1] = mk(__fmaf_rn(C, t1.x, E1.x), __fmaf_rn(C, t1.y, E1.y));
+    u[5] = mk(__fmaf_rn(-C, t1.x, E1.x), __fmaf_rn(-C, t1.y, E1.y));
+    u[3] = mk(__fmaf_rn(C, t3.x, E3.x), __fmaf_rn(C, t3.y, E3.y));
+    u[7] = mk(__fmaf_rn(-C, t3.x, E3.x), __fmaf_rn(-C, t3.y, E3.y));
+}
+
+// e^{j*pi*num/den} with an exactly representable argument (den a power of two)
+__device__ __forceinline__ c32 cispi_ratio(int num, int den)
+{
+    float s, c;
+    sincospif((float)num / (float)den, &s, &c);
+    return mk(c, s);
+}
+
+__device__ __forceinline__ unsigned long long pack_key(float v, unsigned idx)
+{
+    // v >= 0 and not NaN: float bits are monotonic; ties -> the smaller index wins
+    return ((unsigned long long)__float_as_uint(v) << 32) | (unsigned long long)(0xFFFFFFFFu - idx);
+}
+
+}  // namespace jrc

@@ -1,0 +1,777 @@
+// jrc_cuda.cu -- host side of libjrc_cuda.so (the C ABI declared in include/jrc_cuda.h).
+// Build: gr-mimo-ofdm-jrc_b200/Makefile (nvcc -gencode arch=compute_100a,code=sm_100a).
+// There is deliberately no CPU fallback in this file: every entry point either runs
+// CUDA kernels or fails with a status code.
+#include "jrc_cuda.h"
+
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "jrc_fused.cuh"
+#include "jrc_staged.cuh"
+
+using namespace jrc;
+
+static_assert(sizeof(jrc_det) == 32 && sizeof(DetDev) == 32, "detection record is 32 bytes");
+static_assert(sizeof(jrc_c32) == sizeof(c32), "complex layout");
+
+// ---------------------------------------------------------------------------
+// error plumbing
+// ---------------------------------------------------------------------------
+static thread_local std::string g_err;
+static jrc_status fail(jrc_status st, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return st;
+}
+#define CU(expr)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (expr);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+            return fail(JRC_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+#define ST(expr)                                 \
+    do {                                         \
+        jrc_status s_ = (expr);                  \
+        if (s_ != JRC_OK) return s_;             \
+    } while (0)
+
+extern "C" const char *jrc_last_error(void) { return g_err.c_str(); }
+extern "C" int32_t jrc_abi_version(void) { return 1; }
+
+// ---------------------------------------------------------------------------
+// handle
+// ---------------------------------------------------------------------------
+struct GrowBuf {   // grow-only device / pinned-host buffer
+    void *p = nullptr;
+    size_t cap = 0;
+    bool pinned = false;
+    jrc_status need(size_t bytes)
+    {
+        if (bytes <= cap) return JRC_OK;
+        if (p) { if (pinned) cudaFreeHost(p); else cudaFree(p); p = nullptr; cap = 0; }
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = pinned ? cudaMallocHost(&p, want) : cudaMalloc(&p, want);
+        if (e != cudaSuccess) { p = nullptr; return fail(JRC_ERR_CUDA, "allocation of %zu bytes failed: %s", want, cudaGetErrorString(e)); }
+        cap = want;
+        return JRC_OK;
+    }
+    void release()
+    {
+        if (p) { if (pinned) cudaFreeHost(p); else cudaFree(p); }
+        p = nullptr; cap = 0;
+    }
+};
+
+struct jrc_chain {
+    jrc_chain_cfg cfg;
+    int V = 0, Nr = 0, Na = 0;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr, s_h2d = nullptr, s_d2h = nullptr;
+    cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
+    // estimator
+    bool est_set = false;
+    std::vector<float> range_bins, angle_bins;
+    float nd_range_m = 0, nd_angle_deg = 0, snr_thr = 0, pow_thr = 0;
+    float *d_angle_bins = nullptr;
+    // background state (lib/mimo_ofdm_radar_impl.h:48-54)
+    c32 *d_ring = nullptr, *d_temp = nullptr;
+    int ring_size = 0, ring_head = 0;
+    // scratch
+    GrowBuf sH, sY, sC, sKeys, sDet, sIn[2], sMap[2], sDets[2], sMisc, sMisc2;
+    GrowBuf pin_a, pin_b;
+    std::map<std::pair<int, int>, c32 *> twiddles;   // (n, forward) -> device table
+    int last_path = 0;
+    int64_t launches = 0;
+    int fused_ctas_per_sm = 0;
+};
+
+static bool is_pow2(int n) { return n > 0 && (n & (n - 1)) == 0; }
+static int ilog2(int n) { int l = 0; while ((1 << l) < n) l++; return l; }
+
+static jrc_status get_twiddles(jrc_chain *h, int n, int forward, const c32 **out)
+{
+    auto key = std::make_pair(n, forward ? 1 : 0);
+    auto it = h->twiddles.find(key);
+    if (it != h->twiddles.end()) { *out = it->second; return JRC_OK; }
+    // same table as the CPU oracle: cos/sin evaluated in double, rounded to float
+    std::vector<c32> tw((size_t)(n / 2 > 0 ? n / 2 : 1));
+    const double sgn = forward ? -1.0 : 1.0;
+    for (int k = 0; k < n / 2; k++) {
+        double a = sgn * 2.0 * M_PI * (double)k / (double)n;
+        tw[k].x = (float)cos(a); tw[k].y = (float)sin(a);
+    }
+    c32 *d = nullptr;
+    CU(cudaMalloc(&d, tw.size() * sizeof(c32)));
+    CU(cudaMemcpyAsync(d, tw.data(), tw.size() * sizeof(c32), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    h->twiddles[key] = d;
+    *out = d;
+    return JRC_OK;
+}
+
+extern "C" jrc_status jrc_chain_create(const jrc_chain_cfg *cfg, jrc_chain **out)
+{
+    if (!cfg || !out) return fail(JRC_ERR_INVALID, "null argument");
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(JRC_ERR_NO_DEVICE, "no CUDA device (%s); this library has no CPU path",
+                    e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+    if (cfg->device < 0 || cfg->device >= ndev) return fail(JRC_ERR_INVALID, "device %d out of range (%d devices)", cfg->device, ndev);
+    if (!is_pow2(cfg->fft_len)) return fail(JRC_ERR_INVALID, "fft_len must be a power of two");
+    if (cfg->n_tx < 1 || cfg->n_rx < 1 || cfg->n_sym < 1 || cfg->n_pre < 0) return fail(JRC_ERR_INVALID, "bad antenna/symbol counts");
+    if (cfg->interp_range < 1 || cfg->interp_angle < 1) return fail(JRC_ERR_INVALID, "interp factors must be >= 1");
+    const long long Nr = (long long)cfg->fft_len * cfg->interp_range, Na = (long long)cfg->n_tx * cfg->n_rx * cfg->interp_angle;
+    if (!is_pow2((int)Nr) || !is_pow2((int)Na) || Nr > 16384 || Na > 16384)
+        return fail(JRC_ERR_INVALID, "Nr=%lld / Na=%lld must be powers of two <= 16384", Nr, Na);
+    if (cfg->background_removal && cfg->record_len < 0) return fail(JRC_ERR_INVALID, "record_len < 0");
+
+    CU(cudaSetDevice(cfg->device));
+    jrc_chain *h = new jrc_chain();
+    h->cfg = *cfg;
+    h->V = cfg->n_tx * cfg->n_rx; h->Nr = (int)Nr; h->Na = (int)Na;
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, cfg->device));
+    h->sm_count = prop.multiProcessorCount;
+    CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&h->s_h2d, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&h->s_d2h, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; i++) {
+        CU(cudaEventCreateWithFlags(&h->ev_in[i], cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&h->ev_comp[i], cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&h->ev_out[i], cudaEventDisableTiming));
+    }
+    h->pin_a.pinned = h->pin_b.pinned = true;
+    const size_t vn = (size_t)h->V * cfg->fft_len;
+    CU(cudaMalloc(&h->d_temp, vn * sizeof(c32)));
+    CU(cudaMemsetAsync(h->d_temp, 0, vn * sizeof(c32), h->stream));
+    if (cfg->record_len > 0) {
+        CU(cudaMalloc(&h->d_ring, vn * sizeof(c32) * (size_t)cfg->record_len));
+        CU(cudaMemsetAsync(h->d_ring, 0, vn * sizeof(c32) * (size_t)cfg->record_len, h->stream));
+    }
+    CU(cudaStreamSynchronize(h->stream));
+    *out = h;
+    return JRC_OK;
+}
+
+extern "C" void jrc_chain_destroy(jrc_chain *h)
+{
+    if (!h) return;
+    cudaSetDevice(h->cfg.device);
+    cudaDeviceSynchronize();
+    for (auto &kv : h->twiddles) cudaFree(kv.second);
+    GrowBuf *bufs[] = {&h->sH, &h->sY, &h->sC, &h->sKeys, &h->sDet, &h->sIn[0], &h->sIn[1], &h->sMap[0], &h->sMap[1],
+                       &h->sDets[0], &h->sDets[1], &h->sMisc, &h->sMisc2, &h->pin_a, &h->pin_b};
+    for (GrowBuf *b : bufs) b->release();
+    if (h->d_angle_bins) cudaFree(h->d_angle_bins);
+    if (h->d_ring) cudaFree(h->d_ring);
+    if (h->d_temp) cudaFree(h->d_temp);
+    for (int i = 0; i < 2; i++) {
+        if (h->ev_in[i]) cudaEventDestroy(h->ev_in[i]);
+        if (h->ev_comp[i]) cudaEventDestroy(h->ev_comp[i]);
+        if (h->ev_out[i]) cudaEventDestroy(h->ev_out[i]);
+    }
+    if (h->stream) cudaStreamDestroy(h->stream);
+    if (h->s_h2d) cudaStreamDestroy(h->s_h2d);
+    if (h->s_d2h) cudaStreamDestroy(h->s_d2h);
+    delete h;
+}
+
+extern "C" void *jrc_chain_stream(jrc_chain *h) { return h ? (void *)h->stream : nullptr; }
+extern "C" jrc_status jrc_chain_sync(jrc_chain *h)
+{
+    if (!h) return fail(JRC_ERR_INVALID, "null handle");
+    CU(cudaStreamSynchronize(h->stream));
+    return JRC_OK;
+}
+extern "C" int32_t jrc_chain_last_path(const jrc_chain *h) { return h ? h->last_path : 0; }
+extern "C" int64_t jrc_chain_launch_count(const jrc_chain *h) { return h ? h->launches : 0; }
+
+extern "C" jrc_status jrc_chain_set_estimator(jrc_chain *h, const float *range_bins, int32_t n_range,
+                                               const float *angle_bins, int32_t n_angle,
+                                               float noise_discard_range_m, float noise_discard_angle_deg,
+                                               float snr_threshold, float power_threshold)
+{
+    if (!h || !range_bins || !angle_bins) return fail(JRC_ERR_INVALID, "null argument");
+    if (n_range < 2 || n_angle < 2) return fail(JRC_ERR_INVALID, "need at least two range and two angle bins");
+    CU(cudaSetDevice(h->cfg.device));
+    h->range_bins.assign(range_bins, range_bins + n_range);
+    h->angle_bins.assign(angle_bins, angle_bins + n_angle);
+    h->nd_range_m = noise_discard_range_m; h->nd_angle_deg = noise_discard_angle_deg;
+    h->snr_thr = snr_threshold; h->pow_thr = power_threshold;
+    if (h->d_angle_bins) { cudaFree(h->d_angle_bins); h->d_angle_bins = nullptr; }
+    CU(cudaMalloc(&h->d_angle_bins, sizeof(float) * (size_t)n_angle));
+    CU(cudaMemcpyAsync(h->d_angle_bins, angle_bins, sizeof(float) * (size_t)n_angle, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    h->est_set = true;
+    return JRC_OK;
+}
+
+extern "C" jrc_status jrc_chain_set_thresholds(jrc_chain *h, float snr_threshold, float power_threshold)
+{
+    if (!h) return fail(JRC_ERR_INVALID, "null handle");
+    h->snr_thr = snr_threshold; h->pow_thr = power_threshold;
+    return JRC_OK;
+}
+extern "C" jrc_status jrc_chain_set_background_record(jrc_chain *h, int32_t on)
+{
+    if (!h) return fail(JRC_ERR_INVALID, "null handle");
+    h->cfg.background_recording = on ? 1 : 0;
+    return JRC_OK;
+}
+extern "C" jrc_status jrc_chain_reset_background(jrc_chain *h)
+{
+    if (!h) return fail(JRC_ERR_INVALID, "null handle");
+    CU(cudaSetDevice(h->cfg.device));
+    h->ring_size = 0; h->ring_head = 0;
+    CU(cudaMemsetAsync(h->d_temp, 0, (size_t)h->V * h->cfg.fft_len * sizeof(c32), h->stream));
+    return JRC_OK;
+}
+
+static jrc_status est_params(const jrc_chain *h, int n_range, int n_angle, EstParams *P)
+{
+    if (!h->est_set) return fail(JRC_ERR_STATE, "jrc_chain_set_estimator has not been called");
+    if ((int)h->range_bins.size() != n_range || (int)h->angle_bins.size() != n_angle)
+        return fail(JRC_ERR_INVALID, "estimator bins (%zu x %zu) do not match the map (%d x %d)",
+                    h->range_bins.size(), h->angle_bins.size(), n_range, n_angle);
+    P->angle_bins = h->d_angle_bins;
+    P->n_angle = n_angle; P->n_range = n_range;
+    // lib/range_angle_estimator_impl.cc:189 -- float division, truncation to int
+    P->discard_range_idx = (int)(h->nd_range_m / (h->range_bins[1] - h->range_bins[0]));
+    P->noise_discard_angle_deg = h->nd_angle_deg;
+    P->snr_threshold = h->snr_thr; P->power_threshold = h->pow_thr;
+    return JRC_OK;
+}
+
+static int grid_for(long long n, int threads, int sm_count)
+{
+    long long b = (n + threads - 1) / threads;
+    long long cap = (long long)sm_count * 16;
+    if (b > cap) b = cap;
+    if (b < 1) b = 1;
+    return (int)b;
+}
+
+// ---------------------------------------------------------------------------
+// staged kernels: launch helpers (all on h->stream)
+// ---------------------------------------------------------------------------
+static jrc_status launch_fft_rows(jrc_chain *h, const c32 *in, long long in_stride, int n_in, c32 *out, int n,
+                                  long long rows, int forward, int shift)
+{
+    if (!is_pow2(n) || n > 16384) return fail(JRC_ERR_INVALID, "FFT length %d unsupported (power of two <= 16384)", n);
+    if (rows <= 0) return JRC_OK;
+    const c32 *tw = nullptr;
+    ST(get_twiddles(h, n, forward, &tw));
+    int rpc = n >= 512 ? 1 : 512 / n;
+    int threads = 256;
+    size_t smem = (size_t)rpc * n * sizeof(c32);
+    if (smem > 48 * 1024)
+        CU(cudaFuncSetAttribute(k_fft_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    long long ctas = (rows + rpc - 1) / rpc;
+    if (ctas > 0x7fffffffLL) return fail(JRC_ERR_INVALID, "too many FFT rows");
+    k_fft_rows<<<(unsigned)ctas, threads, smem, h->stream>>>(in, in_stride, n_in, out, n, ilog2(n), rows, rpc, forward, shift, tw);
+    CU(cudaGetLastError());
+    h->launches++;
+    return JRC_OK;
+}
+
+static jrc_status launch_transpose(jrc_chain *h, const c32 *in, c32 *out, int K, int L, int W, int mats)
+{
+    if (mats <= 0) return JRC_OK;
+    int kmax = K > W ? K : W;
+    dim3 grid((L + 31) / 32, (kmax + 31) / 32, mats), block(32, 8);
+    k_transpose_pad<<<grid, block, 0, h->stream>>>(in, out, K, L, W);
+    CU(cudaGetLastError());
+    h->launches++;
+    return JRC_OK;
+}
+
+static jrc_status launch_estimate(jrc_chain *h, const c32 *cmap, int n_inputs, int vlen, int mats, int cpi0, DetDev *dets)
+{
+    EstParams P;
+    ST(est_params(h, n_inputs, vlen, &P));
+    ST(h->sKeys.need(sizeof(unsigned long long) * (size_t)mats));
+    unsigned long long *keys = (unsigned long long *)h->sKeys.p;
+    CU(cudaMemsetAsync(keys, 0, sizeof(unsigned long long) * (size_t)mats, h->stream));
+    long long per = (long long)n_inputs * vlen;
+    int bx = (int)((per + 256 * 8 - 1) / (256 * 8));
+    if (bx < 1) bx = 1;
+    if (bx > 256) bx = 256;
+    for (int m0 = 0; m0 < mats; m0 += 65535) {
+        int mc = mats - m0 < 65535 ? mats - m0 : 65535;
+        k_est_argmax<<<dim3(bx, mc), 256, 0, h->stream>>>(cmap + (long long)m0 * per, per, keys + m0);
+        CU(cudaGetLastError());
+        h->launches++;
+    }
+    k_est_finalize<<<mats, 256, 0, h->stream>>>(cmap, per, n_inputs, vlen, keys, P, dets, cpi0);
+    CU(cudaGetLastError());
+    h->launches++;
+    return JRC_OK;
+}
+
+// channel estimates for a batch -> d_H [n_cpi][V][N]  (+ background ring update)
+static jrc_status launch_chan_est(jrc_chain *h, PortDev rx, PortDev tx, int n_cpi, c32 *d_H)
+{
+    const jrc_chain_cfg &c = h->cfg;
+    long long total = (long long)n_cpi * h->V * c.fft_len;
+    k_chan_est<<<grid_for(total, 256, h->sm_count), 256, 0, h->stream>>>(rx, tx, n_cpi, c.fft_len, c.n_tx, c.n_rx, c.n_sym,
+                                                                       c.n_pre, c.tx_interleave, d_H);
+    CU(cudaGetLastError());
+    h->launches++;
+    if (c.background_removal || c.background_recording) {
+        int VN = h->V * c.fft_len;
+        k_background<<<(VN + 127) / 128, 128, 0, h->stream>>>(d_H, n_cpi, VN, h->d_ring, h->d_temp, c.record_len,
+                                                            h->ring_size, h->ring_head, c.background_recording,
+                                                            c.background_removal);
+        CU(cudaGetLastError());
+        h->launches++;
+        if (c.background_removal && c.record_len > 0) {   // mirror the device-side ring evolution
+            for (int i = 0; i < n_cpi; i++) {
+                if (h->ring_size < c.record_len) h->ring_size++;
+                else h->ring_head = (h->ring_head + 1) % c.record_len;
+            }
+        }
+    }
+    return JRC_OK;
+}
+
+// ---------------------------------------------------------------------------
+// fused path dispatch
+// ---------------------------------------------------------------------------
+template <int IR, int IA, bool FROM_H>
+static jrc_status launch_fused_t(jrc_chain *h, const FusedParams &P)
+{
+    using Gm = FusedGeom<IR, IA>;
+    size_t smem = Gm::smem_bytes(P.T, P.R, P.S, FROM_H);
+    auto kern = k_fused64x8<IR, IA, FROM_H>;
+    CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, smem));
+    if (per_sm < 1) return fail(JRC_ERR_INVALID, "fused kernel does not fit (smem %zu bytes)", smem);
+    h->fused_ctas_per_sm = per_sm;
+    long long grid = (long long)h->sm_count * per_sm;
+    if (grid > P.n_cpi) grid = P.n_cpi;
+    kern<<<(unsigned)grid, 256, smem, h->stream>>>(P);
+    CU(cudaGetLastError());
+    h->launches++;
+    return JRC_OK;
+}
+
+template <bool FROM_H>
+static jrc_status launch_fused(jrc_chain *h, const FusedParams &P, bool *supported)
+{
+    const int IR = h->cfg.interp_range, IA = h->cfg.interp_angle;
+    *supported = true;
+#define JRC_FUSED_CASE(ir, ia) if (IR == ir && IA == ia) return launch_fused_t<ir, ia, FROM_H>(h, P);
+    JRC_FUSED_CASE(8, 16)    // shipped flowgraph: 512 x 128 map
+    JRC_FUSED_CASE(16, 8)    // BASELINE configs[1]: 1024 x 64 map
+    JRC_FUSED_CASE(8, 8)
+    JRC_FUSED_CASE(16, 16)
+#undef JRC_FUSED_CASE
+    *supported = false;
+    return JRC_OK;
+}
+
+static bool fused_config_ok(const jrc_chain *h)
+{
+    const int IR = h->cfg.interp_range, IA = h->cfg.interp_angle;
+    if (h->cfg.fft_len != 64 || h->V != 8) return false;
+    return (IR == 8 && IA == 16) || (IR == 16 && IA == 8) || (IR == 8 && IA == 8) || (IR == 16 && IA == 16);
+}
+
+static bool aligned16(const void *p) { return ((uintptr_t)p & 15u) == 0; }
+
+extern "C" jrc_status jrc_chain_run_batch(jrc_chain *h, jrc_port_layout rx, jrc_port_layout tx, int32_t n_cpi,
+                                           int32_t cpi0, float *map, jrc_c32 *cmap, jrc_det *dets, int32_t path)
+{
+    if (!h) return fail(JRC_ERR_INVALID, "null handle");
+    if (n_cpi < 0) return fail(JRC_ERR_INVALID, "n_cpi < 0");
+    if (n_cpi == 0) return JRC_OK;
+    if (!rx.base || !tx.base) return fail(JRC_ERR_INVALID, "null input pointer");
+    if (dets && !h->est_set) return fail(JRC_ERR_STATE, "dets requested but jrc_chain_set_estimator has not been called");
+    CU(cudaSetDevice(h->cfg.device));
+    const jrc_chain_cfg &c = h->cfg;
+    const int N = c.fft_len, V = h->V, Nr = h->Nr, Na = h->Na;
+    PortDev drx{(const c32 *)rx.base, rx.cpi_stride, rx.ant_stride};
+    PortDev dtx{(const c32 *)tx.base, tx.cpi_stride, tx.ant_stride};
+    const bool bg = c.background_removal != 0;
+
+    bool want_fused = (path != JRC_PATH_STAGED) && fused_config_ok(h) && cmap == nullptr;
+    if (want_fused && !bg) {
+        // cp.async moves 16-byte chunks: every antenna row must start 16-byte aligned
+        bool al = aligned16(rx.base) && aligned16(tx.base) && (rx.cpi_stride % 2 == 0) && (rx.ant_stride % 2 == 0) &&
+                  (tx.cpi_stride % 2 == 0) && (tx.ant_stride % 2 == 0);
+        if (!al) want_fused = false;
+    }
+    if (map && !aligned16(map)) want_fused = false;
+    if (path == JRC_PATH_FUSED && !want_fused)
+        return fail(JRC_ERR_INVALID, "fused path requested but this configuration/layout has no fused kernel");
+
+    if (want_fused) {
+        FusedParams P;
+        memset(&P, 0, sizeof(P));
+        P.rx = drx; P.tx = dtx; P.n_cpi = n_cpi; P.cpi0 = cpi0;
+        P.T = c.n_tx; P.R = c.n_rx; P.S = c.n_sym; P.n_pre = c.n_pre; P.tx_interleave = c.tx_interleave;
+        P.map = map; P.dets = (DetDev *)dets;
+        if (dets) ST(est_params(h, Nr, Na, &P.est));
+        bool ok = false;
+        if (bg || c.background_recording) {
+            // background path: raw estimates -> ring update/subtraction -> fused kernel from H
+            ST(h->sH.need((size_t)n_cpi * V * N * sizeof(c32)));
+            ST(launch_chan_est(h, drx, dtx, n_cpi, (c32 *)h->sH.p));
+            P.H = (const c32 *)h->sH.p;
+            ST(launch_fused<true>(h, P, &ok));
+        } else {
+            ST(launch_fused<false>(h, P, &ok));
+        }
+        if (ok) { h->last_path = JRC_PATH_FUSED; return JRC_OK; }
+    }
+
+    // ---- staged path: one kernel per reference block, chunked over CPIs ------
+    h->last_path = JRC_PATH_STAGED;
+    const size_t per_cpi = ((size_t)V * N + (size_t)V * Nr + (cmap ? 0 : (size_t)Nr * Na)) * sizeof(c32);
+    const size_t budget = (size_t)1 << 30;
+    int chunk = (int)(budget / per_cpi);
+    if (chunk < 1) chunk = 1;
+    if (chunk > 32768) chunk = 32768;   // grid.z / grid.y limits of the staged kernels
+    if (chunk > n_cpi) chunk = n_cpi;
+    ST(h->sH.need((size_t)chunk * V * N * sizeof(c32)));
+    ST(h->sY.need((size_t)chunk * V * Nr * sizeof(c32)));
+    if (!cmap) ST(h->sC.need((size_t)chunk * Nr * Na * sizeof(c32)));
+    for (int c0 = 0; c0 < n_cpi; c0 += chunk) {
+        const int nc = n_cpi - c0 < chunk ? n_cpi - c0 : chunk;
+        PortDev crx = drx, ctx = dtx;
+        crx.base += (long long)c0 * rx.cpi_stride;
+        ctx.base += (long long)c0 * tx.cpi_stride;
+        c32 *dH = (c32 *)h->sH.p, *dY = (c32 *)h->sY.p;
+        c32 *dC = cmap ? (c32 *)cmap + (size_t)c0 * Nr * Na : (c32 *)h->sC.p;
+        ST(launch_chan_est(h, crx, ctx, nc, dH));
+        // fft_vcc #A: backward, no shift; the zero-padded tail is implied by n_in = N
+        ST(launch_fft_rows(h, dH, N, N, dY, Nr, (long long)nc * V, 0, 0));
+        // matrix_transpose + fft_vcc #B (forward, shift).  The transpose is materialised
+        // (exactly the reference's data flow) into dC, then transformed in place.
+        ST(launch_transpose(h, dY, dC, V, Nr, Na, nc));
+        ST(launch_fft_rows(h, dC, Na, Na, dC, Na, (long long)nc * Nr, 1, 1));
+        if (map) {
+            long long n = (long long)nc * Nr * Na;
+            k_mag_squared<<<grid_for(n, 256, h->sm_count), 256, 0, h->stream>>>(dC, map + (size_t)c0 * Nr * Na, n);
+            CU(cudaGetLastError());
+            h->launches++;
+        }
+        if (dets) ST(launch_estimate(h, dC, Nr, Na, nc, cpi0 + c0, (DetDev *)dets + c0));
+    }
+    return JRC_OK;
+}
+
+// ---------------------------------------------------------------------------
+// host-buffer chain: pinned double-buffered pipeline
+// ---------------------------------------------------------------------------
+static bool host_ptr_is_pinned(const void *p)
+{
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
+}
+static bool ptr_is_device(const void *p)
+{
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+extern "C" jrc_status jrc_chain_run_host(jrc_chain *h, const jrc_c32 *rx_host, const jrc_c32 *tx_host, int32_t tx_shared,
+                                          int32_t n_cpi, int32_t cpi0, float *map_host, jrc_det *dets_host)
+{
+    if (!h || !rx_host || !tx_host) return fail(JRC_ERR_INVALID, "null argument");
+    if (n_cpi <= 0) return n_cpi == 0 ? JRC_OK : fail(JRC_ERR_INVALID, "n_cpi < 0");
+    if (dets_host && !h->est_set) return fail(JRC_ERR_STATE, "dets requested but jrc_chain_set_estimator has not been called");
+    CU(cudaSetDevice(h->cfg.device));
+    const jrc_chain_cfg &c = h->cfg;
+    const size_t rx_cpi = (size_t)c.n_rx * c.n_sym * c.fft_len, tx_cpi = (size_t)c.n_tx * c.n_sym * c.fft_len;
+    const size_t map_cpi = (size_t)h->Nr * h->Na;
+    // chunk so that one slot's map stays <= 128 MiB
+    int chunk = (int)(((size_t)128 << 20) / (map_cpi * sizeof(float)));
+    if (chunk < 1) chunk = 1;
+    if (chunk > n_cpi) chunk = n_cpi;
+    const bool direct = host_ptr_is_pinned(rx_host) && host_ptr_is_pinned(tx_host) &&
+                        (!map_host || host_ptr_is_pinned(map_host)) && (!dets_host || host_ptr_is_pinned(dets_host));
+    const size_t in_bytes = (rx_cpi + (tx_shared ? 0 : tx_cpi)) * sizeof(c32);
+    for (int s = 0; s < 2; s++) {
+        ST(h->sIn[s].need((size_t)chunk * in_bytes + (tx_shared ? tx_cpi * sizeof(c32) : 0)));
+        if (map_host) ST(h->sMap[s].need((size_t)chunk * map_cpi * sizeof(float)));
+        if (dets_host) ST(h->sDets[s].need((size_t)chunk * sizeof(jrc_det)));
+    }
+    if (!direct) {
+        ST(h->pin_a.need((size_t)chunk * in_bytes + tx_cpi * sizeof(c32)));
+        ST(h->pin_b.need((size_t)chunk * (map_host ? map_cpi * sizeof(float) : 0) + (size_t)chunk * sizeof(jrc_det)));
+    }
+    // jrc_chain_run_batch ignores n_pre here: the host layout is already stripped
+    jrc_chain_cfg saved = h->cfg;
+    h->cfg.n_pre = 0;
+    jrc_status st = JRC_OK;
+    int idx = 0;
+    for (int c0 = 0; c0 < n_cpi && st == JRC_OK; c0 += chunk, idx++) {
+        const int nc = n_cpi - c0 < chunk ? n_cpi - c0 : chunk;
+        const int s = idx & 1;
+        c32 *d_rx = (c32 *)h->sIn[s].p;
+        c32 *d_tx = d_rx + (size_t)chunk * rx_cpi;
+        const c32 *src_rx = (const c32 *)rx_host + (size_t)c0 * rx_cpi;
+        const c32 *src_tx = (const c32 *)tx_host + (tx_shared ? 0 : (size_t)c0 * tx_cpi);
+        const size_t txn = tx_shared ? tx_cpi : (size_t)nc * tx_cpi;
+        cudaError_t e = cudaSuccess;
+        // the slot's previous compute must be done before its inputs are overwritten
+        if (idx >= 2) e = cudaStreamWaitEvent(h->s_h2d, h->ev_comp[s], 0);
+        if (!direct) {
+            // pageable caller memory: stage through pinned buffers, chunk-synchronously
+            if (e == cudaSuccess) e = cudaStreamSynchronize(h->s_h2d);
+            memcpy(h->pin_a.p, src_rx, (size_t)nc * rx_cpi * sizeof(c32));
+            memcpy((c32 *)h->pin_a.p + (size_t)nc * rx_cpi, src_tx, txn * sizeof(c32));
+            src_rx = (const c32 *)h->pin_a.p;
+            src_tx = src_rx + (size_t)nc * rx_cpi;
+        }
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_rx, src_rx, (size_t)nc * rx_cpi * sizeof(c32), cudaMemcpyHostToDevice, h->s_h2d);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_tx, src_tx, txn * sizeof(c32), cudaMemcpyHostToDevice, h->s_h2d);
+        if (e == cudaSuccess) e = cudaEventRecord(h->ev_in[s], h->s_h2d);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(h->stream, h->ev_in[s], 0);
+        // the slot's previous D2H must be done before its outputs are overwritten
+        if (e == cudaSuccess && idx >= 2) e = cudaStreamWaitEvent(h->stream, h->ev_out[s], 0);
+        if (e != cudaSuccess) { st = fail(JRC_ERR_CUDA, "pipeline H2D: %s", cudaGetErrorString(e)); break; }
+        jrc_port_layout lrx{(const jrc_c32 *)d_rx, (int64_t)rx_cpi, (int64_t)c.n_sym * c.fft_len};
+        jrc_port_layout ltx{(const jrc_c32 *)d_tx, tx_shared ? 0 : (int64_t)tx_cpi, (int64_t)c.n_sym * c.fft_len};
+        float *d_map = map_host ? (float *)h->sMap[s].p : nullptr;
+        jrc_det *d_dets = dets_host ? (jrc_det *)h->sDets[s].p : nullptr;
+        st = jrc_chain_run_batch(h, lrx, ltx, nc, cpi0 + c0, d_map, nullptr, d_dets, JRC_PATH_AUTO);
+        if (st != JRC_OK) break;
+        e = cudaEventRecord(h->ev_comp[s], h->stream);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(h->s_d2h, h->ev_comp[s], 0);
+        float *dst_map = map_host ? map_host + (size_t)c0 * map_cpi : nullptr;
+        jrc_det *dst_dets = dets_host ? dets_host + c0 : nullptr;
+        if (!direct) {
+            dst_map = map_host ? (float *)h->pin_b.p : nullptr;
+            dst_dets = dets_host ? (jrc_det *)((char *)h->pin_b.p + (map_host ? (size_t)chunk * map_cpi * sizeof(float) : 0)) : nullptr;
+        }
+        if (e == cudaSuccess && map_host)
+            e = cudaMemcpyAsync(dst_map, d_map, (size_t)nc * map_cpi * sizeof(float), cudaMemcpyDeviceToHost, h->s_d2h);
+        if (e == cudaSuccess && dets_host)
+            e = cudaMemcpyAsync(dst_dets, d_dets, (size_t)nc * sizeof(jrc_det), cudaMemcpyDeviceToHost, h->s_d2h);
+        if (e == cudaSuccess) e = cudaEventRecord(h->ev_out[s], h->s_d2h);
+        if (e == cudaSuccess && !direct) {
+            e = cudaStreamSynchronize(h->s_d2h);
+            if (e == cudaSuccess && map_host) memcpy(map_host + (size_t)c0 * map_cpi, dst_map, (size_t)nc * map_cpi * sizeof(float));
+            if (e == cudaSuccess && dets_host) memcpy(dets_host + c0, dst_dets, (size_t)nc * sizeof(jrc_det));
+        }
+        if (e != cudaSuccess) { st = fail(JRC_ERR_CUDA, "pipeline D2H: %s", cudaGetErrorString(e)); break; }
+    }
+    h->cfg = saved;
+    cudaError_t e1 = cudaStreamSynchronize(h->s_h2d), e2 = cudaStreamSynchronize(h->stream), e3 = cudaStreamSynchronize(h->s_d2h);
+    if (st == JRC_OK && (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess))
+        st = fail(JRC_ERR_CUDA, "pipeline sync: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : (e2 != cudaSuccess ? e2 : e3)));
+    return st;
+}
+
+// ---------------------------------------------------------------------------
+// per-block stage calls.  Pointers may be host or device.
+// ---------------------------------------------------------------------------
+struct Staging {   // maps caller pointers onto device memory for the duration of one call
+    jrc_chain *h;
+    struct Out { void *host; void *dev; size_t bytes; };
+    std::vector<Out> outs;
+    std::vector<void *> temps;
+    explicit Staging(jrc_chain *hh) : h(hh) {}
+    ~Staging() { for (void *p : temps) cudaFree(p); }
+    jrc_status in(const void *p, size_t bytes, const void **dev)
+    {
+        if (ptr_is_device(p)) { *dev = p; return JRC_OK; }
+        void *d = nullptr;
+        CU(cudaMalloc(&d, bytes ? bytes : 1));
+        temps.push_back(d);
+        CU(cudaMemcpyAsync(d, p, bytes, cudaMemcpyHostToDevice, h->stream));
+        *dev = d;
+        return JRC_OK;
+    }
+    jrc_status out(void *p, size_t bytes, void **dev)
+    {
+        if (ptr_is_device(p)) { *dev = p; return JRC_OK; }
+        void *d = nullptr;
+        CU(cudaMalloc(&d, bytes ? bytes : 1));
+        temps.push_back(d);
+        outs.push_back({p, d, bytes});
+        *dev = d;
+        return JRC_OK;
+    }
+    jrc_status finish()
+    {
+        for (auto &o : outs) CU(cudaMemcpyAsync(o.host, o.dev, o.bytes, cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+        return JRC_OK;
+    }
+};
+
+extern "C" jrc_status jrc_radar_estimate(jrc_chain *h, const jrc_c32 *const *tx, const jrc_c32 *const *rx,
+                                          size_t tx_skip_items, jrc_c32 *out, jrc_c32 *chan_est_host)
+{
+    if (!h || !tx || !rx || !out) return fail(JRC_ERR_INVALID, "null argument");
+    CU(cudaSetDevice(h->cfg.device));
+    const jrc_chain_cfg &c = h->cfg;
+    const int N = c.fft_len, V = h->V, Nr = h->Nr;
+    const size_t frame = (size_t)(c.n_pre + c.n_sym) * N;   // items actually read per port
+    Staging sg(h);
+    // gather the per-port packets into one device block [T+R][frame]
+    ST(h->sMisc.need((size_t)(c.n_tx + c.n_rx) * frame * sizeof(c32)));
+    c32 *blk = (c32 *)h->sMisc.p;
+    for (int t = 0; t < c.n_tx; t++) {
+        const jrc_c32 *src = tx[t] + tx_skip_items * (size_t)N;    // lib/mimo_ofdm_radar_impl.cc:260
+        CU(cudaMemcpyAsync(blk + (size_t)t * frame, src, frame * sizeof(c32), cudaMemcpyDefault, h->stream));
+    }
+    for (int r = 0; r < c.n_rx; r++)
+        CU(cudaMemcpyAsync(blk + (size_t)(c.n_tx + r) * frame, rx[r], frame * sizeof(c32), cudaMemcpyDefault, h->stream));
+    PortDev dtx{blk, 0, (long long)frame}, drx{blk + (size_t)c.n_tx * frame, 0, (long long)frame};
+    ST(h->sH.need((size_t)V * N * sizeof(c32)));
+    c32 *dH = (c32 *)h->sH.p;
+    ST(launch_chan_est(h, drx, dtx, 1, dH));
+    void *dout = nullptr;
+    ST(sg.out(out, (size_t)V * Nr * sizeof(c32), &dout));
+    k_pad_rows<<<grid_for((long long)V * Nr, 256, h->sm_count), 256, 0, h->stream>>>(dH, (c32 *)dout, V, N, Nr);
+    CU(cudaGetLastError());
+    h->launches++;
+    if (chan_est_host) CU(cudaMemcpyAsync(chan_est_host, dH, (size_t)V * N * sizeof(c32), cudaMemcpyDeviceToHost, h->stream));
+    return sg.finish();
+}
+
+extern "C" jrc_status jrc_fft_vcc(jrc_chain *h, const jrc_c32 *in, jrc_c32 *out, int32_t n, int32_t batch,
+                                   int32_t forward, int32_t shift)
+{
+    if (!h || !in || !out) return fail(JRC_ERR_INVALID, "null argument");
+    if (batch <= 0) return JRC_OK;
+    CU(cudaSetDevice(h->cfg.device));
+    Staging sg(h);
+    const void *din = nullptr; void *dout = nullptr;
+    size_t bytes = (size_t)n * batch * sizeof(c32);
+    ST(sg.in(in, bytes, &din));
+    ST(sg.out(out, bytes, &dout));
+    ST(launch_fft_rows(h, (const c32 *)din, n, n, (c32 *)dout, n, batch, forward, shift));
+    return sg.finish();
+}
+
+extern "C" jrc_status jrc_transpose_pad(jrc_chain *h, const jrc_c32 *in, int32_t k_items, int32_t input_len,
+                                         int32_t output_len, int32_t interp, jrc_c32 *out)
+{
+    if (!h || !in || !out) return fail(JRC_ERR_INVALID, "null argument");
+    if (k_items < 0 || input_len < 1 || output_len < 1 || interp < 1) return fail(JRC_ERR_INVALID, "bad sizes");
+    // lib/matrix_transpose_impl.cc:82-83: the packet must hold whole columns
+    if (k_items > output_len * interp) return fail(JRC_ERR_INVALID, "input_len and output_len do not match to packet length");
+    CU(cudaSetDevice(h->cfg.device));
+    Staging sg(h);
+    const void *din = nullptr; void *dout = nullptr;
+    ST(sg.in(in, (size_t)k_items * input_len * sizeof(c32), &din));
+    ST(sg.out(out, (size_t)input_len * output_len * interp * sizeof(c32), &dout));
+    ST(launch_transpose(h, (const c32 *)din, (c32 *)dout, k_items, input_len, output_len * interp, 1));
+    return sg.finish();
+}
+
+extern "C" jrc_status jrc_mag_squared(jrc_chain *h, const jrc_c32 *in, float *out, size_t n)
+{
+    if (!h || !in || !out) return fail(JRC_ERR_INVALID, "null argument");
+    if (n == 0) return JRC_OK;
+    CU(cudaSetDevice(h->cfg.device));
+    Staging sg(h);
+    const void *din = nullptr; void *dout = nullptr;
+    ST(sg.in(in, n * sizeof(c32), &din));
+    ST(sg.out(out, n * sizeof(float), &dout));
+    k_mag_squared<<<grid_for((long long)n, 256, h->sm_count), 256, 0, h->stream>>>((const c32 *)din, (float *)dout, (long long)n);
+    CU(cudaGetLastError());
+    h->launches++;
+    return sg.finish();
+}
+
+extern "C" jrc_status jrc_estimate2d(jrc_chain *h, const jrc_c32 *map, int32_t n_inputs, int32_t vlen, jrc_det *det)
+{
+    if (!h || !map || !det) return fail(JRC_ERR_INVALID, "null argument");
+    if (n_inputs < 1 || vlen < 1) return fail(JRC_ERR_INVALID, "empty map");
+    CU(cudaSetDevice(h->cfg.device));
+    Staging sg(h);
+    const void *din = nullptr;
+    ST(sg.in(map, (size_t)n_inputs * vlen * sizeof(c32), &din));
+    ST(h->sDet.need(sizeof(DetDev)));
+    ST(launch_estimate(h, (const c32 *)din, n_inputs, vlen, 1, 0, (DetDev *)h->sDet.p));
+    DetDev d;
+    CU(cudaMemcpyAsync(&d, h->sDet.p, sizeof(d), cudaMemcpyDeviceToHost, h->stream));
+    ST(sg.finish());
+    memcpy(det, &d, sizeof(d));
+    if (det->range_idx >= 0) {
+        // final scalar of lib/range_angle_estimator_impl.cc:227,234 with the host libm so that
+        // the published snr has the reference's bit pattern
+        det->snr_db = 10 * std::log10(det->peak_power / det->noise_power);
+        det->flags = (det->snr_db >= h->snr_thr && det->peak_power >= h->pow_thr) ? JRC_DET_PASSED : 0u;
+    }
+    return JRC_OK;
+}
+
+extern "C" jrc_status jrc_peak1d(jrc_chain *h, const jrc_c32 *in, int32_t n, int32_t samp_rate, float interp_factor,
+                                  float threshold_db, int32_t samp_protect, jrc_peak1d_out *out)
+{
+    if (!h || !in || !out) return fail(JRC_ERR_INVALID, "null argument");
+    if (n < 0) return fail(JRC_ERR_INVALID, "n < 0");
+    CU(cudaSetDevice(h->cfg.device));
+    out->k = -1; out->freq = 0.f; out->phase = 0.f; out->mag = 0.f;
+    if (n == 0) return JRC_OK;
+    Staging sg(h);
+    const void *din = nullptr;
+    ST(sg.in(in, (size_t)n * sizeof(c32), &din));
+    ST(h->sKeys.need(sizeof(unsigned long long)));
+    ST(h->sDet.need(sizeof(Peak1dDev)));
+    CU(cudaMemsetAsync(h->sKeys.p, 0, sizeof(unsigned long long), h->stream));
+    const double thr_lin = std::pow(10, threshold_db / 10.0);      // lib/fft_peak_detect_impl.cc:89
+    k_peak1d_scan<<<grid_for(n, 256, h->sm_count), 256, 0, h->stream>>>((const c32 *)din, n, samp_protect, thr_lin,
+                                                                      (unsigned long long *)h->sKeys.p);
+    CU(cudaGetLastError());
+    k_peak1d_finalize<<<1, 1, 0, h->stream>>>((const c32 *)din, (const unsigned long long *)h->sKeys.p, (Peak1dDev *)h->sDet.p);
+    CU(cudaGetLastError());
+    h->launches += 2;
+    Peak1dDev d;
+    CU(cudaMemcpyAsync(&d, h->sDet.p, sizeof(d), cudaMemcpyDeviceToHost, h->stream));
+    ST(sg.finish());
+    out->k = d.k;
+    if (d.k != -1) {
+        // bin -> Hz conversion and arg() are scalar host work, evaluated exactly as :98-107
+        const int k = d.k;
+        if (k <= n / 2) out->freq = k / (float)n * (samp_rate * interp_factor);
+        else out->freq = -((float)samp_rate * interp_factor) + k * (samp_rate * interp_factor / (float)n);
+        out->phase = std::atan2(d.z.y, d.z.x);
+        out->mag = d.mag;
+    }
+    return JRC_OK;
+}
+
+extern "C" jrc_status jrc_zero_pad(jrc_chain *h, const jrc_c32 *in, int32_t n, uint32_t pad_front, uint32_t pad_tail,
+                                    uint64_t seed, jrc_c32 *out)
+{
+    if (!h || !out || (!in && n > 0)) return fail(JRC_ERR_INVALID, "null argument");
+    if (n < 0) return fail(JRC_ERR_INVALID, "n < 0");
+    CU(cudaSetDevice(h->cfg.device));
+    const size_t total = (size_t)n + pad_front + pad_tail;
+    if (total == 0) return JRC_OK;
+    Staging sg(h);
+    const void *din = nullptr; void *dout = nullptr;
+    if (n > 0) ST(sg.in(in, (size_t)n * sizeof(c32), &din));
+    ST(sg.out(out, total * sizeof(c32), &dout));
+    k_zero_pad<<<grid_for((long long)total, 256, h->sm_count), 256, 0, h->stream>>>((const c32 *)din, n, pad_front, pad_tail,
+                                                                                   (unsigned long long)seed, (c32 *)dout);
+    CU(cudaGetLastError());
+    h->launches++;
+    return sg.finish();
+}

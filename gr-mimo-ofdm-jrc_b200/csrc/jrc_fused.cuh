@@ -1,0 +1,342 @@
+// jrc_fused.cuh -- the fused radar chain for the 64-subcarrier / 8-virtual-channel
+// family (the shipped configuration and BASELINE configs[0..1]):
+//
+//   mimo_ofdm_radar conj-MAC (lib/mimo_ofdm_radar_impl.cc:250-274)
+//   -> range zero-pad + fft_vcc IFFT  (:243,:312-315; ...radar_sim.grc:940-962)
+//   -> matrix_transpose + angle zero-pad (lib/matrix_transpose_impl.cc:97-104)
+//   -> fft_vcc FFT + fftshift          (...radar_sim.grc:963-985)
+//   -> complex_to_mag_squared          (...radar_sim.grc:637-652)
+//   -> range_angle_estimator           (lib/range_angle_estimator_impl.cc:137-253)
+//
+// in ONE persistent kernel, one CTA per CPI at a time.  HBM sees the symbols once
+// (cp.async prefetch of the next CPI), the |.|^2 map once (per-warp TMA bulk stores
+// from a bank-conflict-free staging tile) and a 32-byte detection record; neither
+// zero-pad nor the transpose nor the complex map ever exist in memory.
+//
+// Index algebra (W_N = e^{+j2pi/N}, w_N = e^{-j2pi/N}, Q = Nr/8, Na = 8*IA):
+//   range  y[p][Q*m1 + q] = sum_{k0<8} W_8^{k0 m1} * ( W_Nr^{k0 q} * B[p][k0][q] )
+//          B[p][k0][q0 + IR*m0] = sum_{k1<8} W_8^{k1 m0} * ( W_Q^{k1 q0} * H[p][k0 + 8 k1] )
+//   angle  M[n][b + IA*a] = sum_{p<8} w_8^{p a} * ( (-1)^p w_Na^{p b} * y[p][n] )
+// i.e. three passes of "twiddle 8 inputs, 8-point DFT": the zero-padded inputs of
+// both FFTs are pruned away analytically (only the 64 resp. 8 non-zero inputs are
+// ever touched) and the output fftshift of the angle FFT is the (-1)^p factor.
+// All twiddles are per-thread constants computed once per (persistent) CTA.
+#pragma once
+#include "jrc_common.cuh"
+#include "jrc_staged.cuh"
+
+namespace jrc {
+
+struct FusedParams {
+    PortDev rx, tx;            // symbol inputs (unused when FROM_H)
+    const c32 *H;              // [n_cpi][8][64] channel estimates (FROM_H: background removal path)
+    int n_cpi, cpi0;
+    int T, R, S, n_pre, tx_interleave;
+    float *map;                // [n_cpi][NR][NA] or nullptr
+    DetDev *dets;              // [n_cpi] or nullptr
+    EstParams est;
+};
+
+template <int IR, int IA>
+struct FusedGeom {
+    static constexpr int NSC = 64, V = 8;
+    static constexpr int NR = NSC * IR, NA = V * IA, Q = NR / 8;
+    static constexpr int THREADS = 256, WARPS = 8;
+    static constexpr int G = 32 / IA;                    // range bins per warp iteration
+    static constexpr int ROWS_PER_WARP = NR / WARPS;
+    static constexpr int ITERS = ROWS_PER_WARP / G;
+    static constexpr int SIT = 2;                        // iterations per bulk store
+    static constexpr int NBUF = 2;                       // staging buffers per warp
+    static constexpr int UNROLL = SIT * NBUF;
+    static constexpr int STG_FLOATS = SIT * G * NA;      // floats per staging buffer (SIT KiB)
+    static constexpr int PSTEP = 32 / IR;                // channel step of the two range passes
+    static_assert(IA >= 4 && IA <= 32 && (IA & (IA - 1)) == 0, "angle interp must be 4..32, power of two");
+    static_assert(IR >= 1 && IR <= 32 && (IR & (IR - 1)) == 0, "range interp must be 1..32, power of two");
+    static_assert(ITERS >= UNROLL && ITERS % UNROLL == 0, "map too small for the store pipeline");
+
+    static size_t smem_bytes(int T, int R, int S, bool from_h)
+    {
+        size_t b = (size_t)V * NR * 8 + (size_t)V * NSC * 8 + (size_t)WARPS * NBUF * STG_FLOATS * 4 +
+                   (size_t)NA * 8 + 64 + 64 + 64;
+        if (!from_h) b += (size_t)(T + R) * S * NSC * 8;
+        return b;
+    }
+};
+
+__device__ __forceinline__ void cp_async16(void *sdst, const void *gsrc)
+{
+    unsigned s = (unsigned)__cvta_generic_to_shared(sdst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void bulk_store_s2g(void *gdst, const void *ssrc, unsigned bytes)
+{
+    unsigned s = (unsigned)__cvta_generic_to_shared(ssrc);
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(s), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+
+// one angle row task: 8 channel samples -> twiddle -> forward DFT-8 -> |.|^2.
+// Pure _rn intrinsics: re-evaluating a row reproduces the main loop bit for bit.
+__device__ __forceinline__ void angle_task(const c32 *__restrict__ ys, int NR, int n, const c32 (&tw)[8],
+                                           c32 (&u)[8], float (&v)[8])
+{
+#pragma unroll
+    for (int p = 0; p < 8; p++) u[p] = ys[p * NR + n];
+#pragma unroll
+    for (int p = 1; p < 8; p++) u[p] = cmul_fma(u[p], tw[p]);
+    fft8<-1>(u);
+#pragma unroll
+    for (int a = 0; a < 8; a++) v[a] = __fmaf_rn(u[a].x, u[a].x, __fmul_rn(u[a].y, u[a].y));
+}
+
+template <int IR, int IA, bool FROM_H>
+__global__ void __launch_bounds__(256, 2) k_fused64x8(const FusedParams P)
+{
+    using Gm = FusedGeom<IR, IA>;
+    constexpr int NR = Gm::NR, NA = Gm::NA, Q = Gm::Q, G = Gm::G;
+    constexpr int RPW = Gm::ROWS_PER_WARP, ITERS = Gm::ITERS, SIT = Gm::SIT, NBUF = Gm::NBUF;
+    constexpr int STGF = Gm::STG_FLOATS, PSTEP = Gm::PSTEP;
+
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    c32 *ys = reinterpret_cast<c32 *>(smem_raw);                  // [8][NR]  B then y (in place)
+    c32 *Hs = ys + 8 * NR;                                        // [8][64]
+    float *stg = reinterpret_cast<float *>(Hs + 512);             // [8 warps][NBUF][STGF]
+    c32 *tab = reinterpret_cast<c32 *>(stg + 8 * NBUF * STGF);    // [NA] e^{-j2pi m/NA}
+    unsigned long long *red = reinterpret_cast<unsigned long long *>(tab + NA);   // [8]
+    double *redd = reinterpret_cast<double *>(red + 8);           // [8]
+    int *sint = reinterpret_cast<int *>(redd + 8);                // [16] scalars
+    c32 *inb = reinterpret_cast<c32 *>(sint + 16);                // [(T+R)][S][64]
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    // ---- per-thread constants (once per persistent CTA) --------------------
+    // range pass 1: task (p, k0, q0);  twiddle W_Q^{k1 q0}
+    const int q0 = tid % IR, k0a = (tid / IR) & 7, p1 = tid / (8 * IR);
+    // range pass 2: task (p, q);       twiddle W_Nr^{k0 q}
+    const int q = tid % Q, p2 = tid / Q;
+    // angle pass:   task (n, b);       twiddle (-1)^p w_Na^{p (b + IA*rot)}
+    const int b = lane % IA, g = lane / IA, rot = g;
+    c32 tw1[8], tw2[8], tw3[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        tw1[j] = cispi_ratio(2 * j * q0, Q);
+        tw2[j] = cispi_ratio(2 * j * q, NR);
+        tw3[j] = cispi_ratio(j * (NA - 2 * (b + IA * rot)), NA);
+    }
+    for (int m = tid; m < NA; m += 256) tab[m] = cispi_ratio(-2 * m, NA);
+
+    // staging: slot a' of this thread holds angle bin b + IA*((a'+rot)&7); rotating by
+    // the row group makes the 32 lanes of every st.shared hit 32 different banks
+    float *wstg = stg + warp * NBUF * STGF;
+    float *sp[8];
+#pragma unroll
+    for (int a = 0; a < 8; a++) sp[a] = wstg + g * NA + b + IA * ((a + rot) & 7);
+
+    const int per_ant = P.S * 64;
+    auto prefetch = [&](int cpi) {
+        const int cpa = per_ant >> 1;   // 16-byte chunks per antenna row
+        const int total = (P.T + P.R) * cpa;
+        for (int c = tid; c < total; c += 256) {
+            int a = c / cpa, w = c - a * cpa;
+            const c32 *src = (a < P.T)
+                ? P.tx.base + (long long)cpi * P.tx.cpi_stride + (long long)a * P.tx.ant_stride
+                : P.rx.base + (long long)cpi * P.rx.cpi_stride + (long long)(a - P.T) * P.rx.ant_stride;
+            cp_async16(inb + a * per_ant + 2 * w, src + (long long)P.n_pre * 64 + 2 * w);
+        }
+        cp_async_commit();
+    };
+
+    int cpi = blockIdx.x;
+    if (!FROM_H && cpi < P.n_cpi) prefetch(cpi);
+
+    for (; cpi < P.n_cpi; cpi += gridDim.x) {
+        if (!FROM_H) cp_async_wait_all();
+        __syncthreads();   // (A) symbols landed; previous CPI fully consumed
+
+        // ---- stage 1: channel estimate H[p][k] --------------------------------
+        if (FROM_H) {
+            const c32 *Hg = P.H + (long long)cpi * 512;
+            Hs[tid] = Hg[tid];
+            Hs[tid + 256] = Hg[tid + 256];
+        } else {
+            const int k = tid & 63;
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const int p = (tid >> 6) + 4 * h;
+                int r, t;
+                if (P.tx_interleave) { t = p / P.R; r = p - t * P.R; } else { r = p / P.T; t = p - r * P.T; }
+                const c32 *srx = inb + (P.T + r) * per_ant + k;
+                const c32 *stx = inb + t * per_ant + k;
+                c32 acc = mk(0.f, 0.f);
+                for (int s = 0; s < P.S; s++) {
+                    c32 x = srx[s * 64], c = stx[s * 64];
+                    acc = cadd_exact(acc, cmul_exact(x, mk(c.x, -c.y)));
+                }
+                Hs[p * 64 + k] = acc;
+            }
+        }
+        __syncthreads();   // (B) H ready, symbol buffer free
+        if (!FROM_H) {
+            int nxt = cpi + gridDim.x;
+            if (nxt < P.n_cpi) prefetch(nxt);
+        }
+
+        // ---- stage 2: range pass 1 (pruned: 8 of Q inputs non-zero) ----------
+        for (int p = p1; p < 8; p += PSTEP) {
+            c32 u[8];
+#pragma unroll
+            for (int k1 = 0; k1 < 8; k1++) u[k1] = Hs[p * 64 + k0a + 8 * k1];
+#pragma unroll
+            for (int k1 = 1; k1 < 8; k1++) u[k1] = cmul_fma(u[k1], tw1[k1]);
+            fft8<1>(u);
+#pragma unroll
+            for (int m0 = 0; m0 < 8; m0++) ys[p * NR + k0a * Q + q0 + IR * m0] = u[m0];
+        }
+        __syncthreads();   // (C)
+
+        // ---- stage 3: range pass 2, in place ---------------------------------
+        for (int p = p2; p < 8; p += PSTEP) {
+            c32 u[8];
+#pragma unroll
+            for (int k0 = 0; k0 < 8; k0++) u[k0] = ys[p * NR + k0 * Q + q];
+#pragma unroll
+            for (int k0 = 1; k0 < 8; k0++) u[k0] = cmul_fma(u[k0], tw2[k0]);
+            fft8<1>(u);
+#pragma unroll
+            for (int m1 = 0; m1 < 8; m1++) ys[p * NR + m1 * Q + q] = u[m1];
+        }
+        __syncthreads();   // (D) y[p][n] complete
+
+        // ---- stage 4: angle pass + |.|^2 + store + running max ---------------
+        float best = -1.f;
+        int best_it = 0;
+        const int n_base = warp * RPW + g;
+        float *map_w = P.map ? P.map + ((long long)cpi * NR + warp * RPW) * NA : nullptr;
+        for (int it0 = 0; it0 < ITERS; it0 += Gm::UNROLL) {
+#pragma unroll
+            for (int ui = 0; ui < Gm::UNROLL; ui++) {
+                const int it = it0 + ui;
+                const int buf = ui / SIT, sub = ui % SIT;    // compile-time after unrolling
+                c32 u[8];
+                float v[8];
+                angle_task(ys, NR, n_base + it * G, tw3, u, v);
+                float m8 = fmaxf(fmaxf(fmaxf(v[0], v[1]), fmaxf(v[2], v[3])),
+                                 fmaxf(fmaxf(v[4], v[5]), fmaxf(v[6], v[7])));
+                if (m8 > best) { best = m8; best_it = it; }
+                if (map_w) {
+                    if (sub == 0) {   // the bulk store that last read this buffer must be done with it
+                        if (lane == 0) bulk_wait_read<NBUF - 1>();
+                        __syncwarp();
+                    }
+#pragma unroll
+                    for (int a = 0; a < 8; a++) sp[a][buf * STGF + sub * G * NA] = v[a];
+                    if (sub == SIT - 1) {
+                        fence_proxy_async_smem();
+                        __syncwarp();
+                        if (lane == 0) {
+                            bulk_store_s2g(map_w + (long long)(it - (SIT - 1)) * G * NA, wstg + buf * STGF, STGF * 4);
+                            bulk_commit();
+                        }
+                    }
+                }
+            }
+        }
+
+        // ---- stage 5: range_angle_estimator ----------------------------------
+        if (P.dets) {
+            unsigned long long key = best >= 0.f ? pack_key(best, (unsigned)(n_base + best_it * G)) : 0ull;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                unsigned long long other = __shfl_xor_sync(0xffffffffu, key, o);
+                key = other > key ? other : key;
+            }
+            if (lane == 0) red[warp] = key;
+            __syncthreads();   // (E)
+            key = red[0];
+#pragma unroll
+            for (int w = 1; w < 8; w++) key = red[w] > key ? red[w] : key;
+            if (key == 0ull) {   // NaN-only input: nothing can win the strict '>' scan
+                if (tid == 0) {
+                    DetDev d; d.range_idx = -1; d.angle_idx = -1; d.peak_power = -1.f;
+                    d.noise_power = __int_as_float(0x7fc00000); d.snr_db = d.noise_power;
+                    d.n_noise = 0; d.flags = 0; d.cpi = P.cpi0 + cpi;
+                    P.dets[cpi] = d;
+                }
+            } else {
+                const float gmax = __uint_as_float((unsigned)(key >> 32));
+                const int nstar = (int)(0xFFFFFFFFu - (unsigned)(key & 0xFFFFFFFFull));
+                if (warp == nstar / RPW) {
+                    // the lanes that own row nstar re-evaluate it and pick the first bin == gmax
+                    int icand = 0x7fffffff;
+                    c32 zc = mk(0.f, 0.f);
+                    if (g == (nstar % RPW) % G) {
+                        c32 u[8]; float v[8];
+                        angle_task(ys, NR, nstar, tw3, u, v);
+#pragma unroll
+                        for (int a = 0; a < 8; a++) {
+                            int i = b + IA * ((a + rot) & 7);
+                            if (v[a] == gmax && i < icand) { icand = i; zc = u[a]; }
+                        }
+                    }
+                    int imin = icand;
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) imin = min(imin, __shfl_xor_sync(0xffffffffu, imin, o));
+                    if (icand == imin && imin != 0x7fffffff) {
+                        NoiseWin w = noise_window(P.est, nstar, imin);
+                        sint[0] = nstar; sint[1] = imin;
+                        sint[2] = w.start_r; sint[3] = w.end_r; sint[4] = w.start_a; sint[5] = w.end_a;
+                        sint[6] = __float_as_int((float)ref_pow_abs2(zc));
+                    }
+                }
+                __syncthreads();   // (F)
+                const int start_r = sint[2], end_r = sint[3], start_a = sint[4], end_a = sint[5];
+                const int ncols = end_a - start_a, nrows = end_r - start_r;
+                const int total = (ncols > 0 && nrows > 0) ? nrows * ncols : 0;
+                double acc = 0.0;
+                for (int j = tid; j < total; j += 256) {
+                    int ir = start_r + j / ncols, ia = start_a + j % ncols;
+                    int r_idx = ((ir % NR) + NR) % NR;
+                    int a_idx = ((ia % NA) + NA) % NA;
+                    int m = (a_idx + NA / 2) & (NA - 1);
+                    c32 z = mk(0.f, 0.f);
+#pragma unroll
+                    for (int p = 0; p < 8; p++) {
+                        c32 yv = ys[p * NR + r_idx], t = tab[(p * m) & (NA - 1)];
+                        z.x = __fmaf_rn(yv.x, t.x, __fmaf_rn(-yv.y, t.y, z.x));
+                        z.y = __fmaf_rn(yv.x, t.y, __fmaf_rn(yv.y, t.x, z.y));
+                    }
+                    acc += ref_pow_abs2(z);
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+                if (lane == 0) redd[warp] = acc;
+                __syncthreads();   // (H)
+                if (tid == 0) {
+                    double s = 0.0;
+#pragma unroll
+                    for (int w = 0; w < 8; w++) s += redd[w];
+                    DetDev d;
+                    d.range_idx = sint[0]; d.angle_idx = sint[1];
+                    d.peak_power = __int_as_float(sint[6]);
+                    d.n_noise = total;
+                    d.noise_power = __fdiv_rn((float)s, (float)total);
+                    d.snr_db = __fmul_rn(10.f, log10f(__fdiv_rn(d.peak_power, d.noise_power)));
+                    d.flags = (d.snr_db >= P.est.snr_threshold && d.peak_power >= P.est.power_threshold) ? 1u : 0u;
+                    d.cpi = P.cpi0 + cpi;
+                    P.dets[cpi] = d;
+                }
+            }
+        }
+    }
+    // the CTA's shared memory must outlive the bulk stores that read it
+    if (lane == 0) bulk_wait_read<0>();
+    __syncwarp();
+}
+
+}  // namespace jrc

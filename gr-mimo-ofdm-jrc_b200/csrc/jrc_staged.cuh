@@ -1,0 +1,391 @@
+// jrc_staged.cuh -- one kernel per reference block ("staged" path).
+//
+// These kernels keep the exact per-block semantics of the reference flowgraph
+// (mimo_ofdm_radar -> fft_vcc -> matrix_transpose -> fft_vcc -> mag^2 / estimator)
+// and the exact float evaluation order of the CPU oracle, so that they are
+// bit-identical to it.  They serve the per-block C-ABI entry points, every
+// configuration the fused kernel has no specialisation for, and background removal.
+// Paths in comments are relative to the reference tree.
+#pragma once
+#include "jrc_common.cuh"
+
+namespace jrc {
+
+// ---------------------------------------------------------------------------
+// mimo_ofdm_radar conj-MAC  (lib/mimo_ofdm_radar_impl.cc:250-274)
+// H[cpi][p][k] = sum_s rx[r][(n_pre+s)*N+k] * conj(tx[t][(n_pre+s)*N+k]), s ascending,
+// p = r*T+t (or t*R+r when tx_interleave, :262-269).  One thread per (cpi,p,k).
+// ---------------------------------------------------------------------------
+struct PortDev { const c32 *base; long long cpi_stride; long long ant_stride; };
+
+__global__ void k_chan_est(PortDev rx, PortDev tx, int n_cpi, int N, int T, int R, int S, int n_pre,
+                           int tx_interleave, c32 *__restrict__ H /* [n_cpi][V][N] */)
+{
+    const int V = T * R;
+    const long long total = (long long)n_cpi * V * N;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total;
+         e += (long long)gridDim.x * blockDim.x) {
+        int k = (int)(e % N);
+        int p = (int)((e / N) % V);
+        long long cpi = e / ((long long)N * V);
+        int r, t;
+        if (tx_interleave) { t = p / R; r = p % R; } else { r = p / T; t = p % T; }
+        const c32 *prx = rx.base + cpi * rx.cpi_stride + r * rx.ant_stride + (long long)n_pre * N + k;
+        const c32 *ptx = tx.base + cpi * tx.cpi_stride + t * tx.ant_stride + (long long)n_pre * N + k;
+        c32 acc = mk(0.f, 0.f);
+        for (int s = 0; s < S; s++) {
+            c32 a = prx[(long long)s * N];
+            c32 b = ptx[(long long)s * N];
+            c32 prod = cmul_exact(a, mk(b.x, -b.y));
+            acc = cadd_exact(acc, prod);
+        }
+        H[e] = acc;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// background record / removal  (lib/mimo_ofdm_radar_impl.cc:276-300)
+// One thread per channel-estimate element; the CPIs of the batch are walked in
+// order because the ring buffer evolves frame by frame.  ring: [record_len][VN]
+// (slot (head+b)%record_len is the b-th oldest), temp: radar_chan_est_temp.
+// size/head are the ring state BEFORE this batch; the host advances them.
+// ---------------------------------------------------------------------------
+__global__ void k_background(c32 *__restrict__ H /* [n_cpi][VN] in: raw, out: subtracted */,
+                             int n_cpi, int VN, c32 *__restrict__ ring, c32 *__restrict__ temp,
+                             int record_len, int size0, int head0, int recording, int removal)
+{
+    int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= VN) return;
+    int size = size0, head = head0;
+    c32 tmp = temp[idx];
+    for (int c = 0; c < n_cpi; c++) {
+        c32 h = H[(long long)c * VN + idx];
+        if (recording) tmp = h;                                   // :276-279
+        if (removal) {
+            c32 mean = mk(0.f, 0.f);
+            for (int b = 0; b < size; b++) {                      // :286-289
+                c32 e = ring[(long long)((head + b) % record_len) * VN + idx];
+                mean.x = __fadd_rn(mean.x, __fdiv_rn(e.x, (float)size));
+                mean.y = __fadd_rn(mean.y, __fdiv_rn(e.y, (float)size));
+            }
+            h = csub_exact(h, mean);                              // :291
+            H[(long long)c * VN + idx] = h;
+            if (record_len > 0) {                                 // :297-300 push_back
+                if (size < record_len) { ring[(long long)((head + size) % record_len) * VN + idx] = tmp; size++; }
+                else { ring[(long long)head * VN + idx] = tmp; head = (head + 1) % record_len; }
+            }
+        }
+    }
+    temp[idx] = tmp;
+}
+
+// zero-padded copy H[cpi][p][0:N] -> out[cpi][p][0:N*interp]  (:243, :312-315)
+__global__ void k_pad_rows(const c32 *__restrict__ H, c32 *__restrict__ out, long long rows, int N, int Nout)
+{
+    const long long total = rows * Nout;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total;
+         e += (long long)gridDim.x * blockDim.x) {
+        int n = (int)(e % Nout);
+        long long row = e / Nout;
+        out[e] = (n < N) ? H[row * N + n] : mk(0.f, 0.f);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// gr::fft::fft_vcc  (GNU Radio 3.8 gr-fft semantics): batched radix-2
+// DIT in shared memory with the oracle's butterfly order and the same float32
+// twiddle table (rounded from double on the host) -> bit-identical to the oracle.
+// Row r reads n_in valid samples at in + r*in_stride (the rest of the n-point
+// input is zero: this is how the range zero-pad is never materialised) and writes
+// n samples at out + r*n.  rows_per_cta rows share a CTA when n is small.
+// ---------------------------------------------------------------------------
+__global__ void k_fft_rows(const c32 *__restrict__ in, long long in_stride, int n_in,
+                           c32 *__restrict__ out, int n, int log2n, long long rows, int rows_per_cta,
+                           int forward, int shift, const c32 *__restrict__ tw /* [n/2] */)
+{
+    extern __shared__ c32 sm[];
+    const long long row0 = (long long)blockIdx.x * rows_per_cta;
+    const int offset = (n + 1) / 2;
+    const int tot = rows_per_cta * n;
+    for (int e = threadIdx.x; e < tot; e += blockDim.x) {
+        int lr = e / n, i = e % n;
+        long long row = row0 + lr;
+        c32 v = mk(0.f, 0.f);
+        if (row < rows) {
+            int src = (!forward && shift) ? (i + offset) % n : i;   // swap input halves
+            if (src < n_in) v = in[row * in_stride + src];
+        }
+        unsigned rev = (log2n == 0) ? 0u : (__brev((unsigned)i) >> (32 - log2n));
+        sm[lr * n + rev] = v;
+    }
+    __syncthreads();
+    const int nbf = rows_per_cta * (n >> 1);
+    for (int len = 2; len <= n; len <<= 1) {
+        const int half = len >> 1, step = n / len;
+        for (int b = threadIdx.x; b < nbf; b += blockDim.x) {
+            int lr = b / (n >> 1), bb = b % (n >> 1);
+            int grp = bb / half, j = bb % half;
+            int i0 = lr * n + grp * len + j, i1 = i0 + half;
+            c32 w = tw[j * step];
+            c32 u = sm[i0];
+            c32 v = cmul_exact(sm[i1], w);
+            sm[i0] = cadd_exact(u, v);
+            sm[i1] = csub_exact(u, v);
+        }
+        __syncthreads();
+    }
+    for (int e = threadIdx.x; e < tot; e += blockDim.x) {
+        int lr = e / n, i = e % n;
+        long long row = row0 + lr;
+        if (row < rows) {
+            int src = (forward && shift) ? (i + offset) % n : i;    // swap output halves
+            out[row * n + i] = sm[lr * n + src];
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// matrix_transpose  (lib/matrix_transpose_impl.cc:97-104), batched over mats:
+// in [mat][K][L] -> out [mat][L][W], W = output_len*interp, out[l][k] = in[k][l] for
+// k < K, zero elsewhere.  32x32 shared-memory tiles keep both sides coalesced.
+// ---------------------------------------------------------------------------
+__global__ void k_transpose_pad(const c32 *__restrict__ in, c32 *__restrict__ out, int K, int L, int W)
+{
+    __shared__ c32 tile[32][33];
+    const long long mat = blockIdx.z;
+    const c32 *src = in + mat * (long long)K * L;
+    c32 *dst = out + mat * (long long)L * W;
+    const int l0 = blockIdx.x * 32, k0 = blockIdx.y * 32;
+    for (int dy = threadIdx.y; dy < 32; dy += blockDim.y) {
+        int k = k0 + dy, l = l0 + threadIdx.x;
+        tile[dy][threadIdx.x] = (k < K && l < L) ? src[(long long)k * L + l] : mk(0.f, 0.f);
+    }
+    __syncthreads();
+    for (int dy = threadIdx.y; dy < 32; dy += blockDim.y) {
+        int l = l0 + dy, k = k0 + threadIdx.x;
+        if (l < L && k < W) dst[(long long)l * W + k] = tile[threadIdx.x][dy];
+    }
+}
+
+// blocks_complex_to_mag_squared: VOLK generic kernel, re*re + im*im, no contraction
+__global__ void k_mag_squared(const c32 *__restrict__ in, float *__restrict__ out, long long n)
+{
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n;
+         e += (long long)gridDim.x * blockDim.x) {
+        c32 z = in[e];
+        out[e] = __fadd_rn(__fmul_rn(z.x, z.x), __fmul_rn(z.y, z.y));
+    }
+}
+
+// ---------------------------------------------------------------------------
+// range_angle_estimator  (lib/range_angle_estimator_impl.cc:137-227)
+// pass 1: arg-max of (float)pow(abs(z),2), first maximum in row-major order wins
+// (strict '>' at :144).  keys[mat] must be zeroed first.
+// ---------------------------------------------------------------------------
+__global__ void k_est_argmax(const c32 *__restrict__ map, long long per_mat, unsigned long long *keys)
+{
+    const long long mat = blockIdx.y;
+    const c32 *m = map + mat * per_mat;
+    unsigned long long best = 0ull;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < per_mat;
+         e += (long long)gridDim.x * blockDim.x) {
+        float p = (float)ref_pow_abs2(m[e]);
+        if (p == p) {   // NaN never wins (curr_power > peak_power is false)
+            unsigned long long key = pack_key(p, (unsigned)e);
+            best = key > best ? key : best;
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
+        best = other > best ? other : best;
+    }
+    __shared__ unsigned long long wbest[32];
+    if ((threadIdx.x & 31) == 0) wbest[threadIdx.x >> 5] = best;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        best = threadIdx.x < (blockDim.x >> 5) ? wbest[threadIdx.x] : 0ull;
+        for (int o = 16; o > 0; o >>= 1) {
+            unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
+            best = other > best ? other : best;
+        }
+        if (threadIdx.x == 0 && best) atomicMax(keys + mat, best);
+    }
+}
+
+struct EstParams {
+    const float *angle_bins;   // device [n_angle]
+    int n_angle, n_range;
+    int discard_range_idx;     // int(noise_discard_range_m / (range_bins[1]-range_bins[0])), host-computed (:189)
+    float noise_discard_angle_deg;
+    float snr_threshold, power_threshold;
+};
+
+struct DetDev {   // == jrc_det
+    int range_idx, angle_idx; float peak_power, noise_power, snr_db; int n_noise; unsigned flags; int cpi;
+};
+
+// noise-window geometry (:152-201), shared by the staged and the fused kernels
+struct NoiseWin { int start_r, end_r, start_a, end_a; };
+__device__ __forceinline__ NoiseWin noise_window(const EstParams &P, int peak_r, int peak_a)
+{
+    float angle_val = P.angle_bins[peak_a];
+    float angle_null = __fadd_rn(angle_val, 90.f);                       // :155
+    if (angle_null >= 90.f) angle_null = __fsub_rn(angle_null, 180.f);   // :157-160
+    int lo = 0, hi = P.n_angle;                                          // std::lower_bound :163
+    while (lo < hi) { int mid = lo + ((hi - lo) >> 1); if (P.angle_bins[mid] < angle_null) lo = mid + 1; else hi = mid; }
+    int idx;
+    if (lo == 0) idx = 0;                                                // :172
+    else if (lo == P.n_angle) idx = lo - 1;       // past-the-end read at :170 -> previous bin
+    else {
+        double a = P.angle_bins[lo - 1], b = P.angle_bins[lo];
+        idx = (fabs((double)angle_null - a) < fabs((double)angle_null - b)) ? lo - 1 : lo;   // :175-180
+    }
+    if (idx == P.n_angle - 1) idx = P.n_angle - 2;                       // :184-187
+    float da_f = __fdiv_rn(P.noise_discard_angle_deg,
+                           __fsub_rn(P.angle_bins[(idx + 1) % P.n_angle], P.angle_bins[idx]));   // :190
+    int da = (int)da_f;
+    if (da <= 0) da = 1;                                                 // :192-195
+    NoiseWin w;
+    w.start_r = peak_r + P.n_range / 2 - P.discard_range_idx;            // :197
+    w.end_r   = peak_r + P.n_range / 2 + P.discard_range_idx;            // :198
+    w.start_a = idx - da;                                                // :200
+    w.end_a   = idx + da;                                                // :201
+    return w;
+}
+
+// pass 2: one CTA per map.  The window powers are evaluated in parallel, but the
+// float accumulation runs in the reference's order on one thread (:211-221) so the
+// noise power is bit-identical.  snr/flags are finalised here with device log10f;
+// host-side callers that need the reference's libm bit pattern recompute them.
+__global__ void k_est_finalize(const c32 *__restrict__ map, long long per_mat, int n_inputs, int vlen,
+                               const unsigned long long *__restrict__ keys, EstParams P,
+                               DetDev *__restrict__ dets, int cpi0)
+{
+    const long long mat = blockIdx.x;
+    const c32 *m = map + mat * per_mat;
+    __shared__ float chunk[1024];
+    __shared__ NoiseWin win;
+    __shared__ int s_peak_r, s_peak_a;
+    __shared__ float s_noise;
+    unsigned long long key = keys[mat];
+    if (threadIdx.x == 0) {
+        DetDev d;
+        d.cpi = cpi0 + (int)mat; d.flags = 0; d.n_noise = 0;
+        if (key == 0ull) {   // empty / all-NaN map
+            d.range_idx = -1; d.angle_idx = -1; d.peak_power = -1.f;
+            d.noise_power = __int_as_float(0x7fc00000); d.snr_db = d.noise_power;
+            dets[mat] = d;
+            s_peak_r = -1;
+        } else {
+            unsigned lin = 0xFFFFFFFFu - (unsigned)(key & 0xFFFFFFFFull);
+            s_peak_r = (int)(lin / (unsigned)vlen); s_peak_a = (int)(lin % (unsigned)vlen);
+            win = noise_window(P, s_peak_r, s_peak_a);
+        }
+        s_noise = 0.f;
+    }
+    __syncthreads();
+    if (s_peak_r < 0) return;
+    const int ncols = win.end_a - win.start_a;
+    const int nrows = win.end_r - win.start_r;
+    const long long total = (ncols > 0 && nrows > 0) ? (long long)nrows * ncols : 0;
+    for (long long base = 0; base < total; base += 1024) {
+        int cnt = (int)((total - base) < 1024 ? (total - base) : 1024);
+        for (int j = threadIdx.x; j < cnt; j += blockDim.x) {
+            long long s = base + j;
+            int ir = win.start_r + (int)(s / ncols), ia = win.start_a + (int)(s % ncols);
+            int r_idx = ((ir % n_inputs) + n_inputs) % n_inputs;
+            int a_idx = ((ia % vlen) + vlen) % vlen;
+            chunk[j] = ref_abs(m[a_idx + (long long)vlen * r_idx]);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            float acc = s_noise;
+            for (int j = 0; j < cnt; j++) {
+                double a = (double)chunk[j];
+                acc = (float)((double)acc + a * a);                      // :217 float += double
+            }
+            s_noise = acc;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        DetDev d;
+        d.range_idx = s_peak_r; d.angle_idx = s_peak_a;
+        d.peak_power = __uint_as_float((unsigned)(key >> 32));
+        d.n_noise = (int)total;
+        d.noise_power = __fdiv_rn(s_noise, (float)d.n_noise);            // :226
+        d.snr_db = __fmul_rn(10.f, log10f(__fdiv_rn(d.peak_power, d.noise_power)));   // :227
+        d.flags = (d.snr_db >= P.snr_threshold && d.peak_power >= P.power_threshold) ? 1u : 0u;   // :234
+        d.cpi = cpi0 + (int)mat;
+        dets[mat] = d;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// fft_peak_detect  (lib/fft_peak_detect_impl.cc:88-95): first maximum of abs(in[p])
+// over [protect, n-protect) among samples with pow(abs,2) > 10^(thr/10) (double).
+// abs() is monotone with the key, so the arg-max runs on packed (abs, index) keys.
+// ---------------------------------------------------------------------------
+__global__ void k_peak1d_scan(const c32 *__restrict__ in, int n, int protect, double thr_lin,
+                              unsigned long long *key)
+{
+    unsigned long long best = 0ull;
+    for (long long p = (long long)protect + blockIdx.x * (long long)blockDim.x + threadIdx.x;
+         p < (long long)n - protect; p += (long long)gridDim.x * blockDim.x) {
+        float a = ref_abs(in[p]);
+        if (a == a && (double)a * (double)a > thr_lin) {
+            unsigned long long k = pack_key(a, (unsigned)p);
+            best = k > best ? k : best;
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
+        best = other > best ? other : best;
+    }
+    if ((threadIdx.x & 31) == 0 && best) atomicMax(key, best);
+}
+
+struct Peak1dDev { int k; float freq, phase, mag; c32 z; };
+__global__ void k_peak1d_finalize(const c32 *__restrict__ in, const unsigned long long *key, Peak1dDev *out)
+{
+    unsigned long long k = *key;
+    Peak1dDev o; o.k = -1; o.freq = 0.f; o.phase = 0.f; o.mag = 0.f; o.z = mk(0.f, 0.f);
+    if (k) {
+        o.k = (int)(0xFFFFFFFFu - (unsigned)(k & 0xFFFFFFFFull));
+        o.mag = __uint_as_float((unsigned)(k >> 32));
+        o.z = in[o.k];
+        o.phase = atan2f(o.z.y, o.z.x);   // host callers recompute with libm for bit parity
+    }
+    *out = o;
+}
+
+// ---------------------------------------------------------------------------
+// zero_pad  (lib/zero_pad_impl.cc:76-93): copy + N(0,1e-2) complex noise pads.
+// Counter-based generator (splitmix64 of seed^index, Box-Muller): the reference
+// seeds from std::random_device per call, so only the distribution is defined.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long mix64(unsigned long long z)
+{
+    z += 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+__global__ void k_zero_pad(const c32 *__restrict__ in, int n, unsigned pad_front, unsigned pad_tail,
+                           unsigned long long seed, c32 *__restrict__ out)
+{
+    const long long total = (long long)n + pad_front + pad_tail;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total;
+         e += (long long)gridDim.x * blockDim.x) {
+        if (e >= pad_front && e < (long long)pad_front + n) { out[e] = in[e - pad_front]; continue; }
+        unsigned long long h = mix64(seed ^ (unsigned long long)e * 0xD1342543DE82EF95ull);
+        float u1 = ((float)(unsigned)(h >> 40) + 1.0f) * (1.0f / 16777217.0f);
+        float u2 = (float)(unsigned)((h >> 8) & 0xFFFFFFu) * (1.0f / 16777216.0f);
+        float rad = 1e-2f * sqrtf(-2.0f * logf(u1));
+        float s, c;
+        sincospif(2.0f * u2, &s, &c);
+        out[e] = mk(rad * c, rad * s);
+    }
+}
+
+}  // namespace jrc

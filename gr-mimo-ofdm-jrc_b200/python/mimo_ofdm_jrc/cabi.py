@@ -1,0 +1,256 @@
+"""ctypes binding of libjrc_cuda.so (include/jrc_cuda.h).
+
+This is the only place the Python side touches native code.  The library is the
+product: if it is missing or cannot be loaded, importing a block raises -- there is
+no Python/NumPy fallback for any computation.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+PKG_ROOT = os.path.abspath(os.path.join(_HERE, "..", ".."))          # gr-mimo-ofdm-jrc_b200/
+LIB_PATH = os.path.join(PKG_ROOT, "libjrc_cuda.so")
+
+JRC_OK, JRC_ERR_INVALID, JRC_ERR_CUDA, JRC_ERR_NO_DEVICE, JRC_ERR_STATE = 0, 1, 2, 3, 4
+PATH_AUTO, PATH_FUSED, PATH_STAGED = 0, 1, 2
+
+
+class JrcError(RuntimeError):
+    def __init__(self, status, msg):
+        super().__init__(f"jrc status {status}: {msg}")
+        self.status = status
+
+
+class ChainCfg(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in (
+        "fft_len", "n_tx", "n_rx", "n_sym", "n_pre", "interp_range", "interp_angle",
+        "tx_interleave", "background_removal", "background_recording", "record_len", "device")]
+
+
+class PortLayout(C.Structure):
+    _fields_ = [("base", C.c_void_p), ("cpi_stride", C.c_int64), ("ant_stride", C.c_int64)]
+
+
+class Peak1dOut(C.Structure):
+    _fields_ = [("k", C.c_int32), ("freq", C.c_float), ("phase", C.c_float), ("mag", C.c_float)]
+
+
+DET_DTYPE = np.dtype([("range_idx", "<i4"), ("angle_idx", "<i4"), ("peak_power", "<f4"),
+                      ("noise_power", "<f4"), ("snr_db", "<f4"), ("n_noise", "<i4"),
+                      ("flags", "<u4"), ("cpi", "<i4")])
+assert DET_DTYPE.itemsize == 32
+
+EXPORTS = [
+    "jrc_chain_create", "jrc_chain_destroy", "jrc_last_error", "jrc_abi_version", "jrc_chain_stream",
+    "jrc_chain_sync", "jrc_chain_set_estimator", "jrc_chain_set_thresholds",
+    "jrc_chain_set_background_record", "jrc_chain_reset_background", "jrc_chain_run_batch",
+    "jrc_chain_last_path", "jrc_chain_launch_count", "jrc_chain_run_host", "jrc_radar_estimate",
+    "jrc_fft_vcc", "jrc_transpose_pad", "jrc_mag_squared", "jrc_estimate2d", "jrc_peak1d", "jrc_zero_pad",
+]
+
+_lib = None
+
+
+def load():
+    """Load libjrc_cuda.so; raises if it has not been built (python __graft_entry__.py build)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(f"{LIB_PATH} not built: run `make -C {PKG_ROOT}` (no CPU fallback exists)")
+    lib = C.CDLL(LIB_PATH)
+    vp, i32, i64, f32, u32, u64, sz = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_uint32, C.c_uint64, C.c_size_t
+    lib.jrc_last_error.restype = C.c_char_p
+    lib.jrc_abi_version.restype = i32
+    lib.jrc_chain_create.argtypes = [C.POINTER(ChainCfg), C.POINTER(vp)]
+    lib.jrc_chain_destroy.argtypes = [vp]
+    lib.jrc_chain_destroy.restype = None
+    lib.jrc_chain_stream.argtypes = [vp]
+    lib.jrc_chain_stream.restype = vp
+    lib.jrc_chain_sync.argtypes = [vp]
+    lib.jrc_chain_set_estimator.argtypes = [vp, vp, i32, vp, i32, f32, f32, f32, f32]
+    lib.jrc_chain_set_thresholds.argtypes = [vp, f32, f32]
+    lib.jrc_chain_set_background_record.argtypes = [vp, i32]
+    lib.jrc_chain_reset_background.argtypes = [vp]
+    lib.jrc_chain_run_batch.argtypes = [vp, PortLayout, PortLayout, i32, i32, vp, vp, vp, i32]
+    lib.jrc_chain_last_path.argtypes = [vp]
+    lib.jrc_chain_last_path.restype = i32
+    lib.jrc_chain_launch_count.argtypes = [vp]
+    lib.jrc_chain_launch_count.restype = i64
+    lib.jrc_chain_run_host.argtypes = [vp, vp, vp, i32, i32, i32, vp, vp]
+    lib.jrc_radar_estimate.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), sz, vp, vp]
+    lib.jrc_fft_vcc.argtypes = [vp, vp, vp, i32, i32, i32, i32]
+    lib.jrc_transpose_pad.argtypes = [vp, vp, i32, i32, i32, i32, vp]
+    lib.jrc_mag_squared.argtypes = [vp, vp, vp, sz]
+    lib.jrc_estimate2d.argtypes = [vp, vp, i32, i32, vp]
+    lib.jrc_peak1d.argtypes = [vp, vp, i32, i32, f32, f32, i32, C.POINTER(Peak1dOut)]
+    lib.jrc_zero_pad.argtypes = [vp, vp, i32, u32, u32, u64, vp]
+    for name in EXPORTS:
+        fn = getattr(lib, name)
+        if name not in ("jrc_last_error", "jrc_abi_version", "jrc_chain_destroy", "jrc_chain_stream",
+                        "jrc_chain_last_path", "jrc_chain_launch_count"):
+            fn.restype = i32
+    _lib = lib
+    return lib
+
+
+def check(status):
+    if status != JRC_OK:
+        raise JrcError(status, load().jrc_last_error().decode("utf-8", "replace"))
+
+
+def np_ptr(a: np.ndarray):
+    return C.c_void_p(a.ctypes.data)
+
+
+class Chain:
+    """Owns one jrc_chain handle (one CUDA stream + scratch)."""
+
+    def __init__(self, fft_len=64, n_tx=1, n_rx=1, n_sym=1, n_pre=0, interp_range=1, interp_angle=1,
+                 tx_interleave=False, background_removal=False, background_recording=False,
+                 record_len=0, device=0):
+        lib = load()
+        self.cfg = ChainCfg(fft_len, n_tx, n_rx, n_sym, n_pre, interp_range, interp_angle,
+                            int(bool(tx_interleave)), int(bool(background_removal)),
+                            int(bool(background_recording)), record_len, device)
+        self._h = C.c_void_p()
+        check(lib.jrc_chain_create(C.byref(self.cfg), C.byref(self._h)))
+        self.V = n_tx * n_rx
+        self.Nr = fft_len * interp_range
+        self.Na = self.V * interp_angle
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            load().jrc_chain_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- configuration ------------------------------------------------------
+    def set_estimator(self, range_bins, angle_bins, noise_discard_range_m, noise_discard_angle_deg,
+                      snr_threshold, power_threshold):
+        rb = np.ascontiguousarray(range_bins, dtype=np.float32)
+        ab = np.ascontiguousarray(angle_bins, dtype=np.float32)
+        check(load().jrc_chain_set_estimator(self._h, np_ptr(rb), rb.size, np_ptr(ab), ab.size,
+                                             noise_discard_range_m, noise_discard_angle_deg,
+                                             snr_threshold, power_threshold))
+
+    def set_thresholds(self, snr_threshold, power_threshold):
+        check(load().jrc_chain_set_thresholds(self._h, snr_threshold, power_threshold))
+
+    def set_background_record(self, on):
+        check(load().jrc_chain_set_background_record(self._h, int(bool(on))))
+
+    def reset_background(self):
+        check(load().jrc_chain_reset_background(self._h))
+
+    @property
+    def stream(self):
+        return load().jrc_chain_stream(self._h)
+
+    def sync(self):
+        check(load().jrc_chain_sync(self._h))
+
+    @property
+    def last_path(self):
+        return load().jrc_chain_last_path(self._h)
+
+    @property
+    def launch_count(self):
+        return load().jrc_chain_launch_count(self._h)
+
+    # -- fused chain, device pointers ---------------------------------------
+    def run_batch_ptr(self, rx_ptr, rx_cpi_stride, rx_ant_stride, tx_ptr, tx_cpi_stride, tx_ant_stride,
+                      n_cpi, cpi0=0, map_ptr=None, cmap_ptr=None, dets_ptr=None, path=PATH_AUTO):
+        rx = PortLayout(rx_ptr, rx_cpi_stride, rx_ant_stride)
+        tx = PortLayout(tx_ptr, tx_cpi_stride, tx_ant_stride)
+        check(load().jrc_chain_run_batch(self._h, rx, tx, n_cpi, cpi0, map_ptr, cmap_ptr, dets_ptr, path))
+
+    # -- fused chain, host buffers ------------------------------------------
+    def run_host_ptr(self, rx_ptr, tx_ptr, tx_shared, n_cpi, cpi0=0, map_ptr=None, dets_ptr=None):
+        check(load().jrc_chain_run_host(self._h, rx_ptr, tx_ptr, int(bool(tx_shared)), n_cpi, cpi0,
+                                        map_ptr, dets_ptr))
+
+    def run_host(self, rx: np.ndarray, tx: np.ndarray, want_map=True, want_dets=True, cpi0=0):
+        """rx [n_cpi][R][S][N] complex64, tx [n_cpi or 1][T][S][N] complex64 (NumPy, host)."""
+        rx = np.ascontiguousarray(rx, dtype=np.complex64)
+        tx = np.ascontiguousarray(tx, dtype=np.complex64)
+        n_cpi = rx.shape[0]
+        if tx.ndim == 3:
+            tx = tx[None]
+        tx_shared = tx.shape[0] == 1 and n_cpi > 1
+        m = np.empty((n_cpi, self.Nr, self.Na), dtype=np.float32) if want_map else None
+        d = np.zeros(n_cpi, dtype=DET_DTYPE) if want_dets else None
+        self.run_host_ptr(np_ptr(rx), np_ptr(tx), tx_shared, n_cpi, cpi0,
+                          np_ptr(m) if want_map else None, np_ptr(d) if want_dets else None)
+        return m, d
+
+    # -- per-block stage calls (NumPy host arrays) ---------------------------
+    def radar_estimate(self, tx_ports, rx_ports, tx_skip_items=0, want_chan_est=False):
+        T, R, N = self.cfg.n_tx, self.cfg.n_rx, self.cfg.fft_len
+        txs = [np.ascontiguousarray(a, dtype=np.complex64) for a in tx_ports]
+        rxs = [np.ascontiguousarray(a, dtype=np.complex64) for a in rx_ports]
+        assert len(txs) == T and len(rxs) == R
+        need = (self.cfg.n_pre + self.cfg.n_sym) * N
+        for a in rxs:
+            if a.size < need:
+                raise ValueError("rx packet shorter than n_pre + n_sym symbols")
+        for a in txs:
+            if a.size < need + tx_skip_items * N:
+                raise ValueError("tx packet shorter than skip + n_pre + n_sym symbols")
+        tp = (C.c_void_p * T)(*[a.ctypes.data for a in txs])
+        rp = (C.c_void_p * R)(*[a.ctypes.data for a in rxs])
+        out = np.empty((self.V, self.Nr), dtype=np.complex64)
+        ce = np.empty((self.V, N), dtype=np.complex64) if want_chan_est else None
+        check(load().jrc_radar_estimate(self._h, tp, rp, tx_skip_items, np_ptr(out),
+                                        np_ptr(ce) if want_chan_est else None))
+        return (out, ce) if want_chan_est else out
+
+    def fft_vcc(self, x, forward, shift):
+        x = np.ascontiguousarray(x, dtype=np.complex64)
+        n = x.shape[-1]
+        batch = x.size // n if n else 0
+        out = np.empty_like(x)
+        check(load().jrc_fft_vcc(self._h, np_ptr(x), np_ptr(out), n, batch, int(bool(forward)), int(bool(shift))))
+        return out
+
+    def transpose_pad(self, x, output_len, interp):
+        x = np.ascontiguousarray(x, dtype=np.complex64)
+        k_items, input_len = x.shape
+        out = np.empty((input_len, output_len * interp), dtype=np.complex64)
+        check(load().jrc_transpose_pad(self._h, np_ptr(x), k_items, input_len, output_len, interp, np_ptr(out)))
+        return out
+
+    def mag_squared(self, x):
+        x = np.ascontiguousarray(x, dtype=np.complex64)
+        out = np.empty(x.shape, dtype=np.float32)
+        check(load().jrc_mag_squared(self._h, np_ptr(x), np_ptr(out), x.size))
+        return out
+
+    def estimate2d(self, cmap):
+        cmap = np.ascontiguousarray(cmap, dtype=np.complex64)
+        n_inputs, vlen = cmap.shape
+        det = np.zeros(1, dtype=DET_DTYPE)
+        check(load().jrc_estimate2d(self._h, np_ptr(cmap), n_inputs, vlen, np_ptr(det)))
+        return det[0]
+
+    def peak1d(self, x, samp_rate, interp_factor, threshold_db, samp_protect):
+        x = np.ascontiguousarray(x, dtype=np.complex64)
+        out = Peak1dOut()
+        check(load().jrc_peak1d(self._h, np_ptr(x), x.size, samp_rate, interp_factor, threshold_db,
+                                samp_protect, C.byref(out)))
+        return out.k, out.freq, out.phase, out.mag
+
+    def zero_pad(self, x, pad_front, pad_tail, seed):
+        x = np.ascontiguousarray(x, dtype=np.complex64)
+        out = np.empty(x.size + pad_front + pad_tail, dtype=np.complex64)
+        check(load().jrc_zero_pad(self._h, np_ptr(x), x.size, pad_front, pad_tail, seed, np_ptr(out)))
+        return out

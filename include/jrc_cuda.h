@@ -1,0 +1,193 @@
+/*
+ * jrc_cuda.h -- C ABI of libjrc_cuda.so, the B200 (sm_100a) implementation of the
+ * gr-mimo-ofdm-jrc radar range-angle hot path.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no C++/torch types.
+ * The GNU Radio block wrappers (gr-mimo-ofdm-jrc_b200/lib/<block>_impl.cc) call
+ * ONLY these entry points from their work() functions; INTEGRATION.md shows the
+ * binding a maintainer of the reference adds.  Paths cited below are relative to
+ * the reference tree (ceyhunozkaptan/gr-mimo-ofdm-jrc).
+ *
+ * Conventions
+ *   - every function returns jrc_status; jrc_last_error() gives the message of the
+ *     last failure on the calling thread.  No exceptions cross this boundary; the
+ *     C++ wrappers translate non-zero status to std::runtime_error (the reference's
+ *     own error convention, e.g. lib/matrix_transpose_impl.cc:82-83).
+ *   - a handle owns one CUDA stream, its device scratch and pinned staging buffers.
+ *     Handles are independent; one handle must not be used from two threads at once
+ *     (GNU Radio never calls a block's work() concurrently with itself).
+ *   - "complex" is interleaved float32 (re, im) == gr_complex == std::complex<float>.
+ *   - there is NO CPU fallback: without a usable CUDA device every call fails.
+ */
+#ifndef JRC_CUDA_H
+#define JRC_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define JRC_API
+#else
+#define JRC_API __attribute__((visibility("default")))
+#endif
+
+typedef int32_t jrc_status;
+enum {
+    JRC_OK = 0,
+    JRC_ERR_INVALID = 1,     /* bad argument / unsupported size            */
+    JRC_ERR_CUDA = 2,        /* CUDA runtime error (message has the detail) */
+    JRC_ERR_NO_DEVICE = 3,   /* no CUDA device: the path refuses to run     */
+    JRC_ERR_STATE = 4        /* call order / missing configuration          */
+};
+
+typedef struct { float re, im; } jrc_c32;   /* gr_complex */
+
+typedef struct jrc_chain jrc_chain;         /* opaque handle */
+
+/* Construction parameters == the make() arguments of mimo_ofdm_radar
+ * (include/mimo_ofdm_jrc/mimo_ofdm_radar.h:48-60) plus the angle zero-pad of
+ * matrix_transpose (include/mimo_ofdm_jrc/matrix_transpose.h:48).            */
+typedef struct {
+    int32_t fft_len;               /* subcarriers (power of two)                 */
+    int32_t n_tx, n_rx, n_sym, n_pre;
+    int32_t interp_range;          /* mimo_ofdm_radar interp_factor  (Nr = fft_len*interp_range) */
+    int32_t interp_angle;          /* matrix_transpose interp_factor (Na = n_tx*n_rx*interp_angle) */
+    int32_t tx_interleave;         /* enable_tx_interleave (lib/mimo_ofdm_radar_impl.cc:262-269) */
+    int32_t background_removal;    /* lib/mimo_ofdm_radar_impl.cc:281-292         */
+    int32_t background_recording;  /* lib/mimo_ofdm_radar_impl.cc:276-279         */
+    int32_t record_len;            /* ring-buffer capacity (:115)                 */
+    int32_t device;                /* CUDA device ordinal                         */
+} jrc_chain_cfg;
+
+/* Detection record: what range_angle_estimator publishes per CPI
+ * (lib/range_angle_estimator_impl.cc:137-253), 32 bytes.                     */
+typedef struct {
+    int32_t  range_idx;     /* peak_range_idx                                 */
+    int32_t  angle_idx;     /* peak_angle_idx                                 */
+    float    peak_power;    /* (float)pow(abs(z),2) at the peak               */
+    float    noise_power;   /* mean of pow(abs(z),2) over the noise window    */
+    float    snr_db;        /* 10*log10(peak/noise)                           */
+    int32_t  n_noise;       /* n_noise_samples                                */
+    uint32_t flags;         /* bit0: snr >= snr_threshold && peak >= power_threshold (:234) */
+    int32_t  cpi;           /* sequence number: cpi0 + index in the batch     */
+} jrc_det;
+
+#define JRC_DET_PASSED 1u
+
+/* fft_peak_detect outputs (lib/fft_peak_detect_impl.cc:98-107); k == -1: no
+ * sample passed the threshold (the reference then leaves its outputs unwritten). */
+typedef struct { int32_t k; float freq, phase, mag; } jrc_peak1d_out;
+
+/* Input layout of a batch of CPIs, in units of complex samples.  Element
+ * (cpi, antenna a, LTF symbol s, subcarrier k) of a port lives at
+ *     base + cpi*cpi_stride + a*ant_stride + (n_pre + s)*fft_len + k
+ * i.e. every antenna row is a GNU Radio packet of fft_len-vectors starting at
+ * item 0 of the frame (lib/mimo_ofdm_radar_impl.cc:254-260).  tx.cpi_stride == 0
+ * shares one TX frame between all CPIs of the batch.                          */
+typedef struct { const jrc_c32 *base; int64_t cpi_stride; int64_t ant_stride; } jrc_port_layout;
+
+/* ---- life cycle ---------------------------------------------------------- */
+JRC_API jrc_status jrc_chain_create(const jrc_chain_cfg *cfg, jrc_chain **out);
+JRC_API void       jrc_chain_destroy(jrc_chain *h);
+JRC_API const char *jrc_last_error(void);
+JRC_API int32_t    jrc_abi_version(void);
+/* the handle's stream as a cudaStream_t (so callers can order their own work) */
+JRC_API void      *jrc_chain_stream(jrc_chain *h);
+JRC_API jrc_status jrc_chain_sync(jrc_chain *h);
+
+/* range_angle_estimator::make parameters
+ * (include/mimo_ofdm_jrc/range_angle_estimator.h:48-58).  range_bins/angle_bins are
+ * HOST arrays of n_range/n_angle floats (copied).                             */
+JRC_API jrc_status jrc_chain_set_estimator(jrc_chain *h,
+                                           const float *range_bins, int32_t n_range,
+                                           const float *angle_bins, int32_t n_angle,
+                                           float noise_discard_range_m,
+                                           float noise_discard_angle_deg,
+                                           float snr_threshold, float power_threshold);
+/* GRC callbacks: set_snr_threshold / set_power_threshold
+ * (lib/range_angle_estimator_impl.cc:286-287), set_background_record
+ * (lib/mimo_ofdm_radar_impl.cc:342-346)                                       */
+JRC_API jrc_status jrc_chain_set_thresholds(jrc_chain *h, float snr_threshold, float power_threshold);
+JRC_API jrc_status jrc_chain_set_background_record(jrc_chain *h, int32_t on);
+/* clears the background ring buffer (a freshly constructed block)            */
+JRC_API jrc_status jrc_chain_reset_background(jrc_chain *h);
+
+/* ---- the fused chain (device-resident batch) ------------------------------ *
+ * mimo_ofdm_radar -> fft_vcc(IFFT) -> matrix_transpose -> fft_vcc(FFT,shift) ->
+ * {complex_to_mag_squared, range_angle_estimator} for n_cpi independent CPIs.
+ * All pointers are DEVICE pointers; work is enqueued on the handle's stream and
+ * the call returns without synchronising.
+ *   map   : [n_cpi][Nr][Na] float32 |.|^2, or NULL
+ *   cmap  : [n_cpi][Nr][Na] complex map (what the estimator block would see), or NULL
+ *   dets  : [n_cpi] records, or NULL (needs jrc_chain_set_estimator first)
+ * path: JRC_PATH_AUTO picks the fused single-kernel path when the configuration
+ * has one (fft_len 64, 8 virtual channels, cmap == NULL), else the staged kernels. */
+enum { JRC_PATH_AUTO = 0, JRC_PATH_FUSED = 1, JRC_PATH_STAGED = 2 };
+JRC_API jrc_status jrc_chain_run_batch(jrc_chain *h, jrc_port_layout rx, jrc_port_layout tx,
+                                       int32_t n_cpi, int32_t cpi0,
+                                       float *map, jrc_c32 *cmap, jrc_det *dets, int32_t path);
+/* which path the last run_batch took (JRC_PATH_FUSED / JRC_PATH_STAGED) and how
+ * many kernels it launched                                                    */
+JRC_API int32_t    jrc_chain_last_path(const jrc_chain *h);
+JRC_API int64_t    jrc_chain_launch_count(const jrc_chain *h);
+
+/* Same chain with HOST buffers (packed layout rx[n_cpi][n_rx][n_sym][fft_len],
+ * tx[n_cpi or 1][n_tx][n_sym][fft_len], i.e. n_pre symbols already stripped):
+ * pinned double-buffered H2D -> kernels -> D2H, synchronous on return.
+ * map_host / dets_host may be NULL.                                           */
+JRC_API jrc_status jrc_chain_run_host(jrc_chain *h, const jrc_c32 *rx_host, const jrc_c32 *tx_host,
+                                      int32_t tx_shared, int32_t n_cpi, int32_t cpi0,
+                                      float *map_host, jrc_det *dets_host);
+
+/* ---- per-block stage calls (exact per-block semantics; pointers may be host
+ * or device, detected with cudaPointerGetAttributes; host buffers are staged
+ * through the handle's pinned memory and the call is synchronous) ------------ */
+
+/* mimo_ofdm_radar::general_work body (lib/mimo_ofdm_radar_impl.cc:243-315) for ONE
+ * frame: tx[n_tx], rx[n_rx] are per-port packet pointers (item 0 of the frame),
+ * tx_skip_items = n_tx_samples_discard (:189-197).  out: [V][fft_len*interp_range]
+ * zero-padded.  Updates the background ring buffer exactly like the block.
+ * chan_est_host (optional, host) receives radar_chan_est [V][fft_len] for
+ * capture_radar_data (:348-370).                                              */
+JRC_API jrc_status jrc_radar_estimate(jrc_chain *h, const jrc_c32 *const *tx, const jrc_c32 *const *rx,
+                                      size_t tx_skip_items, jrc_c32 *out, jrc_c32 *chan_est_host);
+
+/* gr::fft::fft_vcc (GNU Radio 3.8 gr-fft; examples/simulation/radar/
+ * mimo_ofdm_jrc_radar_sim.grc:940-985): batch items of length n (power of two,
+ * <= 16384), rectangular window, no scaling.                                  */
+JRC_API jrc_status jrc_fft_vcc(jrc_chain *h, const jrc_c32 *in, jrc_c32 *out,
+                               int32_t n, int32_t batch, int32_t forward, int32_t shift);
+
+/* matrix_transpose::work (lib/matrix_transpose_impl.cc:97-104):
+ * in [k_items][input_len] -> out [input_len][output_len*interp] zero-filled   */
+JRC_API jrc_status jrc_transpose_pad(jrc_chain *h, const jrc_c32 *in, int32_t k_items,
+                                     int32_t input_len, int32_t output_len, int32_t interp,
+                                     jrc_c32 *out);
+
+/* blocks_complex_to_mag_squared (...radar_sim.grc:637-652)                    */
+JRC_API jrc_status jrc_mag_squared(jrc_chain *h, const jrc_c32 *in, float *out, size_t n);
+
+/* range_angle_estimator::work (lib/range_angle_estimator_impl.cc:122-253) on one
+ * complex map [n_inputs][vlen]; det is a HOST record.                         */
+JRC_API jrc_status jrc_estimate2d(jrc_chain *h, const jrc_c32 *map, int32_t n_inputs, int32_t vlen,
+                                  jrc_det *det);
+
+/* fft_peak_detect::work (lib/fft_peak_detect_impl.cc:77-111)                  */
+JRC_API jrc_status jrc_peak1d(jrc_chain *h, const jrc_c32 *in, int32_t n, int32_t samp_rate,
+                              float interp_factor, float threshold_db, int32_t samp_protect,
+                              jrc_peak1d_out *out);
+
+/* zero_pad::work (lib/zero_pad_impl.cc:67-94): out[pad_front + i] = in[i]; the pads
+ * are N(0, 1e-2) complex noise from a counter-based generator keyed by seed
+ * (the reference draws a fresh std::random_device seed per call).             */
+JRC_API jrc_status jrc_zero_pad(jrc_chain *h, const jrc_c32 *in, int32_t n, uint32_t pad_front,
+                                uint32_t pad_tail, uint64_t seed, jrc_c32 *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* JRC_CUDA_H */
