@@ -357,7 +357,7 @@ static jrc_status launch_fused_t(jrc_chain *h, const FusedParams &P)
 {
     using Gm = FusedGeom<IR, IA>;
     size_t smem = Gm::smem_bytes(P.T, P.R, P.S, FROM_H);
-    auto kern = k_fused64x8<IR, IA, FROM_H>;
+    auto kern = P.map ? k_fused64x8<IR, IA, FROM_H, true> : k_fused64x8<IR, IA, FROM_H, false>;
     CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, smem));

@@ -45,19 +45,26 @@ struct FusedGeom {
     static constexpr int G = 32 / IA;                    // range bins per warp iteration
     static constexpr int ROWS_PER_WARP = NR / WARPS;
     static constexpr int ITERS = ROWS_PER_WARP / G;
-    static constexpr int SIT = 2;                        // iterations per bulk store
-    static constexpr int NBUF = 2;                       // staging buffers per warp
-    static constexpr int UNROLL = SIT * NBUF;
+#ifndef JRC_STORE_TMA
+#define JRC_STORE_TMA 0
+#endif
+    // Map store path.  TMA = 0: each warp copies its 1 KiB staging tile with 2 x (LDS.128 + STG.128)
+    // per iteration (fewest issue slots; profiles/README.md).  TMA = 1: per-warp cp.async.bulk
+    // (UBLKCP) stores of SIT KiB from a ring of NBUF staging tiles.
+    static constexpr bool TMA = JRC_STORE_TMA != 0;
+    static constexpr int SIT = TMA ? 2 : 1;              // iterations per store
+    static constexpr int NBUF = TMA ? 2 : 1;             // staging buffers per warp
+    static constexpr int UNROLL = 4;
     static constexpr int STG_FLOATS = SIT * G * NA;      // floats per staging buffer (SIT KiB)
     static constexpr int PSTEP = 32 / IR;                // channel step of the two range passes
     static_assert(IA >= 4 && IA <= 32 && (IA & (IA - 1)) == 0, "angle interp must be 4..32, power of two");
     static_assert(IR >= 1 && IR <= 32 && (IR & (IR - 1)) == 0, "range interp must be 1..32, power of two");
-    static_assert(ITERS >= UNROLL && ITERS % UNROLL == 0, "map too small for the store pipeline");
+    static_assert(ITERS >= UNROLL && ITERS % UNROLL == 0 && UNROLL % (SIT * NBUF) == 0, "map too small for the store pipeline");
 
     static size_t smem_bytes(int T, int R, int S, bool from_h)
     {
         size_t b = (size_t)V * NR * 8 + (size_t)V * NSC * 8 + (size_t)WARPS * NBUF * STG_FLOATS * 4 +
-                   (size_t)NA * 8 + 64 + 64 + 64;
+                   (size_t)NA * 8 + 64 + 1024 + 64;
         if (!from_h) b += (size_t)(T + R) * S * NSC * 8;
         return b;
     }
@@ -80,6 +87,21 @@ __device__ __forceinline__ void bulk_store_s2g(void *gdst, const void *ssrc, uns
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+// lane-0-only forms as predicated instructions (no BSSY/BSYNC divergence scaffolding in the hot loop)
+template <int N>
+__device__ __forceinline__ void bulk_wait_read_lane0(int lane)
+{
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.eq.s32 p, %0, 0;\n\t@p cp.async.bulk.wait_group.read %1;\n\t}" ::"r"(lane), "n"(N)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_store_commit_lane0(int lane, void *gdst, const void *ssrc, unsigned bytes)
+{
+    unsigned s = (unsigned)__cvta_generic_to_shared(ssrc);
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.eq.s32 p, %0, 0;\n\t"
+                 "@p cp.async.bulk.global.shared::cta.bulk_group [%1], [%2], %3;\n\t"
+                 "@p cp.async.bulk.commit_group;\n\t}" ::"r"(lane), "l"(gdst), "r"(s), "r"(bytes)
+                 : "memory");
+}
 
 // one angle row task: 8 channel samples -> twiddle -> forward DFT-8 -> |.|^2.
 // Pure _rn intrinsics: re-evaluating a row reproduces the main loop bit for bit.
@@ -90,12 +112,15 @@ __device__ __forceinline__ void angle_task(const c32 *__restrict__ ys, int NR, i
     for (int p = 0; p < 8; p++) u[p] = ys[p * NR + n];
 #pragma unroll
     for (int p = 1; p < 8; p++) u[p] = cmul_fma(u[p], tw[p]);
-    fft8<-1>(u);
+    JRC_FFT8<-1>(u);
 #pragma unroll
-    for (int a = 0; a < 8; a++) v[a] = __fmaf_rn(u[a].x, u[a].x, __fmul_rn(u[a].y, u[a].y));
+    for (int a = 0; a < 8; a++) {   // volk_32fc_magnitude_squared_32f: re*re + im*im, each product rounded
+        c32 sq = __fmul2_rn(u[a], u[a]);
+        v[a] = __fadd_rn(sq.x, sq.y);
+    }
 }
 
-template <int IR, int IA, bool FROM_H>
+template <int IR, int IA, bool FROM_H, bool WRITE_MAP>
 __global__ void __launch_bounds__(256, 2) k_fused64x8(const FusedParams P)
 {
     using Gm = FusedGeom<IR, IA>;
@@ -109,11 +134,12 @@ __global__ void __launch_bounds__(256, 2) k_fused64x8(const FusedParams P)
     float *stg = reinterpret_cast<float *>(Hs + 512);             // [8 warps][NBUF][STGF]
     c32 *tab = reinterpret_cast<c32 *>(stg + 8 * NBUF * STGF);    // [NA] e^{-j2pi m/NA}
     unsigned long long *red = reinterpret_cast<unsigned long long *>(tab + NA);   // [8]
-    double *redd = reinterpret_cast<double *>(red + 8);           // [8]
-    int *sint = reinterpret_cast<int *>(redd + 8);                // [16] scalars
+    double2 *redA = reinterpret_cast<double2 *>(red + 8);         // [8 warps][8 lags]
+    int *sint = reinterpret_cast<int *>(redA + 64);               // [16] scalars
     c32 *inb = reinterpret_cast<c32 *>(sint + 16);                // [(T+R)][S][64]
 
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // warp-uniform for the compiler
 
     // ---- per-thread constants (once per persistent CTA) --------------------
     // range pass 1: task (p, k0, q0);  twiddle W_Q^{k1 q0}
@@ -194,7 +220,7 @@ __global__ void __launch_bounds__(256, 2) k_fused64x8(const FusedParams P)
             for (int k1 = 0; k1 < 8; k1++) u[k1] = Hs[p * 64 + k0a + 8 * k1];
 #pragma unroll
             for (int k1 = 1; k1 < 8; k1++) u[k1] = cmul_fma(u[k1], tw1[k1]);
-            fft8<1>(u);
+            JRC_FFT8<1>(u);
 #pragma unroll
             for (int m0 = 0; m0 < 8; m0++) ys[p * NR + k0a * Q + q0 + IR * m0] = u[m0];
         }
@@ -207,7 +233,7 @@ __global__ void __launch_bounds__(256, 2) k_fused64x8(const FusedParams P)
             for (int k0 = 0; k0 < 8; k0++) u[k0] = ys[p * NR + k0 * Q + q];
 #pragma unroll
             for (int k0 = 1; k0 < 8; k0++) u[k0] = cmul_fma(u[k0], tw2[k0]);
-            fft8<1>(u);
+            JRC_FFT8<1>(u);
 #pragma unroll
             for (int m1 = 0; m1 < 8; m1++) ys[p * NR + m1 * Q + q] = u[m1];
         }
@@ -217,21 +243,21 @@ __global__ void __launch_bounds__(256, 2) k_fused64x8(const FusedParams P)
         float best = -1.f;
         int best_it = 0;
         const int n_base = warp * RPW + g;
-        float *map_w = P.map ? P.map + ((long long)cpi * NR + warp * RPW) * NA : nullptr;
+        float *map_w = WRITE_MAP ? P.map + ((long long)cpi * NR + warp * RPW) * NA : nullptr;
         for (int it0 = 0; it0 < ITERS; it0 += Gm::UNROLL) {
 #pragma unroll
             for (int ui = 0; ui < Gm::UNROLL; ui++) {
                 const int it = it0 + ui;
-                const int buf = ui / SIT, sub = ui % SIT;    // compile-time after unrolling
+                const int buf = (ui / SIT) % NBUF, sub = ui % SIT;    // compile-time after unrolling
                 c32 u[8];
                 float v[8];
                 angle_task(ys, NR, n_base + it * G, tw3, u, v);
                 float m8 = fmaxf(fmaxf(fmaxf(v[0], v[1]), fmaxf(v[2], v[3])),
                                  fmaxf(fmaxf(v[4], v[5]), fmaxf(v[6], v[7])));
                 if (m8 > best) { best = m8; best_it = it; }
-                if (map_w) {
+                if (WRITE_MAP && Gm::TMA) {
                     if (sub == 0) {   // the bulk store that last read this buffer must be done with it
-                        if (lane == 0) bulk_wait_read<NBUF - 1>();
+                        bulk_wait_read_lane0<NBUF - 1>(lane);
                         __syncwarp();
                     }
 #pragma unroll
@@ -239,11 +265,21 @@ __global__ void __launch_bounds__(256, 2) k_fused64x8(const FusedParams P)
                     if (sub == SIT - 1) {
                         fence_proxy_async_smem();
                         __syncwarp();
-                        if (lane == 0) {
-                            bulk_store_s2g(map_w + (long long)(it - (SIT - 1)) * G * NA, wstg + buf * STGF, STGF * 4);
-                            bulk_commit();
-                        }
+                        bulk_store_commit_lane0(lane, map_w + (long long)(it - (SIT - 1)) * G * NA, wstg + buf * STGF,
+                                                STGF * 4);
                     }
+                } else if (WRITE_MAP) {
+                    // conflict-free scalar st.shared of the strided bins, then the warp streams its
+                    // 1 KiB tile (G whole map rows, contiguous in HBM) out as 2 x 512 B
+#pragma unroll
+                    for (int a = 0; a < 8; a++) sp[a][0] = v[a];
+                    __syncwarp();
+                    const float4 o0 = reinterpret_cast<const float4 *>(wstg)[lane];
+                    const float4 o1 = reinterpret_cast<const float4 *>(wstg)[lane + 32];
+                    __syncwarp();
+                    float4 *dst = reinterpret_cast<float4 *>(map_w + (long long)it * G * NA);
+                    __stcs(dst + lane, o0);
+                    __stcs(dst + lane + 32, o1);
                 }
             }
         }
@@ -295,32 +331,58 @@ __global__ void __launch_bounds__(256, 2) k_fused64x8(const FusedParams P)
                     }
                 }
                 __syncthreads();   // (F)
+                // Noise window (lib/range_angle_estimator_impl.cc:197-226) without evaluating its samples:
+                //   sum_{r,c} |sum_p y[p][r] w^{p c'}|^2 = ncols*A[0] + 2 Re sum_{d=1..7} g[d] A[d],
+                //   A[d] = sum_r sum_q y[q+d][r] conj(y[q][r]),  g[d] = sum_c w^{d c'},  c' = c + Na/2,
+                // (w = e^{-j2pi/Na}; the modulo wrap of rows is the index, that of columns the period of w).
+                // 36 complex MACs per window row instead of 8 per sample; accumulated in double.
                 const int start_r = sint[2], end_r = sint[3], start_a = sint[4], end_a = sint[5];
                 const int ncols = end_a - start_a, nrows = end_r - start_r;
                 const int total = (ncols > 0 && nrows > 0) ? nrows * ncols : 0;
-                double acc = 0.0;
-                for (int j = tid; j < total; j += 256) {
-                    int ir = start_r + j / ncols, ia = start_a + j % ncols;
-                    int r_idx = ((ir % NR) + NR) % NR;
-                    int a_idx = ((ia % NA) + NA) % NA;
-                    int m = (a_idx + NA / 2) & (NA - 1);
-                    c32 z = mk(0.f, 0.f);
-#pragma unroll
-                    for (int p = 0; p < 8; p++) {
-                        c32 yv = ys[p * NR + r_idx], t = tab[(p * m) & (NA - 1)];
-                        z.x = __fmaf_rn(yv.x, t.x, __fmaf_rn(-yv.y, t.y, z.x));
-                        z.y = __fmaf_rn(yv.x, t.y, __fmaf_rn(yv.y, t.x, z.y));
+                const int lag = tid & 7;
+                double ar = 0.0, ai = 0.0;
+                if (total > 0) {
+                    for (int ir = start_r + (tid >> 3); ir < end_r; ir += 32) {
+                        const int r_idx = ((ir % NR) + NR) % NR;
+                        for (int qq = 0; qq + lag < 8; qq++) {
+                            c32 ya = ys[(qq + lag) * NR + r_idx], yb = ys[qq * NR + r_idx];
+                            ar += (double)ya.x * yb.x + (double)ya.y * yb.y;
+                            ai += (double)ya.y * yb.x - (double)ya.x * yb.y;
+                        }
                     }
-                    acc += ref_pow_abs2(z);
                 }
 #pragma unroll
-                for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-                if (lane == 0) redd[warp] = acc;
+                for (int o = 8; o <= 16; o <<= 1) {
+                    ar += __shfl_xor_sync(0xffffffffu, ar, o);
+                    ai += __shfl_xor_sync(0xffffffffu, ai, o);
+                }
+                if (lane < 8) redA[warp * 8 + lane] = make_double2(ar, ai);
                 __syncthreads();   // (H)
-                if (tid == 0) {
-                    double s = 0.0;
+                if (tid < 8) {
+                    double sr = 0.0, si = 0.0;
 #pragma unroll
-                    for (int w = 0; w < 8; w++) s += redd[w];
+                    for (int w = 0; w < 8; w++) { sr += redA[w * 8 + tid].x; si += redA[w * 8 + tid].y; }
+                    double contrib;
+                    if (tid == 0) {
+                        contrib = (double)ncols * sr;
+                    } else {
+                        // g[d] = w^{d m0} (1 - w^{d ncols}) / (1 - w^d),  m0 = start_a + Na/2
+                        const double inv = -2.0 / (double)NA;
+                        double s0, c0, s1, c1, s2, c2;
+                        sincospi(inv * (double)(((long long)tid * (start_a + NA / 2)) % NA), &s0, &c0);
+                        sincospi(inv * (double)(((long long)tid * ncols) % NA), &s1, &c1);
+                        sincospi(inv * (double)tid, &s2, &c2);
+                        const double nr = 1.0 - c1, ni = -s1, dr = 1.0 - c2, di = -s2;
+                        const double den = dr * dr + di * di;
+                        const double qr = (nr * dr + ni * di) / den, qi = (ni * dr - nr * di) / den;
+                        const double gr = c0 * qr - s0 * qi, gi = c0 * qi + s0 * qr;
+                        contrib = 2.0 * (gr * sr - gi * si);
+                    }
+                    contrib += __shfl_xor_sync(0xffu, contrib, 4);
+                    contrib += __shfl_xor_sync(0xffu, contrib, 2);
+                    contrib += __shfl_xor_sync(0xffu, contrib, 1);
+                    const double s = contrib > 0.0 ? contrib : 0.0;
+                  if (tid == 0) {
                     DetDev d;
                     d.range_idx = sint[0]; d.angle_idx = sint[1];
                     d.peak_power = __int_as_float(sint[6]);
@@ -330,13 +392,15 @@ __global__ void __launch_bounds__(256, 2) k_fused64x8(const FusedParams P)
                     d.flags = (d.snr_db >= P.est.snr_threshold && d.peak_power >= P.est.power_threshold) ? 1u : 0u;
                     d.cpi = P.cpi0 + cpi;
                     P.dets[cpi] = d;
+                  }
                 }
             }
         }
     }
-    // the CTA's shared memory must outlive the bulk stores that read it
-    if (lane == 0) bulk_wait_read<0>();
-    __syncwarp();
+    if (Gm::TMA) {   // the CTA's shared memory must outlive the bulk stores that read it
+        if (lane == 0) bulk_wait_read<0>();
+        __syncwarp();
+    }
 }
 
 }  // namespace jrc

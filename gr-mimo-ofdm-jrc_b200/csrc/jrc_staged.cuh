@@ -99,8 +99,8 @@ __global__ void k_pad_rows(const c32 *__restrict__ H, c32 *__restrict__ out, lon
 // input is zero: this is how the range zero-pad is never materialised) and writes
 // n samples at out + r*n.  rows_per_cta rows share a CTA when n is small.
 // ---------------------------------------------------------------------------
-__global__ void k_fft_rows(const c32 *__restrict__ in, long long in_stride, int n_in,
-                           c32 *__restrict__ out, int n, int log2n, long long rows, int rows_per_cta,
+__global__ void k_fft_rows(const c32 *in, long long in_stride, int n_in,   // in may alias out (in place)
+                           c32 *out, int n, int log2n, long long rows, int rows_per_cta,
                            int forward, int shift, const c32 *__restrict__ tw /* [n/2] */)
 {
     extern __shared__ c32 sm[];

@@ -13,7 +13,8 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 PKG_ROOT = os.path.abspath(os.path.join(_HERE, "..", ".."))          # gr-mimo-ofdm-jrc_b200/
-LIB_PATH = os.path.join(PKG_ROOT, "libjrc_cuda.so")
+# JRC_CUDA_LIB selects an experiment build of the same library (kernel A/B runs); never a fallback
+LIB_PATH = os.environ.get("JRC_CUDA_LIB") or os.path.join(PKG_ROOT, "libjrc_cuda.so")
 
 JRC_OK, JRC_ERR_INVALID, JRC_ERR_CUDA, JRC_ERR_NO_DEVICE, JRC_ERR_STATE = 0, 1, 2, 3, 4
 PATH_AUTO, PATH_FUSED, PATH_STAGED = 0, 1, 2

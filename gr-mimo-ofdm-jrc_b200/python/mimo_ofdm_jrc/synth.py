@@ -53,7 +53,7 @@ def tx_symbols(T: int, S: int, nsc: int) -> np.ndarray:
     P = p_matrix(T)
     ltf = ltf_sequence(nsc)
     X = P[:, np.arange(S) % T][:, :, None] * ltf[None, None, :]
-    return X.astype(np.complex64)
+    return np.ascontiguousarray(X.astype(np.complex64))
 
 
 def range_bins(nsc: int, interp: int, samp_rate: float = 125e6) -> np.ndarray:

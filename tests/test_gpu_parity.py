@@ -92,6 +92,7 @@ def test_staged_chain_is_bit_exact(jrc, orc, name):
     cm = torch.empty((n, Nr, Na), dtype=torch.complex64, device="cuda")
     dets = torch.zeros((n, 32), dtype=torch.uint8, device="cuda")
     per_ant = cfg["S"] * cfg["N"]
+    torch.cuda.synchronize()      # the handle runs on its own stream: inputs must have landed
     rc.chain.run_batch_ptr(drx.data_ptr(), cfg["R"] * per_ant, per_ant, dtx.data_ptr(), 0, per_ant, n, 0,
                            m.data_ptr(), cm.data_ptr(), dets.data_ptr(), jrc.PATH_STAGED)
     rc.sync()
