@@ -45,13 +45,16 @@ struct FusedGeom {
     static constexpr int G = 32 / IA;                    // range bins per warp iteration
     static constexpr int ROWS_PER_WARP = NR / WARPS;
     static constexpr int ITERS = ROWS_PER_WARP / G;
-#ifndef JRC_STORE_TMA
-#define JRC_STORE_TMA 0
+#ifndef JRC_STORE_MODE
+#define JRC_STORE_MODE 0
 #endif
-    // Map store path.  TMA = 0: each warp copies its 1 KiB staging tile with 2 x (LDS.128 + STG.128)
-    // per iteration (fewest issue slots; profiles/README.md).  TMA = 1: per-warp cp.async.bulk
-    // (UBLKCP) stores of SIT KiB from a ring of NBUF staging tiles.
-    static constexpr bool TMA = JRC_STORE_TMA != 0;
+    // Map store path (A/B measured on B200, profiles/README.md):
+    //   0: each warp stages its 1 KiB tile (G whole map rows) in shared memory and streams it out
+    //      with 2 x (LDS.128 + STG.128) per iteration;
+    //   1: per-warp cp.async.bulk (UBLKCP) stores of SIT KiB from a ring of NBUF staging tiles;
+    //   2: no staging: 8 STG.32 per thread, every warp store writing G x IA/8 full 32-byte sectors.
+    static constexpr int STORE = JRC_STORE_MODE;
+    static constexpr bool TMA = STORE == 1;
     static constexpr int SIT = TMA ? 2 : 1;              // iterations per store
     static constexpr int NBUF = TMA ? 2 : 1;             // staging buffers per warp
     static constexpr int UNROLL = 4;
@@ -64,7 +67,7 @@ struct FusedGeom {
     static size_t smem_bytes(int T, int R, int S, bool from_h)
     {
         size_t b = (size_t)V * NR * 8 + (size_t)V * NSC * 8 + (size_t)WARPS * NBUF * STG_FLOATS * 4 +
-                   (size_t)NA * 8 + 64 + 1024 + 64;
+                   (size_t)NA * 16 + (size_t)NA * 4 + 64 + 1024 + 64;
         if (!from_h) b += (size_t)(T + R) * S * NSC * 8;
         return b;
     }
@@ -132,8 +135,9 @@ __global__ void __launch_bounds__(256, 2) k_fused64x8(const FusedParams P)
     c32 *ys = reinterpret_cast<c32 *>(smem_raw);                  // [8][NR]  B then y (in place)
     c32 *Hs = ys + 8 * NR;                                        // [8][64]
     float *stg = reinterpret_cast<float *>(Hs + 512);             // [8 warps][NBUF][STGF]
-    c32 *tab = reinterpret_cast<c32 *>(stg + 8 * NBUF * STGF);    // [NA] e^{-j2pi m/NA}
-    unsigned long long *red = reinterpret_cast<unsigned long long *>(tab + NA);   // [8]
+    double2 *tabd = reinterpret_cast<double2 *>(stg + 8 * NBUF * STGF);   // [NA] e^{-j2pi m/NA}
+    float *abin = reinterpret_cast<float *>(tabd + NA);                   // [NA] angle_bins copy
+    unsigned long long *red = reinterpret_cast<unsigned long long *>(abin + NA);   // [8]
     double2 *redA = reinterpret_cast<double2 *>(red + 8);         // [8 warps][8 lags]
     int *sint = reinterpret_cast<int *>(redA + 64);               // [16] scalars
     c32 *inb = reinterpret_cast<c32 *>(sint + 16);                // [(T+R)][S][64]
@@ -147,7 +151,7 @@ __global__ void __launch_bounds__(256, 2) k_fused64x8(const FusedParams P)
     // range pass 2: task (p, q);       twiddle W_Nr^{k0 q}
     const int q = tid % Q, p2 = tid / Q;
     // angle pass:   task (n, b);       twiddle (-1)^p w_Na^{p (b + IA*rot)}
-    const int b = lane % IA, g = lane / IA, rot = g;
+    const int b = lane % IA, g = lane / IA, rot = (Gm::STORE == 2) ? 0 : g;
     c32 tw1[8], tw2[8], tw3[8];
 #pragma unroll
     for (int j = 0; j < 8; j++) {
@@ -155,7 +159,14 @@ __global__ void __launch_bounds__(256, 2) k_fused64x8(const FusedParams P)
         tw2[j] = cispi_ratio(2 * j * q, NR);
         tw3[j] = cispi_ratio(j * (NA - 2 * (b + IA * rot)), NA);
     }
-    for (int m = tid; m < NA; m += 256) tab[m] = cispi_ratio(-2 * m, NA);
+    EstParams est = P.est;
+    for (int m = tid; m < NA; m += 256) {
+        double sn, cs;
+        sincospi(-2.0 * (double)m / (double)NA, &sn, &cs);
+        tabd[m] = make_double2(cs, sn);
+        if (P.dets) abin[m] = P.est.angle_bins[m];
+    }
+    est.angle_bins = abin;   // the window geometry's binary search runs on shared memory
 
     // staging: slot a' of this thread holds angle bin b + IA*((a'+rot)&7); rotating by
     // the row group makes the 32 lanes of every st.shared hit 32 different banks
@@ -268,6 +279,10 @@ __global__ void __launch_bounds__(256, 2) k_fused64x8(const FusedParams P)
                         bulk_store_commit_lane0(lane, map_w + (long long)(it - (SIT - 1)) * G * NA, wstg + buf * STGF,
                                                 STGF * 4);
                     }
+                } else if (WRITE_MAP && Gm::STORE == 2) {
+                    float *dst = map_w + (long long)(it * G + g) * NA + b;
+#pragma unroll
+                    for (int a = 0; a < 8; a++) __stcs(dst + IA * a, v[a]);
                 } else if (WRITE_MAP) {
                     // conflict-free scalar st.shared of the strided bins, then the warp streams its
                     // 1 KiB tile (G whole map rows, contiguous in HBM) out as 2 x 512 B
@@ -324,7 +339,7 @@ __global__ void __launch_bounds__(256, 2) k_fused64x8(const FusedParams P)
 #pragma unroll
                     for (int o = 16; o > 0; o >>= 1) imin = min(imin, __shfl_xor_sync(0xffffffffu, imin, o));
                     if (icand == imin && imin != 0x7fffffff) {
-                        NoiseWin w = noise_window(P.est, nstar, imin);
+                        NoiseWin w = noise_window(est, nstar, imin);
                         sint[0] = nstar; sint[1] = imin;
                         sint[2] = w.start_r; sint[3] = w.end_r; sint[4] = w.start_a; sint[5] = w.end_a;
                         sint[6] = __float_as_int((float)ref_pow_abs2(zc));
@@ -335,22 +350,24 @@ __global__ void __launch_bounds__(256, 2) k_fused64x8(const FusedParams P)
                 //   sum_{r,c} |sum_p y[p][r] w^{p c'}|^2 = ncols*A[0] + 2 Re sum_{d=1..7} g[d] A[d],
                 //   A[d] = sum_r sum_q y[q+d][r] conj(y[q][r]),  g[d] = sum_c w^{d c'},  c' = c + Na/2,
                 // (w = e^{-j2pi/Na}; the modulo wrap of rows is the index, that of columns the period of w).
-                // 36 complex MACs per window row instead of 8 per sample; accumulated in double.
+                // 36 complex MACs per window row instead of 8 per sample.
                 const int start_r = sint[2], end_r = sint[3], start_a = sint[4], end_a = sint[5];
                 const int ncols = end_a - start_a, nrows = end_r - start_r;
                 const int total = (ncols > 0 && nrows > 0) ? nrows * ncols : 0;
                 const int lag = tid & 7;
-                double ar = 0.0, ai = 0.0;
+                // float products / per-thread partial sums (<= 16 terms), double from the first reduction on
+                float arf = 0.f, aif = 0.f;
                 if (total > 0) {
                     for (int ir = start_r + (tid >> 3); ir < end_r; ir += 32) {
                         const int r_idx = ((ir % NR) + NR) % NR;
                         for (int qq = 0; qq + lag < 8; qq++) {
                             c32 ya = ys[(qq + lag) * NR + r_idx], yb = ys[qq * NR + r_idx];
-                            ar += (double)ya.x * yb.x + (double)ya.y * yb.y;
-                            ai += (double)ya.y * yb.x - (double)ya.x * yb.y;
+                            arf = __fmaf_rn(ya.x, yb.x, __fmaf_rn(ya.y, yb.y, arf));
+                            aif = __fmaf_rn(ya.y, yb.x, __fmaf_rn(-ya.x, yb.y, aif));
                         }
                     }
                 }
+                double ar = (double)arf, ai = (double)aif;
 #pragma unroll
                 for (int o = 8; o <= 16; o <<= 1) {
                     ar += __shfl_xor_sync(0xffffffffu, ar, o);
@@ -367,12 +384,11 @@ __global__ void __launch_bounds__(256, 2) k_fused64x8(const FusedParams P)
                         contrib = (double)ncols * sr;
                     } else {
                         // g[d] = w^{d m0} (1 - w^{d ncols}) / (1 - w^d),  m0 = start_a + Na/2
-                        const double inv = -2.0 / (double)NA;
-                        double s0, c0, s1, c1, s2, c2;
-                        sincospi(inv * (double)(((long long)tid * (start_a + NA / 2)) % NA), &s0, &c0);
-                        sincospi(inv * (double)(((long long)tid * ncols) % NA), &s1, &c1);
-                        sincospi(inv * (double)tid, &s2, &c2);
-                        const double nr = 1.0 - c1, ni = -s1, dr = 1.0 - c2, di = -s2;
+                        const double2 w0 = tabd[(tid * (start_a + NA / 2)) & (NA - 1)];
+                        const double2 w1 = tabd[(tid * ncols) & (NA - 1)];
+                        const double2 w2 = tabd[tid];
+                        const double c0 = w0.x, s0 = w0.y;
+                        const double nr = 1.0 - w1.x, ni = -w1.y, dr = 1.0 - w2.x, di = -w2.y;
                         const double den = dr * dr + di * di;
                         const double qr = (nr * dr + ni * di) / den, qi = (ni * dr - nr * di) / den;
                         const double gr = c0 * qr - s0 * qi, gi = c0 * qi + s0 * qr;
