@@ -1,0 +1,1 @@
+#include <gnuradio/shim_runtime.h>

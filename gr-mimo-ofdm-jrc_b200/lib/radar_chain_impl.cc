@@ -1,0 +1,112 @@
+// radar_chain: the fused B200 chain as one GNU Radio block (see include/mimo_ofdm_jrc/radar_chain.h).
+// general_work = mimo_ofdm_radar's frame bookkeeping + one jrc_chain_run_host() call.
+#include <mimo_ofdm_jrc/radar_chain.h>
+
+#include <gnuradio/io_signature.h>
+
+#include <cstring>
+
+#include "jrc_host.h"
+
+namespace gr {
+namespace mimo_ofdm_jrc {
+
+class radar_chain_impl : public radar_chain
+{
+    const int d_fft_len, d_N_tx, d_N_rx, d_N_sym, d_N_pre, d_Nr, d_Na;
+    const std::vector<float> d_range_bins, d_angle_bins;
+    float d_snr_threshold, d_power_threshold;
+    host::stats_log d_log;
+    const bool d_debug;
+    host::chain_handle d_chain;
+    std::vector<gr_complex> d_rx, d_tx;   // frame without the preamble, packed [ant][sym][fft_len]
+
+    void push_thresholds() { host::check(jrc_chain_set_thresholds(d_chain.get(), d_snr_threshold, d_power_threshold), "RADAR CHAIN"); }
+
+public:
+    radar_chain_impl(int fft_len, int N_tx, int N_rx, int N_sym, int N_pre, bool background_removal, bool background_recording,
+                     int record_len, int ir, int ia, bool enable_tx_interleave, const std::vector<float> &range_bins,
+                     const std::vector<float> &angle_bins, float nd_range_m, float nd_angle_deg, float snr_threshold,
+                     float power_threshold, const std::string &stats_path, bool stats_record, bool debug)
+        : gr::block("radar_chain", gr::io_signature::make(N_tx + N_rx, N_tx + N_rx, sizeof(gr_complex) * fft_len),
+                    gr::io_signature::make(1, 1, sizeof(float) * N_tx * N_rx * ia)),
+          d_fft_len(fft_len), d_N_tx(N_tx), d_N_rx(N_rx), d_N_sym(N_sym), d_N_pre(N_pre), d_Nr(fft_len * ir),
+          d_Na(N_tx * N_rx * ia), d_range_bins(range_bins), d_angle_bins(angle_bins), d_snr_threshold(snr_threshold),
+          d_power_threshold(power_threshold), d_debug(debug), d_rx((size_t)N_rx * N_sym * fft_len),
+          d_tx((size_t)N_tx * N_sym * fft_len)
+    {
+        jrc_chain_cfg cfg{};
+        cfg.fft_len = fft_len; cfg.n_tx = N_tx; cfg.n_rx = N_rx; cfg.n_sym = N_sym; cfg.n_pre = 0;
+        cfg.interp_range = ir; cfg.interp_angle = ia; cfg.tx_interleave = enable_tx_interleave;
+        cfg.background_removal = background_removal; cfg.background_recording = background_recording;
+        cfg.record_len = record_len;
+        d_chain.open(cfg, "RADAR CHAIN");
+        host::check(jrc_chain_set_estimator(d_chain.get(), d_range_bins.data(), (int)d_range_bins.size(), d_angle_bins.data(),
+                                            (int)d_angle_bins.size(), nd_range_m, nd_angle_deg, snr_threshold, power_threshold),
+                    "RADAR CHAIN");
+        d_log.path = stats_path; d_log.record = stats_record;
+        message_port_register_out(pmt::mp("params"));
+        set_tag_propagation_policy(TPP_DONT);
+        set_output_multiple(d_Nr);
+    }
+
+    void set_background_record(bool on) override { host::check(jrc_chain_set_background_record(d_chain.get(), on), "RADAR CHAIN"); }
+    void set_snr_threshold(float v) override { d_snr_threshold = v; push_thresholds(); }
+    void set_power_threshold(float v) override { d_power_threshold = v; push_thresholds(); }
+    void set_stats_record(bool on) override { d_log.record = on; d_log.header_written = false; }
+
+    int general_work(int noutput_items, gr_vector_int &ninput_items, gr_vector_const_void_star &input_items,
+                     gr_vector_void_star &output_items) override
+    {
+        host::frame_plan plan = host::plan_frame(*this, d_N_tx, ninput_items, d_N_pre + d_N_sym);
+        if (plan.action == host::frame_plan::NO_RX_TAG) {
+            for (size_t i = 0; i < ninput_items.size(); i++) consume((int)i, ninput_items[i]);
+            return 0;
+        }
+        if (plan.action == host::frame_plan::WAIT) return 0;
+        if (plan.action == host::frame_plan::DROP_RX) {
+            for (int r = 0; r < d_N_rx; r++) consume(d_N_tx + r, (int)plan.rx_packet_len);
+            return 0;
+        }
+        if (noutput_items < d_Nr) return 0;
+        const size_t per_ant = (size_t)d_N_sym * d_fft_len;
+        for (int t = 0; t < d_N_tx; t++)
+            std::memcpy(&d_tx[t * per_ant], static_cast<const gr_complex *>(input_items[t]) + (plan.tx_skip_items + d_N_pre) * d_fft_len,
+                        per_ant * sizeof(gr_complex));
+        for (int r = 0; r < d_N_rx; r++)
+            std::memcpy(&d_rx[r * per_ant], static_cast<const gr_complex *>(input_items[d_N_tx + r]) + (size_t)d_N_pre * d_fft_len,
+                        per_ant * sizeof(gr_complex));
+        jrc_det det;
+        host::check(jrc_chain_run_host(d_chain.get(), reinterpret_cast<const jrc_c32 *>(d_rx.data()),
+                                       reinterpret_cast<const jrc_c32 *>(d_tx.data()), 1, 1, 0,
+                                       static_cast<float *>(output_items[0]), &det),
+                    "RADAR CHAIN");
+        add_item_tag(0, nitems_written(0), pmt::string_to_symbol("packet_len"), pmt::from_long(d_Nr), pmt::string_to_symbol(alias()));
+        if (det.flags & JRC_DET_PASSED) {
+            const float range_val = d_range_bins[det.range_idx], angle_val = d_angle_bins[det.angle_idx];
+            message_port_pub(pmt::mp("params"), host::params_message(range_val, angle_val, det.peak_power, det.snr_db));
+            if (d_log.record && !d_log.append(det.peak_power, det.snr_db, range_val, angle_val))
+                throw std::runtime_error("[RADAR CHAIN] Could not open file!!");
+        }
+        for (int r = 0; r < d_N_rx; r++) consume(d_N_tx + r, (int)plan.rx_packet_len);
+        for (int t = 0; t < d_N_tx; t++) consume(t, (int)(plan.tx_skip_items + plan.tx_packet_len));
+        return d_Nr;
+    }
+};
+
+radar_chain::sptr radar_chain::make(int fft_len, int N_tx, int N_rx, int N_sym, int N_pre, bool background_removal,
+                                    bool background_recording, int record_len, int interp_factor_range,
+                                    int interp_factor_angle, bool enable_tx_interleave, std::vector<float> range_bins,
+                                    std::vector<float> angle_bins, float noise_discard_range_m, float noise_discard_angle_deg,
+                                    float snr_threshold, float power_threshold, const std::string &stats_path,
+                                    bool stats_record, const std::string & /*len_tag_key*/, bool debug)
+{
+    return gnuradio::get_initial_sptr(new radar_chain_impl(fft_len, N_tx, N_rx, N_sym, N_pre, background_removal,
+                                                           background_recording, record_len, interp_factor_range,
+                                                           interp_factor_angle, enable_tx_interleave, range_bins, angle_bins,
+                                                           noise_discard_range_m, noise_discard_angle_deg, snr_threshold,
+                                                           power_threshold, stats_path, stats_record, debug));
+}
+
+}  // namespace mimo_ofdm_jrc
+}  // namespace gr

@@ -1,0 +1,282 @@
+// test_blocks.cc -- drives the C++ GNU Radio block wrappers (gr-mimo-ofdm-jrc_b200/lib) through the
+// runtime stand-in, one general_work() call at a time, and checks them against the CPU oracle on
+// identical inputs.  Needs a GPU (the blocks have no CPU path).  Run by tests/test_cpp_blocks.py.
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <random>
+
+#include <mimo_ofdm_jrc/fft_peak_detect.h>
+#include <mimo_ofdm_jrc/matrix_transpose.h>
+#include <mimo_ofdm_jrc/mimo_ofdm_radar.h>
+#include <mimo_ofdm_jrc/radar_chain.h>
+#include <mimo_ofdm_jrc/range_angle_estimator.h>
+#include <mimo_ofdm_jrc/zero_pad.h>
+
+#include <jrc_cuda.h>
+#include "../../oracle/jrc_oracle.h"
+
+using namespace gr;
+using namespace gr::mimo_ofdm_jrc;
+typedef std::vector<gr_complex> cvec;
+
+static int g_fail = 0;
+#define CHECK(cond, ...)                                                     \
+    do {                                                                     \
+        if (!(cond)) { g_fail++; std::printf("FAIL %s:%d: ", __FILE__, __LINE__); std::printf(__VA_ARGS__); std::printf("\n"); } \
+    } while (0)
+
+static std::mt19937 rng(12345);
+static cvec randvec(size_t n, float scale = 1.f)
+{
+    std::normal_distribution<float> d(0.f, scale);
+    cvec v(n);
+    for (auto &z : v) z = gr_complex(d(rng), d(rng));
+    return v;
+}
+static bool same(const gr_complex *a, const orc_c32 *b, size_t n) { return std::memcmp(a, b, n * sizeof(gr_complex)) == 0; }
+
+static std::vector<float> range_bins(int nsc, int ir)
+{
+    std::vector<float> v(nsc * ir);
+    double rmax = 3e8 * nsc / (2 * 125e6);
+    for (int i = 0; i < nsc * ir; i++) v[i] = (float)(rmax * i / (nsc * ir - 1));
+    return v;
+}
+static std::vector<float> angle_bins(int Na)
+{
+    std::vector<float> v(Na);
+    for (int i = 0; i < Na; i++) v[i] = (float)(std::asin(2.0 / Na * (i - std::floor(Na / 2.0) + 0.5)) * 180.0 / M_PI);
+    return v;
+}
+
+// one frame: per-port packets of (pre+S) fft_len-vectors
+struct frame_t { std::vector<cvec> tx, rx; };
+static frame_t make_frame(int T, int R, int items, int N)
+{
+    frame_t f;
+    for (int t = 0; t < T; t++) f.tx.push_back(randvec((size_t)items * N));
+    for (int r = 0; r < R; r++) f.rx.push_back(randvec((size_t)items * N));
+    return f;
+}
+
+static void test_radar_block()
+{
+    const int N = 64, T = 4, R = 2, S = 4, pre = 5, IR = 8, V = T * R, items = pre + S + 3;
+    for (int interleave = 0; interleave < 2; interleave++) {
+        auto blk = mimo_ofdm_radar::make(N, T, R, S, pre, true, true, 3, IR, interleave, "/tmp/jrc_cpp_chan.csv");
+        orc_radar *ref = orc_radar_create(N, T, R, S, pre, 1, 1, 3, IR, interleave);
+        cvec out((size_t)V * N * IR), refout((size_t)V * N * IR);
+        uint64_t rd = 0;
+        for (int it = 0; it < 6; it++) {
+            frame_t f = make_frame(T, R, items, N);
+            std::vector<shim::input_t> in(T + R);
+            for (int t = 0; t < T; t++) { in[t].items = f.tx[t].data(); in[t].n_items = items; }
+            for (int r = 0; r < R; r++) { in[T + r].items = f.rx[r].data(); in[T + r].n_items = items; }
+            in[0].tags.push_back(shim::make_tag(rd, "packet_len", pmt::from_long(items)));
+            in[T].tags.push_back(shim::make_tag(rd, "packet_len", pmt::from_long(items)));
+            in[T].tags.push_back(shim::make_tag(rd, "rx_time", pmt::make_tuple(pmt::from_uint64(1), pmt::from_double(0.5))));
+            auto res = shim::run_once(*blk, in, {{out.data(), 64}});
+            std::vector<const orc_c32 *> tp, rp;
+            for (auto &v : f.tx) tp.push_back((const orc_c32 *)v.data());
+            for (auto &v : f.rx) rp.push_back((const orc_c32 *)v.data());
+            orc_radar_work(ref, tp.data(), rp.data(), 0, (orc_c32 *)refout.data());
+            CHECK(res.produced == V, "radar produced %d", res.produced);
+            CHECK(same(out.data(), (const orc_c32 *)refout.data(), out.size()), "radar output differs (interleave %d frame %d)", interleave, it);
+            CHECK(res.out_tags[0].size() == 1 && pmt::to_long(res.out_tags[0][0].value) == V &&
+                      res.out_tags[0][0].offset == (uint64_t)it * V && pmt::symbol_to_string(res.out_tags[0][0].srcid) == blk->alias(),
+                  "radar output tag");
+            for (int p = 0; p < T + R; p++) CHECK(res.consumed[p] == items, "radar consumed[%d]=%d", p, res.consumed[p]);
+            rd += items;
+            if (it == 3) { blk->set_background_record(false); orc_radar_set_background_record(ref, 0); }
+        }
+        orc_radar_destroy(ref);
+        blk->capture_radar_data(true);
+    }
+    // stale TX frame in front + no-tag flush
+    auto blk = mimo_ofdm_radar::make(N, T, R, S, pre, false, false, 1, IR, false, "/tmp/jrc_cpp_chan.csv");
+    orc_radar *ref = orc_radar_create(N, T, R, S, pre, 0, 0, 1, IR, 0);
+    frame_t f1 = make_frame(T, R, items, N), f2 = make_frame(T, R, items, N);
+    std::vector<cvec> txcat(T);
+    for (int t = 0; t < T; t++) { txcat[t] = f1.tx[t]; txcat[t].insert(txcat[t].end(), f2.tx[t].begin(), f2.tx[t].end()); }
+    std::vector<shim::input_t> in(T + R);
+    for (int t = 0; t < T; t++) { in[t].items = txcat[t].data(); in[t].n_items = 2 * items; }
+    for (int r = 0; r < R; r++) { in[T + r].items = f2.rx[r].data(); in[T + r].n_items = items; }
+    in[0].tags = {shim::make_tag(0, "packet_len", pmt::from_long(items)), shim::make_tag(items, "packet_len", pmt::from_long(items))};
+    in[T].tags = {shim::make_tag(0, "packet_len", pmt::from_long(items))};
+    cvec out((size_t)V * N * IR), refout((size_t)V * N * IR);
+    auto res = shim::run_once(*blk, in, {{out.data(), 64}});
+    std::vector<const orc_c32 *> tp, rp;
+    for (auto &v : f2.tx) tp.push_back((const orc_c32 *)v.data());
+    for (auto &v : f2.rx) rp.push_back((const orc_c32 *)v.data());
+    orc_radar_work(ref, tp.data(), rp.data(), 0, (orc_c32 *)refout.data());
+    CHECK(res.produced == V && same(out.data(), (const orc_c32 *)refout.data(), out.size()), "stale TX frame not skipped");
+    CHECK(res.consumed[0] == 2 * items && res.consumed[T] == items, "stale TX consume %d %d", res.consumed[0], res.consumed[T]);
+    for (auto &i : in) i.tags.clear();
+    res = shim::run_once(*blk, in, {{out.data(), 64}});
+    CHECK(res.produced == 0 && res.consumed[0] == 2 * items && res.consumed[T] == items, "no-tag flush");
+    orc_radar_destroy(ref);
+}
+
+static void test_chain_of_blocks()
+{
+    // radar -> fft_vcc(IFFT) -> matrix_transpose -> fft_vcc(FFT, shift) -> range_angle_estimator,
+    // block by block like the shipped flowgraph; the two stock fft_vxx blocks are jrc_fft_vcc calls.
+    const int N = 64, T = 4, R = 2, S = 4, pre = 5, IR = 8, IA = 16, V = 8, Nr = N * IR, Na = V * IA, items = pre + S;
+    auto rb = range_bins(N, IR); auto ab = angle_bins(Na);
+    const float ndr = 2.4f, nda = 2 * 14.4775f;
+    auto radar = mimo_ofdm_radar::make(N, T, R, S, pre, false, false, 8, IR, false, "/tmp/jrc_cpp_chan.csv");
+    auto transp = matrix_transpose::make(Nr, V, IA, false);
+    auto estim = range_angle_estimator::make(Na, rb, ab, ndr, nda, -100.f, 0.f, "/tmp/jrc_cpp_log.csv", true);
+    jrc_chain_cfg ucfg{}; ucfg.fft_len = 64; ucfg.n_tx = ucfg.n_rx = ucfg.n_sym = 1; ucfg.interp_range = ucfg.interp_angle = 1;
+    jrc_chain *util = nullptr;
+    CHECK(jrc_chain_create(&ucfg, &util) == JRC_OK, "%s", jrc_last_error());
+    orc_radar *ref = orc_radar_create(N, T, R, S, pre, 0, 0, 8, IR, 0);
+    uint64_t rd = 0, rd2 = 0, rd3 = 0;
+    for (int it = 0; it < 3; it++) {
+        frame_t f = make_frame(T, R, items, N);
+        std::vector<shim::input_t> in(T + R);
+        for (int t = 0; t < T; t++) { in[t].items = f.tx[t].data(); in[t].n_items = items; }
+        for (int r = 0; r < R; r++) { in[T + r].items = f.rx[r].data(); in[T + r].n_items = items; }
+        in[0].tags.push_back(shim::make_tag(rd, "packet_len", pmt::from_long(items)));
+        in[T].tags.push_back(shim::make_tag(rd, "packet_len", pmt::from_long(items)));
+        rd += items;
+        cvec pad((size_t)V * Nr), y((size_t)V * Nr), tr((size_t)Nr * Na), cm((size_t)Nr * Na);
+        auto r1 = shim::run_once(*radar, in, {{pad.data(), 64}});
+        CHECK(r1.produced == V, "radar");
+        CHECK(jrc_fft_vcc(util, (const jrc_c32 *)pad.data(), (jrc_c32 *)y.data(), Nr, V, 0, 0) == JRC_OK, "%s", jrc_last_error());
+        shim::input_t ti; ti.items = y.data(); ti.n_items = V; ti.tags.push_back(shim::make_tag(rd2, "packet_len", pmt::from_long(V)));
+        rd2 += V;
+        auto r2 = shim::run_once(*transp, {ti}, {{tr.data(), Nr}});
+        CHECK(r2.produced == Nr && r2.consumed[0] == V, "transpose produced %d consumed %d", r2.produced, r2.consumed[0]);
+        CHECK(!r2.out_tags[0].empty() && pmt::to_long(r2.out_tags[0].back().value) == Nr, "transpose length tag");
+        CHECK(jrc_fft_vcc(util, (const jrc_c32 *)tr.data(), (jrc_c32 *)cm.data(), Na, Nr, 1, 1) == JRC_OK, "%s", jrc_last_error());
+        shim::input_t ei; ei.items = cm.data(); ei.n_items = Nr; ei.tags.push_back(shim::make_tag(rd3, "packet_len", pmt::from_long(Nr)));
+        rd3 += Nr;
+        auto r3 = shim::run_once(*estim, {ei}, {});
+        CHECK(r3.produced == 0 && r3.consumed[0] == Nr, "estimator is a sink that consumes the packet");
+        // oracle, same data
+        std::vector<const orc_c32 *> tp, rp;
+        for (auto &v : f.tx) tp.push_back((const orc_c32 *)v.data());
+        for (auto &v : f.rx) rp.push_back((const orc_c32 *)v.data());
+        cvec opad((size_t)V * Nr), oy((size_t)V * Nr), otr((size_t)Nr * Na), ocm((size_t)Nr * Na);
+        orc_radar_work(ref, tp.data(), rp.data(), 0, (orc_c32 *)opad.data());
+        orc_fft_vcc_batch((orc_c32 *)opad.data(), (orc_c32 *)oy.data(), Nr, V, 0, 0);
+        orc_matrix_transpose((orc_c32 *)oy.data(), V, Nr, V, IA, (orc_c32 *)otr.data());
+        orc_fft_vcc_batch((orc_c32 *)otr.data(), (orc_c32 *)ocm.data(), Na, Nr, 1, 1);
+        CHECK(same(cm.data(), (const orc_c32 *)ocm.data(), cm.size()), "chain of blocks: complex map differs");
+        orc_det od;
+        orc_range_angle_estimate((orc_c32 *)ocm.data(), Nr, Na, rb.data(), Nr, ab.data(), Na, ndr, nda, -100.f, 0.f, &od, nullptr);
+        auto &msgs = estim->shim_published["params"];
+        CHECK((int)msgs.size() == it + 1, "params message count %zu", msgs.size());
+        if ((int)msgs.size() == it + 1) {
+            auto m = msgs.back();
+            auto field = [&](int k, const char *name) {
+                auto pr = pmt::nth(k, m);
+                CHECK(pmt::symbol_to_string(pmt::nth(0, pr)) == name, "message key %d", k);
+                return pmt::f32vector_elements(pmt::nth(1, pr))[0];
+            };
+            CHECK(field(0, "range") == rb[od.range_idx] && field(1, "angle") == ab[od.angle_idx], "message range/angle");
+            CHECK(field(2, "power") == od.peak_power && field(3, "snr") == od.snr_db, "message power/snr %g %g vs %g %g",
+                  field(2, "power"), field(3, "snr"), od.peak_power, od.snr_db);
+        }
+    }
+    // back-pressure: the transpose block drops the CPI but still consumes it
+    cvec y((size_t)V * Nr), tr((size_t)Nr * Na);
+    shim::input_t ti; ti.items = y.data(); ti.n_items = V; ti.tags.push_back(shim::make_tag(rd2, "packet_len", pmt::from_long(V)));
+    transp->shim_output_fullness = 0.5f;
+    auto rdrop = shim::run_once(*transp, {ti}, {{tr.data(), Nr}});
+    CHECK(rdrop.produced == 0 && rdrop.consumed[0] == V && rdrop.out_tags[0].empty(), "transpose back-pressure drop");
+    orc_radar_destroy(ref);
+    jrc_chain_destroy(util);
+}
+
+static void test_peak_and_pad()
+{
+    const int n = 40000;
+    cvec x = randvec(n);
+    x[31000] = gr_complex(40, 9);
+    auto pk = fft_peak_detect::make(1000000, 8.0f, 10.0f, 25, {0.f}, false, "packet_len");
+    float f = -1, ph = -1, mg = -1;
+    shim::input_t in; in.items = x.data(); in.n_items = n; in.tags.push_back(shim::make_tag(0, "packet_len", pmt::from_long(n)));
+    auto r = shim::run_once(*pk, {in}, {{&f, 1}, {&ph, 1}, {&mg, 1}});
+    orc_peak1d o;
+    orc_fft_peak_detect((orc_c32 *)x.data(), n, 1000000, 8.0f, 10.0f, 25, &o);
+    CHECK(r.produced == 1 && o.k == 31000 && f == o.freq && ph == o.phase && mg == o.mag, "peak detect %g %g %g vs %g %g %g", f, ph, mg, o.freq, o.phase, o.mag);
+    CHECK(r.out_tags.size() == 3 && pmt::to_long(r.out_tags[0][0].value) == 1, "peak detect length tag");
+    pk->set_threshold(90.f);
+    f = 7.f;
+    in.tags[0].offset = n;
+    r = shim::run_once(*pk, {in}, {{&f, 1}, {&ph, 1}, {&mg, 1}});
+    CHECK(r.produced == 1 && f == 7.f, "no peak leaves the output untouched");
+
+    auto zp = zero_pad::make(false, 7, 240);
+    cvec y(720 + 247);
+    shim::input_t zi; zi.items = x.data(); zi.n_items = 720; zi.tags.push_back(shim::make_tag(0, "packet_len", pmt::from_long(720)));
+    r = shim::run_once(*zp, {zi}, {{y.data(), (int)y.size()}});
+    CHECK(r.produced == 967 && std::memcmp(&y[7], x.data(), 720 * sizeof(gr_complex)) == 0, "zero_pad copy");
+    CHECK(pmt::to_long(r.out_tags[0][0].value) == 967, "zero_pad length tag");
+    double s2 = 0;
+    for (int i = 727; i < 967; i++) s2 += std::norm(y[i]);
+    CHECK(std::fabs(std::sqrt(s2 / 240 / 2) - 1e-2) < 2e-3, "zero_pad noise sigma %g", std::sqrt(s2 / 240 / 2));
+}
+
+static void test_fused_block()
+{
+    const int N = 64, T = 4, R = 2, S = 4, pre = 5, IR = 8, IA = 16, V = 8, Nr = N * IR, Na = V * IA, items = pre + S;
+    auto rb = range_bins(N, IR); auto ab = angle_bins(Na);
+    const float ndr = 2.4f, nda = 2 * 14.4775f;
+    auto blk = radar_chain::make(N, T, R, S, pre, false, false, 8, IR, IA, false, rb, ab, ndr, nda, -100.f, 0.f, "/tmp/jrc_cpp_log2.csv", false);
+    uint64_t rd = 0;
+    for (int it = 0; it < 3; it++) {
+        frame_t f = make_frame(T, R, items, N);
+        // a point-target-like structure so the peak is well separated: rx = tx0 * phase ramp
+        for (int r = 0; r < R; r++)
+            for (int s = 0; s < items; s++)
+                for (int k = 0; k < N; k++) {
+                    gr_complex acc = 0;
+                    for (int t = 0; t < T; t++)
+                        acc += f.tx[t][(size_t)s * N + k] * std::polar(1.0f, (float)(-2 * M_PI * 0.13 * (it + 1) * k + 0.9 * (t + T * r)));
+                    f.rx[r][(size_t)s * N + k] = acc;
+                }
+        std::vector<shim::input_t> in(T + R);
+        for (int t = 0; t < T; t++) { in[t].items = f.tx[t].data(); in[t].n_items = items; }
+        for (int r = 0; r < R; r++) { in[T + r].items = f.rx[r].data(); in[T + r].n_items = items; }
+        in[0].tags.push_back(shim::make_tag(rd, "packet_len", pmt::from_long(items)));
+        in[T].tags.push_back(shim::make_tag(rd, "packet_len", pmt::from_long(items)));
+        rd += items;
+        std::vector<float> map((size_t)Nr * Na);
+        auto res = shim::run_once(*blk, in, {{map.data(), Nr}});
+        CHECK(res.produced == Nr && pmt::to_long(res.out_tags[0][0].value) == Nr, "fused block produced %d", res.produced);
+        // oracle chain on the preamble-stripped frame
+        cvec rxp((size_t)R * S * N), txp((size_t)T * S * N);
+        for (int t = 0; t < T; t++) std::memcpy(&txp[(size_t)t * S * N], &f.tx[t][(size_t)pre * N], sizeof(gr_complex) * S * N);
+        for (int r = 0; r < R; r++) std::memcpy(&rxp[(size_t)r * S * N], &f.rx[r][(size_t)pre * N], sizeof(gr_complex) * S * N);
+        orc_chain_cfg oc{N, T, R, S, 0, IR, IA, 0, rb.data(), ab.data(), ndr, nda, -100.f, 0.f};
+        std::vector<float> omap((size_t)Nr * Na);
+        orc_det od;
+        orc_chain_batch(&oc, (orc_c32 *)rxp.data(), (orc_c32 *)txp.data(), 1, 1, 0, omap.data(), nullptr, &od);
+        float peak = 0, err = 0;
+        for (size_t i = 0; i < omap.size(); i++) { peak = std::max(peak, omap[i]); err = std::max(err, std::fabs(omap[i] - map[i])); }
+        CHECK(err <= 1e-4f * peak, "fused block map error %g of peak", err / peak);
+        auto &msgs = blk->shim_published["params"];
+        CHECK((int)msgs.size() == it + 1, "fused block message");
+        if (!msgs.empty()) {
+            float rv = pmt::f32vector_elements(pmt::nth(1, pmt::nth(0, msgs.back())))[0];
+            float av = pmt::f32vector_elements(pmt::nth(1, pmt::nth(1, msgs.back())))[0];
+            CHECK(rv == rb[od.range_idx] && av == ab[od.angle_idx], "fused block peak (%g, %g) vs oracle (%g, %g)", rv, av, rb[od.range_idx], ab[od.angle_idx]);
+        }
+    }
+}
+
+int main()
+{
+    test_radar_block();
+    test_chain_of_blocks();
+    test_peak_and_pad();
+    test_fused_block();
+    if (g_fail) { std::printf("%d check(s) FAILED\n", g_fail); return 1; }
+    std::printf("ALL BLOCK TESTS PASSED\n");
+    return 0;
+}

@@ -264,3 +264,35 @@ def test_peak1d_and_zero_pad(jrc, orc):
     assert abs(p.real.std() - 1e-2) < 2e-4 and abs(p.imag.std() - 1e-2) < 2e-4 and abs(p.mean()) < 2e-4
     assert not np.array_equal(zp.work(x[:720]), zp.work(x[:720]))     # fresh seed per call
     assert zp.work(x[:0], seed=1).size == 247
+
+
+import glob as _glob
+import os as _os
+_GOLDEN = sorted(_glob.glob(_os.path.join(_os.path.dirname(_os.path.abspath(__file__)), "golden", "*.npz")))
+
+
+@pytest.mark.parametrize("path", _GOLDEN, ids=[_os.path.basename(p) for p in _GOLDEN])
+def test_fused_chain_vs_reference_golden_vectors(jrc, path):
+    """Fixtures produced by the reference's own block code (tests/golden/make_golden.py)."""
+    g = np.load(path)
+    T, R, S, N, IR, IA = (int(v) for v in g["cfg"])
+    est = synth.default_estimator_params(N, T * R, IR, IA)
+    ch = jrc.Chain(N, T, R, S, 0, IR, IA)
+    ch.set_estimator(**est)
+    m, d = ch.run_host(g["rx"], g["tx"])
+    assert ch.last_path == jrc.PATH_FUSED
+    assert np.array_equal(d["range_idx"], g["range_idx"]) and np.array_equal(d["angle_idx"], g["angle_idx"])
+    np.testing.assert_allclose(d["peak_power"], g["peak_power"], rtol=5e-6)
+    np.testing.assert_allclose(d["snr_db"], g["snr_db"], atol=2e-3)
+    assert np.abs(m[0] - g["map0"]).max() <= 1e-4 * g["map0"].max()
+    assert np.abs(m[0] - g["map0"]).max() <= 5e-6 * g["map0"].max()
+    np.testing.assert_allclose(m.reshape(len(d), -1).max(axis=1), g["map_max"], rtol=5e-6)
+    # staged path: the same bits as the reference build
+    import torch
+    rc = jrc.radar_chain(N, T, R, S, IR, IA, estimator=est)
+    drx, dtx = torch.from_numpy(g["rx"]).cuda(), torch.from_numpy(g["tx"]).cuda()
+    m2, d2 = rc.run(drx, dtx, path=jrc.PATH_STAGED)
+    rc.sync()
+    d2 = rc.dets_to_numpy(d2)
+    assert np.array_equal(m2[0].cpu().numpy(), g["map0"])
+    assert np.array_equal(d2["range_idx"], g["range_idx"]) and np.array_equal(d2["peak_power"], g["peak_power"])
