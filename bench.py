@@ -216,10 +216,13 @@ def run_ours(args):
     ext = torch.cuda.ExternalStream(rc.chain.stream, device=dev)
     torch.cuda.synchronize()
 
+    counts = [B] * world                       # contiguous equal shards: no size exchange needed
+    gbufs = [torch.empty_like(ddet) for _ in range(world)] if (world > 1 and rank == 0) else None
+
     def step():
         rc.run(rx, tx, map_out=dmap, dets_out=ddet, path=jrc.PATH_FUSED, sync_inputs=False)
         if world > 1:
-            return shard.gather_detections(ddet, dst=0)
+            return shard.gather_detections(ddet, dst=0, counts=counts, bufs=gbufs)
         return ddet
 
     with torch.cuda.stream(ext):
@@ -241,7 +244,7 @@ def run_ours(args):
             rc.run(rx, tx, map_out=dmap, dets_out=ddet, path=jrc.PATH_FUSED, sync_inputs=False)
             ev[k][1].record(ext)
             if world > 1:
-                shard.gather_detections(ddet, dst=0)
+                shard.gather_detections(ddet, dst=0, counts=counts, bufs=gbufs)
         e1.record(ext)
     torch.cuda.synchronize()
     clocks = sampler.stop() if sampler else None

@@ -59,14 +59,13 @@ struct FusedGeom {
     static constexpr int NBUF = TMA ? 2 : 1;             // staging buffers per warp
     static constexpr int UNROLL = 4;
     static constexpr int STG_FLOATS = SIT * G * NA;      // floats per staging buffer (SIT KiB)
-    static constexpr int PSTEP = 32 / IR;                // channel step of the two range passes
     static_assert(IA >= 4 && IA <= 32 && (IA & (IA - 1)) == 0, "angle interp must be 4..32, power of two");
     static_assert(IR >= 1 && IR <= 32 && (IR & (IR - 1)) == 0, "range interp must be 1..32, power of two");
     static_assert(ITERS >= UNROLL && ITERS % UNROLL == 0 && UNROLL % (SIT * NBUF) == 0, "map too small for the store pipeline");
 
     static size_t smem_bytes(int T, int R, int S, bool from_h)
     {
-        size_t b = (size_t)V * NR * 8 + (size_t)V * NSC * 8 + (size_t)WARPS * NBUF * STG_FLOATS * 4 +
+        size_t b = (size_t)V * NR * 8 + (size_t)V * NSC * 8 + (size_t)8 * Q * 8 + (size_t)WARPS * NBUF * STG_FLOATS * 4 +
                    (size_t)NA * 16 + (size_t)NA * 4 + 64 + 1024 + 64;
         if (!from_h) b += (size_t)(T + R) * S * NSC * 8;
         return b;
@@ -129,12 +128,15 @@ __global__ void __launch_bounds__(256, 2) k_fused64x8(const FusedParams P)
     using Gm = FusedGeom<IR, IA>;
     constexpr int NR = Gm::NR, NA = Gm::NA, Q = Gm::Q, G = Gm::G;
     constexpr int RPW = Gm::ROWS_PER_WARP, ITERS = Gm::ITERS, SIT = Gm::SIT, NBUF = Gm::NBUF;
-    constexpr int STGF = Gm::STG_FLOATS, PSTEP = Gm::PSTEP;
+    constexpr int STGF = Gm::STG_FLOATS;
+    constexpr int T1 = (8 * IR + 31) / 32;     // range pass 1 tasks per lane (channel = warp)
+    constexpr int T2 = (Q + 31) / 32;          // range pass 2 tasks per lane
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
     c32 *ys = reinterpret_cast<c32 *>(smem_raw);                  // [8][NR]  B then y (in place)
     c32 *Hs = ys + 8 * NR;                                        // [8][64]
-    float *stg = reinterpret_cast<float *>(Hs + 512);             // [8 warps][NBUF][STGF]
+    c32 *tw2t = Hs + 512;                                         // [8][Q]   W_Nr^{k0 q}
+    float *stg = reinterpret_cast<float *>(tw2t + 8 * Q);         // [8 warps][NBUF][STGF]
     double2 *tabd = reinterpret_cast<double2 *>(stg + 8 * NBUF * STGF);   // [NA] e^{-j2pi m/NA}
     float *abin = reinterpret_cast<float *>(tabd + NA);                   // [NA] angle_bins copy
     unsigned long long *red = reinterpret_cast<unsigned long long *>(abin + NA);   // [8]
@@ -146,19 +148,20 @@ __global__ void __launch_bounds__(256, 2) k_fused64x8(const FusedParams P)
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // warp-uniform for the compiler
 
     // ---- per-thread constants (once per persistent CTA) --------------------
-    // range pass 1: task (p, k0, q0);  twiddle W_Q^{k1 q0}
-    const int q0 = tid % IR, k0a = (tid / IR) & 7, p1 = tid / (8 * IR);
-    // range pass 2: task (p, q);       twiddle W_Nr^{k0 q}
-    const int q = tid % Q, p2 = tid / Q;
-    // angle pass:   task (n, b);       twiddle (-1)^p w_Na^{p (b + IA*rot)}
+    // Stages 1-3 give every warp ONE virtual channel (p = warp), so the channel estimate and both
+    // range passes only need warp-level synchronisation.
+    // range pass 1: task (k0, q0), q0 = lane % IR fixed per lane;  twiddle W_Q^{k1 q0}
+    // range pass 2: task q = lane + 32 j;                           twiddle W_Nr^{k0 q} from tw2t
+    // angle pass:   task (n, b);                                    twiddle (-1)^p w_Na^{p (b + IA*rot)}
+    const int q0 = lane % IR;
     const int b = lane % IA, g = lane / IA, rot = (Gm::STORE == 2) ? 0 : g;
-    c32 tw1[8], tw2[8], tw3[8];
+    c32 tw1[8], tw3[8];
 #pragma unroll
     for (int j = 0; j < 8; j++) {
         tw1[j] = cispi_ratio(2 * j * q0, Q);
-        tw2[j] = cispi_ratio(2 * j * q, NR);
         tw3[j] = cispi_ratio(j * (NA - 2 * (b + IA * rot)), NA);
     }
+    for (int e = tid; e < 8 * Q; e += 256) tw2t[e] = cispi_ratio(2 * (e / Q) * (e % Q), NR);
     EstParams est = P.est;
     for (int m = tid; m < NA; m += 256) {
         double sn, cs;
@@ -168,6 +171,15 @@ __global__ void __launch_bounds__(256, 2) k_fused64x8(const FusedParams P)
     }
     est.angle_bins = abin;   // the window geometry's binary search runs on shared memory
 
+    // channel of this warp -> (rx antenna, tx antenna)  (lib/mimo_ofdm_radar_impl.cc:262-269)
+    const int per_ant = P.S * 64;
+    int ch_r, ch_t;
+    if (P.tx_interleave) { ch_t = warp / P.R; ch_r = warp - ch_t * P.R; } else { ch_r = warp / P.T; ch_t = warp - ch_r * P.T; }
+    const c32 *srx = inb + (P.T + ch_r) * per_ant + lane;
+    const c32 *stx = inb + ch_t * per_ant + lane;
+    c32 *Hw = Hs + warp * 64;          // this warp's channel estimate
+    c32 *yw = ys + warp * NR;          // this warp's range spectrum
+
     // staging: slot a' of this thread holds angle bin b + IA*((a'+rot)&7); rotating by
     // the row group makes the 32 lanes of every st.shared hit 32 different banks
     float *wstg = stg + warp * NBUF * STGF;
@@ -175,7 +187,6 @@ __global__ void __launch_bounds__(256, 2) k_fused64x8(const FusedParams P)
 #pragma unroll
     for (int a = 0; a < 8; a++) sp[a] = wstg + g * NA + b + IA * ((a + rot) & 7);
 
-    const int per_ant = P.S * 64;
     auto prefetch = [&](int cpi) {
         const int cpa = per_ant >> 1;   // 16-byte chunks per antenna row
         const int total = (P.T + P.R) * cpa;
@@ -189,66 +200,112 @@ __global__ void __launch_bounds__(256, 2) k_fused64x8(const FusedParams P)
         cp_async_commit();
     };
 
+    // Detection record of the previous CPI: its last step only needs the shared scratch (not y), so it
+    // runs after the next CPI's first barrier instead of costing a barrier of its own.
+    bool pending = false;
+    auto finalize = [&]() {
+        if (tid < 8) {
+            const int start_a = sint[4], end_a = sint[5], total = sint[8];
+            const int ncols = end_a - start_a;
+            double sr = 0.0, si = 0.0;
+#pragma unroll
+            for (int w = 0; w < 8; w++) { sr += redA[w * 8 + tid].x; si += redA[w * 8 + tid].y; }
+            double contrib;
+            if (tid == 0) {
+                contrib = (double)ncols * sr;
+            } else {
+                // g[d] = w^{d m0} (1 - w^{d ncols}) / (1 - w^d),  m0 = start_a + Na/2
+                const double2 w0 = tabd[(tid * (start_a + NA / 2)) & (NA - 1)];
+                const double2 w1 = tabd[(tid * ncols) & (NA - 1)];
+                const double2 w2 = tabd[tid];
+                const double c0 = w0.x, s0 = w0.y;
+                const double nr = 1.0 - w1.x, ni = -w1.y, dr = 1.0 - w2.x, di = -w2.y;
+                const double den = dr * dr + di * di;
+                const double qr = (nr * dr + ni * di) / den, qi = (ni * dr - nr * di) / den;
+                const double gr = c0 * qr - s0 * qi, gi = c0 * qi + s0 * qr;
+                contrib = 2.0 * (gr * sr - gi * si);
+            }
+            contrib += __shfl_xor_sync(0xffu, contrib, 4);
+            contrib += __shfl_xor_sync(0xffu, contrib, 2);
+            contrib += __shfl_xor_sync(0xffu, contrib, 1);
+            if (tid == 0) {
+                const double s = contrib > 0.0 ? contrib : 0.0;
+                DetDev d;
+                d.range_idx = sint[0]; d.angle_idx = sint[1];
+                d.peak_power = __int_as_float(sint[6]);
+                d.n_noise = total;
+                d.noise_power = __fdiv_rn((float)s, (float)total);
+                d.snr_db = __fmul_rn(10.f, log10f(__fdiv_rn(d.peak_power, d.noise_power)));
+                d.flags = (d.snr_db >= est.snr_threshold && d.peak_power >= est.power_threshold) ? 1u : 0u;
+                d.cpi = P.cpi0 + sint[7];
+                P.dets[sint[7]] = d;
+            }
+        }
+    };
+
     int cpi = blockIdx.x;
     if (!FROM_H && cpi < P.n_cpi) prefetch(cpi);
 
     for (; cpi < P.n_cpi; cpi += gridDim.x) {
         if (!FROM_H) cp_async_wait_all();
         __syncthreads();   // (A) symbols landed; previous CPI fully consumed
+        if (pending) finalize();
 
-        // ---- stage 1: channel estimate H[p][k] --------------------------------
+        // ---- stage 1: channel estimate H[p = warp][k] --------------------------
         if (FROM_H) {
-            const c32 *Hg = P.H + (long long)cpi * 512;
-            Hs[tid] = Hg[tid];
-            Hs[tid + 256] = Hg[tid + 256];
+            const c32 *Hg = P.H + (long long)cpi * 512 + warp * 64;
+            Hw[lane] = Hg[lane];
+            Hw[lane + 32] = Hg[lane + 32];
         } else {
-            const int k = tid & 63;
+            c32 acc0 = mk(0.f, 0.f), acc1 = mk(0.f, 0.f);
+            for (int s = 0; s < P.S; s++) {
+                c32 x0 = srx[s * 64], c0 = stx[s * 64], x1 = srx[s * 64 + 32], c1 = stx[s * 64 + 32];
+                acc0 = cadd_exact(acc0, cmul_exact(x0, mk(c0.x, -c0.y)));
+                acc1 = cadd_exact(acc1, cmul_exact(x1, mk(c1.x, -c1.y)));
+            }
+            Hw[lane] = acc0;
+            Hw[lane + 32] = acc1;
+        }
+        __syncwarp();
+
+        // ---- stage 2: range pass 1 (pruned: 8 of Q inputs non-zero) ----------
 #pragma unroll
-            for (int h = 0; h < 2; h++) {
-                const int p = (tid >> 6) + 4 * h;
-                int r, t;
-                if (P.tx_interleave) { t = p / P.R; r = p - t * P.R; } else { r = p / P.T; t = p - r * P.T; }
-                const c32 *srx = inb + (P.T + r) * per_ant + k;
-                const c32 *stx = inb + t * per_ant + k;
-                c32 acc = mk(0.f, 0.f);
-                for (int s = 0; s < P.S; s++) {
-                    c32 x = srx[s * 64], c = stx[s * 64];
-                    acc = cadd_exact(acc, cmul_exact(x, mk(c.x, -c.y)));
-                }
-                Hs[p * 64 + k] = acc;
+        for (int j = 0; j < T1; j++) {
+            const int task = lane + 32 * j;
+            if (8 * IR >= 32 || task < 8 * IR) {
+                const int k0 = task / IR;
+                c32 u[8];
+#pragma unroll
+                for (int k1 = 0; k1 < 8; k1++) u[k1] = Hw[k0 + 8 * k1];
+#pragma unroll
+                for (int k1 = 1; k1 < 8; k1++) u[k1] = cmul_fma(u[k1], tw1[k1]);
+                JRC_FFT8<1>(u);
+#pragma unroll
+                for (int m0 = 0; m0 < 8; m0++) yw[k0 * Q + q0 + IR * m0] = u[m0];
             }
         }
-        __syncthreads();   // (B) H ready, symbol buffer free
+        __syncwarp();
+
+        // ---- stage 3: range pass 2, in place ---------------------------------
+#pragma unroll
+        for (int j = 0; j < T2; j++) {
+            const int q = lane + 32 * j;
+            if (Q >= 32 || q < Q) {
+                c32 u[8];
+#pragma unroll
+                for (int k0 = 0; k0 < 8; k0++) u[k0] = yw[k0 * Q + q];
+#pragma unroll
+                for (int k0 = 1; k0 < 8; k0++) u[k0] = cmul_fma(u[k0], tw2t[k0 * Q + q]);
+                JRC_FFT8<1>(u);
+#pragma unroll
+                for (int m1 = 0; m1 < 8; m1++) yw[m1 * Q + q] = u[m1];
+            }
+        }
+        __syncthreads();   // (D) y[p][n] complete for all channels; symbol buffer free
         if (!FROM_H) {
             int nxt = cpi + gridDim.x;
             if (nxt < P.n_cpi) prefetch(nxt);
         }
-
-        // ---- stage 2: range pass 1 (pruned: 8 of Q inputs non-zero) ----------
-        for (int p = p1; p < 8; p += PSTEP) {
-            c32 u[8];
-#pragma unroll
-            for (int k1 = 0; k1 < 8; k1++) u[k1] = Hs[p * 64 + k0a + 8 * k1];
-#pragma unroll
-            for (int k1 = 1; k1 < 8; k1++) u[k1] = cmul_fma(u[k1], tw1[k1]);
-            JRC_FFT8<1>(u);
-#pragma unroll
-            for (int m0 = 0; m0 < 8; m0++) ys[p * NR + k0a * Q + q0 + IR * m0] = u[m0];
-        }
-        __syncthreads();   // (C)
-
-        // ---- stage 3: range pass 2, in place ---------------------------------
-        for (int p = p2; p < 8; p += PSTEP) {
-            c32 u[8];
-#pragma unroll
-            for (int k0 = 0; k0 < 8; k0++) u[k0] = ys[p * NR + k0 * Q + q];
-#pragma unroll
-            for (int k0 = 1; k0 < 8; k0++) u[k0] = cmul_fma(u[k0], tw2[k0]);
-            JRC_FFT8<1>(u);
-#pragma unroll
-            for (int m1 = 0; m1 < 8; m1++) ys[p * NR + m1 * Q + q] = u[m1];
-        }
-        __syncthreads();   // (D) y[p][n] complete
 
         // ---- stage 4: angle pass + |.|^2 + store + running max ---------------
         float best = -1.f;
@@ -300,6 +357,7 @@ __global__ void __launch_bounds__(256, 2) k_fused64x8(const FusedParams P)
         }
 
         // ---- stage 5: range_angle_estimator ----------------------------------
+        pending = false;
         if (P.dets) {
             unsigned long long key = best >= 0.f ? pack_key(best, (unsigned)(n_base + best_it * G)) : 0ull;
 #pragma unroll
@@ -340,9 +398,12 @@ __global__ void __launch_bounds__(256, 2) k_fused64x8(const FusedParams P)
                     for (int o = 16; o > 0; o >>= 1) imin = min(imin, __shfl_xor_sync(0xffffffffu, imin, o));
                     if (icand == imin && imin != 0x7fffffff) {
                         NoiseWin w = noise_window(est, nstar, imin);
+                        const int ncols = w.end_a - w.start_a, nrows = w.end_r - w.start_r;
                         sint[0] = nstar; sint[1] = imin;
                         sint[2] = w.start_r; sint[3] = w.end_r; sint[4] = w.start_a; sint[5] = w.end_a;
                         sint[6] = __float_as_int((float)ref_pow_abs2(zc));
+                        sint[7] = cpi;
+                        sint[8] = (ncols > 0 && nrows > 0) ? nrows * ncols : 0;
                     }
                 }
                 __syncthreads();   // (F)
@@ -350,20 +411,21 @@ __global__ void __launch_bounds__(256, 2) k_fused64x8(const FusedParams P)
                 //   sum_{r,c} |sum_p y[p][r] w^{p c'}|^2 = ncols*A[0] + 2 Re sum_{d=1..7} g[d] A[d],
                 //   A[d] = sum_r sum_q y[q+d][r] conj(y[q][r]),  g[d] = sum_c w^{d c'},  c' = c + Na/2,
                 // (w = e^{-j2pi/Na}; the modulo wrap of rows is the index, that of columns the period of w).
-                // 36 complex MACs per window row instead of 8 per sample.
-                const int start_r = sint[2], end_r = sint[3], start_a = sint[4], end_a = sint[5];
-                const int ncols = end_a - start_a, nrows = end_r - start_r;
-                const int total = (ncols > 0 && nrows > 0) ? nrows * ncols : 0;
+                // 36 complex MACs per window row instead of 8 per sample.  Float products and per-thread
+                // partial sums (<= 16 terms), double from the first reduction on.
+                const int start_r = sint[2], end_r = sint[3], total = sint[8];
                 const int lag = tid & 7;
-                // float products / per-thread partial sums (<= 16 terms), double from the first reduction on
                 float arf = 0.f, aif = 0.f;
                 if (total > 0) {
                     for (int ir = start_r + (tid >> 3); ir < end_r; ir += 32) {
                         const int r_idx = ((ir % NR) + NR) % NR;
-                        for (int qq = 0; qq + lag < 8; qq++) {
-                            c32 ya = ys[(qq + lag) * NR + r_idx], yb = ys[qq * NR + r_idx];
-                            arf = __fmaf_rn(ya.x, yb.x, __fmaf_rn(ya.y, yb.y, arf));
-                            aif = __fmaf_rn(ya.y, yb.x, __fmaf_rn(-ya.x, yb.y, aif));
+#pragma unroll
+                        for (int qq = 0; qq < 8; qq++) {
+                            if (qq + lag < 8) {
+                                c32 ya = ys[(qq + lag) * NR + r_idx], yb = ys[qq * NR + r_idx];
+                                arf = __fmaf_rn(ya.x, yb.x, __fmaf_rn(ya.y, yb.y, arf));
+                                aif = __fmaf_rn(ya.y, yb.x, __fmaf_rn(-ya.x, yb.y, aif));
+                            }
                         }
                     }
                 }
@@ -374,44 +436,13 @@ __global__ void __launch_bounds__(256, 2) k_fused64x8(const FusedParams P)
                     ai += __shfl_xor_sync(0xffffffffu, ai, o);
                 }
                 if (lane < 8) redA[warp * 8 + lane] = make_double2(ar, ai);
-                __syncthreads();   // (H)
-                if (tid < 8) {
-                    double sr = 0.0, si = 0.0;
-#pragma unroll
-                    for (int w = 0; w < 8; w++) { sr += redA[w * 8 + tid].x; si += redA[w * 8 + tid].y; }
-                    double contrib;
-                    if (tid == 0) {
-                        contrib = (double)ncols * sr;
-                    } else {
-                        // g[d] = w^{d m0} (1 - w^{d ncols}) / (1 - w^d),  m0 = start_a + Na/2
-                        const double2 w0 = tabd[(tid * (start_a + NA / 2)) & (NA - 1)];
-                        const double2 w1 = tabd[(tid * ncols) & (NA - 1)];
-                        const double2 w2 = tabd[tid];
-                        const double c0 = w0.x, s0 = w0.y;
-                        const double nr = 1.0 - w1.x, ni = -w1.y, dr = 1.0 - w2.x, di = -w2.y;
-                        const double den = dr * dr + di * di;
-                        const double qr = (nr * dr + ni * di) / den, qi = (ni * dr - nr * di) / den;
-                        const double gr = c0 * qr - s0 * qi, gi = c0 * qi + s0 * qr;
-                        contrib = 2.0 * (gr * sr - gi * si);
-                    }
-                    contrib += __shfl_xor_sync(0xffu, contrib, 4);
-                    contrib += __shfl_xor_sync(0xffu, contrib, 2);
-                    contrib += __shfl_xor_sync(0xffu, contrib, 1);
-                    const double s = contrib > 0.0 ? contrib : 0.0;
-                  if (tid == 0) {
-                    DetDev d;
-                    d.range_idx = sint[0]; d.angle_idx = sint[1];
-                    d.peak_power = __int_as_float(sint[6]);
-                    d.n_noise = total;
-                    d.noise_power = __fdiv_rn((float)s, (float)total);
-                    d.snr_db = __fmul_rn(10.f, log10f(__fdiv_rn(d.peak_power, d.noise_power)));
-                    d.flags = (d.snr_db >= P.est.snr_threshold && d.peak_power >= P.est.power_threshold) ? 1u : 0u;
-                    d.cpi = P.cpi0 + cpi;
-                    P.dets[cpi] = d;
-                  }
-                }
+                pending = true;   // finished after the next barrier (A) / after the loop
             }
         }
+    }
+    if (pending) {
+        __syncthreads();
+        finalize();
     }
     if (Gm::TMA) {   // the CTA's shared memory must outlive the bulk stores that read it
         if (lane == 0) bulk_wait_read<0>();

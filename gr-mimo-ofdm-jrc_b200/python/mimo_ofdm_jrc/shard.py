@@ -19,10 +19,15 @@ def shard_range(n_cpi: int, rank: int, world: int):
     return lo, lo + base + (1 if rank < rem else 0)
 
 
-def gather_detections(dets, dst: int = 0, group=None):
+def gather_detections(dets, dst: int = 0, group=None, counts=None, bufs=None):
     """dets: uint8 tensor [n_local][32] (device tensor under NCCL, CPU tensor under gloo).
     Returns on rank dst the concatenation over ranks in rank order (ragged shards allowed),
-    None elsewhere."""
+    None elsewhere.
+
+    counts: per-rank record counts when the caller already knows them (contiguous shards of a known
+    batch: shard_range) -- skips the size exchange and its host synchronisation, so the gather is
+    a single asynchronous NCCL call on the current stream.  bufs: optional preallocated receive
+    buffers on rank dst (list of world tensors [max(counts)][32]) to keep the step allocation-free."""
     import torch
     import torch.distributed as dist
 
@@ -30,17 +35,21 @@ def gather_detections(dets, dst: int = 0, group=None):
     rank = dist.get_rank(group)
     if world == 1:
         return dets
-    n_local = torch.tensor([dets.shape[0]], dtype=torch.int64, device=dets.device)
-    counts = [torch.zeros_like(n_local) for _ in range(world)]
-    dist.all_gather(counts, n_local, group=group)
-    counts = [int(c.item()) for c in counts]
+    if counts is None:
+        n_local = torch.tensor([dets.shape[0]], dtype=torch.int64, device=dets.device)
+        cts = [torch.zeros_like(n_local) for _ in range(world)]
+        dist.all_gather(cts, n_local, group=group)
+        counts = [int(c.item()) for c in cts]
     n_max = max(counts)
     padded = dets
     if dets.shape[0] < n_max:
         padded = torch.zeros((n_max, dets.shape[1]), dtype=dets.dtype, device=dets.device)
         padded[: dets.shape[0]] = dets
-    bufs = [torch.empty_like(padded) for _ in range(world)] if rank == dst else None
-    dist.gather(padded.contiguous(), bufs, dst=dst, group=group)
+    if rank == dst and bufs is None:
+        bufs = [torch.empty_like(padded) for _ in range(world)]
+    dist.gather(padded.contiguous(), bufs if rank == dst else None, dst=dst, group=group)
     if rank != dst:
         return None
+    if all(c == n_max for c in counts):
+        return bufs            # equal shards: the per-rank blocks, in rank order, no copy
     return torch.cat([b[:c] for b, c in zip(bufs, counts)], dim=0)

@@ -45,6 +45,11 @@ WORKER = textwrap.dedent("""
         print("GATHER_OK")
     else:
         assert out is None
+    # equal shards with known counts: no size exchange, per-rank blocks returned in rank order
+    e = torch.full((5, 32), rank, dtype=torch.uint8)
+    out = shard.gather_detections(e, dst=0, counts=[5] * world)
+    if rank == 0:
+        assert len(out) == world and all(int(b[0, 0]) == r for r, b in enumerate(out))
     dist.barrier(); dist.destroy_process_group()
 """)
 
