@@ -9,12 +9,14 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
 #include <vector>
 
 #include "jrc_fused.cuh"
+#include "jrc_stream.cuh"
 #include "jrc_staged.cuh"
 
 using namespace jrc;
@@ -96,6 +98,8 @@ struct jrc_chain {
     int last_path = 0;
     int64_t launches = 0;
     int fused_ctas_per_sm = 0;
+    c32 *d_tw1g = nullptr, *d_tw2g = nullptr;   // slice-streaming kernel twiddle tables
+    int stream_mode = 0;                        // 1 (JRC_FUSED_KERNEL=stream): k_stream64x8 when a map is requested; 0: k_fused64x8
 };
 
 static bool is_pow2(int n) { return n > 0 && (n & (n - 1)) == 0; }
@@ -156,6 +160,7 @@ extern "C" jrc_status jrc_chain_create(const jrc_chain_cfg *cfg, jrc_chain **out
         CU(cudaEventCreateWithFlags(&h->ev_out[i], cudaEventDisableTiming));
     }
     h->pin_a.pinned = h->pin_b.pinned = true;
+    if (const char *e = getenv("JRC_FUSED_KERNEL")) h->stream_mode = strcmp(e, "stream") == 0;   // A/B switch for measurements
     const size_t vn = (size_t)h->V * cfg->fft_len;
     CU(cudaMalloc(&h->d_temp, vn * sizeof(c32)));
     CU(cudaMemsetAsync(h->d_temp, 0, vn * sizeof(c32), h->stream));
@@ -178,6 +183,8 @@ extern "C" void jrc_chain_destroy(jrc_chain *h)
                        &h->sDets[0], &h->sDets[1], &h->sMisc, &h->sMisc2, &h->pin_a, &h->pin_b};
     for (GrowBuf *b : bufs) b->release();
     if (h->d_angle_bins) cudaFree(h->d_angle_bins);
+    if (h->d_tw1g) cudaFree(h->d_tw1g);
+    if (h->d_tw2g) cudaFree(h->d_tw2g);
     if (h->d_ring) cudaFree(h->d_ring);
     if (h->d_temp) cudaFree(h->d_temp);
     for (int i = 0; i < 2; i++) {
@@ -386,6 +393,72 @@ static jrc_status launch_fused(jrc_chain *h, const FusedParams &P, bool *support
     return JRC_OK;
 }
 
+
+// ---------------------------------------------------------------------------
+// slice-streaming path (jrc_stream.cuh): k_chan_est -> k_stream64x8 -> k_stream_finalize
+// ---------------------------------------------------------------------------
+static jrc_status stream_tables(jrc_chain *h)
+{
+    if (h->d_tw1g) return JRC_OK;
+    const int IR = h->cfg.interp_range, NR = h->Nr, Q = NR / 8;
+    std::vector<c32> t1((size_t)IR * 8), t2((size_t)IR * 64);
+    for (int q0 = 0; q0 < IR; q0++)
+        for (int k = 0; k < 8; k++) {
+            double a = 2.0 * M_PI * (double)((k * q0) % Q) / (double)Q;
+            t1[q0 * 8 + k].x = (float)cos(a); t1[q0 * 8 + k].y = (float)sin(a);
+            for (int m0 = 0; m0 < 8; m0++) {
+                double a2 = 2.0 * M_PI * (double)((k * (q0 + IR * m0)) % NR) / (double)NR;
+                t2[(q0 * 8 + k) * 8 + m0].x = (float)cos(a2); t2[(q0 * 8 + k) * 8 + m0].y = (float)sin(a2);
+            }
+        }
+    CU(cudaMalloc(&h->d_tw1g, t1.size() * sizeof(c32)));
+    CU(cudaMalloc(&h->d_tw2g, t2.size() * sizeof(c32)));
+    CU(cudaMemcpyAsync(h->d_tw1g, t1.data(), t1.size() * sizeof(c32), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(h->d_tw2g, t2.data(), t2.size() * sizeof(c32), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return JRC_OK;
+}
+
+template <int IR, int IA>
+static jrc_status launch_stream_t(jrc_chain *h, const StreamParams &P)
+{
+    using Gm = StreamGeom<IR, IA>;
+    constexpr int WPC = 4, SPU = (IR >= 2) ? 2 : 1;
+    auto kern = k_stream64x8<IR, IA, SPU, WPC>;
+    const size_t smem = (size_t)WPC * Gm::WARP_SMEM;
+    CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, WPC * 32, smem));
+    if (per_sm < 1) return fail(JRC_ERR_INVALID, "stream kernel does not fit (smem %zu bytes)", smem);
+    h->fused_ctas_per_sm = per_sm;
+    const long long units = (long long)P.n_cpi * (IR / SPU);
+    long long grid = (long long)h->sm_count * per_sm;
+    if (grid * WPC > units) grid = (units + WPC - 1) / WPC;
+    kern<<<(unsigned)grid, WPC * 32, smem, h->stream>>>(P);
+    CU(cudaGetLastError());
+    h->launches++;
+    if (P.dets) {
+        auto fin = k_stream_finalize<IR, IA, WPC>;
+        CU(cudaFuncSetAttribute(fin, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        fin<<<(unsigned)((P.n_cpi + WPC - 1) / WPC), WPC * 32, smem, h->stream>>>(P);
+        CU(cudaGetLastError());
+        h->launches++;
+    }
+    return JRC_OK;
+}
+
+static jrc_status launch_stream(jrc_chain *h, const StreamParams &P)
+{
+    const int IR = h->cfg.interp_range, IA = h->cfg.interp_angle;
+#define JRC_STREAM_CASE(ir, ia) if (IR == ir && IA == ia) return launch_stream_t<ir, ia>(h, P);
+    JRC_STREAM_CASE(8, 16)
+    JRC_STREAM_CASE(16, 8)
+    JRC_STREAM_CASE(8, 8)
+    JRC_STREAM_CASE(16, 16)
+#undef JRC_STREAM_CASE
+    return fail(JRC_ERR_INVALID, "no stream kernel for this configuration");
+}
+
 static bool fused_config_ok(const jrc_chain *h)
 {
     const int IR = h->cfg.interp_range, IA = h->cfg.interp_angle;
@@ -421,6 +494,26 @@ extern "C" jrc_status jrc_chain_run_batch(jrc_chain *h, jrc_port_layout rx, jrc_
     if (path == JRC_PATH_FUSED && !want_fused)
         return fail(JRC_ERR_INVALID, "fused path requested but this configuration/layout has no fused kernel");
 
+    if (want_fused && map && h->stream_mode) {
+        // map-producing hot path: channel estimates (+ background ring) -> slice-streaming kernel
+        ST(stream_tables(h));
+        ST(h->sH.need((size_t)n_cpi * V * N * sizeof(c32)));
+        ST(launch_chan_est(h, drx, dtx, n_cpi, (c32 *)h->sH.p));
+        StreamParams SP;
+        memset(&SP, 0, sizeof(SP));
+        SP.H = (const c32 *)h->sH.p; SP.n_cpi = n_cpi; SP.cpi0 = cpi0; SP.map = map;
+        SP.tw1g = h->d_tw1g; SP.tw2g = h->d_tw2g;
+        if (dets) {
+            ST(est_params(h, Nr, Na, &SP.est));
+            ST(h->sKeys.need(sizeof(unsigned long long) * (size_t)n_cpi));
+            CU(cudaMemsetAsync(h->sKeys.p, 0, sizeof(unsigned long long) * (size_t)n_cpi, h->stream));
+            SP.keys = (unsigned long long *)h->sKeys.p;
+            SP.dets = (DetDev *)dets;
+        }
+        ST(launch_stream(h, SP));
+        h->last_path = JRC_PATH_FUSED;
+        return JRC_OK;
+    }
     if (want_fused) {
         FusedParams P;
         memset(&P, 0, sizeof(P));
