@@ -217,17 +217,30 @@ def run_ours(args):
     torch.cuda.synchronize()
 
     counts = [B] * world                       # contiguous equal shards: no size exchange needed
-    gbufs = [torch.empty_like(ddet) for _ in range(world)] if (world > 1 and rank == 0) else None
+    # two detection buffers per rank: the gather of step k overlaps the kernel of step k+1
+    ddets = [ddet, torch.zeros_like(ddet)] if world > 1 else [ddet]
+    gbufs = [[torch.empty_like(ddet) for _ in range(world)] for _ in range(2)] if (world > 1 and rank == 0) else [None, None]
+    pending = [None, None]
 
-    def step():
-        rc.run(rx, tx, map_out=dmap, dets_out=ddet, path=jrc.PATH_FUSED, sync_inputs=False)
+    def step(k=0):
+        slot = k & 1 if world > 1 else 0
+        if pending[slot] is not None:
+            pending[slot].wait()               # the gather that last read this buffer
+            pending[slot] = None
+        rc.run(rx, tx, map_out=dmap, dets_out=ddets[slot], path=jrc.PATH_FUSED, sync_inputs=False)
         if world > 1:
-            return shard.gather_detections(ddet, dst=0, counts=counts, bufs=gbufs)
-        return ddet
+            pending[slot], _ = shard.gather_detections(ddets[slot], dst=0, counts=counts, bufs=gbufs[slot], async_op=True)
+
+    def drain():
+        for i in range(2):
+            if pending[i] is not None:
+                pending[i].wait()
+                pending[i] = None
 
     with torch.cuda.stream(ext):
-        for _ in range(W):
-            step()
+        for k in range(W):
+            step(k)
+        drain()
     torch.cuda.synchronize()
     launches0 = rc.chain.launch_count
     sampler = ClockSampler(local) if rank == 0 else None
@@ -241,10 +254,9 @@ def run_ours(args):
         e0.record(ext)
         for k in range(K):
             ev[k][0].record(ext)
-            rc.run(rx, tx, map_out=dmap, dets_out=ddet, path=jrc.PATH_FUSED, sync_inputs=False)
+            step(k)
             ev[k][1].record(ext)
-            if world > 1:
-                shard.gather_detections(ddet, dst=0, counts=counts, bufs=gbufs)
+        drain()
         e1.record(ext)
     torch.cuda.synchronize()
     clocks = sampler.stop() if sampler else None

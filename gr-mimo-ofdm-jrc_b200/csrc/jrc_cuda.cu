@@ -616,6 +616,43 @@ extern "C" jrc_status jrc_chain_run_host(jrc_chain *h, const jrc_c32 *rx_host, c
     jrc_chain_cfg saved = h->cfg;
     h->cfg.n_pre = 0;
     jrc_status st = JRC_OK;
+    if (n_cpi <= chunk) {
+        // streaming / latency mode (one chunk, typically one CPI per work() call): a single stream,
+        // no cross-stream events -- copy in, kernels, copy out, one synchronisation
+        c32 *d_rx = (c32 *)h->sIn[0].p, *d_tx = d_rx + (size_t)chunk * rx_cpi;
+        const c32 *src_rx = (const c32 *)rx_host, *src_tx = (const c32 *)tx_host;
+        const size_t txn = tx_shared ? tx_cpi : (size_t)n_cpi * tx_cpi;
+        if (!direct) {
+            memcpy(h->pin_a.p, src_rx, (size_t)n_cpi * rx_cpi * sizeof(c32));
+            memcpy((c32 *)h->pin_a.p + (size_t)n_cpi * rx_cpi, src_tx, txn * sizeof(c32));
+            src_rx = (const c32 *)h->pin_a.p;
+            src_tx = src_rx + (size_t)n_cpi * rx_cpi;
+        }
+        cudaError_t e = cudaMemcpyAsync(d_rx, src_rx, (size_t)n_cpi * rx_cpi * sizeof(c32), cudaMemcpyHostToDevice, h->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_tx, src_tx, txn * sizeof(c32), cudaMemcpyHostToDevice, h->stream);
+        if (e != cudaSuccess) { h->cfg = saved; return fail(JRC_ERR_CUDA, "H2D: %s", cudaGetErrorString(e)); }
+        jrc_port_layout lrx{(const jrc_c32 *)d_rx, (int64_t)rx_cpi, (int64_t)c.n_sym * c.fft_len};
+        jrc_port_layout ltx{(const jrc_c32 *)d_tx, tx_shared ? 0 : (int64_t)tx_cpi, (int64_t)c.n_sym * c.fft_len};
+        float *d_map = map_host ? (float *)h->sMap[0].p : nullptr;
+        jrc_det *d_dets = dets_host ? (jrc_det *)h->sDets[0].p : nullptr;
+        st = jrc_chain_run_batch(h, lrx, ltx, n_cpi, cpi0, d_map, nullptr, d_dets, JRC_PATH_AUTO);
+        h->cfg = saved;
+        if (st != JRC_OK) return st;
+        float *dst_map = map_host;
+        jrc_det *dst_dets = dets_host;
+        if (!direct) {
+            dst_map = map_host ? (float *)h->pin_b.p : nullptr;
+            dst_dets = dets_host ? (jrc_det *)((char *)h->pin_b.p + (map_host ? (size_t)chunk * map_cpi * sizeof(float) : 0)) : nullptr;
+        }
+        if (map_host) CU(cudaMemcpyAsync(dst_map, d_map, (size_t)n_cpi * map_cpi * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+        if (dets_host) CU(cudaMemcpyAsync(dst_dets, d_dets, (size_t)n_cpi * sizeof(jrc_det), cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+        if (!direct) {
+            if (map_host) memcpy(map_host, dst_map, (size_t)n_cpi * map_cpi * sizeof(float));
+            if (dets_host) memcpy(dets_host, dst_dets, (size_t)n_cpi * sizeof(jrc_det));
+        }
+        return JRC_OK;
+    }
     int idx = 0;
     for (int c0 = 0; c0 < n_cpi && st == JRC_OK; c0 += chunk, idx++) {
         const int nc = n_cpi - c0 < chunk ? n_cpi - c0 : chunk;

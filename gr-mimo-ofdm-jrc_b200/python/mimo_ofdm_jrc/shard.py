@@ -19,7 +19,7 @@ def shard_range(n_cpi: int, rank: int, world: int):
     return lo, lo + base + (1 if rank < rem else 0)
 
 
-def gather_detections(dets, dst: int = 0, group=None, counts=None, bufs=None):
+def gather_detections(dets, dst: int = 0, group=None, counts=None, bufs=None, async_op=False):
     """dets: uint8 tensor [n_local][32] (device tensor under NCCL, CPU tensor under gloo).
     Returns on rank dst the concatenation over ranks in rank order (ragged shards allowed),
     None elsewhere.
@@ -27,7 +27,10 @@ def gather_detections(dets, dst: int = 0, group=None, counts=None, bufs=None):
     counts: per-rank record counts when the caller already knows them (contiguous shards of a known
     batch: shard_range) -- skips the size exchange and its host synchronisation, so the gather is
     a single asynchronous NCCL call on the current stream.  bufs: optional preallocated receive
-    buffers on rank dst (list of world tensors [max(counts)][32]) to keep the step allocation-free."""
+    buffers on rank dst (list of world tensors [max(counts)][32]) to keep the step allocation-free.
+    async_op=True (needs counts): returns (work, result) without making the current stream wait for
+    the collective, so the next step's kernel overlaps the gather; call work.wait() before the
+    records (or the send buffer) are touched again."""
     import torch
     import torch.distributed as dist
 
@@ -47,9 +50,13 @@ def gather_detections(dets, dst: int = 0, group=None, counts=None, bufs=None):
         padded[: dets.shape[0]] = dets
     if rank == dst and bufs is None:
         bufs = [torch.empty_like(padded) for _ in range(world)]
-    dist.gather(padded.contiguous(), bufs if rank == dst else None, dst=dst, group=group)
+    work = dist.gather(padded.contiguous(), bufs if rank == dst else None, dst=dst, group=group, async_op=async_op)
     if rank != dst:
-        return None
-    if all(c == n_max for c in counts):
-        return bufs            # equal shards: the per-rank blocks, in rank order, no copy
-    return torch.cat([b[:c] for b, c in zip(bufs, counts)], dim=0)
+        res = None
+    elif all(c == n_max for c in counts):
+        res = bufs             # equal shards: the per-rank blocks, in rank order, no copy
+    else:
+        if async_op:
+            raise ValueError("async gather needs equal shard sizes")
+        res = torch.cat([b[:c] for b, c in zip(bufs, counts)], dim=0)
+    return (work, res) if async_op else res

@@ -19,6 +19,8 @@ CFGS = {
     "sq16": dict(T=8, R=1, S=8, N=64, IR=16, IA=16),
     "C3s": dict(T=4, R=8, S=4, N=256, IR=4, IA=2),     # 32 virtual channels (staged path)
     "odd": dict(T=2, R=2, S=3, N=32, IR=2, IA=4),
+    "C3": dict(T=4, R=8, S=4, N=256, IR=16, IA=8),     # BASELINE configs[2]: 4096 x 256 map
+    "C5": dict(T=8, R=16, S=8, N=2048, IR=1, IA=1),    # BASELINE configs[4]: 8 x 16 array, 2048 sc
 }
 
 
@@ -78,12 +80,13 @@ def test_fused_chain_vs_oracle(jrc, orc, name):
 
 @pytest.mark.parametrize("name", list(CFGS))
 def test_staged_chain_is_bit_exact(jrc, orc, name):
-    """One kernel per reference block, oracle float order -> identical bits."""
+    """One kernel per reference block, oracle float order -> identical bits (full-size BASELINE
+    configs[2] and configs[4] included, multi-target scenes)."""
     import torch
     cfg = CFGS[name]
     est = est_for(cfg)
-    n = 12
-    rx, tx, _ = scene(cfg, n, seed=3, n_targets=3, amp_db_span=20.0)
+    n = 3 if name in ("C3", "C5") else 12
+    rx, tx, _ = scene(cfg, n, seed=3, n_targets=5 if name == "C3" else 3, amp_db_span=20.0)
     mo, cmo, do = oracle(orc, rx, tx, cfg, est, want_cmap=True)
     rc = jrc.radar_chain(cfg["N"], cfg["T"], cfg["R"], cfg["S"], cfg["IR"], cfg["IA"], estimator=est)
     drx, dtx = torch.from_numpy(rx).cuda(), torch.from_numpy(tx).cuda()
