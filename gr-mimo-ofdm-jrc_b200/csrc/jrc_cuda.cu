@@ -17,6 +17,7 @@
 
 #include "jrc_fused.cuh"
 #include "jrc_stream.cuh"
+#include "jrc_tc.cuh"
 #include "jrc_staged.cuh"
 
 using namespace jrc;
@@ -99,7 +100,8 @@ struct jrc_chain {
     int64_t launches = 0;
     int fused_ctas_per_sm = 0;
     c32 *d_tw1g = nullptr, *d_tw2g = nullptr;   // slice-streaming kernel twiddle tables
-    int stream_mode = 0;                        // 1 (JRC_FUSED_KERNEL=stream): k_stream64x8 when a map is requested; 0: k_fused64x8
+    float *d_bblob = nullptr;                   // tensor-core kernel: swizzled [Bhi | Blo] angle-DFT operand
+    int stream_mode = 0;                        // map-producing kernel: 0 k_fused64x8, 1 k_stream64x8, 2 k_tc64x8 (JRC_FUSED_KERNEL)
 };
 
 static bool is_pow2(int n) { return n > 0 && (n & (n - 1)) == 0; }
@@ -160,7 +162,8 @@ extern "C" jrc_status jrc_chain_create(const jrc_chain_cfg *cfg, jrc_chain **out
         CU(cudaEventCreateWithFlags(&h->ev_out[i], cudaEventDisableTiming));
     }
     h->pin_a.pinned = h->pin_b.pinned = true;
-    if (const char *e = getenv("JRC_FUSED_KERNEL")) h->stream_mode = strcmp(e, "stream") == 0;   // A/B switch for measurements
+    if (const char *e = getenv("JRC_FUSED_KERNEL"))   // A/B switch for measurements: cta | stream | tc
+        h->stream_mode = !strcmp(e, "stream") ? 1 : (!strcmp(e, "tc") ? 2 : 0);
     const size_t vn = (size_t)h->V * cfg->fft_len;
     CU(cudaMalloc(&h->d_temp, vn * sizeof(c32)));
     CU(cudaMemsetAsync(h->d_temp, 0, vn * sizeof(c32), h->stream));
@@ -183,6 +186,7 @@ extern "C" void jrc_chain_destroy(jrc_chain *h)
                        &h->sDets[0], &h->sDets[1], &h->sMisc, &h->sMisc2, &h->pin_a, &h->pin_b};
     for (GrowBuf *b : bufs) b->release();
     if (h->d_angle_bins) cudaFree(h->d_angle_bins);
+    if (h->d_bblob) cudaFree(h->d_bblob);
     if (h->d_tw1g) cudaFree(h->d_tw1g);
     if (h->d_tw2g) cudaFree(h->d_tw2g);
     if (h->d_ring) cudaFree(h->d_ring);
@@ -459,6 +463,86 @@ static jrc_status launch_stream(jrc_chain *h, const StreamParams &P)
     return fail(JRC_ERR_INVALID, "no stream kernel for this configuration");
 }
 
+// ---------------------------------------------------------------------------
+// tensor-core path (jrc_tc.cuh): k_chan_est -> k_tc64x8 -> k_tc_finalize
+// ---------------------------------------------------------------------------
+static float tf32_hi(float x)
+{
+    uint32_t u;
+    memcpy(&u, &x, 4);
+    u &= 0xFFFFE000u;
+    memcpy(&x, &u, 4);
+    return x;
+}
+
+static jrc_status tc_operand(jrc_chain *h)
+{
+    if (h->d_bblob) return JRC_OK;
+    const int NA = h->Na, N = 2 * NA;
+    std::vector<float> img((size_t)N * 32, 0.f);
+    for (int i = 0; i < NA; i++)
+        for (int p = 0; p < 8; p++) {
+            // D[p][i] = (-1)^p e^{-j 2 pi p i / NA}: the angle DFT with its output fftshift folded in
+            const double a = -2.0 * M_PI * (double)((p * i) % NA) / (double)NA, sg = (p & 1) ? -1.0 : 1.0;
+            const double dr = sg * cos(a), di = sg * sin(a);
+            const double rows[2][2] = {{dr, -di}, {di, dr}};   // Re row: (yr, yi) -> dr, -di;  Im row: di, dr
+            for (int ri = 0; ri < 2; ri++)
+                for (int c = 0; c < 2; c++) {
+                    const int j = 2 * i + ri, k = 2 * p + c;
+                    const float full = (float)rows[ri][c], hi = tf32_hi(full), lo = tf32_hi(full - hi);
+                    auto at = [&](int kk) { return (size_t)(j >> 3) * 256 + (j & 7) * 32 + ((((kk >> 2) ^ (j & 7)) << 2) + (kk & 3)); };
+                    img[at(k)] = hi;
+                    img[at(16 + k)] = lo;
+                }
+        }
+    CU(cudaMalloc(&h->d_bblob, img.size() * sizeof(float)));
+    CU(cudaMemcpyAsync(h->d_bblob, img.data(), img.size() * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return JRC_OK;
+}
+
+template <int IR, int IA>
+static jrc_status launch_tc_t(jrc_chain *h, const TcParams &P)
+{
+    using Gm = TcGeom<IR, IA>;
+    auto kern = k_tc64x8<IR, IA>;
+    // a TMEM kernel gets one CTA per SM; the CTA holds Gm::GROUPS independent 4-warp groups
+    const size_t smem = Gm::SMEM;
+    CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 1;
+    h->fused_ctas_per_sm = per_sm;
+    const long long units = (long long)P.n_cpi * (IR / 2);
+    long long grid = (long long)h->sm_count * per_sm;
+    if (grid * Gm::GROUPS > units) grid = (units + Gm::GROUPS - 1) / Gm::GROUPS;
+    kern<<<(unsigned)grid, Gm::THREADS, smem, h->stream>>>(P);
+    CU(cudaGetLastError());
+    h->launches++;
+    if (P.dets) {
+        k_tc_finalize<IR, IA><<<(unsigned)((P.n_cpi + 3) / 4), 128, 0, h->stream>>>(P);
+        CU(cudaGetLastError());
+        h->launches++;
+    }
+    return JRC_OK;
+}
+
+static bool tc_config_ok(const jrc_chain *h)
+{
+    const int IR = h->cfg.interp_range, IA = h->cfg.interp_angle;
+    return h->cfg.fft_len == 64 && h->V == 8 && ((IR == 16 && IA == 8) || (IR == 8 && IA == 16) || (IR == 8 && IA == 8) || (IR == 16 && IA == 16));
+}
+
+static jrc_status launch_tc(jrc_chain *h, const TcParams &P)
+{
+    const int IR = h->cfg.interp_range, IA = h->cfg.interp_angle;
+#define JRC_TC_CASE(ir, ia) if (IR == ir && IA == ia) return launch_tc_t<ir, ia>(h, P);
+    JRC_TC_CASE(16, 8)
+    JRC_TC_CASE(8, 16)
+    JRC_TC_CASE(8, 8)
+    JRC_TC_CASE(16, 16)
+#undef JRC_TC_CASE
+    return fail(JRC_ERR_INVALID, "no tensor-core kernel for this configuration");
+}
+
 static bool fused_config_ok(const jrc_chain *h)
 {
     const int IR = h->cfg.interp_range, IA = h->cfg.interp_angle;
@@ -494,7 +578,28 @@ extern "C" jrc_status jrc_chain_run_batch(jrc_chain *h, jrc_port_layout rx, jrc_
     if (path == JRC_PATH_FUSED && !want_fused)
         return fail(JRC_ERR_INVALID, "fused path requested but this configuration/layout has no fused kernel");
 
-    if (want_fused && map && h->stream_mode) {
+    if (want_fused && map && h->stream_mode == 2 && tc_config_ok(h)) {
+        // tensor-core hot path: channel estimates (+ background ring) -> range passes + tcgen05 angle DFT
+        ST(stream_tables(h));
+        ST(tc_operand(h));
+        ST(h->sH.need((size_t)n_cpi * V * N * sizeof(c32)));
+        ST(launch_chan_est(h, drx, dtx, n_cpi, (c32 *)h->sH.p));
+        TcParams TP;
+        memset(&TP, 0, sizeof(TP));
+        TP.H = (const c32 *)h->sH.p; TP.n_cpi = n_cpi; TP.cpi0 = cpi0; TP.map = map;
+        TP.tw1g = h->d_tw1g; TP.tw2g = h->d_tw2g; TP.bblob = h->d_bblob;
+        if (dets) {
+            ST(est_params(h, Nr, Na, &TP.est));
+            ST(h->sKeys.need(sizeof(unsigned long long) * (size_t)n_cpi));
+            CU(cudaMemsetAsync(h->sKeys.p, 0, sizeof(unsigned long long) * (size_t)n_cpi, h->stream));
+            TP.keys = (unsigned long long *)h->sKeys.p;
+            TP.dets = (DetDev *)dets;
+        }
+        ST(launch_tc(h, TP));
+        h->last_path = JRC_PATH_FUSED;
+        return JRC_OK;
+    }
+    if (want_fused && map && h->stream_mode == 1) {
         // map-producing hot path: channel estimates (+ background ring) -> slice-streaming kernel
         ST(stream_tables(h));
         ST(h->sH.need((size_t)n_cpi * V * N * sizeof(c32)));
