@@ -100,6 +100,7 @@ struct jrc_chain {
     int64_t launches = 0;
     int fused_ctas_per_sm = 0;
     c32 *d_tw1g = nullptr, *d_tw2g = nullptr;   // slice-streaming kernel twiddle tables
+    int det_mode = 1;                           // 1: in-kernel estimator (faster on B200); 0 (JRC_DET=map): key + k_map_finalize when the map is written
     float *d_bblob = nullptr;                   // tensor-core kernel: swizzled [Bhi | Blo] angle-DFT operand
     int stream_mode = 0;                        // map-producing kernel: 0 k_fused64x8, 1 k_stream64x8, 2 k_tc64x8 (JRC_FUSED_KERNEL)
 };
@@ -162,6 +163,7 @@ extern "C" jrc_status jrc_chain_create(const jrc_chain_cfg *cfg, jrc_chain **out
         CU(cudaEventCreateWithFlags(&h->ev_out[i], cudaEventDisableTiming));
     }
     h->pin_a.pinned = h->pin_b.pinned = true;
+    if (const char *e = getenv("JRC_DET")) h->det_mode = !strcmp(e, "map") ? 0 : 1;
     if (const char *e = getenv("JRC_FUSED_KERNEL"))   // A/B switch for measurements: cta | stream | tc
         h->stream_mode = !strcmp(e, "stream") ? 1 : (!strcmp(e, "tc") ? 2 : 0);
     const size_t vn = (size_t)h->V * cfg->fft_len;
@@ -518,7 +520,8 @@ static jrc_status launch_tc_t(jrc_chain *h, const TcParams &P)
     CU(cudaGetLastError());
     h->launches++;
     if (P.dets) {
-        k_tc_finalize<IR, IA><<<(unsigned)((P.n_cpi + 3) / 4), 128, 0, h->stream>>>(P);
+        k_map_finalize<<<(unsigned)((P.n_cpi + 3) / 4), 128, (size_t)Gm::NA * sizeof(float), h->stream>>>(
+            P.map, P.keys, P.n_cpi, Gm::NR, Gm::NA, P.est, P.dets, P.cpi0);
         CU(cudaGetLastError());
         h->launches++;
     }
@@ -626,6 +629,13 @@ extern "C" jrc_status jrc_chain_run_batch(jrc_chain *h, jrc_port_layout rx, jrc_
         P.T = c.n_tx; P.R = c.n_rx; P.S = c.n_sym; P.n_pre = c.n_pre; P.tx_interleave = c.tx_interleave;
         P.map = map; P.dets = (DetDev *)dets;
         if (dets) ST(est_params(h, Nr, Na, &P.est));
+        const bool map_backed = dets && map && h->det_mode == 0;   // detections from key + map after the kernel
+        if (map_backed) {
+            ST(h->sKeys.need(sizeof(unsigned long long) * (size_t)n_cpi));
+            CU(cudaMemsetAsync(h->sKeys.p, 0, sizeof(unsigned long long) * (size_t)n_cpi, h->stream));
+            P.keys = (unsigned long long *)h->sKeys.p;
+            P.dets = nullptr;
+        }
         bool ok = false;
         if (bg || c.background_recording) {
             // background path: raw estimates -> ring update/subtraction -> fused kernel from H
@@ -635,6 +645,12 @@ extern "C" jrc_status jrc_chain_run_batch(jrc_chain *h, jrc_port_layout rx, jrc_
             ST(launch_fused<true>(h, P, &ok));
         } else {
             ST(launch_fused<false>(h, P, &ok));
+        }
+        if (ok && map_backed) {
+            k_map_finalize<<<(unsigned)((n_cpi + 3) / 4), 128, (size_t)Na * sizeof(float), h->stream>>>(
+                map, (const unsigned long long *)h->sKeys.p, n_cpi, Nr, Na, P.est, (DetDev *)dets, cpi0);
+            CU(cudaGetLastError());
+            h->launches++;
         }
         if (ok) { h->last_path = JRC_PATH_FUSED; return JRC_OK; }
     }

@@ -33,7 +33,8 @@ struct FusedParams {
     int n_cpi, cpi0;
     int T, R, S, n_pre, tx_interleave;
     float *map;                // [n_cpi][NR][NA] or nullptr
-    DetDev *dets;              // [n_cpi] or nullptr
+    DetDev *dets;              // [n_cpi] or nullptr (in-kernel estimator)
+    unsigned long long *keys;  // [n_cpi] zeroed, or nullptr: per-CPI arg-max key for k_map_finalize instead of dets
     EstParams est;
 };
 
@@ -358,7 +359,17 @@ __global__ void __launch_bounds__(256, 2) k_fused64x8(const FusedParams P)
 
         // ---- stage 5: range_angle_estimator ----------------------------------
         pending = false;
-        if (P.dets) {
+        if (P.keys) {
+            // map-backed detection: fold this CTA's maximum into the CPI's 64-bit key (no CTA barrier);
+            // k_map_finalize turns key + map into the record after the kernel
+            unsigned long long key = best >= 0.f ? pack_key(best, (unsigned)(n_base + best_it * G)) : 0ull;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                unsigned long long other = __shfl_xor_sync(0xffffffffu, key, o);
+                key = other > key ? other : key;
+            }
+            if (lane == 0 && key) atomicMax(P.keys + cpi, key);
+        } else if (P.dets) {
             unsigned long long key = best >= 0.f ? pack_key(best, (unsigned)(n_base + best_it * G)) : 0ull;
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {

@@ -321,6 +321,80 @@ __global__ void k_est_finalize(const c32 *__restrict__ map, long long per_mat, i
     }
 }
 
+
+// ---------------------------------------------------------------------------
+// Detection record from a per-CPI arg-max key and the |.|^2 map (used behind the fused kernels when the
+// map is written anyway): key = (map value bits << 32) | (0xFFFFFFFF - range bin n), the earliest row
+// among equal values.  One warp per CPI: first bin of row n that holds the value, noise window
+// (lib/range_angle_estimator_impl.cc:152-227) read back from the map, SNR gate (:234).
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_map_finalize(const float *__restrict__ map, const unsigned long long *__restrict__ keys,
+                                                      int n_cpi, int NR, int NA, EstParams P, DetDev *__restrict__ dets, int cpi0)
+{
+    extern __shared__ float s_abins[];     // angle_bins copy: the window geometry's binary search stays on chip
+    for (int i = threadIdx.x; i < NA; i += blockDim.x) s_abins[i] = P.angle_bins[i];
+    __syncthreads();
+    EstParams est = P;
+    est.angle_bins = s_abins;
+    const int lane = threadIdx.x & 31;
+    const int cpi = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (cpi >= n_cpi) return;
+    const unsigned long long key = keys[cpi];
+    if (key == 0ull) {   // NaN-only input: nothing can win the strict '>' scan
+        if (lane == 0) {
+            DetDev d; d.range_idx = -1; d.angle_idx = -1; d.peak_power = -1.f;
+            d.noise_power = __int_as_float(0x7fc00000); d.snr_db = d.noise_power;
+            d.n_noise = 0; d.flags = 0; d.cpi = cpi0 + cpi;
+            dets[cpi] = d;
+        }
+        return;
+    }
+    const float peak = __uint_as_float((unsigned)(key >> 32));
+    const int nstar = (int)(0xFFFFFFFFu - (unsigned)(key & 0xFFFFFFFFull));
+    const float *map_c = map + (long long)cpi * NR * NA;
+    int istar = 0x7fffffff;
+    for (int i0 = 0; i0 < NA && istar == 0x7fffffff; i0 += 128) {    // 4 loads in flight per lane
+        float v[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) { const int i = i0 + lane + 32 * q; v[q] = i < NA ? __ldcg(map_c + (long long)nstar * NA + i) : -1.f; }
+#pragma unroll
+        for (int q = 3; q >= 0; q--) if (v[q] == peak) istar = i0 + lane + 32 * q;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) istar = min(istar, __shfl_xor_sync(0xffffffffu, istar, o));
+    }
+    if (istar == 0x7fffffff) istar = 0;      // cannot happen: the key was built from this row
+    const NoiseWin w = noise_window(est, nstar, istar);
+    const int ncols = w.end_a - w.start_a, nrows = w.end_r - w.start_r;
+    const int total = (ncols > 0 && nrows > 0) ? nrows * ncols : 0;
+    double acc = 0.0;
+    for (int j0 = lane; j0 < total; j0 += 32 * 8) {      // 8 independent loads in flight per lane
+        float v[8];
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+            const int j = j0 + 32 * q;
+            v[q] = 0.f;
+            if (j < total) {
+                const int ir = w.start_r + j / ncols, ia = w.start_a + j % ncols;
+                const int r_idx = ((ir % NR) + NR) % NR, a_idx = ((ia % NA) + NA) % NA;
+                v[q] = __ldcg(map_c + (long long)r_idx * NA + a_idx);
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < 8; q++) acc += (double)v[q];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) {
+        DetDev d;
+        d.range_idx = nstar; d.angle_idx = istar; d.peak_power = peak; d.n_noise = total;
+        d.noise_power = __fdiv_rn((float)acc, (float)total);
+        d.snr_db = __fmul_rn(10.f, log10f(__fdiv_rn(d.peak_power, d.noise_power)));
+        d.flags = (d.snr_db >= P.snr_threshold && d.peak_power >= P.power_threshold) ? 1u : 0u;
+        d.cpi = cpi0 + cpi;
+        dets[cpi] = d;
+    }
+}
+
 // ---------------------------------------------------------------------------
 // fft_peak_detect  (lib/fft_peak_detect_impl.cc:88-95): first maximum of abs(in[p])
 // over [protect, n-protect) among samples with pow(abs,2) > 10^(thr/10) (double).
