@@ -1008,6 +1008,37 @@ extern "C" jrc_status jrc_peak1d(jrc_chain *h, const jrc_c32 *in, int32_t n, int
     return JRC_OK;
 }
 
+extern "C" jrc_status jrc_cp_remove(jrc_chain *h, const jrc_c32 *in, int32_t n_sym, int32_t fft_len, int32_t cp_len, jrc_c32 *out)
+{
+    if (!h || !in || !out) return fail(JRC_ERR_INVALID, "null argument");
+    if (n_sym < 0 || fft_len < 1 || cp_len < 0) return fail(JRC_ERR_INVALID, "bad sizes");
+    if (n_sym == 0) return JRC_OK;
+    CU(cudaSetDevice(h->cfg.device));
+    Staging sg(h);
+    const void *din = nullptr; void *dout = nullptr;
+    ST(sg.in(in, (size_t)n_sym * (fft_len + cp_len) * sizeof(c32), &din));
+    ST(sg.out(out, (size_t)n_sym * fft_len * sizeof(c32), &dout));
+    // strided copy: symbol k of the packet starts at k*(fft_len+cp_len) + cp_len  (:92-95)
+    CU(cudaMemcpy2DAsync(dout, (size_t)fft_len * sizeof(c32), (const c32 *)din + cp_len, (size_t)(fft_len + cp_len) * sizeof(c32),
+                         (size_t)fft_len * sizeof(c32), (size_t)n_sym, cudaMemcpyDeviceToDevice, h->stream));
+    return sg.finish();
+}
+
+extern "C" jrc_status jrc_ofdm_demod(jrc_chain *h, const jrc_c32 *in, int32_t n_sym, int32_t fft_len, int32_t cp_len, jrc_c32 *out)
+{
+    if (!h || !in || !out) return fail(JRC_ERR_INVALID, "null argument");
+    if (n_sym < 0 || fft_len < 1 || cp_len < 0) return fail(JRC_ERR_INVALID, "bad sizes");
+    if (n_sym == 0) return JRC_OK;
+    CU(cudaSetDevice(h->cfg.device));
+    Staging sg(h);
+    const void *din = nullptr; void *dout = nullptr;
+    ST(sg.in(in, (size_t)n_sym * (fft_len + cp_len) * sizeof(c32), &din));
+    ST(sg.out(out, (size_t)n_sym * fft_len * sizeof(c32), &dout));
+    // the cyclic-prefix removal is the row stride of the FFT's input: nothing is copied
+    ST(launch_fft_rows(h, (const c32 *)din + cp_len, fft_len + cp_len, fft_len, (c32 *)dout, fft_len, n_sym, 1, 1));
+    return sg.finish();
+}
+
 extern "C" jrc_status jrc_zero_pad(jrc_chain *h, const jrc_c32 *in, int32_t n, uint32_t pad_front, uint32_t pad_tail,
                                     uint64_t seed, jrc_c32 *out)
 {

@@ -92,6 +92,13 @@ BLOCKS = {
         inputs=[dict(domain="stream", dtype="complex", multiplicity="1")],
         outputs=[dict(domain="stream", dtype="complex", multiplicity="1")],
         asserts=["${ pad_front >= 0 }", "${ pad_tail >= 0 }"]),
+    "ofdm_cyclic_prefix_remover": dict(
+        label="OFDM Cyclic Prefix Remover",
+        make=call("ofdm_cyclic_prefix_remover", "fft_len", "cp_len", "len_key"),
+        parameters=[P("fft_len", "FFT length", "int"), P("cp_len", "CP length", "int"),
+                    P("len_key", "Packet length key", "string", '"packet_len"')],
+        inputs=[dict(domain="stream", dtype="complex")],
+        outputs=[dict(domain="stream", dtype="complex", vlen="${ fft_len }")]),
     # not in the reference: the fused chain as one block (include/mimo_ofdm_jrc/radar_chain.h)
     "radar_chain": dict(
         label="MIMO OFDM Radar Chain (fused, B200)",

@@ -234,6 +234,25 @@ class zero_pad:
         return self._chain.zero_pad(items, self.pad_front, self.pad_tail, seed)
 
 
+class ofdm_cyclic_prefix_remover:
+    """include/mimo_ofdm_jrc/ofdm_cyclic_prefix_remover.h, lib/ofdm_cyclic_prefix_remover_impl.cc:62-99 -- the block
+    in front of the radar path.  `demod=True` additionally applies the flowgraph's RX
+    fft_vxx(fft_len, forward, shift) in the same kernel (jrc_ofdm_demod)."""
+
+    def __init__(self, fft_len, cp_len, len_key="packet_len", device=0):
+        self.fft_len, self.cp_len, self.len_key = int(fft_len), int(cp_len), len_key
+        self._chain = cabi.Chain(device=device)
+
+    def calculate_output_stream_length(self, ninput_items):
+        return ninput_items // (self.fft_len + self.cp_len)
+
+    def work(self, items, demod=False):
+        items = np.asarray(items, dtype=np.complex64).reshape(-1)
+        n_sym = items.size // (self.fft_len + self.cp_len)
+        f = self._chain.ofdm_demod if demod else self._chain.cp_remove
+        return f(items, n_sym, self.fft_len, self.cp_len)
+
+
 class radar_chain:
     """The fused chain over a batch of CPIs resident in device memory (torch tensors are only
     used as device buffers).  rx [n_cpi][R][S][N] / tx [n_cpi or 1][T][S][N] complex64 CUDA."""

@@ -51,6 +51,7 @@ EXPORTS = [
     "jrc_chain_set_background_record", "jrc_chain_reset_background", "jrc_chain_run_batch",
     "jrc_chain_last_path", "jrc_chain_launch_count", "jrc_chain_run_host", "jrc_radar_estimate",
     "jrc_fft_vcc", "jrc_transpose_pad", "jrc_mag_squared", "jrc_estimate2d", "jrc_peak1d", "jrc_zero_pad",
+    "jrc_cp_remove", "jrc_ofdm_demod",
 ]
 
 _lib = None
@@ -90,6 +91,8 @@ def load():
     lib.jrc_estimate2d.argtypes = [vp, vp, i32, i32, vp]
     lib.jrc_peak1d.argtypes = [vp, vp, i32, i32, f32, f32, i32, C.POINTER(Peak1dOut)]
     lib.jrc_zero_pad.argtypes = [vp, vp, i32, u32, u32, u64, vp]
+    lib.jrc_cp_remove.argtypes = [vp, vp, i32, i32, i32, vp]
+    lib.jrc_ofdm_demod.argtypes = [vp, vp, i32, i32, i32, vp]
     for name in EXPORTS:
         fn = getattr(lib, name)
         if name not in ("jrc_last_error", "jrc_abi_version", "jrc_chain_destroy", "jrc_chain_stream",
@@ -249,6 +252,20 @@ class Chain:
         check(load().jrc_peak1d(self._h, np_ptr(x), x.size, samp_rate, interp_factor, threshold_db,
                                 samp_protect, C.byref(out)))
         return out.k, out.freq, out.phase, out.mag
+
+    def cp_remove(self, x, n_sym, fft_len, cp_len):
+        x = np.ascontiguousarray(x, dtype=np.complex64)
+        assert x.size >= n_sym * (fft_len + cp_len)
+        out = np.empty((n_sym, fft_len), dtype=np.complex64)
+        check(load().jrc_cp_remove(self._h, np_ptr(x), n_sym, fft_len, cp_len, np_ptr(out)))
+        return out
+
+    def ofdm_demod(self, x, n_sym, fft_len, cp_len):
+        x = np.ascontiguousarray(x, dtype=np.complex64)
+        assert x.size >= n_sym * (fft_len + cp_len)
+        out = np.empty((n_sym, fft_len), dtype=np.complex64)
+        check(load().jrc_ofdm_demod(self._h, np_ptr(x), n_sym, fft_len, cp_len, np_ptr(out)))
+        return out
 
     def zero_pad(self, x, pad_front, pad_tail, seed):
         x = np.ascontiguousarray(x, dtype=np.complex64)

@@ -181,6 +181,18 @@ JRC_API jrc_status jrc_peak1d(jrc_chain *h, const jrc_c32 *in, int32_t n, int32_
                               float interp_factor, float threshold_db, int32_t samp_protect,
                               jrc_peak1d_out *out);
 
+/* ofdm_cyclic_prefix_remover::work (lib/ofdm_cyclic_prefix_remover_impl.cc:86-96): n_sym symbols of
+ * fft_len + cp_len time samples -> n_sym vectors of fft_len samples (the step in front of the radar path,
+ * SURVEY.md 8(f) rank 1).                                                                          */
+JRC_API jrc_status jrc_cp_remove(jrc_chain *h, const jrc_c32 *in, int32_t n_sym, int32_t fft_len,
+                                 int32_t cp_len, jrc_c32 *out);
+
+/* The RX OFDM demodulator of the flowgraph in one kernel: cyclic-prefix removal followed by
+ * fft_vxx(fft_len, forward, shift=True, no window) (...radar_sim.grc:898-939, 2189-2190): time samples in,
+ * DC-centred subcarrier vectors out (what the radar block's rx ports receive).                      */
+JRC_API jrc_status jrc_ofdm_demod(jrc_chain *h, const jrc_c32 *in, int32_t n_sym, int32_t fft_len,
+                                  int32_t cp_len, jrc_c32 *out);
+
 /* zero_pad::work (lib/zero_pad_impl.cc:67-94): out[pad_front + i] = in[i]; the pads
  * are N(0, 1e-2) complex noise from a counter-based generator keyed by seed
  * (the reference draws a fresh std::random_device seed per call).             */

@@ -10,6 +10,7 @@
 #include <mimo_ofdm_jrc/fft_peak_detect.h>
 #include <mimo_ofdm_jrc/matrix_transpose.h>
 #include <mimo_ofdm_jrc/mimo_ofdm_radar.h>
+#include <mimo_ofdm_jrc/ofdm_cyclic_prefix_remover.h>
 #include <mimo_ofdm_jrc/radar_chain.h>
 #include <mimo_ofdm_jrc/range_angle_estimator.h>
 #include <mimo_ofdm_jrc/zero_pad.h>
@@ -220,6 +221,21 @@ static void test_peak_and_pad()
     double s2 = 0;
     for (int i = 727; i < 967; i++) s2 += std::norm(y[i]);
     CHECK(std::fabs(std::sqrt(s2 / 240 / 2) - 1e-2) < 2e-3, "zero_pad noise sigma %g", std::sqrt(s2 / 240 / 2));
+
+    // ofdm_cyclic_prefix_remover: payload, length tag, and the packet-start tags travel to the first output item
+    auto cp = ofdm_cyclic_prefix_remover::make(64, 16, "packet_len");
+    cvec t = randvec(9 * 80), u(9 * 64), ou(9 * 64);
+    shim::input_t ci; ci.items = t.data(); ci.n_items = 720;
+    ci.tags = {shim::make_tag(0, "packet_len", pmt::from_long(720)), shim::make_tag(0, "rx_time", pmt::from_double(1.5))};
+    r = shim::run_once(*cp, {ci}, {{u.data(), 9}});
+    orc_cp_remove((const orc_c32 *)t.data(), 9, 64, 16, (orc_c32 *)ou.data());
+    CHECK(r.produced == 9 && r.consumed[0] == 720 && std::memcmp(u.data(), ou.data(), u.size() * sizeof(gr_complex)) == 0, "cp remover");
+    bool has_time = false, has_len = false;
+    for (auto &tg : r.out_tags[0]) {
+        if (pmt::symbol_to_string(tg.key) == "rx_time" && tg.offset == 0) has_time = true;
+        if (pmt::symbol_to_string(tg.key) == "packet_len" && pmt::to_long(tg.value) == 9) has_len = true;
+    }
+    CHECK(has_time && has_len, "cp remover tags");
 }
 
 static void test_fused_block()

@@ -321,3 +321,16 @@ def test_stream_kernel_variant_matches_oracle(jrc, orc, monkeypatch):
         np.testing.assert_allclose(d["peak_power"][ok], do["peak_power"][ok], rtol=5e-6)
         np.testing.assert_allclose(d["noise_power"][ok], do["noise_power"][ok], rtol=2e-4)
         assert np.array_equal(d["flags"][ok], do["flags"][ok])
+
+
+def test_ofdm_demod_front_end(jrc, orc):
+    """cyclic-prefix removal (+ the RX OFDM FFT) in front of the radar path."""
+    rng = np.random.default_rng(31)
+    for (N, cp, nsym) in ((64, 16, 12), (256, 64, 9), (2048, 512, 3), (64, 0, 5)):
+        x = (rng.standard_normal(nsym * (N + cp) + 7) + 1j * rng.standard_normal(nsym * (N + cp) + 7)).astype(np.complex64)
+        blk = jrc.ofdm_cyclic_prefix_remover(N, cp)
+        assert blk.calculate_output_stream_length(x.size) == nsym
+        td = blk.work(x)
+        assert np.array_equal(td, orc.cp_remove(x, nsym, N, cp))
+        fd = blk.work(x, demod=True)
+        assert np.array_equal(fd, orc.fft_vcc(orc.cp_remove(x, nsym, N, cp), True, True))

@@ -11,7 +11,8 @@ import yaml
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 OURS = os.path.join(ROOT, "gr-mimo-ofdm-jrc_b200", "grc")
 REF = "/root/reference/grc"
-BLOCKS = ["mimo_ofdm_radar", "matrix_transpose", "range_angle_estimator", "fft_peak_detect", "zero_pad"]
+BLOCKS = ["mimo_ofdm_radar", "matrix_transpose", "range_angle_estimator", "fft_peak_detect", "zero_pad",
+          "ofdm_cyclic_prefix_remover"]
 
 
 def norm(s):
