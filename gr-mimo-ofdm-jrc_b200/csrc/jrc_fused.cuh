@@ -141,7 +141,7 @@ __global__ void __launch_bounds__(256, 2) k_fused64x8(const FusedParams P)
     double2 *tabd = reinterpret_cast<double2 *>(stg + 8 * NBUF * STGF);   // [NA] e^{-j2pi m/NA}
     float *abin = reinterpret_cast<float *>(tabd + NA);                   // [NA] angle_bins copy
     unsigned long long *red = reinterpret_cast<unsigned long long *>(abin + NA);   // [8]
-    double2 *redA = reinterpret_cast<double2 *>(red + 8);         // [8 warps][8 lags]
+    double2 *redA = reinterpret_cast<double2 *>(red + 8);         // [8 lags] (room for 64)
     int *sint = reinterpret_cast<int *>(redA + 64);               // [16] scalars
     c32 *inb = reinterpret_cast<c32 *>(sint + 16);                // [(T+R)][S][64]
 
@@ -208,9 +208,7 @@ __global__ void __launch_bounds__(256, 2) k_fused64x8(const FusedParams P)
         if (tid < 8) {
             const int start_a = sint[4], end_a = sint[5], total = sint[8];
             const int ncols = end_a - start_a;
-            double sr = 0.0, si = 0.0;
-#pragma unroll
-            for (int w = 0; w < 8; w++) { sr += redA[w * 8 + tid].x; si += redA[w * 8 + tid].y; }
+            const double sr = redA[tid].x, si = redA[tid].y;
             double contrib;
             if (tid == 0) {
                 contrib = (double)ncols * sr;
@@ -392,7 +390,9 @@ __global__ void __launch_bounds__(256, 2) k_fused64x8(const FusedParams P)
                 const float gmax = __uint_as_float((unsigned)(key >> 32));
                 const int nstar = (int)(0xFFFFFFFFu - (unsigned)(key & 0xFFFFFFFFull));
                 if (warp == nstar / RPW) {
-                    // the lanes that own row nstar re-evaluate it and pick the first bin == gmax
+                    // Everything that is left runs in the warp that owns row nstar; the other warps go on
+                    // to the next CPI's barrier (A).  The lanes that own the row re-evaluate it and pick the
+                    // first bin == gmax.
                     int icand = 0x7fffffff;
                     c32 zc = mk(0.f, 0.f);
                     if (g == (nstar % RPW) % G) {
@@ -407,46 +407,86 @@ __global__ void __launch_bounds__(256, 2) k_fused64x8(const FusedParams P)
                     int imin = icand;
 #pragma unroll
                     for (int o = 16; o > 0; o >>= 1) imin = min(imin, __shfl_xor_sync(0xffffffffu, imin, o));
-                    if (icand == imin && imin != 0x7fffffff) {
+                    const int src = __ffs(__ballot_sync(0xffffffffu, icand == imin)) - 1;
+                    int start_r = 0, end_r = 0, total = 0;
+                    if (lane == src) {
                         NoiseWin w = noise_window(est, nstar, imin);
                         const int ncols = w.end_a - w.start_a, nrows = w.end_r - w.start_r;
+                        start_r = w.start_r; end_r = w.end_r;
+                        total = (ncols > 0 && nrows > 0) ? nrows * ncols : 0;
                         sint[0] = nstar; sint[1] = imin;
-                        sint[2] = w.start_r; sint[3] = w.end_r; sint[4] = w.start_a; sint[5] = w.end_a;
+                        sint[4] = w.start_a; sint[5] = w.end_a;
                         sint[6] = __float_as_int((float)ref_pow_abs2(zc));
                         sint[7] = cpi;
-                        sint[8] = (ncols > 0 && nrows > 0) ? nrows * ncols : 0;
+                        sint[8] = total;
                     }
-                }
-                __syncthreads();   // (F)
-                // Noise window (lib/range_angle_estimator_impl.cc:197-226) without evaluating its samples:
-                //   sum_{r,c} |sum_p y[p][r] w^{p c'}|^2 = ncols*A[0] + 2 Re sum_{d=1..7} g[d] A[d],
-                //   A[d] = sum_r sum_q y[q+d][r] conj(y[q][r]),  g[d] = sum_c w^{d c'},  c' = c + Na/2,
-                // (w = e^{-j2pi/Na}; the modulo wrap of rows is the index, that of columns the period of w).
-                // 36 complex MACs per window row instead of 8 per sample.  Float products and per-thread
-                // partial sums (<= 16 terms), double from the first reduction on.
-                const int start_r = sint[2], end_r = sint[3], total = sint[8];
-                const int lag = tid & 7;
-                float arf = 0.f, aif = 0.f;
-                if (total > 0) {
-                    for (int ir = start_r + (tid >> 3); ir < end_r; ir += 32) {
-                        const int r_idx = ((ir % NR) + NR) % NR;
+                    start_r = __shfl_sync(0xffffffffu, start_r, src);
+                    end_r = __shfl_sync(0xffffffffu, end_r, src);
+                    total = __shfl_sync(0xffffffffu, total, src);
+                    // Noise window (lib/range_angle_estimator_impl.cc:197-226) without evaluating its samples:
+                    //   sum_{r,c} |sum_p y[p][r] w^{p c'}|^2 = ncols*A[0] + 2 Re sum_{d=1..7} g[d] A[d],
+                    //   A[d] = sum_r sum_q y[q+d][r] conj(y[q][r]),  g[d] = sum_c w^{d c'},  c' = c + Na/2,
+                    // (w = e^{-j2pi/Na}; the modulo wrap of rows is the index, that of columns the period of w).
+                    // One window row per lane (consecutive rows: conflict-free loads), 36 complex MACs per row
+                    // instead of 8 per sample; float within a lane, double from the first reduction on.
+                    float acc[16];   // [0..7] Re A[d], [8..15] Im A[d]
 #pragma unroll
-                        for (int qq = 0; qq < 8; qq++) {
-                            if (qq + lag < 8) {
-                                c32 ya = ys[(qq + lag) * NR + r_idx], yb = ys[qq * NR + r_idx];
-                                arf = __fmaf_rn(ya.x, yb.x, __fmaf_rn(ya.y, yb.y, arf));
-                                aif = __fmaf_rn(ya.y, yb.x, __fmaf_rn(-ya.x, yb.y, aif));
+                    for (int d = 0; d < 16; d++) acc[d] = 0.f;
+                    if (total > 0) {
+                        for (int ir = start_r + lane; ir < end_r; ir += 32) {
+                            const int r_idx = ((ir % NR) + NR) % NR;
+                            c32 yv[8];
+#pragma unroll
+                            for (int p = 0; p < 8; p++) yv[p] = ys[p * NR + r_idx];
+#pragma unroll
+                            for (int d = 0; d < 8; d++) {
+#pragma unroll
+                                for (int qq = 0; qq + d < 8; qq++) {
+                                    const c32 ya = yv[qq + d], yb = yv[qq];
+                                    acc[d] = __fmaf_rn(ya.x, yb.x, __fmaf_rn(ya.y, yb.y, acc[d]));
+                                    acc[8 + d] = __fmaf_rn(ya.y, yb.x, __fmaf_rn(-ya.x, yb.y, acc[8 + d]));
+                                }
                             }
                         }
                     }
-                }
-                double ar = (double)arf, ai = (double)aif;
+                    // transposing reduction: every step halves the values a lane carries; lane l ends up
+                    // with the warp total of value l >> 1
+                    double s8[8], s4[4], s2[2], s1;
+                    {
+                        const bool hi = lane & 16;
 #pragma unroll
-                for (int o = 8; o <= 16; o <<= 1) {
-                    ar += __shfl_xor_sync(0xffffffffu, ar, o);
-                    ai += __shfl_xor_sync(0xffffffffu, ai, o);
+                        for (int k = 0; k < 8; k++) {
+                            const float keep = hi ? acc[8 + k] : acc[k], give = hi ? acc[k] : acc[8 + k];
+                            s8[k] = (double)keep + (double)__shfl_xor_sync(0xffffffffu, give, 16);
+                        }
+                    }
+                    {
+                        const bool hi = lane & 8;
+#pragma unroll
+                        for (int k = 0; k < 4; k++) {
+                            const double keep = hi ? s8[4 + k] : s8[k], give = hi ? s8[k] : s8[4 + k];
+                            s4[k] = keep + __shfl_xor_sync(0xffffffffu, give, 8);
+                        }
+                    }
+                    {
+                        const bool hi = lane & 4;
+#pragma unroll
+                        for (int k = 0; k < 2; k++) {
+                            const double keep = hi ? s4[2 + k] : s4[k], give = hi ? s4[k] : s4[2 + k];
+                            s2[k] = keep + __shfl_xor_sync(0xffffffffu, give, 4);
+                        }
+                    }
+                    {
+                        const bool hi = lane & 2;
+                        const double keep = hi ? s2[1] : s2[0], give = hi ? s2[0] : s2[1];
+                        s1 = keep + __shfl_xor_sync(0xffffffffu, give, 2);
+                    }
+                    s1 += __shfl_xor_sync(0xffffffffu, s1, 1);
+                    if (!(lane & 1)) {
+                        const int idx = lane >> 1;   // < 8: Re A[idx], else Im A[idx - 8]
+                        reinterpret_cast<double *>(redA)[2 * (idx & 7) + (idx >> 3)] = s1;
+                    }
                 }
-                if (lane < 8) redA[warp * 8 + lane] = make_double2(ar, ai);
                 pending = true;   // finished after the next barrier (A) / after the loop
             }
         }
