@@ -143,6 +143,66 @@ __device__ __forceinline__ void fft8p(c32 (&u)[8])
     u[7] = __ffma2_rn(t3, NC, E3);
 }
 
+// ---------------------------------------------------------------------------
+// TWO independent 8-point DFTs per call on the packed pipe, split-complex: re[k] / im[k] hold the real /
+// imaginary parts of element k of DFT 0 (.x) and DFT 1 (.y).  No lane of a packed instruction is
+// wasted on re/im swaps, so the pair costs the 52 issue slots of ONE scalar fft8<DIR> (26 per DFT),
+// and each half is bit-identical to fft8<DIR> of that DFT (a - b is fma(b, -1, a); the -(x+y)
+// term of the 3*pi/4 twiddle is carried as x+y with the sign moved into the constant).
+// ---------------------------------------------------------------------------
+template <int DIR>
+__device__ __forceinline__ void fft8s(float2 (&re)[8], float2 (&im)[8])
+{
+    const float C = 0.70710678118654752440f;
+    const float2 N1 = mk(-1.f, -1.f), CC = mk(C, C), NC = mk(-C, -C);
+#define JRC_ADD(a, b) __fadd2_rn(a, b)
+#define JRC_SUB(a, b) __ffma2_rn(b, N1, a)
+    const float2 a0r = JRC_ADD(re[0], re[4]), a0i = JRC_ADD(im[0], im[4]);
+    const float2 a1r = JRC_SUB(re[0], re[4]), a1i = JRC_SUB(im[0], im[4]);
+    const float2 a2r = JRC_ADD(re[2], re[6]), a2i = JRC_ADD(im[2], im[6]);
+    const float2 a3r = JRC_SUB(re[2], re[6]), a3i = JRC_SUB(im[2], im[6]);
+    const float2 a4r = JRC_ADD(re[1], re[5]), a4i = JRC_ADD(im[1], im[5]);
+    const float2 a5r = JRC_SUB(re[1], re[5]), a5i = JRC_SUB(im[1], im[5]);
+    const float2 a6r = JRC_ADD(re[3], re[7]), a6i = JRC_ADD(im[3], im[7]);
+    const float2 a7r = JRC_SUB(re[3], re[7]), a7i = JRC_SUB(im[3], im[7]);
+    const float2 E0r = JRC_ADD(a0r, a2r), E0i = JRC_ADD(a0i, a2i);
+    const float2 E2r = JRC_SUB(a0r, a2r), E2i = JRC_SUB(a0i, a2i);
+    const float2 O0r = JRC_ADD(a4r, a6r), O0i = JRC_ADD(a4i, a6i);
+    const float2 O2r = JRC_SUB(a4r, a6r), O2i = JRC_SUB(a4i, a6i);
+    float2 E1r, E1i, E3r, E3i, O1r, O1i, O3r, O3i, t1r, t1i, t3r, s3;
+    if (DIR < 0) {   // multiply by -j: (x,y) -> (y,-x)
+        E1r = JRC_ADD(a1r, a3i); E1i = JRC_SUB(a1i, a3r);
+        E3r = JRC_SUB(a1r, a3i); E3i = JRC_ADD(a1i, a3r);
+        O1r = JRC_ADD(a5r, a7i); O1i = JRC_SUB(a5i, a7r);
+        O3r = JRC_SUB(a5r, a7i); O3i = JRC_ADD(a5i, a7r);
+        t1r = JRC_ADD(O1r, O1i); t1i = JRC_SUB(O1i, O1r);     // O1*(1-j)
+        t3r = JRC_SUB(O3i, O3r); s3 = JRC_ADD(O3r, O3i);      // O3*(-1-j) = (t3r, -s3)
+        re[2] = JRC_ADD(E2r, O2i); im[2] = JRC_SUB(E2i, O2r);
+        re[6] = JRC_SUB(E2r, O2i); im[6] = JRC_ADD(E2i, O2r);
+        re[1] = __ffma2_rn(CC, t1r, E1r); im[1] = __ffma2_rn(CC, t1i, E1i);
+        re[5] = __ffma2_rn(NC, t1r, E1r); im[5] = __ffma2_rn(NC, t1i, E1i);
+        re[3] = __ffma2_rn(CC, t3r, E3r); im[3] = __ffma2_rn(NC, s3, E3i);
+        re[7] = __ffma2_rn(NC, t3r, E3r); im[7] = __ffma2_rn(CC, s3, E3i);
+    } else {         // multiply by +j: (x,y) -> (-y,x)
+        E1r = JRC_SUB(a1r, a3i); E1i = JRC_ADD(a1i, a3r);
+        E3r = JRC_ADD(a1r, a3i); E3i = JRC_SUB(a1i, a3r);
+        O1r = JRC_SUB(a5r, a7i); O1i = JRC_ADD(a5i, a7r);
+        O3r = JRC_ADD(a5r, a7i); O3i = JRC_SUB(a5i, a7r);
+        t1r = JRC_SUB(O1r, O1i); t1i = JRC_ADD(O1r, O1i);     // O1*(1+j)
+        s3 = JRC_ADD(O3r, O3i); t3r = JRC_SUB(O3r, O3i);      // O3*(-1+j) = (-s3, t3r)
+        re[2] = JRC_SUB(E2r, O2i); im[2] = JRC_ADD(E2i, O2r);
+        re[6] = JRC_ADD(E2r, O2i); im[6] = JRC_SUB(E2i, O2r);
+        re[1] = __ffma2_rn(CC, t1r, E1r); im[1] = __ffma2_rn(CC, t1i, E1i);
+        re[5] = __ffma2_rn(NC, t1r, E1r); im[5] = __ffma2_rn(NC, t1i, E1i);
+        re[3] = __ffma2_rn(NC, s3, E3r); im[3] = __ffma2_rn(CC, t3r, E3i);
+        re[7] = __ffma2_rn(CC, s3, E3r); im[7] = __ffma2_rn(NC, t3r, E3i);
+    }
+    re[0] = JRC_ADD(E0r, O0r); im[0] = JRC_ADD(E0i, O0i);
+    re[4] = JRC_SUB(E0r, O0r); im[4] = JRC_SUB(E0i, O0i);
+#undef JRC_ADD
+#undef JRC_SUB
+}
+
 #ifndef JRC_SCALAR_FFT8
 #define JRC_FFT8 fft8p
 #else

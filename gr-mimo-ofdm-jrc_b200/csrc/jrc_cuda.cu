@@ -89,6 +89,8 @@ struct jrc_chain {
     std::vector<float> range_bins, angle_bins;
     float nd_range_m = 0, nd_angle_deg = 0, snr_thr = 0, pow_thr = 0;
     float *d_angle_bins = nullptr;
+    int2 *d_win_tab = nullptr;                  // k_est_tables: per-angle-bin noise window columns
+    double2 *d_g_tab = nullptr;                 //               and their closed-form column sums
     // background state (lib/mimo_ofdm_radar_impl.h:48-54)
     c32 *d_ring = nullptr, *d_temp = nullptr;
     int ring_size = 0, ring_head = 0;
@@ -188,6 +190,8 @@ extern "C" void jrc_chain_destroy(jrc_chain *h)
                        &h->sDets[0], &h->sDets[1], &h->sMisc, &h->sMisc2, &h->pin_a, &h->pin_b};
     for (GrowBuf *b : bufs) b->release();
     if (h->d_angle_bins) cudaFree(h->d_angle_bins);
+    if (h->d_win_tab) cudaFree(h->d_win_tab);
+    if (h->d_g_tab) cudaFree(h->d_g_tab);
     if (h->d_bblob) cudaFree(h->d_bblob);
     if (h->d_tw1g) cudaFree(h->d_tw1g);
     if (h->d_tw2g) cudaFree(h->d_tw2g);
@@ -229,6 +233,17 @@ extern "C" jrc_status jrc_chain_set_estimator(jrc_chain *h, const float *range_b
     if (h->d_angle_bins) { cudaFree(h->d_angle_bins); h->d_angle_bins = nullptr; }
     CU(cudaMalloc(&h->d_angle_bins, sizeof(float) * (size_t)n_angle));
     CU(cudaMemcpyAsync(h->d_angle_bins, angle_bins, sizeof(float) * (size_t)n_angle, cudaMemcpyHostToDevice, h->stream));
+    if (h->d_win_tab) { cudaFree(h->d_win_tab); h->d_win_tab = nullptr; }
+    if (h->d_g_tab) { cudaFree(h->d_g_tab); h->d_g_tab = nullptr; }
+    CU(cudaMalloc(&h->d_win_tab, sizeof(int2) * (size_t)n_angle));
+    CU(cudaMalloc(&h->d_g_tab, sizeof(double2) * 8 * (size_t)n_angle));
+    {
+        EstParams TP;
+        memset(&TP, 0, sizeof(TP));
+        TP.angle_bins = h->d_angle_bins; TP.n_angle = n_angle; TP.noise_discard_angle_deg = noise_discard_angle_deg;
+        k_est_tables<<<(n_angle + 127) / 128, 128, 0, h->stream>>>(TP, h->d_win_tab, h->d_g_tab);
+        CU(cudaGetLastError());
+    }
     CU(cudaStreamSynchronize(h->stream));
     h->est_set = true;
     return JRC_OK;
@@ -628,7 +643,11 @@ extern "C" jrc_status jrc_chain_run_batch(jrc_chain *h, jrc_port_layout rx, jrc_
         P.rx = drx; P.tx = dtx; P.n_cpi = n_cpi; P.cpi0 = cpi0;
         P.T = c.n_tx; P.R = c.n_rx; P.S = c.n_sym; P.n_pre = c.n_pre; P.tx_interleave = c.tx_interleave;
         P.map = map; P.dets = (DetDev *)dets;
-        if (dets) ST(est_params(h, Nr, Na, &P.est));
+        if (dets) {
+            ST(est_params(h, Nr, Na, &P.est));
+            P.win_tab = h->d_win_tab; P.g_tab = h->d_g_tab;
+            { const char *e = getenv("JRC_DBG"); P.dbg = e ? atoi(e) : 0; }
+        }
         const bool map_backed = dets && map && h->det_mode == 0;   // detections from key + map after the kernel
         if (map_backed) {
             ST(h->sKeys.need(sizeof(unsigned long long) * (size_t)n_cpi));

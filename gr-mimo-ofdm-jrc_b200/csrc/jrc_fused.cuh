@@ -9,8 +9,8 @@
 //   -> range_angle_estimator           (lib/range_angle_estimator_impl.cc:137-253)
 //
 // in ONE persistent kernel, one CTA per CPI at a time.  HBM sees the symbols once
-// (cp.async prefetch of the next CPI), the |.|^2 map once (per-warp TMA bulk stores
-// from a bank-conflict-free staging tile) and a 32-byte detection record; neither
+// (cp.async prefetch of the next CPI), the |.|^2 map once (whole map rows streamed out of
+// a bank-conflict-free per-warp staging tile) and a 32-byte detection record; neither
 // zero-pad nor the transpose nor the complex map ever exist in memory.
 //
 // Index algebra (W_N = e^{+j2pi/N}, w_N = e^{-j2pi/N}, Q = Nr/8, Na = 8*IA):
@@ -36,6 +36,9 @@ struct FusedParams {
     DetDev *dets;              // [n_cpi] or nullptr (in-kernel estimator)
     unsigned long long *keys;  // [n_cpi] zeroed, or nullptr: per-CPI arg-max key for k_map_finalize instead of dets
     EstParams est;
+    const int2 *win_tab;       // [NA] k_est_tables
+    const double2 *g_tab;      // [NA][8]
+    int dbg;
 };
 
 template <int IR, int IA>
@@ -43,31 +46,20 @@ struct FusedGeom {
     static constexpr int NSC = 64, V = 8;
     static constexpr int NR = NSC * IR, NA = V * IA, Q = NR / 8;
     static constexpr int THREADS = 256, WARPS = 8;
-    static constexpr int G = 32 / IA;                    // range bins per warp iteration
-    static constexpr int ROWS_PER_WARP = NR / WARPS;
-    static constexpr int ITERS = ROWS_PER_WARP / G;
-#ifndef JRC_STORE_MODE
-#define JRC_STORE_MODE 0
-#endif
-    // Map store path (A/B measured on B200, profiles/README.md):
-    //   0: each warp stages its 1 KiB tile (G whole map rows) in shared memory and streams it out
-    //      with 2 x (LDS.128 + STG.128) per iteration;
-    //   1: per-warp cp.async.bulk (UBLKCP) stores of SIT KiB from a ring of NBUF staging tiles;
-    //   2: no staging: 8 STG.32 per thread, every warp store writing G x IA/8 full 32-byte sectors.
-    static constexpr int STORE = JRC_STORE_MODE;
-    static constexpr bool TMA = STORE == 1;
-    static constexpr int SIT = TMA ? 2 : 1;              // iterations per store
-    static constexpr int NBUF = TMA ? 2 : 1;             // staging buffers per warp
-    static constexpr int UNROLL = 4;
-    static constexpr int STG_FLOATS = SIT * G * NA;      // floats per staging buffer (SIT KiB)
+    static constexpr int G = 32 / IA;                    // range bins (map rows) per tile
+    static constexpr int TILE = G * NA;                  // 256 floats = 1 KiB: G whole map rows
+    // angle pass: a thread evaluates rows n and n + Q together (split-complex packed arithmetic), so a
+    // warp owns the row pairs {(2j'Q + q, (2j'+1)Q + q)} with j' = warp / 2, q in its half of [0, Q)
+    static constexpr int PITERS = (Q / 2) / G;           // pair iterations per warp
+    static constexpr int UNROLL = 2;
     static_assert(IA >= 4 && IA <= 32 && (IA & (IA - 1)) == 0, "angle interp must be 4..32, power of two");
-    static_assert(IR >= 1 && IR <= 32 && (IR & (IR - 1)) == 0, "range interp must be 1..32, power of two");
-    static_assert(ITERS >= UNROLL && ITERS % UNROLL == 0 && UNROLL % (SIT * NBUF) == 0, "map too small for the store pipeline");
+    static_assert(IR >= 8 && IR <= 32 && (IR & (IR - 1)) == 0, "range interp must be 8..32, power of two");
+    static_assert(PITERS >= UNROLL && PITERS % UNROLL == 0, "map too small");
 
     static size_t smem_bytes(int T, int R, int S, bool from_h)
     {
-        size_t b = (size_t)V * NR * 8 + (size_t)V * NSC * 8 + (size_t)8 * Q * 8 + (size_t)WARPS * NBUF * STG_FLOATS * 4 +
-                   (size_t)NA * 16 + (size_t)NA * 4 + 64 + 1024 + 64;
+        size_t b = (size_t)V * NR * 8 + (size_t)V * NSC * 8 + (size_t)8 * Q * 8 + (size_t)WARPS * 2 * TILE * 4 +
+                   64 + 512 + 64;
         if (!from_h) b += (size_t)(T + R) * S * NSC * 8;
         return b;
     }
@@ -80,47 +72,33 @@ __device__ __forceinline__ void cp_async16(void *sdst, const void *gsrc)
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void bulk_store_s2g(void *gdst, const void *ssrc, unsigned bytes)
-{
-    unsigned s = (unsigned)__cvta_generic_to_shared(ssrc);
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(s), "r"(bytes)
-                 : "memory");
-}
-__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
-// lane-0-only forms as predicated instructions (no BSSY/BSYNC divergence scaffolding in the hot loop)
-template <int N>
-__device__ __forceinline__ void bulk_wait_read_lane0(int lane)
-{
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.eq.s32 p, %0, 0;\n\t@p cp.async.bulk.wait_group.read %1;\n\t}" ::"r"(lane), "n"(N)
-                 : "memory");
-}
-__device__ __forceinline__ void bulk_store_commit_lane0(int lane, void *gdst, const void *ssrc, unsigned bytes)
-{
-    unsigned s = (unsigned)__cvta_generic_to_shared(ssrc);
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.eq.s32 p, %0, 0;\n\t"
-                 "@p cp.async.bulk.global.shared::cta.bulk_group [%1], [%2], %3;\n\t"
-                 "@p cp.async.bulk.commit_group;\n\t}" ::"r"(lane), "l"(gdst), "r"(s), "r"(bytes)
-                 : "memory");
-}
+// Angle twiddles of one thread, duplicated into both halves of a register pair.
+struct AngleTw { float2 r[8], i[8], n[8]; };   // (re,re), (im,im), (-im,-im); index 0 unused
 
-// one angle row task: 8 channel samples -> twiddle -> forward DFT-8 -> |.|^2.
-// Pure _rn intrinsics: re-evaluating a row reproduces the main loop bit for bit.
-__device__ __forceinline__ void angle_task(const c32 *__restrict__ ys, int NR, int n, const c32 (&tw)[8],
-                                           c32 (&u)[8], float (&v)[8])
+// One angle task: rows n0 = 2j'Q + q and n1 = n0 + Q, 8 channel samples each -> twiddle -> forward DFT-8
+// -> |.|^2.  re/im/v: .x belongs to row n0, .y to row n1.  Pure _rn intrinsics: re-evaluating a row
+// pair reproduces the main loop bit for bit.
+// ys holds the range spectra as ys[pr * NR + (4c + j') * Q + q] = (Re y[p][n0], Re y[p][n1], Im y[p][n0],
+// Im y[p][n1]) for channel p = 2 pr + c.
+__device__ __forceinline__ void angle_pair(const float4 *__restrict__ ys, int NR, int Q, int jq, const AngleTw &tw,
+                                           float2 (&re)[8], float2 (&im)[8], float2 (&v)[8])
 {
 #pragma unroll
-    for (int p = 0; p < 8; p++) u[p] = ys[p * NR + n];
-#pragma unroll
-    for (int p = 1; p < 8; p++) u[p] = cmul_fma(u[p], tw[p]);
-    JRC_FFT8<-1>(u);
-#pragma unroll
-    for (int a = 0; a < 8; a++) {   // volk_32fc_magnitude_squared_32f: re*re + im*im, each product rounded
-        c32 sq = __fmul2_rn(u[a], u[a]);
-        v[a] = __fadd_rn(sq.x, sq.y);
+    for (int p = 0; p < 8; p++) {
+        const float4 t = ys[(p >> 1) * NR + 4 * (p & 1) * Q + jq];
+        re[p] = mk(t.x, t.y);
+        im[p] = mk(t.z, t.w);
     }
+#pragma unroll
+    for (int p = 1; p < 8; p++) {
+        const float2 r = __ffma2_rn(im[p], tw.n[p], __fmul2_rn(re[p], tw.r[p]));
+        const float2 i = __ffma2_rn(im[p], tw.r[p], __fmul2_rn(re[p], tw.i[p]));
+        re[p] = r;
+        im[p] = i;
+    }
+    fft8s<-1>(re, im);
+#pragma unroll
+    for (int a = 0; a < 8; a++) v[a] = __ffma2_rn(im[a], im[a], __fmul2_rn(re[a], re[a]));
 }
 
 template <int IR, int IA, bool FROM_H, bool WRITE_MAP>
@@ -128,20 +106,18 @@ __global__ void __launch_bounds__(256, 2) k_fused64x8(const FusedParams P)
 {
     using Gm = FusedGeom<IR, IA>;
     constexpr int NR = Gm::NR, NA = Gm::NA, Q = Gm::Q, G = Gm::G;
-    constexpr int RPW = Gm::ROWS_PER_WARP, ITERS = Gm::ITERS, SIT = Gm::SIT, NBUF = Gm::NBUF;
-    constexpr int STGF = Gm::STG_FLOATS;
-    constexpr int T1 = (8 * IR + 31) / 32;     // range pass 1 tasks per lane (channel = warp)
-    constexpr int T2 = (Q + 31) / 32;          // range pass 2 tasks per lane
+    constexpr int PITERS = Gm::PITERS, TILE = Gm::TILE;
+    constexpr int T1 = (8 * IR) / 64;          // range pass 1 tasks per lane (channel pair = warp pair)
+    constexpr int T2 = Q / 64;                 // range pass 2 tasks per lane
+    static_assert(IR >= 8, "the channel-pair front end needs 8*IR >= 64 pass-1 tasks per pair");
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    c32 *ys = reinterpret_cast<c32 *>(smem_raw);                  // [8][NR]  B then y (in place)
-    c32 *Hs = ys + 8 * NR;                                        // [8][64]
-    c32 *tw2t = Hs + 512;                                         // [8][Q]   W_Nr^{k0 q}
-    float *stg = reinterpret_cast<float *>(tw2t + 8 * Q);         // [8 warps][NBUF][STGF]
-    double2 *tabd = reinterpret_cast<double2 *>(stg + 8 * NBUF * STGF);   // [NA] e^{-j2pi m/NA}
-    float *abin = reinterpret_cast<float *>(tabd + NA);                   // [NA] angle_bins copy
-    unsigned long long *red = reinterpret_cast<unsigned long long *>(abin + NA);   // [8]
-    double2 *redA = reinterpret_cast<double2 *>(red + 8);         // [8 lags] (room for 64)
+    float4 *ys = reinterpret_cast<float4 *>(smem_raw);            // [4 pairs][NR][2]  B then y (in place)
+    float4 *Hs = ys + 4 * NR;                                     // [4 pairs][64][2]
+    c32 *tw2t = reinterpret_cast<c32 *>(Hs + 256);                // [8][Q]   W_Nr^{k0 q}
+    float *stg = reinterpret_cast<float *>(tw2t + 8 * Q);         // [8 warps][2][TILE]
+    unsigned long long *red = reinterpret_cast<unsigned long long *>(stg + 8 * 2 * TILE);   // [8]
+    double *redA = reinterpret_cast<double *>(red + 8);           // [8 warps][8] partial lag sums
     int *sint = reinterpret_cast<int *>(redA + 64);               // [16] scalars
     c32 *inb = reinterpret_cast<c32 *>(sint + 16);                // [(T+R)][S][64]
 
@@ -149,41 +125,46 @@ __global__ void __launch_bounds__(256, 2) k_fused64x8(const FusedParams P)
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // warp-uniform for the compiler
 
     // ---- per-thread constants (once per persistent CTA) --------------------
-    // Stages 1-3 give every warp ONE virtual channel (p = warp), so the channel estimate and both
-    // range passes only need warp-level synchronisation.
+    // Stages 1-3 give every warp PAIR one pair of virtual channels (2j, 2j+1; j = warp / 2) and keep the
+    // two channels interleaved in shared memory, so every access of the front end and the angle pass's
+    // loads are 128 bit wide; the stages only need a 64-thread named barrier between them.
     // range pass 1: task (k0, q0), q0 = lane % IR fixed per lane;  twiddle W_Q^{k1 q0}
-    // range pass 2: task q = lane + 32 j;                           twiddle W_Nr^{k0 q} from tw2t
+    // range pass 2: task q = 32 half + lane + 64 i;                 twiddle W_Nr^{k0 q} from tw2t
     // angle pass:   task (n, b);                                    twiddle (-1)^p w_Na^{p (b + IA*rot)}
     const int q0 = lane % IR;
-    const int b = lane % IA, g = lane / IA, rot = (Gm::STORE == 2) ? 0 : g;
-    c32 tw1[8], tw3[8];
+    const int b = lane % IA, g = lane / IA, rot = g;
+    c32 tw1[8];
+    AngleTw tw3;
 #pragma unroll
     for (int j = 0; j < 8; j++) {
         tw1[j] = cispi_ratio(2 * j * q0, Q);
-        tw3[j] = cispi_ratio(j * (NA - 2 * (b + IA * rot)), NA);
+        const c32 t = cispi_ratio(j * (NA - 2 * (b + IA * rot)), NA);
+        tw3.r[j] = mk(t.x, t.x);
+        tw3.i[j] = mk(t.y, t.y);
+        tw3.n[j] = mk(-t.y, -t.y);
     }
     for (int e = tid; e < 8 * Q; e += 256) tw2t[e] = cispi_ratio(2 * (e / Q) * (e % Q), NR);
-    EstParams est = P.est;
-    for (int m = tid; m < NA; m += 256) {
-        double sn, cs;
-        sincospi(-2.0 * (double)m / (double)NA, &sn, &cs);
-        tabd[m] = make_double2(cs, sn);
-        if (P.dets) abin[m] = P.est.angle_bins[m];
-    }
-    est.angle_bins = abin;   // the window geometry's binary search runs on shared memory
+    const EstParams est = P.est;
 
-    // channel of this warp -> (rx antenna, tx antenna)  (lib/mimo_ofdm_radar_impl.cc:262-269)
+    // channels of this warp pair -> (rx antenna, tx antenna)  (lib/mimo_ofdm_radar_impl.cc:262-269)
     const int per_ant = P.S * 64;
-    int ch_r, ch_t;
-    if (P.tx_interleave) { ch_t = warp / P.R; ch_r = warp - ch_t * P.R; } else { ch_r = warp / P.T; ch_t = warp - ch_r * P.T; }
-    const c32 *srx = inb + (P.T + ch_r) * per_ant + lane;
-    const c32 *stx = inb + ch_t * per_ant + lane;
-    c32 *Hw = Hs + warp * 64;          // this warp's channel estimate
-    c32 *yw = ys + warp * NR;          // this warp's range spectrum
+    const int pair = warp >> 1, half = warp & 1;
+    const c32 *srx[2], *stx[2];
+#pragma unroll
+    for (int c = 0; c < 2; c++) {
+        const int p = 2 * pair + c;
+        int ch_r, ch_t;
+        if (P.tx_interleave) { ch_t = p / P.R; ch_r = p - ch_t * P.R; } else { ch_r = p / P.T; ch_t = p - ch_r * P.T; }
+        srx[c] = inb + (P.T + ch_r) * per_ant + 32 * half + lane;
+        stx[c] = inb + ch_t * per_ant + 32 * half + lane;
+    }
+    float4 *Hw = Hs + pair * 64;       // this pair's channel estimates
+    float4 *yw = ys + pair * NR;       // this pair's range spectra
+    auto pair_sync = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(pair + 1) : "memory"); };
 
     // staging: slot a' of this thread holds angle bin b + IA*((a'+rot)&7); rotating by
     // the row group makes the 32 lanes of every st.shared hit 32 different banks
-    float *wstg = stg + warp * NBUF * STGF;
+    float *wstg = stg + warp * 2 * TILE;   // tile 0: rows n0.., tile 1: rows n0 + Q..
     float *sp[8];
 #pragma unroll
     for (int a = 0; a < 8; a++) sp[a] = wstg + g * NA + b + IA * ((a + rot) & 7);
@@ -202,181 +183,183 @@ __global__ void __launch_bounds__(256, 2) k_fused64x8(const FusedParams P)
     };
 
     // Detection record of the previous CPI: its last step only needs the shared scratch (not y), so it
-    // runs after the next CPI's first barrier instead of costing a barrier of its own.
+    // runs after the next CPI's barrier (A) instead of costing a barrier of its own.
+    // Lag d is accumulated by warp pair part(d): 0 -> {0}, 1 -> {1,7}, 2 -> {2,6}, 3 -> {3,4,5}.
     bool pending = false;
     auto finalize = [&]() {
         if (tid < 8) {
-            const int start_a = sint[4], end_a = sint[5], total = sint[8];
-            const int ncols = end_a - start_a;
-            const double sr = redA[tid].x, si = redA[tid].y;
-            double contrib;
-            if (tid == 0) {
-                contrib = (double)ncols * sr;
-            } else {
-                // g[d] = w^{d m0} (1 - w^{d ncols}) / (1 - w^d),  m0 = start_a + Na/2
-                const double2 w0 = tabd[(tid * (start_a + NA / 2)) & (NA - 1)];
-                const double2 w1 = tabd[(tid * ncols) & (NA - 1)];
-                const double2 w2 = tabd[tid];
-                const double c0 = w0.x, s0 = w0.y;
-                const double nr = 1.0 - w1.x, ni = -w1.y, dr = 1.0 - w2.x, di = -w2.y;
-                const double den = dr * dr + di * di;
-                const double qr = (nr * dr + ni * di) / den, qi = (ni * dr - nr * di) / den;
-                const double gr = c0 * qr - s0 * qi, gi = c0 * qi + s0 * qr;
-                contrib = 2.0 * (gr * sr - gi * si);
-            }
+            const int d = tid;
+            const int part = d == 0 ? 0 : (d == 1 || d == 7) ? 1 : (d == 2 || d == 6) ? 2 : 3;
+            const int slot = (d <= 3) ? 0 : (d == 4) ? 2 : (d == 5) ? 4 : 2;   // d=7 -> 2, d=6 -> 2
+            const double *r0 = redA + (2 * part) * 8 + slot, *r1 = r0 + 8;
+            const double ar = r0[0] + r1[0], ai = d ? r0[1] + r1[1] : 0.0;
+            const int imin = sint[1];
+            const double2 gd = P.g_tab[imin * 8 + d];
+            double contrib = 2.0 * (gd.x * ar - gd.y * ai);
             contrib += __shfl_xor_sync(0xffu, contrib, 4);
             contrib += __shfl_xor_sync(0xffu, contrib, 2);
             contrib += __shfl_xor_sync(0xffu, contrib, 1);
             if (tid == 0) {
+                const int2 wa = P.win_tab[imin];
+                const int ncols = wa.y - wa.x, nrows = 2 * est.discard_range_idx;
+                const int total = (ncols > 0 && nrows > 0) ? nrows * ncols : 0;
                 const double s = contrib > 0.0 ? contrib : 0.0;
-                DetDev d;
-                d.range_idx = sint[0]; d.angle_idx = sint[1];
-                d.peak_power = __int_as_float(sint[6]);
-                d.n_noise = total;
-                d.noise_power = __fdiv_rn((float)s, (float)total);
-                d.snr_db = __fmul_rn(10.f, log10f(__fdiv_rn(d.peak_power, d.noise_power)));
-                d.flags = (d.snr_db >= est.snr_threshold && d.peak_power >= est.power_threshold) ? 1u : 0u;
-                d.cpi = P.cpi0 + sint[7];
-                P.dets[sint[7]] = d;
+                DetDev dd;
+                dd.range_idx = sint[0]; dd.angle_idx = imin;
+                dd.peak_power = __int_as_float(sint[6]);
+                dd.n_noise = total;
+                dd.noise_power = __fdiv_rn(total > 0 ? (float)s : 0.f, (float)total);
+                dd.snr_db = __fmul_rn(10.f, log10f(__fdiv_rn(dd.peak_power, dd.noise_power)));
+                dd.flags = (dd.snr_db >= est.snr_threshold && dd.peak_power >= est.power_threshold) ? 1u : 0u;
+                dd.cpi = P.cpi0 + sint[7];
+                P.dets[sint[7]] = dd;
             }
         }
     };
 
     int cpi = blockIdx.x;
-    if (!FROM_H && cpi < P.n_cpi) prefetch(cpi);
+    if (!FROM_H && cpi < P.n_cpi) {
+        prefetch(cpi);
+        cp_async_wait_all();
+    }
+    __syncthreads();
 
     for (; cpi < P.n_cpi; cpi += gridDim.x) {
-        if (!FROM_H) cp_async_wait_all();
-        __syncthreads();   // (A) symbols landed; previous CPI fully consumed
-        if (pending) finalize();
+        // The symbols of this CPI were published by barrier (E) of the previous one, and stage 1 does not
+        // touch y: it overlaps the tail of the previous CPI's estimator.
 
-        // ---- stage 1: channel estimate H[p = warp][k] --------------------------
+        // ---- stage 1: channel estimates H[2 pair + {0,1}][k = 32 half + lane] ------
         if (FROM_H) {
-            const c32 *Hg = P.H + (long long)cpi * 512 + warp * 64;
-            Hw[lane] = Hg[lane];
-            Hw[lane + 32] = Hg[lane + 32];
+            const c32 *Hg = P.H + (long long)cpi * 512 + (2 * pair) * 64 + 32 * half + lane;
+            const c32 h0 = Hg[0], h1 = Hg[64];
+            Hw[32 * half + lane] = make_float4(h0.x, h0.y, h1.x, h1.y);
         } else {
             c32 acc0 = mk(0.f, 0.f), acc1 = mk(0.f, 0.f);
             for (int s = 0; s < P.S; s++) {
-                c32 x0 = srx[s * 64], c0 = stx[s * 64], x1 = srx[s * 64 + 32], c1 = stx[s * 64 + 32];
+                c32 x0 = srx[0][s * 64], c0 = stx[0][s * 64], x1 = srx[1][s * 64], c1 = stx[1][s * 64];
                 acc0 = cadd_exact(acc0, cmul_exact(x0, mk(c0.x, -c0.y)));
                 acc1 = cadd_exact(acc1, cmul_exact(x1, mk(c1.x, -c1.y)));
             }
-            Hw[lane] = acc0;
-            Hw[lane + 32] = acc1;
+            Hw[32 * half + lane] = make_float4(acc0.x, acc0.y, acc1.x, acc1.y);
         }
-        __syncwarp();
-
-        // ---- stage 2: range pass 1 (pruned: 8 of Q inputs non-zero) ----------
-#pragma unroll
-        for (int j = 0; j < T1; j++) {
-            const int task = lane + 32 * j;
-            if (8 * IR >= 32 || task < 8 * IR) {
-                const int k0 = task / IR;
-                c32 u[8];
-#pragma unroll
-                for (int k1 = 0; k1 < 8; k1++) u[k1] = Hw[k0 + 8 * k1];
-#pragma unroll
-                for (int k1 = 1; k1 < 8; k1++) u[k1] = cmul_fma(u[k1], tw1[k1]);
-                JRC_FFT8<1>(u);
-#pragma unroll
-                for (int m0 = 0; m0 < 8; m0++) yw[k0 * Q + q0 + IR * m0] = u[m0];
-            }
-        }
-        __syncwarp();
-
-        // ---- stage 3: range pass 2, in place ---------------------------------
-#pragma unroll
-        for (int j = 0; j < T2; j++) {
-            const int q = lane + 32 * j;
-            if (Q >= 32 || q < Q) {
-                c32 u[8];
-#pragma unroll
-                for (int k0 = 0; k0 < 8; k0++) u[k0] = yw[k0 * Q + q];
-#pragma unroll
-                for (int k0 = 1; k0 < 8; k0++) u[k0] = cmul_fma(u[k0], tw2t[k0 * Q + q]);
-                JRC_FFT8<1>(u);
-#pragma unroll
-                for (int m1 = 0; m1 < 8; m1++) yw[m1 * Q + q] = u[m1];
-            }
-        }
-        __syncthreads();   // (D) y[p][n] complete for all channels; symbol buffer free
+        __syncthreads();   // (A) H complete; symbol buffer free; previous CPI's y fully consumed
+        if (pending && !(P.dbg & 4)) finalize();
         if (!FROM_H) {
             int nxt = cpi + gridDim.x;
             if (nxt < P.n_cpi) prefetch(nxt);
         }
 
+        // ---- stage 2: range pass 1 (pruned: 8 of Q inputs non-zero) ----------
+#pragma unroll
+        for (int j = 0; j < T1; j++) {
+            const int k0 = (32 * half + lane + 64 * j) / IR;
+            c32 u0[8], u1[8];
+#pragma unroll
+            for (int k1 = 0; k1 < 8; k1++) {
+                const float4 t = Hw[k0 + 8 * k1];
+                u0[k1] = mk(t.x, t.y);
+                u1[k1] = mk(t.z, t.w);
+            }
+#pragma unroll
+            for (int k1 = 1; k1 < 8; k1++) { u0[k1] = cmul_fma(u0[k1], tw1[k1]); u1[k1] = cmul_fma(u1[k1], tw1[k1]); }
+            JRC_FFT8<1>(u0);
+            JRC_FFT8<1>(u1);
+#pragma unroll
+            for (int m0 = 0; m0 < 8; m0++)
+                yw[k0 * Q + q0 + IR * m0] = make_float4(u0[m0].x, u0[m0].y, u1[m0].x, u1[m0].y);
+        }
+        pair_sync();
+
+        // ---- stage 3: range pass 2, in place ---------------------------------
+#pragma unroll
+        for (int j = 0; j < T2; j++) {
+            const int q = 32 * half + lane + 64 * j;
+            c32 u0[8], u1[8];
+#pragma unroll
+            for (int k0 = 0; k0 < 8; k0++) {
+                const float4 t = yw[k0 * Q + q];
+                u0[k0] = mk(t.x, t.y);
+                u1[k0] = mk(t.z, t.w);
+            }
+#pragma unroll
+            for (int k0 = 1; k0 < 8; k0++) {
+                const c32 w = tw2t[k0 * Q + q];
+                u0[k0] = cmul_fma(u0[k0], w);
+                u1[k0] = cmul_fma(u1[k0], w);
+            }
+            JRC_FFT8<1>(u0);
+            JRC_FFT8<1>(u1);
+            // in place per thread, regrouped for the angle pass: rows (2j'Q + q, (2j'+1)Q + q) of one channel
+#pragma unroll
+            for (int jj = 0; jj < 4; jj++) {
+                yw[jj * Q + q] = make_float4(u0[2 * jj].x, u0[2 * jj + 1].x, u0[2 * jj].y, u0[2 * jj + 1].y);
+                yw[(4 + jj) * Q + q] = make_float4(u1[2 * jj].x, u1[2 * jj + 1].x, u1[2 * jj].y, u1[2 * jj + 1].y);
+            }
+        }
+        __syncthreads();   // (D) y[p][n] complete for all channels
+
         // ---- stage 4: angle pass + |.|^2 + store + running max ---------------
-        float best = -1.f;
-        int best_it = 0;
-        const int n_base = warp * RPW + g;
-        float *map_w = WRITE_MAP ? P.map + ((long long)cpi * NR + warp * RPW) * NA : nullptr;
-        for (int it0 = 0; it0 < ITERS; it0 += Gm::UNROLL) {
+        float best0 = -1.f, best1 = -1.f;   // rows of tile 0 all precede those of tile 1
+        int bit0 = 0, bit1 = 0;
+        const int jp = warp >> 1;
+        const int qw = (warp & 1) * (Q / 2);             // first q of this warp
+        const int row0 = 2 * jp * Q + qw;                // first map row of tile 0
+        float4 *map_w = WRITE_MAP ? reinterpret_cast<float4 *>(P.map + ((long long)cpi * NR + row0) * NA) : nullptr;
+        for (int itb = 0; itb < PITERS; itb += Gm::UNROLL) {
 #pragma unroll
             for (int ui = 0; ui < Gm::UNROLL; ui++) {
-                const int it = it0 + ui;
-                const int buf = (ui / SIT) % NBUF, sub = ui % SIT;    // compile-time after unrolling
-                c32 u[8];
-                float v[8];
-                angle_task(ys, NR, n_base + it * G, tw3, u, v);
-                float m8 = fmaxf(fmaxf(fmaxf(v[0], v[1]), fmaxf(v[2], v[3])),
-                                 fmaxf(fmaxf(v[4], v[5]), fmaxf(v[6], v[7])));
-                if (m8 > best) { best = m8; best_it = it; }
-                if (WRITE_MAP && Gm::TMA) {
-                    if (sub == 0) {   // the bulk store that last read this buffer must be done with it
-                        bulk_wait_read_lane0<NBUF - 1>(lane);
-                        __syncwarp();
-                    }
+                const int it = itb + ui;
+                float2 re[8], im[8], v[8];
+                angle_pair(ys, NR, Q, jp * Q + qw + g + it * G, tw3, re, im, v);
+                const float m0 = fmaxf(fmaxf(fmaxf(v[0].x, v[1].x), fmaxf(v[2].x, v[3].x)),
+                                       fmaxf(fmaxf(v[4].x, v[5].x), fmaxf(v[6].x, v[7].x)));
+                const float m1 = fmaxf(fmaxf(fmaxf(v[0].y, v[1].y), fmaxf(v[2].y, v[3].y)),
+                                       fmaxf(fmaxf(v[4].y, v[5].y), fmaxf(v[6].y, v[7].y)));
+                if (m0 > best0) { best0 = m0; bit0 = it; }
+                if (m1 > best1) { best1 = m1; bit1 = it; }
+                if (WRITE_MAP) {
+                    // conflict-free scalar st.shared of the strided bins, then the warp streams its two
+                    // 1 KiB tiles (G whole map rows each, contiguous in HBM) out as 4 x 512 B
 #pragma unroll
-                    for (int a = 0; a < 8; a++) sp[a][buf * STGF + sub * G * NA] = v[a];
-                    if (sub == SIT - 1) {
-                        fence_proxy_async_smem();
-                        __syncwarp();
-                        bulk_store_commit_lane0(lane, map_w + (long long)(it - (SIT - 1)) * G * NA, wstg + buf * STGF,
-                                                STGF * 4);
-                    }
-                } else if (WRITE_MAP && Gm::STORE == 2) {
-                    float *dst = map_w + (long long)(it * G + g) * NA + b;
-#pragma unroll
-                    for (int a = 0; a < 8; a++) __stcs(dst + IA * a, v[a]);
-                } else if (WRITE_MAP) {
-                    // conflict-free scalar st.shared of the strided bins, then the warp streams its
-                    // 1 KiB tile (G whole map rows, contiguous in HBM) out as 2 x 512 B
-#pragma unroll
-                    for (int a = 0; a < 8; a++) sp[a][0] = v[a];
+                    for (int a = 0; a < 8; a++) { sp[a][0] = v[a].x; sp[a][TILE] = v[a].y; }
                     __syncwarp();
-                    const float4 o0 = reinterpret_cast<const float4 *>(wstg)[lane];
-                    const float4 o1 = reinterpret_cast<const float4 *>(wstg)[lane + 32];
+                    const float4 *src = reinterpret_cast<const float4 *>(wstg);
+                    const float4 o0 = src[lane], o1 = src[lane + 32], o2 = src[lane + 64], o3 = src[lane + 96];
                     __syncwarp();
-                    float4 *dst = reinterpret_cast<float4 *>(map_w + (long long)it * G * NA);
+                    float4 *dst = map_w + it * (TILE / 4);
                     __stcs(dst + lane, o0);
                     __stcs(dst + lane + 32, o1);
+                    __stcs(dst + Q * NA / 4 + lane, o2);
+                    __stcs(dst + Q * NA / 4 + lane + 32, o3);
                 }
             }
         }
+        // this thread's candidate: lowest row among its maxima
+        const float best = best0 >= best1 ? best0 : best1;
+        const int best_row = best0 >= best1 ? row0 + g + bit0 * G : row0 + Q + g + bit1 * G;
 
         // ---- stage 5: range_angle_estimator ----------------------------------
         pending = false;
-        if (P.keys) {
-            // map-backed detection: fold this CTA's maximum into the CPI's 64-bit key (no CTA barrier);
-            // k_map_finalize turns key + map into the record after the kernel
-            unsigned long long key = best >= 0.f ? pack_key(best, (unsigned)(n_base + best_it * G)) : 0ull;
+        const bool in_kernel_est = P.dets && !P.keys;
+        if (P.keys || P.dets) {
+            unsigned long long key = best >= 0.f ? pack_key(best, (unsigned)best_row) : 0ull;
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {
                 unsigned long long other = __shfl_xor_sync(0xffffffffu, key, o);
                 key = other > key ? other : key;
             }
-            if (lane == 0 && key) atomicMax(P.keys + cpi, key);
-        } else if (P.dets) {
-            unsigned long long key = best >= 0.f ? pack_key(best, (unsigned)(n_base + best_it * G)) : 0ull;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                unsigned long long other = __shfl_xor_sync(0xffffffffu, key, o);
-                key = other > key ? other : key;
+            if (P.keys) {
+                // map-backed detection: fold this CTA's maximum into the CPI's 64-bit key;
+                // k_map_finalize turns key + map into the record after the kernel
+                if (lane == 0 && key) atomicMax(P.keys + cpi, key);
+            } else if (lane == 0) {
+                red[warp] = key;
             }
-            if (lane == 0) red[warp] = key;
-            __syncthreads();   // (E)
-            key = red[0];
+        }
+        if (!FROM_H) cp_async_wait_all();
+        __syncthreads();   // (E) block maximum; the next CPI's symbols are visible to every thread
+        if (in_kernel_est && !(P.dbg & 8)) {
+            unsigned long long key = red[0];
 #pragma unroll
             for (int w = 1; w < 8; w++) key = red[w] > key ? red[w] : key;
             if (key == 0ull) {   // NaN-only input: nothing can win the strict '>' scan
@@ -389,102 +372,97 @@ __global__ void __launch_bounds__(256, 2) k_fused64x8(const FusedParams P)
             } else {
                 const float gmax = __uint_as_float((unsigned)(key >> 32));
                 const int nstar = (int)(0xFFFFFFFFu - (unsigned)(key & 0xFFFFFFFFull));
-                if (warp == nstar / RPW) {
-                    // Everything that is left runs in the warp that owns row nstar; the other warps go on
-                    // to the next CPI's barrier (A).  The lanes that own the row re-evaluate it and pick the
-                    // first bin == gmax.
+                // Noise window (lib/range_angle_estimator_impl.cc:197-226) without evaluating its samples:
+                //   sum_{r,c} |sum_p y[p][r] w^{p c'}|^2 = ncols*A[0] + 2 Re sum_{d=1..7} g[d] A[d],
+                //   A[d] = sum_r sum_q y[q+d][r] conj(y[q][r]),  g[d] = sum_c w^{d c'},  c' = c + Na/2,
+                // (w = e^{-j2pi/Na}; the modulo wrap of rows is the index, that of columns the period of w).
+                // The window ROWS only depend on the peak's range bin, so every warp starts on them at once:
+                // one row per lane (conflict-free loads), the 36 lag products split over the four warp pairs,
+                // float within a lane, double from the first reduction on.  g[d] comes from k_est_tables.
+                {
+                    const int start_r = nstar + NR / 2 - est.discard_range_idx;
+                    const int end_r = nstar + NR / 2 + est.discard_range_idx;
+                    const int part = warp >> 1;
+                    float acc[6];
+#pragma unroll
+                    for (int k = 0; k < 6; k++) acc[k] = 0.f;
+                    for (int ir = start_r + 32 * (warp & 1) + lane; ir < end_r && !(P.dbg & 1); ir += 64) {
+                        const int r_idx = ((ir % NR) + NR) % NR;
+                        const int rq = r_idx % Q, rm = r_idx / Q;
+                        c32 yv[8];
+#pragma unroll
+                        for (int p = 0; p < 8; p++) {
+                            const float4 t = ys[(p >> 1) * NR + (4 * (p & 1) + (rm >> 1)) * Q + rq];
+                            yv[p] = (rm & 1) ? mk(t.y, t.w) : mk(t.x, t.z);
+                        }
+                        auto lagsum = [&](int d, float &sr, float &si) {
+#pragma unroll
+                            for (int qq = 0; qq < 8; qq++) {
+                                if (qq + d < 8) {
+                                    const c32 ya = yv[qq + d], yb = yv[qq];
+                                    sr = __fmaf_rn(ya.x, yb.x, __fmaf_rn(ya.y, yb.y, sr));
+                                    si = __fmaf_rn(ya.y, yb.x, __fmaf_rn(-ya.x, yb.y, si));
+                                }
+                            }
+                        };
+                        if (part == 0) { lagsum(0, acc[0], acc[1]); }
+                        else if (part == 1) { lagsum(1, acc[0], acc[1]); lagsum(7, acc[2], acc[3]); }
+                        else if (part == 2) { lagsum(2, acc[0], acc[1]); lagsum(6, acc[2], acc[3]); }
+                        else { lagsum(3, acc[0], acc[1]); lagsum(4, acc[2], acc[3]); lagsum(5, acc[4], acc[5]); }
+                    }
+                    // transposing reduction (13 shuffles instead of 60): every step halves the values a
+                    // lane carries; lanes 0,4,8 / 16,20,24 end up with the warp totals of acc[0..2] / acc[3..5]
+                    double t3[3], t2[2], t1;
+                    {
+                        const bool hi = lane & 16;
+#pragma unroll
+                        for (int k = 0; k < 3; k++) {
+                            const float keep = hi ? acc[3 + k] : acc[k], give = hi ? acc[k] : acc[3 + k];
+                            t3[k] = (double)keep + (double)__shfl_xor_sync(0xffffffffu, give, 16);
+                        }
+                    }
+                    {
+                        const bool hi = lane & 8;
+                        const double k0 = hi ? t3[2] : t3[0], g0 = hi ? t3[0] : t3[2];
+                        const double k1 = hi ? 0.0 : t3[1], g1 = hi ? t3[1] : 0.0;
+                        t2[0] = k0 + __shfl_xor_sync(0xffffffffu, g0, 8);
+                        t2[1] = k1 + __shfl_xor_sync(0xffffffffu, g1, 8);
+                    }
+                    {
+                        const bool hi = lane & 4;
+                        const double keep = hi ? t2[1] : t2[0], give = hi ? t2[0] : t2[1];
+                        t1 = keep + __shfl_xor_sync(0xffffffffu, give, 4);
+                    }
+                    t1 += __shfl_xor_sync(0xffffffffu, t1, 2);
+                    t1 += __shfl_xor_sync(0xffffffffu, t1, 1);
+                    if ((lane & 3) == 0 && (lane & 12) != 12) {
+                        // value index: (lane & 16 ? 3 : 0) + (lane & 8 ? 2 : 0) + (lane & 4 ? 1 : 0)
+                        redA[warp * 8 + ((lane >> 4) * 3 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1))] = t1;
+                    }
+                }
+                const int sq = nstar % Q, sm1 = nstar / Q;
+                if (warp == (sm1 >> 1) * 2 + (sq >= Q / 2) && !(P.dbg & 2)) {
+                    // the lanes that own row nstar re-evaluate it and pick the first bin == gmax
                     int icand = 0x7fffffff;
                     c32 zc = mk(0.f, 0.f);
-                    if (g == (nstar % RPW) % G) {
-                        c32 u[8]; float v[8];
-                        angle_task(ys, NR, nstar, tw3, u, v);
+                    if (g == sq % G) {
+                        float2 re[8], im[8], v[8];
+                        angle_pair(ys, NR, Q, (sm1 >> 1) * Q + sq, tw3, re, im, v);
+                        const bool odd = sm1 & 1;
 #pragma unroll
                         for (int a = 0; a < 8; a++) {
-                            int i = b + IA * ((a + rot) & 7);
-                            if (v[a] == gmax && i < icand) { icand = i; zc = u[a]; }
+                            const int i = b + IA * ((a + rot) & 7);
+                            const float va = odd ? v[a].y : v[a].x;
+                            if (va == gmax && i < icand) { icand = i; zc = odd ? mk(re[a].y, im[a].y) : mk(re[a].x, im[a].x); }
                         }
                     }
                     int imin = icand;
 #pragma unroll
                     for (int o = 16; o > 0; o >>= 1) imin = min(imin, __shfl_xor_sync(0xffffffffu, imin, o));
-                    const int src = __ffs(__ballot_sync(0xffffffffu, icand == imin)) - 1;
-                    int start_r = 0, end_r = 0, total = 0;
-                    if (lane == src) {
-                        NoiseWin w = noise_window(est, nstar, imin);
-                        const int ncols = w.end_a - w.start_a, nrows = w.end_r - w.start_r;
-                        start_r = w.start_r; end_r = w.end_r;
-                        total = (ncols > 0 && nrows > 0) ? nrows * ncols : 0;
-                        sint[0] = nstar; sint[1] = imin;
-                        sint[4] = w.start_a; sint[5] = w.end_a;
+                    if (icand == imin) {   // exactly one lane (bins are distinct); imin is always found
+                        sint[0] = nstar; sint[1] = imin & (NA - 1);
                         sint[6] = __float_as_int((float)ref_pow_abs2(zc));
                         sint[7] = cpi;
-                        sint[8] = total;
-                    }
-                    start_r = __shfl_sync(0xffffffffu, start_r, src);
-                    end_r = __shfl_sync(0xffffffffu, end_r, src);
-                    total = __shfl_sync(0xffffffffu, total, src);
-                    // Noise window (lib/range_angle_estimator_impl.cc:197-226) without evaluating its samples:
-                    //   sum_{r,c} |sum_p y[p][r] w^{p c'}|^2 = ncols*A[0] + 2 Re sum_{d=1..7} g[d] A[d],
-                    //   A[d] = sum_r sum_q y[q+d][r] conj(y[q][r]),  g[d] = sum_c w^{d c'},  c' = c + Na/2,
-                    // (w = e^{-j2pi/Na}; the modulo wrap of rows is the index, that of columns the period of w).
-                    // One window row per lane (consecutive rows: conflict-free loads), 36 complex MACs per row
-                    // instead of 8 per sample; float within a lane, double from the first reduction on.
-                    float acc[16];   // [0..7] Re A[d], [8..15] Im A[d]
-#pragma unroll
-                    for (int d = 0; d < 16; d++) acc[d] = 0.f;
-                    if (total > 0) {
-                        for (int ir = start_r + lane; ir < end_r; ir += 32) {
-                            const int r_idx = ((ir % NR) + NR) % NR;
-                            c32 yv[8];
-#pragma unroll
-                            for (int p = 0; p < 8; p++) yv[p] = ys[p * NR + r_idx];
-#pragma unroll
-                            for (int d = 0; d < 8; d++) {
-#pragma unroll
-                                for (int qq = 0; qq + d < 8; qq++) {
-                                    const c32 ya = yv[qq + d], yb = yv[qq];
-                                    acc[d] = __fmaf_rn(ya.x, yb.x, __fmaf_rn(ya.y, yb.y, acc[d]));
-                                    acc[8 + d] = __fmaf_rn(ya.y, yb.x, __fmaf_rn(-ya.x, yb.y, acc[8 + d]));
-                                }
-                            }
-                        }
-                    }
-                    // transposing reduction: every step halves the values a lane carries; lane l ends up
-                    // with the warp total of value l >> 1
-                    double s8[8], s4[4], s2[2], s1;
-                    {
-                        const bool hi = lane & 16;
-#pragma unroll
-                        for (int k = 0; k < 8; k++) {
-                            const float keep = hi ? acc[8 + k] : acc[k], give = hi ? acc[k] : acc[8 + k];
-                            s8[k] = (double)keep + (double)__shfl_xor_sync(0xffffffffu, give, 16);
-                        }
-                    }
-                    {
-                        const bool hi = lane & 8;
-#pragma unroll
-                        for (int k = 0; k < 4; k++) {
-                            const double keep = hi ? s8[4 + k] : s8[k], give = hi ? s8[k] : s8[4 + k];
-                            s4[k] = keep + __shfl_xor_sync(0xffffffffu, give, 8);
-                        }
-                    }
-                    {
-                        const bool hi = lane & 4;
-#pragma unroll
-                        for (int k = 0; k < 2; k++) {
-                            const double keep = hi ? s4[2 + k] : s4[k], give = hi ? s4[k] : s4[2 + k];
-                            s2[k] = keep + __shfl_xor_sync(0xffffffffu, give, 4);
-                        }
-                    }
-                    {
-                        const bool hi = lane & 2;
-                        const double keep = hi ? s2[1] : s2[0], give = hi ? s2[0] : s2[1];
-                        s1 = keep + __shfl_xor_sync(0xffffffffu, give, 2);
-                    }
-                    s1 += __shfl_xor_sync(0xffffffffu, s1, 1);
-                    if (!(lane & 1)) {
-                        const int idx = lane >> 1;   // < 8: Re A[idx], else Im A[idx - 8]
-                        reinterpret_cast<double *>(redA)[2 * (idx & 7) + (idx >> 3)] = s1;
                     }
                 }
                 pending = true;   // finished after the next barrier (A) / after the loop
@@ -494,10 +472,6 @@ __global__ void __launch_bounds__(256, 2) k_fused64x8(const FusedParams P)
     if (pending) {
         __syncthreads();
         finalize();
-    }
-    if (Gm::TMA) {   // the CTA's shared memory must outlive the bulk stores that read it
-        if (lane == 0) bulk_wait_read<0>();
-        __syncwarp();
     }
 }
 

@@ -253,6 +253,31 @@ __device__ __forceinline__ NoiseWin noise_window(const EstParams &P, int peak_r,
     return w;
 }
 
+// Per-angle-bin tables for the fused kernel's estimator (the column window only depends on the peak's
+// angle bin): win[m] = (start_a, end_a) of noise_window(., m) and the closed-form column sums
+//   g[m][d] = sum_{c in window} w^{d (c + Na/2)},  w = e^{-j2pi/Na},  d = 1..7;   g[m][0] = ncols / 2,
+// so that the window power is 2 Re sum_d g[d] A[d] with the lag autocorrelations A[d] of the 8 channels.
+__global__ void k_est_tables(EstParams P, int2 *__restrict__ win, double2 *__restrict__ g)
+{
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= P.n_angle) return;
+    const NoiseWin w = noise_window(P, 0, m);
+    win[m] = make_int2(w.start_a, w.end_a);
+    const int ncols = w.end_a - w.start_a, NA = P.n_angle;
+    g[m * 8] = make_double2(0.5 * (double)ncols, 0.0);
+    const long long m0 = w.start_a + NA / 2;
+    for (int d = 1; d < 8; d++) {
+        double s0, c0, s1, c1, s2, c2;
+        sincospi(-2.0 * (double)(((d * m0) % NA + NA) % NA) / (double)NA, &s0, &c0);
+        sincospi(-2.0 * (double)(((long long)d * ncols % NA + NA) % NA) / (double)NA, &s1, &c1);
+        sincospi(-2.0 * (double)d / (double)NA, &s2, &c2);
+        const double nr = 1.0 - c1, ni = -s1, dr = 1.0 - c2, di = -s2;
+        const double den = dr * dr + di * di;
+        const double qr = (nr * dr + ni * di) / den, qi = (ni * dr - nr * di) / den;
+        g[m * 8 + d] = make_double2(c0 * qr - s0 * qi, c0 * qi + s0 * qr);
+    }
+}
+
 // pass 2: one CTA per map.  The window powers are evaluated in parallel, but the
 // float accumulation runs in the reference's order on one thread (:211-221) so the
 // noise power is bit-identical.  snr/flags are finalised here with device log10f;
