@@ -646,7 +646,6 @@ extern "C" jrc_status jrc_chain_run_batch(jrc_chain *h, jrc_port_layout rx, jrc_
         if (dets) {
             ST(est_params(h, Nr, Na, &P.est));
             P.win_tab = h->d_win_tab; P.g_tab = h->d_g_tab;
-            { const char *e = getenv("JRC_DBG"); P.dbg = e ? atoi(e) : 0; }
         }
         const bool map_backed = dets && map && h->det_mode == 0;   // detections from key + map after the kernel
         if (map_backed) {

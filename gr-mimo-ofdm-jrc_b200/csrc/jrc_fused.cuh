@@ -25,6 +25,10 @@
 #include "jrc_common.cuh"
 #include "jrc_staged.cuh"
 
+#ifndef JRC_STORE_MODE
+#define JRC_STORE_MODE 0   // 0: LDS.128 + STG.128 from the staging tiles; 1: per-warp cp.async.bulk (A/B build)
+#endif
+
 namespace jrc {
 
 struct FusedParams {
@@ -38,7 +42,6 @@ struct FusedParams {
     EstParams est;
     const int2 *win_tab;       // [NA] k_est_tables
     const double2 *g_tab;      // [NA][8]
-    int dbg;
 };
 
 template <int IR, int IA>
@@ -72,6 +75,22 @@ __device__ __forceinline__ void cp_async16(void *sdst, const void *gsrc)
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+// per-warp bulk (TMA) store of a staging tile, issued by one elected lane
+__device__ __forceinline__ bool elect_one()
+{
+    unsigned p;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(p));
+    return p != 0;
+}
+__device__ __forceinline__ void bulk_s2g(void *gdst, const void *ssrc, unsigned bytes)
+{
+    unsigned sa = (unsigned)__cvta_generic_to_shared(ssrc);
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(sa), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
 // Angle twiddles of one thread, duplicated into both halves of a register pair.
 struct AngleTw { float2 r[8], i[8], n[8]; };   // (re,re), (im,im), (-im,-im); index 0 unused
 
@@ -243,7 +262,7 @@ __global__ void __launch_bounds__(256, 2) k_fused64x8(const FusedParams P)
             Hw[32 * half + lane] = make_float4(acc0.x, acc0.y, acc1.x, acc1.y);
         }
         __syncthreads();   // (A) H complete; symbol buffer free; previous CPI's y fully consumed
-        if (pending && !(P.dbg & 4)) finalize();
+        if (pending) finalize();
         if (!FROM_H) {
             int nxt = cpi + gridDim.x;
             if (nxt < P.n_cpi) prefetch(nxt);
@@ -320,6 +339,22 @@ __global__ void __launch_bounds__(256, 2) k_fused64x8(const FusedParams P)
                 if (WRITE_MAP) {
                     // conflict-free scalar st.shared of the strided bins, then the warp streams its two
                     // 1 KiB tiles (G whole map rows each, contiguous in HBM) out as 4 x 512 B
+#if JRC_STORE_MODE == 1
+                    // A/B: the two tiles leave through the bulk-copy engine instead of LDS.128 + STG.128
+                    if (elect_one()) bulk_wait_read0();   // the previous iteration's copies have read the tiles
+                    __syncwarp();
+#pragma unroll
+                    for (int a = 0; a < 8; a++) { sp[a][0] = v[a].x; sp[a][TILE] = v[a].y; }
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (elect_one()) {
+                        float *dstb = reinterpret_cast<float *>(map_w + it * (TILE / 4));
+                        bulk_s2g(dstb, wstg, TILE * 4);
+                        bulk_s2g(dstb + Q * NA, wstg + TILE, TILE * 4);
+                        bulk_commit();
+                    }
+                    continue;
+#endif
 #pragma unroll
                     for (int a = 0; a < 8; a++) { sp[a][0] = v[a].x; sp[a][TILE] = v[a].y; }
                     __syncwarp();
@@ -358,7 +393,7 @@ __global__ void __launch_bounds__(256, 2) k_fused64x8(const FusedParams P)
         }
         if (!FROM_H) cp_async_wait_all();
         __syncthreads();   // (E) block maximum; the next CPI's symbols are visible to every thread
-        if (in_kernel_est && !(P.dbg & 8)) {
+        if (in_kernel_est) {
             unsigned long long key = red[0];
 #pragma unroll
             for (int w = 1; w < 8; w++) key = red[w] > key ? red[w] : key;
@@ -386,7 +421,7 @@ __global__ void __launch_bounds__(256, 2) k_fused64x8(const FusedParams P)
                     float acc[6];
 #pragma unroll
                     for (int k = 0; k < 6; k++) acc[k] = 0.f;
-                    for (int ir = start_r + 32 * (warp & 1) + lane; ir < end_r && !(P.dbg & 1); ir += 64) {
+                    for (int ir = start_r + 32 * (warp & 1) + lane; ir < end_r; ir += 64) {
                         const int r_idx = ((ir % NR) + NR) % NR;
                         const int rq = r_idx % Q, rm = r_idx / Q;
                         c32 yv[8];
@@ -441,7 +476,7 @@ __global__ void __launch_bounds__(256, 2) k_fused64x8(const FusedParams P)
                     }
                 }
                 const int sq = nstar % Q, sm1 = nstar / Q;
-                if (warp == (sm1 >> 1) * 2 + (sq >= Q / 2) && !(P.dbg & 2)) {
+                if (warp == (sm1 >> 1) * 2 + (sq >= Q / 2)) {
                     // the lanes that own row nstar re-evaluate it and pick the first bin == gmax
                     int icand = 0x7fffffff;
                     c32 zc = mk(0.f, 0.f);
@@ -469,6 +504,9 @@ __global__ void __launch_bounds__(256, 2) k_fused64x8(const FusedParams P)
             }
         }
     }
+#if JRC_STORE_MODE == 1
+    if (elect_one()) bulk_wait_read0();   // the CTA's shared memory must outlive the bulk copies that read it
+#endif
     if (pending) {
         __syncthreads();
         finalize();
