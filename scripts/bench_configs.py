@@ -19,8 +19,11 @@ CONFIGS = {
 def b_alg(c):
     return (c["T"] + c["R"]) * c["S"] * c["N"] * 8 + (c["N"] * c["IR"]) * (c["T"] * c["R"] * c["IA"]) * 4 + 32
 
+ONLY = [a for a in sys.argv[1:] if not a.startswith('-')]   # e.g. "configs[2]"
+REPS = 2 if '--short' in sys.argv else 20
 out = {}
 for name, c in CONFIGS.items():
+    if ONLY and not any(name.startswith(o) for o in ONLY): continue
     T, R, S, N, IR, IA, n = (c[k] for k in ("T", "R", "S", "N", "IR", "IA", "n"))
     rng = np.random.default_rng(5)
     tx = synth.tx_symbols(T, S, N)
@@ -38,7 +41,7 @@ for name, c in CONFIGS.items():
     with torch.cuda.stream(ext):
         for _ in range(3): step()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        reps = 20
+        reps = REPS
         e0.record(ext)
         for _ in range(reps): step()
         e1.record(ext)
