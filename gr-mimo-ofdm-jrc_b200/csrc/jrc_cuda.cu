@@ -16,6 +16,7 @@
 #include <vector>
 
 #include "jrc_fused.cuh"
+#include "jrc_tiled.cuh"
 #include "jrc_stream.cuh"
 #include "jrc_tc.cuh"
 #include "jrc_staged.cuh"
@@ -88,6 +89,7 @@ struct jrc_chain {
     bool est_set = false;
     std::vector<float> range_bins, angle_bins;
     float nd_range_m = 0, nd_angle_deg = 0, snr_thr = 0, pow_thr = 0;
+    std::map<std::pair<int, int>, c32 *> twiddles_full;   // (n, forward) -> w_n^i, i < n (tiled kernels)
     float *d_angle_bins = nullptr;
     int2 *d_win_tab = nullptr;                  // k_est_tables: per-angle-bin noise window columns
     double2 *d_g_tab = nullptr;                 //               and their closed-form column sums
@@ -189,6 +191,7 @@ extern "C" void jrc_chain_destroy(jrc_chain *h)
     GrowBuf *bufs[] = {&h->sH, &h->sY, &h->sC, &h->sKeys, &h->sDet, &h->sIn[0], &h->sIn[1], &h->sMap[0], &h->sMap[1],
                        &h->sDets[0], &h->sDets[1], &h->sMisc, &h->sMisc2, &h->pin_a, &h->pin_b};
     for (GrowBuf *b : bufs) b->release();
+    for (auto &kv : h->twiddles_full) cudaFree(kv.second);
     if (h->d_angle_bins) cudaFree(h->d_angle_bins);
     if (h->d_win_tab) cudaFree(h->d_win_tab);
     if (h->d_g_tab) cudaFree(h->d_g_tab);
@@ -326,6 +329,99 @@ static jrc_status launch_transpose(jrc_chain *h, const c32 *in, c32 *out, int K,
     CU(cudaGetLastError());
     h->launches++;
     return JRC_OK;
+}
+
+// ---------------------------------------------------------------------------
+// tiled path (jrc_tiled.cuh): k_chan_est -> k_fft8_rows -> k_angle_mag -> k_map_finalize
+// ---------------------------------------------------------------------------
+static jrc_status get_twiddles_full(jrc_chain *h, int n, int forward, const c32 **out)
+{
+    auto key = std::make_pair(n, forward ? 1 : 0);
+    auto it = h->twiddles_full.find(key);
+    if (it != h->twiddles_full.end()) { *out = it->second; return JRC_OK; }
+    std::vector<c32> tw((size_t)n);
+    const double sgn = forward ? -1.0 : 1.0;
+    for (int k = 0; k < n; k++) {
+        double a = sgn * 2.0 * M_PI * (double)k / (double)n;
+        tw[k].x = (float)cos(a); tw[k].y = (float)sin(a);
+    }
+    c32 *d = nullptr;
+    CU(cudaMalloc(&d, tw.size() * sizeof(c32)));
+    CU(cudaMemcpyAsync(d, tw.data(), tw.size() * sizeof(c32), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    h->twiddles_full[key] = d;
+    *out = d;
+    return JRC_OK;
+}
+
+template <int LOG2N>
+static jrc_status launch_fft8_rows_t(jrc_chain *h, const c32 *in, long long in_stride, int n_in, c32 *out, long long rows,
+                                     const c32 *tw)
+{
+    using Gm = TiledGeom<LOG2N>;
+    auto kern = (n_in <= Gm::N / 8) ? k_fft8_rows<LOG2N, 1, true> : k_fft8_rows<LOG2N, 1, false>;
+    CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Gm::SMEM));
+    int per_sm = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, Gm::THREADS, Gm::SMEM));
+    if (per_sm < 1) return fail(JRC_ERR_INVALID, "range FFT kernel does not fit");
+    long long grid = (rows + Gm::RPC - 1) / Gm::RPC, cap = (long long)h->sm_count * per_sm;
+    if (grid > cap) grid = cap;
+    kern<<<(unsigned)grid, Gm::THREADS, Gm::SMEM, h->stream>>>(in, in_stride, n_in, out, rows, tw);
+    CU(cudaGetLastError());
+    h->launches++;
+    return JRC_OK;
+}
+
+template <int LOG2NA>
+static jrc_status launch_angle_mag_t(jrc_chain *h, const c32 *Y, int V, int Nr, int n_cpi, float *map,
+                                     unsigned long long *keys, const c32 *tw)
+{
+    using Gm = TiledGeom<LOG2NA>;
+    auto kern = (V <= Gm::N / 8) ? k_angle_mag<LOG2NA, true> : k_angle_mag<LOG2NA, false>;
+    CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Gm::SMEM));
+    int per_sm = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, Gm::SMEM));
+    if (per_sm < 1) return fail(JRC_ERR_INVALID, "angle kernel does not fit");
+    long long grid = (long long)n_cpi * (Nr / Gm::RPC), cap = (long long)h->sm_count * per_sm;
+    if (grid > cap) grid = cap;
+    kern<<<(unsigned)grid, 256, Gm::SMEM, h->stream>>>(Y, V, Nr, n_cpi, map, keys, tw);
+    CU(cudaGetLastError());
+    h->launches++;
+    return JRC_OK;
+}
+
+static bool tiled_config_ok(const jrc_chain *h)
+{
+    const int lr = ilog2(h->Nr), la = ilog2(h->Na);
+    if (!is_pow2(h->Nr) || !is_pow2(h->Na) || lr < 6 || lr > 13 || la < 6 || la > 11) return false;
+    if (h->V > h->Na || h->cfg.fft_len > h->Nr) return false;
+    const int rpc = 256 / (h->Na / 8);     // range bins per angle tile
+    return h->Nr % rpc == 0;
+}
+
+static jrc_status launch_fft8_rows(jrc_chain *h, const c32 *in, long long in_stride, int n_in, c32 *out, int n, long long rows)
+{
+    const c32 *tw = nullptr;
+    ST(get_twiddles_full(h, n, 0, &tw));
+    switch (ilog2(n)) {
+#define JRC_CASE(l) case l: return launch_fft8_rows_t<l>(h, in, in_stride, n_in, out, rows, tw);
+        JRC_CASE(6) JRC_CASE(7) JRC_CASE(8) JRC_CASE(9) JRC_CASE(10) JRC_CASE(11) JRC_CASE(12) JRC_CASE(13)
+#undef JRC_CASE
+    }
+    return fail(JRC_ERR_INVALID, "range FFT length %d unsupported by the tiled path", n);
+}
+
+static jrc_status launch_angle_mag(jrc_chain *h, const c32 *Y, int V, int Nr, int Na, int n_cpi, float *map,
+                                   unsigned long long *keys)
+{
+    const c32 *tw = nullptr;
+    ST(get_twiddles_full(h, Na, 1, &tw));
+    switch (ilog2(Na)) {
+#define JRC_CASE(l) case l: return launch_angle_mag_t<l>(h, Y, V, Nr, n_cpi, map, keys, tw);
+        JRC_CASE(6) JRC_CASE(7) JRC_CASE(8) JRC_CASE(9) JRC_CASE(10) JRC_CASE(11)
+#undef JRC_CASE
+    }
+    return fail(JRC_ERR_INVALID, "angle FFT length %d unsupported by the tiled path", Na);
 }
 
 static jrc_status launch_estimate(jrc_chain *h, const c32 *cmap, int n_inputs, int vlen, int mats, int cpi0, DetDev *dets)
@@ -585,7 +681,7 @@ extern "C" jrc_status jrc_chain_run_batch(jrc_chain *h, jrc_port_layout rx, jrc_
     PortDev dtx{(const c32 *)tx.base, tx.cpi_stride, tx.ant_stride};
     const bool bg = c.background_removal != 0;
 
-    bool want_fused = (path != JRC_PATH_STAGED) && fused_config_ok(h) && cmap == nullptr;
+    bool want_fused = (path == JRC_PATH_AUTO || path == JRC_PATH_FUSED) && fused_config_ok(h) && cmap == nullptr;
     if (want_fused && !bg) {
         // cp.async moves 16-byte chunks: every antenna row must start 16-byte aligned
         bool al = aligned16(rx.base) && aligned16(tx.base) && (rx.cpi_stride % 2 == 0) && (rx.ant_stride % 2 == 0) &&
@@ -671,6 +767,47 @@ extern "C" jrc_status jrc_chain_run_batch(jrc_chain *h, jrc_port_layout rx, jrc_
             h->launches++;
         }
         if (ok) { h->last_path = JRC_PATH_FUSED; return JRC_OK; }
+    }
+
+    // ---- tiled path: configurations without a fused specialisation -------------
+    const bool want_tiled = (path == JRC_PATH_AUTO || path == JRC_PATH_TILED) && cmap == nullptr && tiled_config_ok(h) &&
+                            (map || dets);
+    if (path == JRC_PATH_TILED && !want_tiled)
+        return fail(JRC_ERR_INVALID, "tiled path requested but this configuration has no tiled kernel");
+    if (want_tiled) {
+        h->last_path = JRC_PATH_TILED;
+        const size_t per = ((size_t)V * N + (size_t)V * Nr) * sizeof(c32) + (map ? 0 : (size_t)Nr * Na * sizeof(float));
+        int chunk = (int)(((size_t)1 << 30) / per);
+        if (chunk < 1) chunk = 1;
+        if (chunk > n_cpi) chunk = n_cpi;
+        ST(h->sH.need((size_t)chunk * V * N * sizeof(c32)));
+        ST(h->sY.need((size_t)chunk * V * Nr * sizeof(c32)));
+        if (!map) ST(h->sC.need((size_t)chunk * Nr * Na * sizeof(float)));
+        EstParams EP;
+        if (dets) {
+            ST(est_params(h, Nr, Na, &EP));
+            ST(h->sKeys.need(sizeof(unsigned long long) * (size_t)chunk));
+        }
+        for (int c0 = 0; c0 < n_cpi; c0 += chunk) {
+            const int nc = n_cpi - c0 < chunk ? n_cpi - c0 : chunk;
+            PortDev crx = drx, ctx = dtx;
+            crx.base += (long long)c0 * rx.cpi_stride;
+            ctx.base += (long long)c0 * tx.cpi_stride;
+            c32 *dH = (c32 *)h->sH.p, *dY = (c32 *)h->sY.p;
+            float *dM = map ? map + (size_t)c0 * Nr * Na : (float *)h->sC.p;
+            unsigned long long *dK = dets ? (unsigned long long *)h->sKeys.p : nullptr;
+            ST(launch_chan_est(h, crx, ctx, nc, dH));
+            ST(launch_fft8_rows(h, dH, N, N, dY, Nr, (long long)nc * V));
+            if (dK) CU(cudaMemsetAsync(dK, 0, sizeof(unsigned long long) * (size_t)nc, h->stream));
+            ST(launch_angle_mag(h, dY, V, Nr, Na, nc, dM, dK));
+            if (dets) {
+                k_map_finalize<<<(unsigned)((nc + 3) / 4), 128, (size_t)Na * sizeof(float), h->stream>>>(
+                    dM, dK, nc, Nr, Na, EP, (DetDev *)dets + c0, cpi0 + c0);
+                CU(cudaGetLastError());
+                h->launches++;
+            }
+        }
+        return JRC_OK;
     }
 
     // ---- staged path: one kernel per reference block, chunked over CPIs ------

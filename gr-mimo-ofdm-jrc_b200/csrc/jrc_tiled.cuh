@@ -1,0 +1,280 @@
+// jrc_tiled.cuh -- the radar chain for configurations without a k_fused64x8 specialisation
+// (BASELINE configs[2]: 32 virtual channels, 256 subcarriers, 4096 x 256 map; configs[4]: 128
+// virtual channels, 2048 subcarriers, 2048 x 128 map), as two tiled kernels around k_chan_est:
+//
+//   k_fft8_rows   range IFFT of every channel row      (fft_vcc #A, ...radar_sim.grc:940-962; the
+//                 zero-pad of lib/mimo_ofdm_radar_impl.cc:312-315 is implied by n_in < N)
+//   k_angle_mag   matrix_transpose + angle zero-pad    (lib/matrix_transpose_impl.cc:97-104)
+//                 + fft_vcc #B with fftshift           (...radar_sim.grc:963-985)
+//                 + complex_to_mag_squared             (...radar_sim.grc:637-652)
+//                 + the arg-max scan of range_angle_estimator (lib/range_angle_estimator_impl.cc:137-151)
+//                 as a per-CPI 64-bit key that k_map_finalize turns into the detection record.
+//
+// The transposed / angle-padded [Nr][Na] matrix, the complex map and the arg-max pass never touch
+// HBM (the staged path moves ~11x the algorithmic bytes at configs[2]); HBM sees the symbols, the
+// channel estimates, the range spectra [V][Nr] (written and read once) and the |.|^2 map.
+//
+// FFT: decimation-in-frequency with radix-8 passes in registers (8 points per thread per pass, the
+// packed DFT-8 of jrc_common.cuh), remaining factor 4 or 2 in the last pass.  A row lives in shared
+// memory between passes (padded: one float2 per 8), twiddles w_N^i come from one table per (N,
+// direction).  When the zero-pad leaves at most N/8 non-zero inputs the first pass degenerates to
+// "copy the input to 8 places with a twiddle" and is fed straight from HBM; the last pass hands its
+// results to the caller in registers (frequency f of position p = dif_freq(p)), so neither the load nor
+// the digit-reversing store goes through shared memory.
+// Same float32 arithmetic class as the oracle's radix-2 FFT, not its rounding: the parity criterion is
+// 1e-4 of the map peak (tests), detections bit-exact whenever the peak is not a rounding-level tie.
+#pragma once
+#include "jrc_common.cuh"
+#include "jrc_staged.cuh"
+
+namespace jrc {
+
+__device__ __host__ __forceinline__ constexpr int fpad(int i) { return i + (i >> 3); }
+
+// frequency whose result the DIF passes (radix 8, ..., 8, then 4 or 2) leave at position p
+template <int LOG2N>
+__device__ __forceinline__ int dif_freq(int p)
+{
+    int f = 0, shift = 0, rem = LOG2N;
+#pragma unroll
+    for (; rem >= 3; rem -= 3) { f |= ((p >> (rem - 3)) & 7) << shift; shift += 3; }
+    if (rem > 0) f |= (p & ((1 << rem) - 1)) << shift;
+    return f;
+}
+
+template <int LOG2N>
+struct TiledGeom {
+    static constexpr int N = 1 << LOG2N;
+    static constexpr int TPR = N / 8;                          // threads per row
+    static constexpr int THREADS = TPR > 256 ? TPR : 256;
+    static constexpr int RPC = THREADS / TPR;                  // rows per CTA
+    // row stride in shared memory: when lanes run over rows first (transposing loads), 16 consecutive lanes
+    // (min(16, RPC) rows x 16/RPC columns) must hit 16 different 8-byte banks
+    static constexpr int RS = ((fpad(N - 1) + 1 + 15) / 16) * 16 + (RPC >= 16 ? 1 : RPC >= 2 ? 16 / RPC : 0);
+    static constexpr int NTW = (LOG2N + 2) / 3 - 1;            // passes that apply twiddles (all but the last)
+    static constexpr size_t SMEM = (size_t)RPC * RS * sizeof(c32);
+    static constexpr bool WARP_SYNC = TPR <= 32;
+};
+
+template <bool WARP_SYNC>
+__device__ __forceinline__ void row_sync() { if (WARP_SYNC) __syncwarp(); else __syncthreads(); }
+
+// Twiddles of one thread for all passes but the last, loaded once per kernel: pass i works on blocks of
+// L = N / 8^i points, thread index j_i within the block, factors w_L^{j_i k} = w_N^{8^i j_i k}, k = 1..7.
+template <int LOG2N>
+struct DifTw {
+    c32 w[TiledGeom<LOG2N>::NTW > 0 ? TiledGeom<LOG2N>::NTW : 1][7];
+    // j0: index of this thread in the first pass (the caller's choice when that pass is pruned), t: index
+    // within the row for the other passes
+    __device__ __forceinline__ void load(const c32 *__restrict__ tw, int j0, int t)
+    {
+#pragma unroll
+        for (int i = 0; i < TiledGeom<LOG2N>::NTW; i++) {
+            const int log2L = LOG2N - 3 * i;
+            const int j = i == 0 ? j0 : (t & ((1 << (log2L - 3)) - 1));
+            const int q = j << (3 * i);
+#pragma unroll
+            for (int k = 1; k < 8; k++) {
+                c32 v = __ldg(tw + q * k);
+                asm volatile("" : "+f"(v.x), "+f"(v.y));   // keep it in registers: ptxas would re-load it inside the tile loop
+                w[i][k - 1] = v;
+            }
+        }
+    }
+};
+
+// First pass when only inputs j < N/8 can be non-zero: u[k] = x_j * w_N^{j k}, written to the 8 places
+// the full pass would write.  (r, j) of this thread is the caller's choice (coalesced HBM reads).
+template <int LOG2N>
+__device__ __forceinline__ void dif_first_pruned(c32 *x, int j, c32 xj, const DifTw<LOG2N> &T)
+{
+    constexpr int s = 1 << (LOG2N - 3);
+    x[fpad(j)] = xj;
+#pragma unroll
+    for (int k = 1; k < 8; k++) x[fpad(j + k * s)] = cmul_fma(xj, T.w[0][k - 1]);
+}
+
+// Passes of one row of N = 2^LOG2N points in shared memory (index i at x[fpad(i)]) by N/8 threads,
+// t = this thread's index within the row.  DIR = -1 forward, +1 backward.  SKIP_FIRST: the first pass was
+// done by dif_first_pruned.  The last pass leaves 8 results per thread in out[]: out[c] belongs to
+// position 8t + c, i.e. frequency dif_freq(8t + c).
+// The caller must synchronise the row before this call; all threads of the CTA must call it together
+// unless WARP_SYNC.
+template <int LOG2N, int DIR, bool WARP_SYNC, bool SKIP_FIRST>
+__device__ __forceinline__ void dif_passes(c32 *x, int t, const DifTw<LOG2N> &T, c32 (&out)[8])
+{
+    int log2L = SKIP_FIRST ? LOG2N - 3 : LOG2N;
+#pragma unroll
+    for (int i = SKIP_FIRST ? 1 : 0; i < TiledGeom<LOG2N>::NTW; i++, log2L -= 3) {
+        const int s = 1 << (log2L - 3);              // distance of the 8 inputs = L/8
+        const int j = t & (s - 1), base = ((t >> (log2L - 3)) << log2L) + j;
+        c32 u[8];
+#pragma unroll
+        for (int m = 0; m < 8; m++) u[m] = x[fpad(base + m * s)];
+        JRC_FFT8<DIR>(u);
+#pragma unroll
+        for (int k = 1; k < 8; k++) u[k] = cmul_fma(u[k], T.w[i][k - 1]);
+#pragma unroll
+        for (int k = 0; k < 8; k++) x[fpad(base + k * s)] = u[k];
+        row_sync<WARP_SYNC>();
+    }
+    // last pass: 8 consecutive points 8t .. 8t+7
+#pragma unroll
+    for (int m = 0; m < 8; m++) out[m] = x[fpad(8 * t + m)];
+    if (log2L == 3) {
+        JRC_FFT8<DIR>(out);
+    } else if (log2L == 2) {
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const c32 a = out[4 * h], b = out[4 * h + 1], c = out[4 * h + 2], d = out[4 * h + 3];
+            const c32 s0 = cadd_exact(a, c), s1 = csub_exact(a, c), s2 = cadd_exact(b, d), s3 = csub_exact(b, d);
+            const c32 r3 = DIR < 0 ? mk(s3.y, -s3.x) : mk(-s3.y, s3.x);    // -j / +j times (b - d)
+            out[4 * h] = cadd_exact(s0, s2);
+            out[4 * h + 2] = csub_exact(s0, s2);
+            out[4 * h + 1] = cadd_exact(s1, r3);
+            out[4 * h + 3] = csub_exact(s1, r3);
+        }
+    } else {
+#pragma unroll
+        for (int h = 0; h < 4; h++) {
+            const c32 a = out[2 * h], b = out[2 * h + 1];
+            out[2 * h] = cadd_exact(a, b);
+            out[2 * h + 1] = csub_exact(a, b);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// range IFFT: row r reads n_in samples at in + r*in_stride (the rest of the N-point input is zero) and
+// writes N samples at out + r*N, natural order.
+// ---------------------------------------------------------------------------
+template <int LOG2N, int DIR, bool PRUNED>
+__global__ void __launch_bounds__(TiledGeom<LOG2N>::THREADS) k_fft8_rows(const c32 *__restrict__ in, long long in_stride, int n_in,
+                                                                         c32 *__restrict__ out, long long rows,
+                                                                         const c32 *__restrict__ tw)
+{
+    using Gm = TiledGeom<LOG2N>;
+    constexpr int N = Gm::N, RPC = Gm::RPC, RS = Gm::RS, THREADS = Gm::THREADS, TPR = Gm::TPR;
+    extern __shared__ __align__(16) unsigned char smem_raw_t[];
+    c32 *sm = reinterpret_cast<c32 *>(smem_raw_t);
+    const int tid = threadIdx.x;
+    const int lr_t = tid / TPR, t = tid % TPR;
+    c32 *xrow = sm + lr_t * RS;
+    DifTw<LOG2N> T;
+    T.load(tw, t, t);
+    c32 xn = mk(0.f, 0.f);     // PRUNED: this thread's input of the next row, fetched one iteration ahead
+    if (PRUNED) {
+        const long long row = (long long)blockIdx.x * RPC + lr_t;
+        if (t < n_in && row < rows) xn = in[row * in_stride + t];
+    }
+    for (long long row0 = (long long)blockIdx.x * RPC; row0 < rows; row0 += (long long)gridDim.x * RPC) {
+        const long long row = row0 + lr_t;
+        if (PRUNED) {      // n_in <= N/8: thread (row, j = t) takes its single non-zero input straight from HBM
+            const c32 xj = xn;
+            const long long nrow = row + (long long)gridDim.x * RPC;
+            xn = mk(0.f, 0.f);
+            if (t < n_in && nrow < rows) xn = in[nrow * in_stride + t];
+            dif_first_pruned<LOG2N>(xrow, t, xj, T);
+        } else {
+#pragma unroll 4
+            for (int e = tid; e < RPC * N; e += THREADS) {
+                const int lr = e >> LOG2N, i = e & (N - 1);
+                c32 v = mk(0.f, 0.f);
+                if (i < n_in && row0 + lr < rows) v = in[(row0 + lr) * in_stride + i];
+                sm[lr * RS + fpad(i)] = v;
+            }
+        }
+        __syncthreads();
+        c32 o[8];
+        dif_passes<LOG2N, DIR, Gm::WARP_SYNC, PRUNED>(xrow, t, T, o);
+        if (row < rows) {
+            c32 *orow = out + row * N;
+#pragma unroll
+            for (int c = 0; c < 8; c++) orow[dif_freq<LOG2N>(8 * t + c)] = o[c];
+        }
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------
+// angle stage: tile = RPC consecutive range bins of one CPI.
+//   Y   [n_cpi][V][Nr]   range spectra
+//   map [n_cpi][Nr][NA]  |.|^2, angle bin fastest, fftshifted
+//   keys[n_cpi]          (map value bits << 32) | (0xFFFFFFFF - range bin): atomicMax, zeroed by the host
+// ---------------------------------------------------------------------------
+template <int LOG2NA, bool PRUNED>
+__global__ void __launch_bounds__(256, 2) k_angle_mag(const c32 *__restrict__ Y, int V, int Nr, int n_cpi, float *__restrict__ map,
+                                                   unsigned long long *__restrict__ keys, const c32 *__restrict__ tw)
+{
+    using Gm = TiledGeom<LOG2NA>;
+    constexpr int NA = Gm::N, RPC = Gm::RPC, RS = Gm::RS, TPR = Gm::TPR;
+    static_assert(Gm::THREADS == 256, "angle FFT length above 2048 is not supported");
+    extern __shared__ __align__(16) unsigned char smem_raw_t[];
+    c32 *sm = reinterpret_cast<c32 *>(smem_raw_t);
+    __shared__ unsigned long long s_key[8];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int lr_t = tid / TPR, t = tid % TPR;
+    // output: position 8t + c holds frequency f = dif_freq; after the fftshift it is angle bin (f + NA/2) mod NA
+    int obin[8];
+#pragma unroll
+    for (int c = 0; c < 8; c++) obin[c] = (dif_freq<LOG2NA>(8 * t + c) + NA / 2) & (NA - 1);
+    const int tiles_per_cpi = Nr / RPC;
+    const long long n_tiles = (long long)n_cpi * tiles_per_cpi;
+    // PRUNED (V <= NA/8): (range bin r fastest, channel p) per thread -> coalesced reads, first pass on the fly,
+    // the input of the next tile fetched one iteration ahead
+    const int pr = tid % RPC, pp = tid / RPC;
+    DifTw<LOG2NA> T;
+    T.load(tw, PRUNED ? pp : t, t);
+    auto fetch = [&](long long tile) {
+        const int cpi = (int)(tile / tiles_per_cpi), n0 = (int)(tile % tiles_per_cpi) * RPC;
+        return (tile < n_tiles && pp < V) ? Y[((long long)cpi * V + pp) * Nr + n0 + pr] : mk(0.f, 0.f);
+    };
+    c32 xn = mk(0.f, 0.f);
+    if (PRUNED) xn = fetch(blockIdx.x);
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int cpi = (int)(tile / tiles_per_cpi), n0 = (int)(tile % tiles_per_cpi) * RPC;
+        const c32 *Yc = Y + (long long)cpi * V * Nr + n0;
+        if (PRUNED) {
+            const c32 xj = xn;
+            xn = fetch(tile + gridDim.x);
+            dif_first_pruned<LOG2NA>(sm + pr * RS, pp, xj, T);
+        } else {
+            // transposing load: for every channel RPC consecutive range bins (contiguous in HBM)
+            for (int e = tid; e < NA * RPC; e += 256) {
+                const int p = e / RPC, r = e % RPC;
+                sm[r * RS + fpad(p)] = p < V ? Yc[(long long)p * Nr + r] : mk(0.f, 0.f);   // angle zero-pad
+            }
+        }
+        __syncthreads();
+        c32 o[8];
+        dif_passes<LOG2NA, -1, Gm::WARP_SYNC, PRUNED>(sm + lr_t * RS, t, T, o);
+        float best = -1.f;
+        float *mrow = map ? map + ((long long)cpi * Nr + n0 + lr_t) * NA : nullptr;
+#pragma unroll
+        for (int c = 0; c < 8; c++) {
+            const float v = __fadd_rn(__fmul_rn(o[c].x, o[c].x), __fmul_rn(o[c].y, o[c].y));
+            if (mrow) __stcs(mrow + obin[c], v);
+            best = fmaxf(best, v);
+        }
+        if (keys) {
+            unsigned long long key = best >= 0.f ? pack_key(best, (unsigned)(n0 + lr_t)) : 0ull;
+#pragma unroll
+            for (int o2 = 16; o2 > 0; o2 >>= 1) {
+                unsigned long long other = __shfl_xor_sync(0xffffffffu, key, o2);
+                key = other > key ? other : key;
+            }
+            if (lane == 0) s_key[warp] = key;
+        }
+        __syncthreads();      // rows are free for the next tile; s_key complete
+        if (keys && tid == 0) {
+            unsigned long long key = s_key[0];
+#pragma unroll
+            for (int w = 1; w < 8; w++) key = s_key[w] > key ? s_key[w] : key;
+            // most tiles lose against the running maximum: a plain read filters them before the (same-address,
+            // hence serialised) atomic
+            if (key && key > *reinterpret_cast<volatile unsigned long long *>(keys + cpi)) atomicMax(keys + cpi, key);
+        }
+    }
+}
+
+}  // namespace jrc

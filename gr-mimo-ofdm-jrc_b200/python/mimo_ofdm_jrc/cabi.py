@@ -17,7 +17,7 @@ PKG_ROOT = os.path.abspath(os.path.join(_HERE, "..", ".."))          # gr-mimo-o
 LIB_PATH = os.environ.get("JRC_CUDA_LIB") or os.path.join(PKG_ROOT, "libjrc_cuda.so")
 
 JRC_OK, JRC_ERR_INVALID, JRC_ERR_CUDA, JRC_ERR_NO_DEVICE, JRC_ERR_STATE = 0, 1, 2, 3, 4
-PATH_AUTO, PATH_FUSED, PATH_STAGED = 0, 1, 2
+PATH_AUTO, PATH_FUSED, PATH_STAGED, PATH_TILED = 0, 1, 2, 3
 
 
 class JrcError(RuntimeError):

@@ -125,12 +125,15 @@ JRC_API jrc_status jrc_chain_reset_background(jrc_chain *h);
  *   cmap  : [n_cpi][Nr][Na] complex map (what the estimator block would see), or NULL
  *   dets  : [n_cpi] records, or NULL (needs jrc_chain_set_estimator first)
  * path: JRC_PATH_AUTO picks the fused single-kernel path when the configuration
- * has one (fft_len 64, 8 virtual channels, cmap == NULL), else the staged kernels. */
-enum { JRC_PATH_AUTO = 0, JRC_PATH_FUSED = 1, JRC_PATH_STAGED = 2 };
+ * has one (fft_len 64, 8 virtual channels, cmap == NULL), else the tiled kernels
+ * (power-of-two Nr in 64..8192 and Na in 64..2048, cmap == NULL: radix-8 FFT kernels with
+ * the transpose, |.|^2 and arg-max fused into the angle FFT), else the staged
+ * kernels (one per reference block, bit-identical to the CPU restatement). */
+enum { JRC_PATH_AUTO = 0, JRC_PATH_FUSED = 1, JRC_PATH_STAGED = 2, JRC_PATH_TILED = 3 };
 JRC_API jrc_status jrc_chain_run_batch(jrc_chain *h, jrc_port_layout rx, jrc_port_layout tx,
                                        int32_t n_cpi, int32_t cpi0,
                                        float *map, jrc_c32 *cmap, jrc_det *dets, int32_t path);
-/* which path the last run_batch took (JRC_PATH_FUSED / JRC_PATH_STAGED) and how
+/* which path the last run_batch took (JRC_PATH_FUSED / JRC_PATH_TILED / JRC_PATH_STAGED) and how
  * many kernels it launched                                                    */
 JRC_API int32_t    jrc_chain_last_path(const jrc_chain *h);
 JRC_API int64_t    jrc_chain_launch_count(const jrc_chain *h);

@@ -54,7 +54,7 @@ for name, c in CONFIGS.items():
     err = float((np.abs(mg - mo).reshape(k, -1).max(axis=1) / mo.reshape(k, -1).max(axis=1)).max())
     same = bool(np.array_equal(d["range_idx"][:k], do["range_idx"]) and np.array_equal(d["angle_idx"][:k], do["angle_idx"]))
     rate = n / (ms * 1e-3)
-    out[name] = dict(path="fused" if rc.chain.last_path == jrc.PATH_FUSED else "staged", cpis=n, ms=ms, cpis_per_s=rate,
+    out[name] = dict(path={jrc.PATH_FUSED: "fused", jrc.PATH_TILED: "tiled", jrc.PATH_STAGED: "staged"}[rc.chain.last_path], cpis=n, ms=ms, cpis_per_s=rate,
                      complex_msps=rate * R * S * N / 1e6, alg_gbs=rate * b_alg(c) / 1e9, map_err_of_peak=err,
                      peaks_equal_oracle=same, gate_pass_fraction=float((d["flags"] & 1).mean()))
     del drx, dtx, dmap, ddet, rc

@@ -334,3 +334,45 @@ def test_ofdm_demod_front_end(jrc, orc):
         assert np.array_equal(td, orc.cp_remove(x, nsym, N, cp))
         fd = blk.work(x, demod=True)
         assert np.array_equal(fd, orc.fft_vcc(orc.cp_remove(x, nsym, N, cp), True, True))
+
+
+TILED_CFGS = {
+    "C3": (CFGS["C3"], 3, 5),                                         # BASELINE configs[2], full size
+    "C5": (CFGS["C5"], 2, 3),                                         # BASELINE configs[4], full size
+    "C3s": (CFGS["C3s"], 24, 3),                                      # 1024 x 64 map, 32 channels
+    "n128": (dict(T=4, R=2, S=4, N=128, IR=4, IA=16), 24, 2),         # 512 x 128: radix 8.8.8 / 8.8.2
+    "n64r4": (dict(T=2, R=4, S=2, N=64, IR=4, IA=8), 40, 2),          # 256 x 64, not a k_fused64x8 shape
+    "wide": (dict(T=8, R=8, S=2, N=64, IR=2, IA=8), 16, 2),           # 128 x 512: radix 8.8.2 / 8.8.8
+    "n2048a": (dict(T=4, R=4, S=2, N=512, IR=16, IA=128), 2, 2),      # 8192 x 2048: the largest supported FFTs
+}
+
+
+@pytest.mark.parametrize("name", list(TILED_CFGS))
+def test_tiled_chain_vs_oracle(jrc, orc, name):
+    """Configurations without a k_fused64x8 specialisation run the tiled kernels (radix-8 FFTs, the
+    transpose / |.|^2 / arg-max fused into the angle FFT): maps within 1e-4 of the map peak, detections
+    equal wherever the oracle's top-1/top-2 margin exceeds the float32 FFT error."""
+    cfg, n, n_targets = TILED_CFGS[name]
+    est = est_for(cfg)
+    rx, tx, _ = scene(cfg, n, seed=13, n_targets=n_targets, amp_db_span=12.0)
+    ch = gpu_chain(jrc, cfg, est)
+    m, d = ch.run_host(rx, tx)
+    assert ch.last_path == jrc.PATH_TILED
+    mo, _, do = oracle(orc, rx, tx, cfg, est)
+    peak = mo.reshape(n, -1).max(axis=1)
+    err = np.abs(m - mo).reshape(n, -1).max(axis=1) / peak
+    assert err.max() <= 1e-4, err.max()               # north_star tolerance
+    assert err.max() <= 1e-5, err.max()               # what float32 should actually deliver
+    ok = top2_margin(mo) > 1e-5
+    assert ok.sum() >= n - 2
+    for f in ("range_idx", "angle_idx", "n_noise"):
+        assert np.array_equal(d[f][ok], do[f][ok]), f
+    assert np.array_equal(d["cpi"], np.arange(n))
+    np.testing.assert_allclose(d["peak_power"][ok], do["peak_power"][ok], rtol=1e-5)
+    np.testing.assert_allclose(d["noise_power"][ok], do["noise_power"][ok], rtol=2e-4)
+    np.testing.assert_allclose(d["snr_db"][ok], do["snr_db"][ok], atol=2e-3)
+    assert np.array_equal(d["flags"][ok], do["flags"][ok])
+    # detections without a caller-provided map use the handle's scratch map
+    _, d2 = ch.run_host(rx, tx, want_map=False)
+    for f in ("range_idx", "angle_idx", "peak_power", "noise_power", "flags"):
+        assert np.array_equal(d2[f], d[f]), f
