@@ -378,13 +378,14 @@ static jrc_status launch_angle_mag_t(jrc_chain *h, const c32 *Y, int V, int Nr, 
 {
     using Gm = TiledGeom<LOG2NA>;
     auto kern = (V <= Gm::N / 8) ? k_angle_mag<LOG2NA, true> : k_angle_mag<LOG2NA, false>;
-    CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Gm::SMEM));
+    const size_t smem = 2 * Gm::SMEM;      // double-buffered tiles
+    CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, Gm::SMEM));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, smem));
     if (per_sm < 1) return fail(JRC_ERR_INVALID, "angle kernel does not fit");
     long long grid = (long long)n_cpi * (Nr / Gm::RPC), cap = (long long)h->sm_count * per_sm;
     if (grid > cap) grid = cap;
-    kern<<<(unsigned)grid, 256, Gm::SMEM, h->stream>>>(Y, V, Nr, n_cpi, map, keys, tw);
+    kern<<<(unsigned)grid, 256, smem, h->stream>>>(Y, V, Nr, ilog2(Nr / Gm::RPC), n_cpi, map, keys, tw);
     CU(cudaGetLastError());
     h->launches++;
     return JRC_OK;
@@ -452,8 +453,12 @@ static jrc_status launch_chan_est(jrc_chain *h, PortDev rx, PortDev tx, int n_cp
 {
     const jrc_chain_cfg &c = h->cfg;
     long long total = (long long)n_cpi * h->V * c.fft_len;
-    k_chan_est<<<grid_for(total, 256, h->sm_count), 256, 0, h->stream>>>(rx, tx, n_cpi, c.fft_len, c.n_tx, c.n_rx, c.n_sym,
-                                                                       c.n_pre, c.tx_interleave, d_H);
+    if (c.n_tx % 4 == 0 && c.n_rx % 4 == 0)     // large arrays: 4 x 4 antenna blocks per thread
+        k_chan_est_tile<4, 4><<<grid_for(total / 16, 256, h->sm_count), 256, 0, h->stream>>>(
+            rx, tx, n_cpi, c.fft_len, c.n_tx, c.n_rx, c.n_sym, c.n_pre, c.tx_interleave, d_H);
+    else
+        k_chan_est<<<grid_for(total, 256, h->sm_count), 256, 0, h->stream>>>(rx, tx, n_cpi, c.fft_len, c.n_tx, c.n_rx, c.n_sym,
+                                                                           c.n_pre, c.tx_interleave, d_H);
     CU(cudaGetLastError());
     h->launches++;
     if (c.background_removal || c.background_recording) {

@@ -43,6 +43,50 @@ __global__ void k_chan_est(PortDev rx, PortDev tx, int n_cpi, int N, int T, int 
     }
 }
 
+// Same conj-MAC, register tiled for large arrays: one thread owns subcarrier k of a TT x RR block of
+// (tx, rx) antennas, so every symbol sample is loaded once per block instead of once per channel
+// (TT + RR loads per TT*RR products).  Per channel the operation order is that of k_chan_est: the
+// estimates are bit-identical.
+template <int TT, int RR>
+__global__ void __launch_bounds__(256) k_chan_est_tile(PortDev rx, PortDev tx, int n_cpi, int N, int T, int R, int S, int n_pre,
+                                                       int tx_interleave, c32 *__restrict__ H /* [n_cpi][V][N] */)
+{
+    const int TB = T / TT, RB = R / RR, V = T * R;
+    const long long total = (long long)n_cpi * TB * RB * N;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total;
+         e += (long long)gridDim.x * blockDim.x) {
+        const int k = (int)(e % N);
+        const int blk = (int)((e / N) % (TB * RB));
+        const long long cpi = e / ((long long)N * TB * RB);
+        const int t0 = (blk % TB) * TT, r0 = (blk / TB) * RR;
+        const c32 *prx = rx.base + cpi * rx.cpi_stride + r0 * rx.ant_stride + (long long)n_pre * N + k;
+        const c32 *ptx = tx.base + cpi * tx.cpi_stride + t0 * tx.ant_stride + (long long)n_pre * N + k;
+        c32 acc[RR][TT];
+#pragma unroll
+        for (int r = 0; r < RR; r++)
+#pragma unroll
+            for (int t = 0; t < TT; t++) acc[r][t] = mk(0.f, 0.f);
+        for (int s = 0; s < S; s++) {
+            c32 a[RR], b[TT];
+#pragma unroll
+            for (int r = 0; r < RR; r++) a[r] = prx[r * rx.ant_stride + (long long)s * N];
+#pragma unroll
+            for (int t = 0; t < TT; t++) { c32 v = ptx[t * tx.ant_stride + (long long)s * N]; b[t] = mk(v.x, -v.y); }
+#pragma unroll
+            for (int r = 0; r < RR; r++)
+#pragma unroll
+                for (int t = 0; t < TT; t++) acc[r][t] = cadd_exact(acc[r][t], cmul_exact(a[r], b[t]));
+        }
+#pragma unroll
+        for (int r = 0; r < RR; r++)
+#pragma unroll
+            for (int t = 0; t < TT; t++) {
+                const int p = tx_interleave ? (t0 + t) * R + (r0 + r) : (r0 + r) * T + (t0 + t);
+                H[(cpi * V + p) * N + k] = acc[r][t];
+            }
+    }
+}
+
 // ---------------------------------------------------------------------------
 // background record / removal  (lib/mimo_ofdm_radar_impl.cc:276-300)
 // One thread per channel-estimate element; the CPIs of the batch are walked in

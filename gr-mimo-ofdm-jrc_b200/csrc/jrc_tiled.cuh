@@ -52,7 +52,7 @@ struct TiledGeom {
     // (min(16, RPC) rows x 16/RPC columns) must hit 16 different 8-byte banks
     static constexpr int RS = ((fpad(N - 1) + 1 + 15) / 16) * 16 + (RPC >= 16 ? 1 : RPC >= 2 ? 16 / RPC : 0);
     static constexpr int NTW = (LOG2N + 2) / 3 - 1;            // passes that apply twiddles (all but the last)
-    static constexpr size_t SMEM = (size_t)RPC * RS * sizeof(c32);
+    static constexpr size_t SMEM = (size_t)RPC * RS * sizeof(c32);      // one tile of rows
     static constexpr bool WARP_SYNC = TPR <= 32;
 };
 
@@ -203,78 +203,87 @@ __global__ void __launch_bounds__(TiledGeom<LOG2N>::THREADS) k_fft8_rows(const c
 //   keys[n_cpi]          (map value bits << 32) | (0xFFFFFFFF - range bin): atomicMax, zeroed by the host
 // ---------------------------------------------------------------------------
 template <int LOG2NA, bool PRUNED>
-__global__ void __launch_bounds__(256, 2) k_angle_mag(const c32 *__restrict__ Y, int V, int Nr, int n_cpi, float *__restrict__ map,
-                                                   unsigned long long *__restrict__ keys, const c32 *__restrict__ tw)
+__global__ void __launch_bounds__(256, 2) k_angle_mag(const c32 *__restrict__ Y, int V, int Nr, int log2_tiles_per_cpi, int n_cpi,
+                                                      float *__restrict__ map, unsigned long long *__restrict__ keys,
+                                                      const c32 *__restrict__ tw)
 {
     using Gm = TiledGeom<LOG2NA>;
     constexpr int NA = Gm::N, RPC = Gm::RPC, RS = Gm::RS, TPR = Gm::TPR;
     static_assert(Gm::THREADS == 256, "angle FFT length above 2048 is not supported");
     extern __shared__ __align__(16) unsigned char smem_raw_t[];
-    c32 *sm = reinterpret_cast<c32 *>(smem_raw_t);
-    __shared__ unsigned long long s_key[8];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    c32 *sm = reinterpret_cast<c32 *>(smem_raw_t);          // two tile buffers: one CTA barrier per tile
+    const int tid = threadIdx.x, lane = tid & 31;
     const int lr_t = tid / TPR, t = tid % TPR;
     // output: position 8t + c holds frequency f = dif_freq; after the fftshift it is angle bin (f + NA/2) mod NA
     int obin[8];
 #pragma unroll
     for (int c = 0; c < 8; c++) obin[c] = (dif_freq<LOG2NA>(8 * t + c) + NA / 2) & (NA - 1);
-    const int tiles_per_cpi = Nr / RPC;
-    const long long n_tiles = (long long)n_cpi * tiles_per_cpi;
+    // every CTA takes a contiguous run of tiles, so the running maximum is folded into keys[] once per CPI
+    const long long n_tiles = (long long)n_cpi << log2_tiles_per_cpi;
+    const long long tile_begin = n_tiles * blockIdx.x / gridDim.x, tile_end = n_tiles * (blockIdx.x + 1) / gridDim.x;
+    const int tpc_mask = (1 << log2_tiles_per_cpi) - 1;
     // PRUNED (V <= NA/8): (range bin r fastest, channel p) per thread -> coalesced reads, first pass on the fly,
     // the input of the next tile fetched one iteration ahead
     const int pr = tid % RPC, pp = tid / RPC;
     DifTw<LOG2NA> T;
     T.load(tw, PRUNED ? pp : t, t);
     auto fetch = [&](long long tile) {
-        const int cpi = (int)(tile / tiles_per_cpi), n0 = (int)(tile % tiles_per_cpi) * RPC;
-        return (tile < n_tiles && pp < V) ? Y[((long long)cpi * V + pp) * Nr + n0 + pr] : mk(0.f, 0.f);
+        const long long cpi = tile >> log2_tiles_per_cpi;
+        const int n0 = ((int)tile & tpc_mask) * RPC;
+        return (tile < tile_end && pp < V) ? Y[(cpi * V + pp) * Nr + n0 + pr] : mk(0.f, 0.f);
+    };
+    auto flush = [&](int cpi, float best, int best_row) {
+        if (!keys) return;
+        unsigned long long key = best >= 0.f ? pack_key(best, (unsigned)best_row) : 0ull;
+#pragma unroll
+        for (int o2 = 16; o2 > 0; o2 >>= 1) {
+            unsigned long long other = __shfl_xor_sync(0xffffffffu, key, o2);
+            key = other > key ? other : key;
+        }
+        // most candidates lose against the running maximum: a plain read filters them before the
+        // (same-address, hence serialised) atomic
+        if (lane == 0 && key && key > *reinterpret_cast<volatile unsigned long long *>(keys + cpi)) atomicMax(keys + cpi, key);
     };
     c32 xn = mk(0.f, 0.f);
-    if (PRUNED) xn = fetch(blockIdx.x);
-    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const int cpi = (int)(tile / tiles_per_cpi), n0 = (int)(tile % tiles_per_cpi) * RPC;
-        const c32 *Yc = Y + (long long)cpi * V * Nr + n0;
+    if (PRUNED) xn = fetch(tile_begin);
+    float best = -1.f;
+    int best_row = 0, cur_cpi = (int)(tile_begin >> log2_tiles_per_cpi);
+    int buf = 0;
+    for (long long tile = tile_begin; tile < tile_end; tile++, buf ^= 1) {
+        const int cpi = (int)(tile >> log2_tiles_per_cpi), n0 = ((int)tile & tpc_mask) * RPC;
+        if (cpi != cur_cpi) {
+            flush(cur_cpi, best, best_row);
+            best = -1.f;
+            cur_cpi = cpi;
+        }
+        c32 *rows = sm + buf * (RPC * RS);
         if (PRUNED) {
             const c32 xj = xn;
-            xn = fetch(tile + gridDim.x);
-            dif_first_pruned<LOG2NA>(sm + pr * RS, pp, xj, T);
+            xn = fetch(tile + 1);
+            dif_first_pruned<LOG2NA>(rows + pr * RS, pp, xj, T);
         } else {
             // transposing load: for every channel RPC consecutive range bins (contiguous in HBM)
+            const c32 *Yc = Y + (long long)cpi * V * Nr + n0;
             for (int e = tid; e < NA * RPC; e += 256) {
                 const int p = e / RPC, r = e % RPC;
-                sm[r * RS + fpad(p)] = p < V ? Yc[(long long)p * Nr + r] : mk(0.f, 0.f);   // angle zero-pad
+                rows[r * RS + fpad(p)] = p < V ? Yc[(long long)p * Nr + r] : mk(0.f, 0.f);   // angle zero-pad
             }
         }
         __syncthreads();
         c32 o[8];
-        dif_passes<LOG2NA, -1, Gm::WARP_SYNC, PRUNED>(sm + lr_t * RS, t, T, o);
-        float best = -1.f;
-        float *mrow = map ? map + ((long long)cpi * Nr + n0 + lr_t) * NA : nullptr;
+        dif_passes<LOG2NA, -1, Gm::WARP_SYNC, PRUNED>(rows + lr_t * RS, t, T, o);
+        float v[8];
 #pragma unroll
-        for (int c = 0; c < 8; c++) {
-            const float v = __fadd_rn(__fmul_rn(o[c].x, o[c].x), __fmul_rn(o[c].y, o[c].y));
-            if (mrow) __stcs(mrow + obin[c], v);
-            best = fmaxf(best, v);
-        }
-        if (keys) {
-            unsigned long long key = best >= 0.f ? pack_key(best, (unsigned)(n0 + lr_t)) : 0ull;
+        for (int c = 0; c < 8; c++) v[c] = __fadd_rn(__fmul_rn(o[c].x, o[c].x), __fmul_rn(o[c].y, o[c].y));
+        if (map) {
+            float *mrow = map + ((long long)cpi * Nr + n0 + lr_t) * NA;
 #pragma unroll
-            for (int o2 = 16; o2 > 0; o2 >>= 1) {
-                unsigned long long other = __shfl_xor_sync(0xffffffffu, key, o2);
-                key = other > key ? other : key;
-            }
-            if (lane == 0) s_key[warp] = key;
+            for (int c = 0; c < 8; c++) __stcs(mrow + obin[c], v[c]);
         }
-        __syncthreads();      // rows are free for the next tile; s_key complete
-        if (keys && tid == 0) {
-            unsigned long long key = s_key[0];
-#pragma unroll
-            for (int w = 1; w < 8; w++) key = s_key[w] > key ? s_key[w] : key;
-            // most tiles lose against the running maximum: a plain read filters them before the (same-address,
-            // hence serialised) atomic
-            if (key && key > *reinterpret_cast<volatile unsigned long long *>(keys + cpi)) atomicMax(keys + cpi, key);
-        }
+        const float m8 = fmaxf(fmaxf(fmaxf(v[0], v[1]), fmaxf(v[2], v[3])), fmaxf(fmaxf(v[4], v[5]), fmaxf(v[6], v[7])));
+        if (m8 > best) { best = m8; best_row = n0 + lr_t; }     // rows ascend within a CPI: the first maximum stays
     }
+    if (tile_begin < tile_end) flush(cur_cpi, best, best_row);
 }
 
 }  // namespace jrc
