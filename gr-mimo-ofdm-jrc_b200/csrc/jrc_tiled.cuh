@@ -244,8 +244,10 @@ __global__ void __launch_bounds__(256, 2) k_angle_mag(const c32 *__restrict__ Y,
         // (same-address, hence serialised) atomic
         if (lane == 0 && key && key > *reinterpret_cast<volatile unsigned long long *>(keys + cpi)) atomicMax(keys + cpi, key);
     };
-    c32 xn = mk(0.f, 0.f);
-    if (PRUNED) xn = fetch(tile_begin);
+    constexpr int PF = 2;                           // tiles fetched ahead (one is not enough: measured 0.31 -> 0.23 ms)
+    c32 xq[PF];
+#pragma unroll
+    for (int i = 0; i < PF; i++) xq[i] = PRUNED ? fetch(tile_begin + i) : mk(0.f, 0.f);
     float best = -1.f;
     int best_row = 0, cur_cpi = (int)(tile_begin >> log2_tiles_per_cpi);
     int buf = 0;
@@ -258,8 +260,10 @@ __global__ void __launch_bounds__(256, 2) k_angle_mag(const c32 *__restrict__ Y,
         }
         c32 *rows = sm + buf * (RPC * RS);
         if (PRUNED) {
-            const c32 xj = xn;
-            xn = fetch(tile + 1);
+            const c32 xj = xq[0];
+#pragma unroll
+            for (int i = 0; i + 1 < PF; i++) xq[i] = xq[i + 1];
+            xq[PF - 1] = fetch(tile + PF);
             dif_first_pruned<LOG2NA>(rows + pr * RS, pp, xj, T);
         } else {
             // transposing load: for every channel RPC consecutive range bins (contiguous in HBM)
