@@ -1109,6 +1109,22 @@ extern "C" jrc_status jrc_mag_squared(jrc_chain *h, const jrc_c32 *in, float *ou
     return sg.finish();
 }
 
+extern "C" jrc_status jrc_nlog10(jrc_chain *h, const float *in, float *out, size_t n_items, float n, float k)
+{
+    if (!h || !in || !out) return fail(JRC_ERR_INVALID, "null argument");
+    if (n_items == 0) return JRC_OK;
+    CU(cudaSetDevice(h->cfg.device));
+    Staging sg(h);
+    const void *din = nullptr; void *dout = nullptr;
+    ST(sg.in(in, n_items * sizeof(float), &din));
+    ST(sg.out(out, n_items * sizeof(float), &dout));
+    k_nlog10<<<grid_for((long long)n_items, 256, h->sm_count), 256, 0, h->stream>>>((const float *)din, (float *)dout,
+                                                                                   (long long)n_items, n, k);
+    CU(cudaGetLastError());
+    h->launches++;
+    return sg.finish();
+}
+
 extern "C" jrc_status jrc_estimate2d(jrc_chain *h, const jrc_c32 *map, int32_t n_inputs, int32_t vlen, jrc_det *det)
 {
     if (!h || !map || !det) return fail(JRC_ERR_INVALID, "null argument");

@@ -297,6 +297,14 @@ __device__ __forceinline__ NoiseWin noise_window(const EstParams &P, int peak_r,
     return w;
 }
 
+// blocks_nlog10_ff (...radar_sim.grc:725-745, in front of gui_heatmap_plot): n*log10(max(x, 1e-18)) + k
+__global__ void k_nlog10(const float *__restrict__ in, float *__restrict__ out, long long cnt, float n, float k)
+{
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < cnt;
+         e += (long long)gridDim.x * blockDim.x)
+        out[e] = __fadd_rn(__fmul_rn(n, log10f(fmaxf(in[e], 1e-18f))), k);
+}
+
 // Per-angle-bin tables for the fused kernel's estimator (the column window only depends on the peak's
 // angle bin): win[m] = (start_a, end_a) of noise_window(., m) and the closed-form column sums
 //   g[m][d] = sum_{c in window} w^{d (c + Na/2)},  w = e^{-j2pi/Na},  d = 1..7;   g[m][0] = ncols / 2,

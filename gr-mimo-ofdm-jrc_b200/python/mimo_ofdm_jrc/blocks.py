@@ -127,6 +127,43 @@ class complex_to_mag_squared:
         return self._chain.mag_squared(items)
 
 
+class nlog10_ff:
+    """blocks_nlog10_ff between complex_to_mag_squared and gui_heatmap_plot (...radar_sim.grc:725-745; bypassed
+    in the simulation flowgraph, active in the USRP one): n*log10(max(x, 1e-18)) + k."""
+
+    def __init__(self, n=10.0, vlen=1, k=0.0, device=0):
+        self.n, self.k, self.vlen = float(n), float(k), int(vlen)
+        self.chain = cabi.Chain(device=device)
+
+    def work(self, x):
+        return self.chain.nlog10(x, self.n, self.k)
+
+
+def radar_log_read_last(path):
+    """Consumer side of range_angle_estimator's CSV log: the last record as (time, power, snr, range, angle),
+    or None when the file is missing / empty / ends with the "NEW RECORD" header
+    (lib/mimo_precoder_impl.cc:903-950 reads the last line and takes the 5th comma-separated field)."""
+    try:
+        lines = [l for l in open(path).read().splitlines() if l.strip()]
+    except OSError:
+        return None
+    if not lines:
+        return None
+    f = lines[-1].split(",")
+    if len(f) != 5:
+        return None
+    try:
+        return (f[0].strip(),) + tuple(float(v) for v in f[1:])
+    except ValueError:
+        return None
+
+
+def radar_aided_steering_vector(angle_deg, n_tx):
+    """a[i] = exp(j*pi*sin(angle)*i) for a half-wavelength TX array (lib/mimo_precoder_impl.cc:952-956)."""
+    i = np.arange(n_tx, dtype=np.float64)
+    return np.exp(1j * np.pi * np.sin(np.float32(angle_deg) / 180.0 * np.pi) * i).astype(np.complex64)
+
+
 class range_angle_estimator:
     """include/mimo_ofdm_jrc/range_angle_estimator.h:48-58, lib/range_angle_estimator_impl.cc"""
 

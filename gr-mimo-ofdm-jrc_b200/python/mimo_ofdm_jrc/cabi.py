@@ -50,7 +50,7 @@ EXPORTS = [
     "jrc_chain_sync", "jrc_chain_set_estimator", "jrc_chain_set_thresholds",
     "jrc_chain_set_background_record", "jrc_chain_reset_background", "jrc_chain_run_batch",
     "jrc_chain_last_path", "jrc_chain_launch_count", "jrc_chain_run_host", "jrc_radar_estimate",
-    "jrc_fft_vcc", "jrc_transpose_pad", "jrc_mag_squared", "jrc_estimate2d", "jrc_peak1d", "jrc_zero_pad",
+    "jrc_fft_vcc", "jrc_transpose_pad", "jrc_mag_squared", "jrc_nlog10", "jrc_estimate2d", "jrc_peak1d", "jrc_zero_pad",
     "jrc_cp_remove", "jrc_ofdm_demod",
 ]
 
@@ -88,6 +88,7 @@ def load():
     lib.jrc_fft_vcc.argtypes = [vp, vp, vp, i32, i32, i32, i32]
     lib.jrc_transpose_pad.argtypes = [vp, vp, i32, i32, i32, i32, vp]
     lib.jrc_mag_squared.argtypes = [vp, vp, vp, sz]
+    lib.jrc_nlog10.argtypes = [vp, vp, vp, sz, C.c_float, C.c_float]
     lib.jrc_estimate2d.argtypes = [vp, vp, i32, i32, vp]
     lib.jrc_peak1d.argtypes = [vp, vp, i32, i32, f32, f32, i32, C.POINTER(Peak1dOut)]
     lib.jrc_zero_pad.argtypes = [vp, vp, i32, u32, u32, u64, vp]
@@ -237,6 +238,13 @@ class Chain:
         x = np.ascontiguousarray(x, dtype=np.complex64)
         out = np.empty(x.shape, dtype=np.float32)
         check(load().jrc_mag_squared(self._h, np_ptr(x), np_ptr(out), x.size))
+        return out
+
+    def nlog10(self, x, n=10.0, k=0.0):
+        """blocks_nlog10_ff in front of gui_heatmap_plot: n*log10(max(x, 1e-18)) + k."""
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        out = np.empty(x.shape, dtype=np.float32)
+        check(load().jrc_nlog10(self._h, np_ptr(x), np_ptr(out), x.size, float(n), float(k)))
         return out
 
     def estimate2d(self, cmap):

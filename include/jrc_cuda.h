@@ -174,6 +174,11 @@ JRC_API jrc_status jrc_transpose_pad(jrc_chain *h, const jrc_c32 *in, int32_t k_
 /* blocks_complex_to_mag_squared (...radar_sim.grc:637-652)                    */
 JRC_API jrc_status jrc_mag_squared(jrc_chain *h, const jrc_c32 *in, float *out, size_t n);
 
+/* blocks_nlog10_ff between complex_to_mag_squared and gui_heatmap_plot (...radar_sim.grc:725-745,
+ * 2170-2179; bypassed in the simulation flowgraph, active in the USRP one):
+ * out = n*log10(max(in, 1e-18)) + k                                            */
+JRC_API jrc_status jrc_nlog10(jrc_chain *h, const float *in, float *out, size_t n_items, float n, float k);
+
 /* range_angle_estimator::work (lib/range_angle_estimator_impl.cc:122-253) on one
  * complex map [n_inputs][vlen]; det is a HOST record.                         */
 JRC_API jrc_status jrc_estimate2d(jrc_chain *h, const jrc_c32 *map, int32_t n_inputs, int32_t vlen,

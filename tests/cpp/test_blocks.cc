@@ -11,6 +11,7 @@
 #include <mimo_ofdm_jrc/matrix_transpose.h>
 #include <mimo_ofdm_jrc/mimo_ofdm_radar.h>
 #include <mimo_ofdm_jrc/ofdm_cyclic_prefix_remover.h>
+#include <mimo_ofdm_jrc/radar_log.h>
 #include <mimo_ofdm_jrc/radar_chain.h>
 #include <mimo_ofdm_jrc/range_angle_estimator.h>
 #include <mimo_ofdm_jrc/zero_pad.h>
@@ -181,6 +182,13 @@ static void test_chain_of_blocks()
             CHECK(field(0, "range") == rb[od.range_idx] && field(1, "angle") == ab[od.angle_idx], "message range/angle");
             CHECK(field(2, "power") == od.peak_power && field(3, "snr") == od.snr_db, "message power/snr %g %g vs %g %g",
                   field(2, "power"), field(3, "snr"), od.peak_power, od.snr_db);
+            // the log's consumer (mimo_precoder's radar-aided steering) reads the same detection back
+            radar_log_entry le;
+            CHECK(radar_log_read_last("/tmp/jrc_cpp_log.csv", le), "radar log unreadable");
+            CHECK(std::fabs(le.angle - ab[od.angle_idx]) <= 1e-4f * (1.f + std::fabs(ab[od.angle_idx])) &&
+                  std::fabs(le.range - rb[od.range_idx]) <= 1e-4f * (1.f + rb[od.range_idx]), "radar log %g %g", le.range, le.angle);
+            auto sv = radar_aided_steering_vector(le.angle, T);
+            CHECK((int)sv.size() == T && sv[0] == gr_complex(1.f, 0.f) && std::fabs(std::abs(sv[T - 1]) - 1.f) < 1e-6f, "steering vector");
         }
     }
     // back-pressure: the transpose block drops the CPI but still consumes it

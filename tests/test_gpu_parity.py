@@ -243,6 +243,22 @@ def test_estimator_edge_maps(jrc, orc):
     assert blk.work(m)["flags"] == 0
     lines = [l for l in open("/tmp/jrc_radar_log.csv").read().splitlines() if l.strip()]
     assert any("NEW RECORD" in l for l in lines) and len(lines[-1].split(",")) == 5
+    # the consumer's reader (mimo_precoder's radar-aided steering) sees the last gated detection
+    rec = jrc.radar_log_read_last("/tmp/jrc_radar_log.csv")
+    assert rec is not None and abs(rec[4] - est["angle_bins"][8]) < 1e-3 and abs(rec[3] - est["range_bins"][256]) < 1e-3
+
+
+def test_nlog10_heatmap_feed(jrc):
+    """blocks_nlog10_ff between complex_to_mag_squared and gui_heatmap_plot."""
+    rng = np.random.default_rng(4)
+    x = (rng.random((512, 128)) ** 8).astype(np.float32)
+    x[0, :4] = [0.0, 1e-30, 1.0, 1e-18]
+    y = jrc.nlog10_ff(10.0, 128, 0.0).work(x)
+    ref = (10.0 * np.log10(np.maximum(x, np.float32(1e-18)).astype(np.float64))).astype(np.float32)
+    np.testing.assert_allclose(y, ref, rtol=2e-6, atol=2e-5)
+    assert y[0, 0] == y[0, 1] and abs(y[0, 0] + 180.0) < 1e-4 and y[0, 2] == 0.0     # clamp at 1e-18
+    y2 = jrc.nlog10_ff(20.0, 128, 3.0).work(x)
+    np.testing.assert_allclose(y2, 2.0 * ref + 3.0, rtol=2e-6, atol=5e-5)
 
 
 def test_peak1d_and_zero_pad(jrc, orc):
