@@ -89,6 +89,7 @@ struct jrc_chain {
     bool est_set = false;
     std::vector<float> range_bins, angle_bins;
     float nd_range_m = 0, nd_angle_deg = 0, snr_thr = 0, pow_thr = 0;
+    std::map<std::pair<int, int>, double2 *> dft_tabs;    // (n, forward) -> cos/sin table of k_dft_any
     std::map<std::pair<int, int>, c32 *> twiddles_full;   // (n, forward) -> w_n^i, i < n (tiled kernels)
     float *d_angle_bins = nullptr;
     int2 *d_win_tab = nullptr;                  // k_est_tables: per-angle-bin noise window columns
@@ -192,6 +193,7 @@ extern "C" void jrc_chain_destroy(jrc_chain *h)
                        &h->sDets[0], &h->sDets[1], &h->sMisc, &h->sMisc2, &h->pin_a, &h->pin_b};
     for (GrowBuf *b : bufs) b->release();
     for (auto &kv : h->twiddles_full) cudaFree(kv.second);
+    for (auto &kv : h->dft_tabs) cudaFree(kv.second);
     if (h->d_angle_bins) cudaFree(h->d_angle_bins);
     if (h->d_win_tab) cudaFree(h->d_win_tab);
     if (h->d_g_tab) cudaFree(h->d_g_tab);
@@ -1104,6 +1106,108 @@ extern "C" jrc_status jrc_mag_squared(jrc_chain *h, const jrc_c32 *in, float *ou
     ST(sg.in(in, n * sizeof(c32), &din));
     ST(sg.out(out, n * sizeof(float), &dout));
     k_mag_squared<<<grid_for((long long)n, 256, h->sm_count), 256, 0, h->stream>>>((const c32 *)din, (float *)dout, (long long)n);
+    CU(cudaGetLastError());
+    h->launches++;
+    return sg.finish();
+}
+
+// ---------------------------------------------------------------------------
+// target_simulator (lib/target_simulator_impl.cc:127-385)
+// ---------------------------------------------------------------------------
+static jrc_status fft_any(jrc_chain *h, const c32 *in, c32 *out, int n, long long rows, int forward)
+{
+    if (is_pow2(n) && n <= 16384)      // the staged radix-2 kernel: bit-identical to the CPU restatement
+        return launch_fft_rows(h, in, n, n, out, n, rows, forward, 0);
+    auto key = std::make_pair(n, forward ? 1 : 0);
+    double2 *tab = nullptr;
+    auto it = h->dft_tabs.find(key);
+    if (it != h->dft_tabs.end()) tab = it->second;
+    else {
+        std::vector<double2> t((size_t)n);
+        const double sgn = forward ? -1.0 : 1.0;
+        for (int k = 0; k < n; k++) {
+            double a = sgn * 2.0 * M_PI * (double)k / (double)n;
+            t[k].x = cos(a); t[k].y = sin(a);
+        }
+        CU(cudaMalloc(&tab, t.size() * sizeof(double2)));
+        CU(cudaMemcpyAsync(tab, t.data(), t.size() * sizeof(double2), cudaMemcpyHostToDevice, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+        h->dft_tabs[key] = tab;
+    }
+    dim3 grid((unsigned)((n + 127) / 128), (unsigned)rows);
+    k_dft_any<<<grid, 128, 0, h->stream>>>(in, out, n, tab);
+    CU(cudaGetLastError());
+    h->launches++;
+    return JRC_OK;
+}
+
+extern "C" jrc_status jrc_target_sim(jrc_chain *h, const jrc_c32 *in, int32_t n, const float *range, const float *velocity,
+                                      const float *rcs, const float *azimuth, int32_t n_targets, const float *position_rx,
+                                      int32_t n_rx, int32_t samp_rate, float center_freq, int32_t self_coupling,
+                                      float self_coupling_db, const jrc_c32 *target_phase, int32_t accumulate, jrc_c32 *out)
+{
+    if (!h || !in || !out || !range || !velocity || !rcs || !azimuth || !position_rx) return fail(JRC_ERR_INVALID, "null argument");
+    if (n < 1 || n_targets < 0 || n_rx < 1 || samp_rate <= 0) return fail(JRC_ERR_INVALID, "bad sizes");
+    if ((long long)n_rx * (n_targets > 0 ? n_targets : 1) > 65535) return fail(JRC_ERR_INVALID, "too many (target, rx) pairs");
+    CU(cudaSetDevice(h->cfg.device));
+    const int K = n_targets, L = n_rx;
+    // channel filters exactly as the reference builds them (float arithmetic, :164-188, :264-303)
+    const float c_light = 3e8f;
+    const double FOUR_PI_CUBED_SQRT = 44.54662397465366;
+    std::vector<c32> filt((size_t)(K + K * L) * n + (size_t)K);    // [K] doppler, [L][K] time shift, [K] phase
+    std::vector<float> freq((size_t)n);
+    for (int i = 0; i < n; i++)
+        freq[i] = i < n / 2 ? i * (float)samp_rate / (float)n : i * (float)samp_rate / (float)n - (float)samp_rate;
+    for (int k = 0; k < K; k++) {
+        const float doppler = 2 * velocity[k] * center_freq / c_light;
+        const float scale = (float)(c_light * sqrtf(rcs[k]) / FOUR_PI_CUBED_SQRT / (range[k] * range[k]) / center_freq);
+        float ph = 0.0f;
+        c32 *fd = filt.data() + (size_t)k * n;
+        for (int i = 0; i < n; i++) {
+            fd[i].x = cosf(ph) * scale; fd[i].y = sinf(ph) * scale;
+            ph = (float)fmod(ph + 2 * M_PI * doppler / (float)samp_rate, 2 * M_PI);
+        }
+        for (int l = 0; l < L; l++) {
+            const float timeshift = (float)((2.0 * range[k] - position_rx[l] * sin(azimuth[k] * M_PI / 180.0)) / c_light);
+            c32 *ft = filt.data() + ((size_t)K + (size_t)l * K + k) * n;
+            for (int i = 0; i < n; i++) {
+                const float pt = (float)fmod(2 * M_PI * (timeshift) * (freq[i] + center_freq), 2 * M_PI);
+                ft[i].x = cosf(pt) / (float)n; ft[i].y = -sinf(pt) / (float)n;
+            }
+        }
+    }
+    c32 *ph_host = filt.data() + (size_t)(K + K * L) * n;
+    for (int k = 0; k < K; k++) ph_host[k] = target_phase ? *(const c32 *)&target_phase[k] : make_float2(1.f, 0.f);
+    Staging sg(h);
+    const void *din = nullptr; void *dout = nullptr;
+    ST(sg.in(in, (size_t)n * sizeof(c32), &din));
+    ST(sg.out(out, (size_t)L * n * sizeof(c32), &dout));
+    const size_t KL = (size_t)K * L;
+    ST(h->sMisc.need(filt.size() * sizeof(c32)));
+    ST(h->sMisc2.need(((size_t)2 * K + 2 * KL) * n * sizeof(c32) + 16));
+    c32 *d_filt = (c32 *)h->sMisc.p;
+    c32 *d_bt = (c32 *)h->sMisc2.p, *d_bf = d_bt + (size_t)K * n, *d_g = d_bf + (size_t)K * n, *d_res = d_g + KL * n;
+    CU(cudaMemcpyAsync(d_filt, filt.data(), filt.size() * sizeof(c32), cudaMemcpyHostToDevice, h->stream));
+    if (K > 0) {
+        // in * doppler filter -> FFT                                            (:346-350), once per target
+        k_cmul_rows<<<grid_for((long long)K * n, 256, h->sm_count), 256, 0, h->stream>>>((const c32 *)din, K, d_filt, d_bt, n, K);
+        CU(cudaGetLastError());
+        h->launches++;
+        ST(fft_any(h, d_bt, d_bf, n, K, 1));
+        // * time-shift filter of (rx l, target k) -> IFFT                      (:353-357)
+        // rows ordered [l][k]: the spectrum of target k is row (row % K) -> use a_div trick per l
+        for (int l = 0; l < L; l++) {
+            k_cmul_rows<<<grid_for((long long)K * n, 256, h->sm_count), 256, 0, h->stream>>>(
+                d_bf, 1, d_filt + ((size_t)K + (size_t)l * K) * n, d_g + (size_t)l * K * n, n, K);
+            CU(cudaGetLastError());
+            h->launches++;
+        }
+        ST(fft_any(h, d_g, d_res, n, (long long)KL, 0));
+    }
+    const float g = (float)pow(10, self_coupling_db / 20.0);
+    dim3 grid((unsigned)((n + 255) / 256), (unsigned)L);
+    k_sim_combine<<<grid, 256, 0, h->stream>>>(d_res, (const c32 *)din, target_phase ? d_filt + (size_t)(K + K * L) * n : nullptr, n, K,
+                                               accumulate, self_coupling, g, (c32 *)dout);
     CU(cudaGetLastError());
     h->launches++;
     return sg.finish();

@@ -297,6 +297,70 @@ __device__ __forceinline__ NoiseWin noise_window(const EstParams &P, int peak_r,
     return w;
 }
 
+// ---------------------------------------------------------------------------
+// target_simulator (lib/target_simulator_impl.cc:326-379) building blocks.
+// ---------------------------------------------------------------------------
+// volk_32fc_x2_multiply_32fc (:346,:353): out[row][i] = a[arow][i] * b[brow][i], arow = row / a_div, brow = row
+__global__ void k_cmul_rows(const c32 *__restrict__ a, int a_div, const c32 *__restrict__ b, c32 *__restrict__ out,
+                            int n, int rows)
+{
+    const long long total = (long long)rows * n;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total;
+         e += (long long)gridDim.x * blockDim.x) {
+        const int row = (int)(e / n), i = (int)(e % n);
+        out[e] = cmul_exact(a[(long long)(row / a_div) * n + i], b[e]);
+    }
+}
+
+// FFT of arbitrary length (the packet lengths of the simulation are not powers of two): direct DFT with
+// float64 products and sums in index order and a host-computed cos/sin table -- the arithmetic of the CPU
+// restatement's stand-in for FFTW, result rounded to float32.  One thread per output bin, rows on grid.y.
+__global__ void __launch_bounds__(128) k_dft_any(const c32 *__restrict__ in, c32 *__restrict__ out, int n,
+                                                 const double2 *__restrict__ tab /* [n] e^{-+j2pi k/n} */)
+{
+    __shared__ c32 tile[128];
+    const c32 *x = in + (long long)blockIdx.y * n;
+    const int m = blockIdx.x * 128 + threadIdx.x;
+    double sr = 0.0, si = 0.0;
+    long long idx = 0;
+    for (int k0 = 0; k0 < n; k0 += 128) {
+        if (k0 + threadIdx.x < n) tile[threadIdx.x] = x[k0 + threadIdx.x];
+        __syncthreads();
+        const int cnt = n - k0 < 128 ? n - k0 : 128;
+        if (m < n) {
+            for (int kk = 0; kk < cnt; kk++) {
+                const double2 w = tab[idx];
+                const double re = (double)tile[kk].x, im = (double)tile[kk].y;
+                sr = __dadd_rn(sr, __dsub_rn(__dmul_rn(re, w.x), __dmul_rn(im, w.y)));
+                si = __dadd_rn(si, __dadd_rn(__dmul_rn(re, w.y), __dmul_rn(im, w.x)));
+                idx += m;
+                if (idx >= n) idx -= n;
+            }
+        }
+        __syncthreads();
+    }
+    if (m < n) out[(long long)blockIdx.y * n + m] = mk((float)sr, (float)si);
+}
+
+// per RX antenna: fold the per-target results (:359-367; the reference's memcpy keeps the LAST target, the
+// accumulate option sums them), optional random phase per target (:360-363), self coupling (:372-378)
+__global__ void k_sim_combine(const c32 *__restrict__ res /* [n_rx][n_targets][n] */, const c32 *__restrict__ in,
+                              const c32 *__restrict__ phase /* [n_targets] or null */, int n, int n_targets,
+                              int accumulate, int self_coupling, float g, c32 *__restrict__ out /* [n_rx][n] */)
+{
+    const int l = blockIdx.y;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        c32 o = mk(0.f, 0.f);
+        for (int k = 0; k < n_targets; k++) {
+            c32 r = res[((long long)l * n_targets + k) * n + i];
+            if (phase) r = cmul_exact(r, phase[k]);
+            o = accumulate ? cadd_exact(o, r) : r;
+        }
+        if (self_coupling) o = mk(__fadd_rn(o.x, __fmul_rn(g, in[i].x)), __fadd_rn(o.y, __fmul_rn(g, in[i].y)));
+        out[(long long)l * n + i] = o;
+    }
+}
+
 // blocks_nlog10_ff (...radar_sim.grc:725-745, in front of gui_heatmap_plot): n*log10(max(x, 1e-18)) + k
 __global__ void k_nlog10(const float *__restrict__ in, float *__restrict__ out, long long cnt, float n, float k)
 {

@@ -99,6 +99,22 @@ BLOCKS = {
                     P("len_key", "Packet length key", "string", '"packet_len"')],
         inputs=[dict(domain="stream", dtype="complex")],
         outputs=[dict(domain="stream", dtype="complex", vlen="${ fft_len }")]),
+    "target_simulator": dict(
+        label="Target Simulator",
+        make=call("target_simulator", "range", "velocity", "rcs", "azimuth", "position_rx", "samp_rate", "center_freq",
+                  "self_coupling_db", "rndm_phaseshift", "self_coupling", "len_key", "debug"),
+        callbacks=["setup_targets(${range}, ${velocity}, ${rcs}, ${azimuth}, ${position_rx}, ${samp_rate}, "
+                   "${center_freq}, ${self_coupling_db}, ${rndm_phaseshift}, ${self_coupling})"],
+        parameters=[P("range", "Range [m]", "real_vector"), P("velocity", "Velocity [m/s]", "real_vector"),
+                    P("azimuth", "Azimuth [Degrees]", "real_vector"), P("rcs", "RCS [m2]", "real_vector"),
+                    P("position_rx", "Position of RX Antennas (relative to TX)", "real_vector", "0,", hide="part"),
+                    P("samp_rate", "Sample Rate [Hz]", "int"), P("center_freq", "Center Frequency [Hz]", "float"),
+                    P("self_coupling_db", "Self Coupling [dB]", "float", hide="part"),
+                    P("rndm_phaseshift", "Enable Random Phase Shift", "bool", "False", options=["True", "False"], hide="part"),
+                    P("self_coupling", "Enable Self Coupling", "bool", "False", options=["True", "False"], hide="part"),
+                    P("len_key", "Packet length key", "string", '"packet_len"'), flag("debug", "Debug", "False")],
+        inputs=[dict(domain="stream", dtype="complex")],
+        outputs=[dict(domain="stream", dtype="complex", multiplicity="${ len(position_rx) }")]),
     # not in the reference: the fused chain as one block (include/mimo_ofdm_jrc/radar_chain.h)
     "radar_chain": dict(
         label="MIMO OFDM Radar Chain (fused, B200)",

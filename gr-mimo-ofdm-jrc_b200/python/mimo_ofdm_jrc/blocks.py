@@ -127,6 +127,43 @@ class complex_to_mag_squared:
         return self._chain.mag_squared(items)
 
 
+class target_simulator:
+    """target_simulator (include/mimo_ofdm_jrc/target_simulator.h:48-71, lib/target_simulator_impl.cc): one input
+    packet of time samples -> one packet per RX antenna.  `accumulate=True` sums the targets; the default keeps
+    the reference's behaviour (its memcpy at :366 leaves only the last target in the output)."""
+
+    def __init__(self, range, velocity, rcs, azimuth, position_rx, samp_rate, center_freq, self_coupling_db,
+                 rndm_phaseshift=False, self_coupling=False, len_key="packet_len", debug=False, device=0,
+                 accumulate=False):
+        self.len_key, self.debug, self.accumulate = len_key, debug, accumulate
+        self.chain = cabi.Chain(device=device)
+        self.nitems_written = 0
+        self.setup_targets(range, velocity, rcs, azimuth, position_rx, samp_rate, center_freq, self_coupling_db,
+                           rndm_phaseshift, self_coupling)
+
+    def setup_targets(self, range, velocity, rcs, azimuth, position_rx, samp_rate, center_freq, self_coupling_db,
+                      rndm_phaseshift, self_coupling):
+        self.range, self.velocity, self.rcs, self.azimuth = (np.asarray(v, dtype=np.float32) for v in
+                                                             (range, velocity, rcs, azimuth))
+        self.position_rx = np.asarray(position_rx, dtype=np.float32)
+        self.samp_rate, self.center_freq = int(samp_rate), float(center_freq)
+        self.self_coupling_db, self.rndm_phaseshift, self.self_coupling = float(self_coupling_db), bool(rndm_phaseshift), bool(self_coupling)
+
+    def work(self, x):
+        """-> (out [n_rx][n], tags): tags[l] = ("rx_time", (sec, frac), "stat_targ_sim") at the packet start (:333-336)."""
+        phase = None
+        if self.rndm_phaseshift:     # :311-320, one random phase per target and packet
+            u = (np.random.randint(0, 1000, size=self.range.size) + 1) / 1000.0
+            phase = np.exp(1j * 2 * np.pi * u.astype(np.float32)).astype(np.complex64)
+        out = self.chain.target_sim(x, self.range, self.velocity, self.rcs, self.azimuth, self.position_rx, self.samp_rate,
+                                    self.center_freq, self.self_coupling, self.self_coupling_db, phase, self.accumulate)
+        sec = self.nitems_written // self.samp_rate
+        frac = float(np.float32(self.nitems_written) / np.float32(self.samp_rate)) - sec
+        tags = [("rx_time", (int(sec), frac), "stat_targ_sim")] * self.position_rx.size
+        self.nitems_written += np.asarray(x).size
+        return out, tags
+
+
 class nlog10_ff:
     """blocks_nlog10_ff between complex_to_mag_squared and gui_heatmap_plot (...radar_sim.grc:725-745; bypassed
     in the simulation flowgraph, active in the USRP one): n*log10(max(x, 1e-18)) + k."""

@@ -50,7 +50,7 @@ EXPORTS = [
     "jrc_chain_sync", "jrc_chain_set_estimator", "jrc_chain_set_thresholds",
     "jrc_chain_set_background_record", "jrc_chain_reset_background", "jrc_chain_run_batch",
     "jrc_chain_last_path", "jrc_chain_launch_count", "jrc_chain_run_host", "jrc_radar_estimate",
-    "jrc_fft_vcc", "jrc_transpose_pad", "jrc_mag_squared", "jrc_nlog10", "jrc_estimate2d", "jrc_peak1d", "jrc_zero_pad",
+    "jrc_fft_vcc", "jrc_transpose_pad", "jrc_mag_squared", "jrc_target_sim", "jrc_nlog10", "jrc_estimate2d", "jrc_peak1d", "jrc_zero_pad",
     "jrc_cp_remove", "jrc_ofdm_demod",
 ]
 
@@ -88,6 +88,7 @@ def load():
     lib.jrc_fft_vcc.argtypes = [vp, vp, vp, i32, i32, i32, i32]
     lib.jrc_transpose_pad.argtypes = [vp, vp, i32, i32, i32, i32, vp]
     lib.jrc_mag_squared.argtypes = [vp, vp, vp, sz]
+    lib.jrc_target_sim.argtypes = [vp, vp, i32, vp, vp, vp, vp, i32, vp, i32, i32, C.c_float, i32, C.c_float, vp, i32, vp]
     lib.jrc_nlog10.argtypes = [vp, vp, vp, sz, C.c_float, C.c_float]
     lib.jrc_estimate2d.argtypes = [vp, vp, i32, i32, vp]
     lib.jrc_peak1d.argtypes = [vp, vp, i32, i32, f32, f32, i32, C.POINTER(Peak1dOut)]
@@ -238,6 +239,21 @@ class Chain:
         x = np.ascontiguousarray(x, dtype=np.complex64)
         out = np.empty(x.shape, dtype=np.float32)
         check(load().jrc_mag_squared(self._h, np_ptr(x), np_ptr(out), x.size))
+        return out
+
+    def target_sim(self, x, range_m, velocity, rcs, azimuth, position_rx, samp_rate, center_freq,
+                   self_coupling=False, self_coupling_db=0.0, target_phase=None, accumulate=False):
+        """target_simulator::work for one packet x of time samples -> [n_rx][n]."""
+        x = np.ascontiguousarray(x, dtype=np.complex64)
+        f32 = lambda a: np.ascontiguousarray(a, dtype=np.float32)   # noqa: E731
+        r, v, s, a, p = f32(range_m), f32(velocity), f32(rcs), f32(azimuth), f32(position_rx)
+        assert r.size == v.size == s.size == a.size
+        ph = None if target_phase is None else np.ascontiguousarray(target_phase, dtype=np.complex64)
+        out = np.empty((p.size, x.size), dtype=np.complex64)
+        check(load().jrc_target_sim(self._h, np_ptr(x), x.size, np_ptr(r), np_ptr(v), np_ptr(s), np_ptr(a), r.size,
+                                    np_ptr(p), p.size, int(samp_rate), float(center_freq), int(bool(self_coupling)),
+                                    float(self_coupling_db), None if ph is None else np_ptr(ph), int(bool(accumulate)),
+                                    np_ptr(out)))
         return out
 
     def nlog10(self, x, n=10.0, k=0.0):

@@ -174,6 +174,20 @@ JRC_API jrc_status jrc_transpose_pad(jrc_chain *h, const jrc_c32 *in, int32_t k_
 /* blocks_complex_to_mag_squared (...radar_sim.grc:637-652)                    */
 JRC_API jrc_status jrc_mag_squared(jrc_chain *h, const jrc_c32 *in, float *out, size_t n);
 
+/* target_simulator::work (lib/target_simulator_impl.cc:201-385) for one packet of n time samples (any n):
+ * per RX antenna l and target k  IFFT( FFT(in * doppler_k) * timeshift_{l,k} ), the per-target results
+ * folded as the reference does (accumulate = 0: its memcpy keeps the last target, :366) or summed
+ * (accumulate = 1), optional per-target phase factor (rndm_phaseshift, :311-320; NULL = none), self
+ * coupling (:372-378).  out: [n_rx][n].  The channel filters are built on the host with the reference's
+ * float arithmetic (:164-188, :264-303).                                                       */
+JRC_API jrc_status jrc_target_sim(jrc_chain *h, const jrc_c32 *in, int32_t n,
+                                  const float *range, const float *velocity, const float *rcs,
+                                  const float *azimuth, int32_t n_targets,
+                                  const float *position_rx, int32_t n_rx,
+                                  int32_t samp_rate, float center_freq,
+                                  int32_t self_coupling, float self_coupling_db,
+                                  const jrc_c32 *target_phase, int32_t accumulate, jrc_c32 *out);
+
 /* blocks_nlog10_ff between complex_to_mag_squared and gui_heatmap_plot (...radar_sim.grc:725-745,
  * 2170-2179; bypassed in the simulation flowgraph, active in the USRP one):
  * out = n*log10(max(in, 1e-18)) + k                                            */

@@ -12,6 +12,7 @@
 #include <mimo_ofdm_jrc/mimo_ofdm_radar.h>
 #include <mimo_ofdm_jrc/ofdm_cyclic_prefix_remover.h>
 #include <mimo_ofdm_jrc/radar_log.h>
+#include <mimo_ofdm_jrc/target_simulator.h>
 #include <mimo_ofdm_jrc/radar_chain.h>
 #include <mimo_ofdm_jrc/range_angle_estimator.h>
 #include <mimo_ofdm_jrc/zero_pad.h>
@@ -244,6 +245,25 @@ static void test_peak_and_pad()
         if (pmt::symbol_to_string(tg.key) == "packet_len" && pmt::to_long(tg.value) == 9) has_len = true;
     }
     CHECK(has_time && has_len, "cp remover tags");
+
+    // target_simulator: R output packets identical to the CPU restatement, rx_time tag on every port
+    {
+        std::vector<float> rg = {7.5f, 30.f}, vel = {3.f, -8.f}, rcs = {1.f, 20.f}, az = {-25.f, 40.f}, pos = {0.f, 0.00625f};
+        auto sim = target_simulator::make(rg, vel, rcs, az, pos, 125000000, 24e9f, -10.f, false, true, "packet_len");
+        const int n = 1040;
+        cvec x = randvec(n), o0(n), o1(n), ro(2 * (size_t)n);
+        shim::input_t si; si.items = x.data(); si.n_items = n; si.tags = {shim::make_tag(0, "packet_len", pmt::from_long(n))};
+        auto rs = shim::run_once(*sim, {si}, {{o0.data(), n}, {o1.data(), n}});
+        orc_target_simulator((const orc_c32 *)x.data(), n, rg.data(), vel.data(), rcs.data(), az.data(), 2, pos.data(), 2, 125000000,
+                             24e9f, 1, -10.f, 0, (orc_c32 *)ro.data());
+        CHECK(rs.produced == n && rs.consumed[0] == n, "target simulator produced %d", rs.produced);
+        CHECK(std::memcmp(o0.data(), ro.data(), n * sizeof(gr_complex)) == 0 &&
+              std::memcmp(o1.data(), ro.data() + n, n * sizeof(gr_complex)) == 0, "target simulator output differs");
+        bool t0 = false, t1 = false;
+        for (auto &tg : rs.out_tags[0]) if (pmt::symbol_to_string(tg.key) == "rx_time" && pmt::symbol_to_string(tg.srcid) == "stat_targ_sim") t0 = true;
+        for (auto &tg : rs.out_tags[1]) if (pmt::symbol_to_string(tg.key) == "rx_time") t1 = true;
+        CHECK(t0 && t1, "target simulator rx_time tags");
+    }
 }
 
 static void test_fused_block()

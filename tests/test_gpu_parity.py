@@ -392,3 +392,30 @@ def test_tiled_chain_vs_oracle(jrc, orc, name):
     _, d2 = ch.run_host(rx, tx, want_map=False)
     for f in ("range_idx", "angle_idx", "peak_power", "noise_power", "flags"):
         assert np.array_equal(d2[f], d[f]), f
+
+
+@pytest.mark.parametrize("n", [1040, 1024, 250])
+def test_target_simulator_is_bit_exact(jrc, orc, n):
+    """target_simulator on the GPU.  Filters with the reference's float arithmetic on
+    the host, FFT/IFFT on the device with the CPU restatement's arithmetic (radix-2 float32 for powers of two,
+    float64 direct DFT otherwise): identical bits, for 1-3 targets, both folding rules, self coupling."""
+    rng = np.random.default_rng(n)
+    x = (rng.standard_normal(n) + 1j * rng.standard_normal(n)).astype(np.complex64)
+    pos = [0.0, 0.00625, 0.0125, 0.01875]                     # lambda/2 spacing at 24 GHz
+    for (rg, vel, rcs, az, sc, acc) in [([12.0], [0.0], [1.0], [10.0], False, False),
+                                        ([7.5, 30.0], [3.0, -8.0], [1.0, 20.0], [-25.0, 40.0], True, False),
+                                        ([7.5, 30.0, 18.0], [0.0, 0.0, 5.0], [1.0, 20.0, 3.0], [-25.0, 40.0, 0.0], True, True)]:
+        blk = jrc.target_simulator(rg, vel, rcs, az, pos, 125000000, 24e9, -10.0, False, sc, accumulate=acc)
+        out, tags = blk.work(x)
+        ref = orc.target_simulator(x, rg, vel, rcs, az, pos, 125000000, 24e9, sc, -10.0, acc)
+        assert out.shape == ref.shape == (4, n)
+        assert np.array_equal(out.view(np.uint32), ref.view(np.uint32)), (n, len(rg), np.abs(out - ref).max())
+        assert tags[0] == ("rx_time", (0, 0.0), "stat_targ_sim") and len(tags) == 4
+        out2, tags2 = blk.work(x)                                # second packet: same samples, later rx_time
+        assert np.array_equal(out2, out) and tags2[0][1][0] == 0 and abs(tags2[0][1][1] - n / 125e6) < 1e-9
+    # random phase shift: every target's echo rotated by a unit-modulus factor
+    blk = jrc.target_simulator([12.0], [0.0], [1.0], [10.0], pos, 125000000, 24e9, -10.0, True, False)
+    o1, _ = blk.work(x)
+    base = orc.target_simulator(x, [12.0], [0.0], [1.0], [10.0], pos, 125000000, 24e9, False, -10.0, False)
+    ratio = o1[0][np.abs(base[0]) > 1e-9] / base[0][np.abs(base[0]) > 1e-9]
+    assert np.allclose(np.abs(ratio), 1.0, atol=1e-4) and np.allclose(ratio, ratio[0], atol=1e-3)

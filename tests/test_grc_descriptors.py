@@ -12,7 +12,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 OURS = os.path.join(ROOT, "gr-mimo-ofdm-jrc_b200", "grc")
 REF = "/root/reference/grc"
 BLOCKS = ["mimo_ofdm_radar", "matrix_transpose", "range_angle_estimator", "fft_peak_detect", "zero_pad",
-          "ofdm_cyclic_prefix_remover"]
+          "ofdm_cyclic_prefix_remover", "target_simulator"]
 
 
 def norm(s):

@@ -75,3 +75,39 @@ def test_time_domain_sim_on_gpu(jrc, orc, target, peak):
     det = blk.work(cm)
     assert (det["range_idx"], det["angle_idx"]) == peak and det["snr_db"] == do[0]["snr_db"]
     assert blk.messages and blk.messages[0][0][1][0] == est["range_bins"][peak[0]]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("target,peak", KATS)
+def test_time_domain_sim_every_block_on_gpu(jrc, orc, target, peak):
+    """The whole simulation flowgraph through the GPU blocks: TX IFFT, zero_pad, target_simulator (one per TX),
+    ofdm_cyclic_prefix_remover fused with the RX FFT, fused radar chain.  With the oracle's pad noise the
+    received symbols are bit-identical to the CPU flow; with the block's own noise the peak is unchanged."""
+    rng_m, az_deg = target
+    rng = np.random.default_rng(42)
+    ltf = synth.tx_symbols(T, S, N)
+    qpsk = ((rng.integers(0, 2, (T, PRE, N)) * 2 - 1) + 1j * (rng.integers(0, 2, (T, PRE, N)) * 2 - 1)) / np.sqrt(2)
+    qpsk[:, :, synth.LTF_64 == 0] = 0
+    txf = np.concatenate([qpsk, ltf], axis=1).astype(np.complex64)
+    nsym = PRE + S
+    ifft = jrc.fft_vcc(N, False, shift=True)
+    zp = jrc.zero_pad(False, 0, 3 * (N + CP))
+    cpr = jrc.ofdm_cyclic_prefix_remover(N, CP)
+    est = synth.default_estimator_params(N, T * R, IR, IA)
+    ch = jrc.Chain(N, T, R, S, 0, IR, IA)
+    ch.set_estimator(**est)
+    _, rxf_cpu = sim_frames(orc, rng_m, az_deg)
+    for own_noise in (False, True):
+        rx_time = np.zeros((R, nsym * (N + CP) + 3 * (N + CP)), dtype=np.complex64)
+        for t in range(T):
+            td = ifft.work(txf[t] * np.float32(1 / 8))
+            td = np.concatenate([td[:, -CP:], td], axis=1).reshape(-1)
+            pkt = zp.work(td) if own_noise else orc.zero_pad(td, 0, 3 * (N + CP), seed=7 + t)
+            pos = [(1 + 0.5 * t) * LAM, (3 + 0.5 * t) * LAM]
+            sim = jrc.target_simulator([rng_m], [0.0], [10.0], [az_deg], pos, FS, FC, 0.0)
+            rx_time += sim.work(pkt)[0]
+        rxf = np.stack([cpr.work(rx_time[r][:nsym * (N + CP)], demod=True) for r in range(R)]).astype(np.complex64)
+        if not own_noise:
+            assert np.array_equal(rxf, rxf_cpu)
+        m, d = ch.run_host(rxf[None, :, PRE:], txf[None, :, PRE:])
+        assert (d[0]["range_idx"], d[0]["angle_idx"]) == peak and d[0]["flags"] == 1
