@@ -147,16 +147,16 @@ __device__ __forceinline__ void fft8p(c32 (&u)[8])
 // TWO independent 8-point DFTs per call on the packed pipe, split-complex: re[k] / im[k] hold the real /
 // imaginary parts of element k of DFT 0 (.x) and DFT 1 (.y).  No lane of a packed instruction is
 // wasted on re/im swaps, so the pair costs the 52 issue slots of ONE scalar fft8<DIR> (26 per DFT),
-// and each half is bit-identical to fft8<DIR> of that DFT (a - b is fma(b, -1, a); the -(x+y)
+// and each half is bit-identical to fft8<DIR> of that DFT (a - b is FADD2 with a negated operand; the -(x+y)
 // term of the 3*pi/4 twiddle is carried as x+y with the sign moved into the constant).
 // ---------------------------------------------------------------------------
 template <int DIR>
 __device__ __forceinline__ void fft8s(float2 (&re)[8], float2 (&im)[8])
 {
     const float C = 0.70710678118654752440f;
-    const float2 N1 = mk(-1.f, -1.f), CC = mk(C, C), NC = mk(-C, -C);
+    const float2 CC = mk(C, C), NC = mk(-C, -C);
 #define JRC_ADD(a, b) __fadd2_rn(a, b)
-#define JRC_SUB(a, b) __ffma2_rn(b, N1, a)
+#define JRC_SUB(a, b) __fadd2_rn(a, mk(-(b).x, -(b).y))   /* FADD2 a, -b: the negation is an operand modifier */
     const float2 a0r = JRC_ADD(re[0], re[4]), a0i = JRC_ADD(im[0], im[4]);
     const float2 a1r = JRC_SUB(re[0], re[4]), a1i = JRC_SUB(im[0], im[4]);
     const float2 a2r = JRC_ADD(re[2], re[6]), a2i = JRC_ADD(im[2], im[6]);

@@ -92,7 +92,7 @@ __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // Angle twiddles of one thread, duplicated into both halves of a register pair.
-struct AngleTw { float2 r[8], i[8], n[8]; };   // (re,re), (im,im), (-im,-im); index 0 unused
+struct AngleTw { float2 r[8], i[8]; };   // (re,re), (im,im); index 0 unused
 
 // One angle task: rows n0 = 2j'Q + q and n1 = n0 + Q, 8 channel samples each -> twiddle -> forward DFT-8
 // -> |.|^2.  re/im/v: .x belongs to row n0, .y to row n1.  Pure _rn intrinsics: re-evaluating a row
@@ -110,7 +110,7 @@ __device__ __forceinline__ void angle_pair(const float4 *__restrict__ ys, int NR
     }
 #pragma unroll
     for (int p = 1; p < 8; p++) {
-        const float2 r = __ffma2_rn(im[p], tw.n[p], __fmul2_rn(re[p], tw.r[p]));
+        const float2 r = __ffma2_rn(mk(-im[p].x, -im[p].y), tw.i[p], __fmul2_rn(re[p], tw.r[p]));   // negation: operand modifier
         const float2 i = __ffma2_rn(im[p], tw.r[p], __fmul2_rn(re[p], tw.i[p]));
         re[p] = r;
         im[p] = i;
@@ -160,7 +160,6 @@ __global__ void __launch_bounds__(256, 2) k_fused64x8(const FusedParams P)
         const c32 t = cispi_ratio(j * (NA - 2 * (b + IA * rot)), NA);
         tw3.r[j] = mk(t.x, t.x);
         tw3.i[j] = mk(t.y, t.y);
-        tw3.n[j] = mk(-t.y, -t.y);
     }
     for (int e = tid; e < 8 * Q; e += 256) tw2t[e] = cispi_ratio(2 * (e / Q) * (e % Q), NR);
     const EstParams est = P.est;
