@@ -380,7 +380,7 @@ static jrc_status launch_angle_mag_t(jrc_chain *h, const c32 *Y, int V, int Nr, 
 {
     using Gm = TiledGeom<LOG2NA>;
     auto kern = (V <= Gm::N / 8) ? k_angle_mag<LOG2NA, true> : k_angle_mag<LOG2NA, false>;
-    const size_t smem = 2 * Gm::SMEM;      // double-buffered tiles
+    const size_t smem = 2 * Gm::SMEM + (size_t)DifTwS<LOG2NA>::table_entries() * sizeof(c32);   // double-buffered tiles + twiddles
     CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, smem));

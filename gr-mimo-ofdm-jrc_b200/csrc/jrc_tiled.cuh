@@ -24,6 +24,7 @@
 // Same float32 arithmetic class as the oracle's radix-2 FFT, not its rounding: the parity criterion is
 // 1e-4 of the map peak (tests), detections bit-exact whenever the peak is not a rounding-level tie.
 #pragma once
+#include <type_traits>
 #include "jrc_common.cuh"
 #include "jrc_staged.cuh"
 
@@ -81,17 +82,48 @@ struct DifTw {
             }
         }
     }
+    __device__ __forceinline__ c32 get(int i, int k) const { return w[i][k - 1]; }
+};
+
+// The same factors kept in shared memory (7 per distinct thread index and pass) instead of 14 registers per
+// pass: k_angle_mag trades 14 broadcast LDS per pass for a third resident CTA per SM.
+template <int LOG2N>
+struct DifTwS {
+    const c32 *p[TiledGeom<LOG2N>::NTW > 0 ? TiledGeom<LOG2N>::NTW : 1];
+    static constexpr int table_entries()      // sum over passes of 7 * (distinct j of the pass)
+    {
+        int n = 0;
+        for (int i = 0; i < TiledGeom<LOG2N>::NTW; i++) n += 7 << (LOG2N - 3 * i - 3);
+        return n;
+    }
+    // fills the table (all threads of the CTA, followed by the caller's __syncthreads) and points at this thread's rows
+    __device__ __forceinline__ void init(c32 *table, const c32 *__restrict__ tw, int j0, int t, int tid, int nthreads)
+    {
+        int off = 0;
+#pragma unroll
+        for (int i = 0; i < TiledGeom<LOG2N>::NTW; i++) {
+            const int nj = 1 << (LOG2N - 3 * i - 3);
+            for (int e = tid; e < 7 * nj; e += nthreads) {
+                const int j = e / 7, k = e % 7 + 1;
+                table[off + e] = __ldg(tw + (j << (3 * i)) * k);
+            }
+            const int j = i == 0 ? j0 : (t & (nj - 1));
+            p[i] = table + off + 7 * j;
+            off += 7 * nj;
+        }
+    }
+    __device__ __forceinline__ c32 get(int i, int k) const { return p[i][k - 1]; }
 };
 
 // First pass when only inputs j < N/8 can be non-zero: u[k] = x_j * w_N^{j k}, written to the 8 places
 // the full pass would write.  (r, j) of this thread is the caller's choice (coalesced HBM reads).
-template <int LOG2N>
-__device__ __forceinline__ void dif_first_pruned(c32 *x, int j, c32 xj, const DifTw<LOG2N> &T)
+template <int LOG2N, class TW>
+__device__ __forceinline__ void dif_first_pruned(c32 *x, int j, c32 xj, const TW &T)
 {
     constexpr int s = 1 << (LOG2N - 3);
     x[fpad(j)] = xj;
 #pragma unroll
-    for (int k = 1; k < 8; k++) x[fpad(j + k * s)] = cmul_fma(xj, T.w[0][k - 1]);
+    for (int k = 1; k < 8; k++) x[fpad(j + k * s)] = cmul_fma(xj, T.get(0, k));
 }
 
 // Passes of one row of N = 2^LOG2N points in shared memory (index i at x[fpad(i)]) by N/8 threads,
@@ -100,8 +132,8 @@ __device__ __forceinline__ void dif_first_pruned(c32 *x, int j, c32 xj, const Di
 // position 8t + c, i.e. frequency dif_freq(8t + c).
 // The caller must synchronise the row before this call; all threads of the CTA must call it together
 // unless WARP_SYNC.
-template <int LOG2N, int DIR, bool WARP_SYNC, bool SKIP_FIRST>
-__device__ __forceinline__ void dif_passes(c32 *x, int t, const DifTw<LOG2N> &T, c32 (&out)[8])
+template <int LOG2N, int DIR, bool WARP_SYNC, bool SKIP_FIRST, class TW>
+__device__ __forceinline__ void dif_passes(c32 *x, int t, const TW &T, c32 (&out)[8])
 {
     int log2L = SKIP_FIRST ? LOG2N - 3 : LOG2N;
 #pragma unroll
@@ -113,7 +145,7 @@ __device__ __forceinline__ void dif_passes(c32 *x, int t, const DifTw<LOG2N> &T,
         for (int m = 0; m < 8; m++) u[m] = x[fpad(base + m * s)];
         JRC_FFT8<DIR>(u);
 #pragma unroll
-        for (int k = 1; k < 8; k++) u[k] = cmul_fma(u[k], T.w[i][k - 1]);
+        for (int k = 1; k < 8; k++) u[k] = cmul_fma(u[k], T.get(i, k));
 #pragma unroll
         for (int k = 0; k < 8; k++) x[fpad(base + k * s)] = u[k];
         row_sync<WARP_SYNC>();
@@ -202,8 +234,10 @@ __global__ void __launch_bounds__(TiledGeom<LOG2N>::THREADS) k_fft8_rows(const c
 //   map [n_cpi][Nr][NA]  |.|^2, angle bin fastest, fftshifted
 //   keys[n_cpi]          (map value bits << 32) | (0xFFFFFFFF - range bin): atomicMax, zeroed by the host
 // ---------------------------------------------------------------------------
+// Twiddles: registers (2 CTAs per SM) when the first pass is pruned, shared memory (3 CTAs per SM) otherwise --
+// measured on configs[2] (registers 0.234 ms vs shared 0.250 ms) and configs[4] (0.160 ms vs 0.134 ms).
 template <int LOG2NA, bool PRUNED>
-__global__ void __launch_bounds__(256, 2) k_angle_mag(const c32 *__restrict__ Y, int V, int Nr, int log2_tiles_per_cpi, int n_cpi,
+__global__ void __launch_bounds__(256, PRUNED ? 2 : 3) k_angle_mag(const c32 *__restrict__ Y, int V, int Nr, int log2_tiles_per_cpi, int n_cpi,
                                                       float *__restrict__ map, unsigned long long *__restrict__ keys,
                                                       const c32 *__restrict__ tw)
 {
@@ -225,8 +259,13 @@ __global__ void __launch_bounds__(256, 2) k_angle_mag(const c32 *__restrict__ Y,
     // PRUNED (V <= NA/8): (range bin r fastest, channel p) per thread -> coalesced reads, first pass on the fly,
     // the input of the next tile fetched one iteration ahead
     const int pr = tid % RPC, pp = tid / RPC;
-    DifTw<LOG2NA> T;
-    T.load(tw, PRUNED ? pp : t, t);
+    typename std::conditional<PRUNED, DifTw<LOG2NA>, DifTwS<LOG2NA>>::type T;
+    if constexpr (PRUNED) {
+        T.load(tw, pp, t);
+    } else {
+        T.init(sm + 2 * RPC * RS, tw, t, t, tid, 256);     // table behind the two tile buffers
+        __syncthreads();
+    }
     auto fetch = [&](long long tile) {
         const long long cpi = tile >> log2_tiles_per_cpi;
         const int n0 = ((int)tile & tpc_mask) * RPC;
