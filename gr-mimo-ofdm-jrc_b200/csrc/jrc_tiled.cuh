@@ -126,9 +126,21 @@ __device__ __forceinline__ void dif_first_pruned(c32 *x, int j, c32 xj, const TW
     for (int k = 1; k < 8; k++) x[fpad(j + k * s)] = cmul_fma(xj, T.get(0, k));
 }
 
+// First pass in general, fed from HBM as well: u[m] = x[j + m N/8] (zero beyond n_in), DFT-8, twiddle, store.
+template <int LOG2N, int DIR, class TW>
+__device__ __forceinline__ void dif_first_full(c32 *x, int j, c32 (&u)[8], const TW &T)
+{
+    constexpr int s = 1 << (LOG2N - 3);
+    JRC_FFT8<DIR>(u);
+#pragma unroll
+    for (int k = 1; k < 8; k++) u[k] = cmul_fma(u[k], T.get(0, k));
+#pragma unroll
+    for (int k = 0; k < 8; k++) x[fpad(j + k * s)] = u[k];
+}
+
 // Passes of one row of N = 2^LOG2N points in shared memory (index i at x[fpad(i)]) by N/8 threads,
 // t = this thread's index within the row.  DIR = -1 forward, +1 backward.  SKIP_FIRST: the first pass was
-// done by dif_first_pruned.  The last pass leaves 8 results per thread in out[]: out[c] belongs to
+// done by dif_first_pruned / dif_first_full.  The last pass leaves 8 results per thread in out[]: out[c] belongs to
 // position 8t + c, i.e. frequency dif_freq(8t + c).
 // The caller must synchronise the row before this call; all threads of the CTA must call it together
 // unless WARP_SYNC.
@@ -186,7 +198,7 @@ __global__ void __launch_bounds__(TiledGeom<LOG2N>::THREADS) k_fft8_rows(const c
                                                                          const c32 *__restrict__ tw)
 {
     using Gm = TiledGeom<LOG2N>;
-    constexpr int N = Gm::N, RPC = Gm::RPC, RS = Gm::RS, THREADS = Gm::THREADS, TPR = Gm::TPR;
+    constexpr int N = Gm::N, RPC = Gm::RPC, RS = Gm::RS, TPR = Gm::TPR;
     extern __shared__ __align__(16) unsigned char smem_raw_t[];
     c32 *sm = reinterpret_cast<c32 *>(smem_raw_t);
     const int tid = threadIdx.x;
@@ -207,18 +219,18 @@ __global__ void __launch_bounds__(TiledGeom<LOG2N>::THREADS) k_fft8_rows(const c
             xn = mk(0.f, 0.f);
             if (t < n_in && nrow < rows) xn = in[nrow * in_stride + t];
             dif_first_pruned<LOG2N>(xrow, t, xj, T);
-        } else {
-#pragma unroll 4
-            for (int e = tid; e < RPC * N; e += THREADS) {
-                const int lr = e >> LOG2N, i = e & (N - 1);
-                c32 v = mk(0.f, 0.f);
-                if (i < n_in && row0 + lr < rows) v = in[(row0 + lr) * in_stride + i];
-                sm[lr * RS + fpad(i)] = v;
+        } else {           // every thread reads its 8 inputs (stride N/8, coalesced across the row's threads) from HBM
+            c32 u[8];
+#pragma unroll
+            for (int m = 0; m < 8; m++) {
+                const int i = t + m * TPR;
+                u[m] = (i < n_in && row < rows) ? in[row * in_stride + i] : mk(0.f, 0.f);
             }
+            dif_first_full<LOG2N, DIR>(xrow, t, u, T);
         }
         __syncthreads();
         c32 o[8];
-        dif_passes<LOG2N, DIR, Gm::WARP_SYNC, PRUNED>(xrow, t, T, o);
+        dif_passes<LOG2N, DIR, Gm::WARP_SYNC, true>(xrow, t, T, o);
         if (row < rows) {
             c32 *orow = out + row * N;
 #pragma unroll
@@ -263,7 +275,7 @@ __global__ void __launch_bounds__(256, PRUNED ? 2 : 3) k_angle_mag(const c32 *__
     if constexpr (PRUNED) {
         T.load(tw, pp, t);
     } else {
-        T.init(sm + 2 * RPC * RS, tw, t, t, tid, 256);     // table behind the two tile buffers
+        T.init(sm + 2 * RPC * RS, tw, pp, t, tid, 256);     // table behind the two tile buffers
         __syncthreads();
     }
     auto fetch = [&](long long tile) {
@@ -305,16 +317,20 @@ __global__ void __launch_bounds__(256, PRUNED ? 2 : 3) k_angle_mag(const c32 *__
             xq[PF - 1] = fetch(tile + PF);
             dif_first_pruned<LOG2NA>(rows + pr * RS, pp, xj, T);
         } else {
-            // transposing load: for every channel RPC consecutive range bins (contiguous in HBM)
-            const c32 *Yc = Y + (long long)cpi * V * Nr + n0;
-            for (int e = tid; e < NA * RPC; e += 256) {
-                const int p = e / RPC, r = e % RPC;
-                rows[r * RS + fpad(p)] = p < V ? Yc[(long long)p * Nr + r] : mk(0.f, 0.f);   // angle zero-pad
+            // transposing load: thread (range bin r fastest, j) reads channels j + m NA/8 -- per channel RPC consecutive
+            // range bins, contiguous in HBM -- and runs the first pass on them
+            const c32 *Yc = Y + (long long)cpi * V * Nr + n0 + pr;
+            c32 u[8];
+#pragma unroll
+            for (int m = 0; m < 8; m++) {
+                const int p = pp + m * TPR;
+                u[m] = p < V ? Yc[(long long)p * Nr] : mk(0.f, 0.f);   // angle zero-pad
             }
+            dif_first_full<LOG2NA, -1>(rows + pr * RS, pp, u, T);
         }
         __syncthreads();
         c32 o[8];
-        dif_passes<LOG2NA, -1, Gm::WARP_SYNC, PRUNED>(rows + lr_t * RS, t, T, o);
+        dif_passes<LOG2NA, -1, Gm::WARP_SYNC, true>(rows + lr_t * RS, t, T, o);
         float v[8];
 #pragma unroll
         for (int c = 0; c < 8; c++) v[c] = __fadd_rn(__fmul_rn(o[c].x, o[c].x), __fmul_rn(o[c].y, o[c].y));
