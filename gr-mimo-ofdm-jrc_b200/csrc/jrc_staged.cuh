@@ -66,6 +66,7 @@ __global__ void __launch_bounds__(256) k_chan_est_tile(PortDev rx, PortDev tx, i
         for (int r = 0; r < RR; r++)
 #pragma unroll
             for (int t = 0; t < TT; t++) acc[r][t] = mk(0.f, 0.f);
+#pragma unroll 2
         for (int s = 0; s < S; s++) {
             c32 a[RR], b[TT];
 #pragma unroll
