@@ -638,7 +638,7 @@ static jrc_status launch_tc_t(jrc_chain *h, const TcParams &P)
     CU(cudaGetLastError());
     h->launches++;
     if (P.dets) {
-        k_map_finalize<<<(unsigned)((P.n_cpi + 3) / 4), 128, (size_t)Gm::NA * sizeof(float), h->stream>>>(
+        k_map_finalize<<<(unsigned)P.n_cpi, 128, (size_t)Gm::NA * sizeof(float), h->stream>>>(
             P.map, P.keys, P.n_cpi, Gm::NR, Gm::NA, P.est, P.dets, P.cpi0);
         CU(cudaGetLastError());
         h->launches++;
@@ -768,7 +768,7 @@ extern "C" jrc_status jrc_chain_run_batch(jrc_chain *h, jrc_port_layout rx, jrc_
             ST(launch_fused<false>(h, P, &ok));
         }
         if (ok && map_backed) {
-            k_map_finalize<<<(unsigned)((n_cpi + 3) / 4), 128, (size_t)Na * sizeof(float), h->stream>>>(
+            k_map_finalize<<<(unsigned)n_cpi, 128, (size_t)Na * sizeof(float), h->stream>>>(
                 map, (const unsigned long long *)h->sKeys.p, n_cpi, Nr, Na, P.est, (DetDev *)dets, cpi0);
             CU(cudaGetLastError());
             h->launches++;
@@ -808,7 +808,7 @@ extern "C" jrc_status jrc_chain_run_batch(jrc_chain *h, jrc_port_layout rx, jrc_
             if (dK) CU(cudaMemsetAsync(dK, 0, sizeof(unsigned long long) * (size_t)nc, h->stream));
             ST(launch_angle_mag(h, dY, V, Nr, Na, nc, dM, dK));
             if (dets) {
-                k_map_finalize<<<(unsigned)((nc + 3) / 4), 128, (size_t)Na * sizeof(float), h->stream>>>(
+                k_map_finalize<<<(unsigned)nc, 128, (size_t)Na * sizeof(float), h->stream>>>(
                     dM, dK, nc, Nr, Na, EP, (DetDev *)dets + c0, cpi0 + c0);
                 CU(cudaGetLastError());
                 h->launches++;

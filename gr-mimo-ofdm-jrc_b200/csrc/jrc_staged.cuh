@@ -467,23 +467,25 @@ __global__ void k_est_finalize(const c32 *__restrict__ map, long long per_mat, i
 // ---------------------------------------------------------------------------
 // Detection record from a per-CPI arg-max key and the |.|^2 map (used behind the fused kernels when the
 // map is written anyway): key = (map value bits << 32) | (0xFFFFFFFF - range bin n), the earliest row
-// among equal values.  One warp per CPI: first bin of row n that holds the value, noise window
+// among equal values.  One CTA per CPI: first bin of row n that holds the value, noise window
 // (lib/range_angle_estimator_impl.cc:152-227) read back from the map, SNR gate (:234).
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) k_map_finalize(const float *__restrict__ map, const unsigned long long *__restrict__ keys,
                                                       int n_cpi, int NR, int NA, EstParams P, DetDev *__restrict__ dets, int cpi0)
 {
     extern __shared__ float s_abins[];     // angle_bins copy: the window geometry's binary search stays on chip
+    __shared__ int s_istar[4];
+    __shared__ double s_acc[4];
     for (int i = threadIdx.x; i < NA; i += blockDim.x) s_abins[i] = P.angle_bins[i];
     __syncthreads();
     EstParams est = P;
     est.angle_bins = s_abins;
-    const int lane = threadIdx.x & 31;
-    const int cpi = blockIdx.x * 4 + (threadIdx.x >> 5);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int cpi = blockIdx.x;            // one CTA per CPI: the window reads are latency bound, 128 lanes keep 1024 in flight
     if (cpi >= n_cpi) return;
     const unsigned long long key = keys[cpi];
     if (key == 0ull) {   // NaN-only input: nothing can win the strict '>' scan
-        if (lane == 0) {
+        if (tid == 0) {
             DetDev d; d.range_idx = -1; d.angle_idx = -1; d.peak_power = -1.f;
             d.noise_power = __int_as_float(0x7fc00000); d.snr_db = d.noise_power;
             d.n_noise = 0; d.flags = 0; d.cpi = cpi0 + cpi;
@@ -495,25 +497,23 @@ __global__ void __launch_bounds__(128) k_map_finalize(const float *__restrict__ 
     const int nstar = (int)(0xFFFFFFFFu - (unsigned)(key & 0xFFFFFFFFull));
     const float *map_c = map + (long long)cpi * NR * NA;
     int istar = 0x7fffffff;
-    for (int i0 = 0; i0 < NA && istar == 0x7fffffff; i0 += 128) {    // 4 loads in flight per lane
-        float v[4];
+    for (int i = tid; i < NA; i += 128)
+        if (__ldcg(map_c + (long long)nstar * NA + i) == peak && i < istar) istar = i;
 #pragma unroll
-        for (int q = 0; q < 4; q++) { const int i = i0 + lane + 32 * q; v[q] = i < NA ? __ldcg(map_c + (long long)nstar * NA + i) : -1.f; }
-#pragma unroll
-        for (int q = 3; q >= 0; q--) if (v[q] == peak) istar = i0 + lane + 32 * q;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) istar = min(istar, __shfl_xor_sync(0xffffffffu, istar, o));
-    }
+    for (int o = 16; o > 0; o >>= 1) istar = min(istar, __shfl_xor_sync(0xffffffffu, istar, o));
+    if (lane == 0) s_istar[warp] = istar;
+    __syncthreads();
+    istar = min(min(s_istar[0], s_istar[1]), min(s_istar[2], s_istar[3]));
     if (istar == 0x7fffffff) istar = 0;      // cannot happen: the key was built from this row
     const NoiseWin w = noise_window(est, nstar, istar);
     const int ncols = w.end_a - w.start_a, nrows = w.end_r - w.start_r;
     const int total = (ncols > 0 && nrows > 0) ? nrows * ncols : 0;
     double acc = 0.0;
-    for (int j0 = lane; j0 < total; j0 += 32 * 8) {      // 8 independent loads in flight per lane
+    for (int j0 = tid; j0 < total; j0 += 128 * 8) {      // 8 independent loads in flight per lane
         float v[8];
 #pragma unroll
         for (int q = 0; q < 8; q++) {
-            const int j = j0 + 32 * q;
+            const int j = j0 + 128 * q;
             v[q] = 0.f;
             if (j < total) {
                 const int ir = w.start_r + j / ncols, ia = w.start_a + j % ncols;
@@ -526,7 +526,10 @@ __global__ void __launch_bounds__(128) k_map_finalize(const float *__restrict__ 
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if (lane == 0) {
+    if (lane == 0) s_acc[warp] = acc;
+    __syncthreads();
+    if (tid == 0) {
+        acc = (s_acc[0] + s_acc[1]) + (s_acc[2] + s_acc[3]);
         DetDev d;
         d.range_idx = nstar; d.angle_idx = istar; d.peak_power = peak; d.n_noise = total;
         d.noise_power = __fdiv_rn((float)acc, (float)total);
