@@ -57,6 +57,11 @@ struct TiledGeom {
     static constexpr bool WARP_SYNC = TPR <= 32;
 };
 
+// fpad(base + m*s) - fpad(base) for base = (multiple of 8) + j, j < s, s a power of two: a compile-time
+// constant (m*s never straddles a multiple of 8 together with j), so the 8 accesses of a pass are one base
+// address plus immediates
+__device__ __forceinline__ constexpr int fpad_step(int m, int s) { return m * s + ((m * s) >> 3); }
+
 template <bool WARP_SYNC>
 __device__ __forceinline__ void row_sync() { if (WARP_SYNC) __syncwarp(); else __syncthreads(); }
 
@@ -121,9 +126,10 @@ template <int LOG2N, class TW>
 __device__ __forceinline__ void dif_first_pruned(c32 *x, int j, c32 xj, const TW &T)
 {
     constexpr int s = 1 << (LOG2N - 3);
-    x[fpad(j)] = xj;
+    c32 *xb = x + fpad(j);
+    xb[0] = xj;
 #pragma unroll
-    for (int k = 1; k < 8; k++) x[fpad(j + k * s)] = cmul_fma(xj, T.get(0, k));
+    for (int k = 1; k < 8; k++) xb[fpad_step(k, s)] = cmul_fma(xj, T.get(0, k));
 }
 
 // First pass in general, fed from HBM as well: u[m] = x[j + m N/8] (zero beyond n_in), DFT-8, twiddle, store.
@@ -134,8 +140,9 @@ __device__ __forceinline__ void dif_first_full(c32 *x, int j, c32 (&u)[8], const
     JRC_FFT8<DIR>(u);
 #pragma unroll
     for (int k = 1; k < 8; k++) u[k] = cmul_fma(u[k], T.get(0, k));
+    c32 *xb = x + fpad(j);
 #pragma unroll
-    for (int k = 0; k < 8; k++) x[fpad(j + k * s)] = u[k];
+    for (int k = 0; k < 8; k++) xb[fpad_step(k, s)] = u[k];
 }
 
 // Passes of one row of N = 2^LOG2N points in shared memory (index i at x[fpad(i)]) by N/8 threads,
@@ -152,38 +159,43 @@ __device__ __forceinline__ void dif_passes(c32 *x, int t, const TW &T, c32 (&out
     for (int i = SKIP_FIRST ? 1 : 0; i < TiledGeom<LOG2N>::NTW; i++, log2L -= 3) {
         const int s = 1 << (log2L - 3);              // distance of the 8 inputs = L/8
         const int j = t & (s - 1), base = ((t >> (log2L - 3)) << log2L) + j;
+        c32 *xb = x + fpad(base);
         c32 u[8];
 #pragma unroll
-        for (int m = 0; m < 8; m++) u[m] = x[fpad(base + m * s)];
+        for (int m = 0; m < 8; m++) u[m] = xb[fpad_step(m, s)];
         JRC_FFT8<DIR>(u);
 #pragma unroll
         for (int k = 1; k < 8; k++) u[k] = cmul_fma(u[k], T.get(i, k));
 #pragma unroll
-        for (int k = 0; k < 8; k++) x[fpad(base + k * s)] = u[k];
+        for (int k = 0; k < 8; k++) xb[fpad_step(k, s)] = u[k];
         row_sync<WARP_SYNC>();
     }
     // last pass: 8 consecutive points 8t .. 8t+7
+    {
+        const c32 *xb = x + 9 * t;                    // fpad(8t + m) = 9t + m
 #pragma unroll
-    for (int m = 0; m < 8; m++) out[m] = x[fpad(8 * t + m)];
+        for (int m = 0; m < 8; m++) out[m] = xb[m];
+    }
     if (log2L == 3) {
         JRC_FFT8<DIR>(out);
     } else if (log2L == 2) {
 #pragma unroll
         for (int h = 0; h < 2; h++) {
             const c32 a = out[4 * h], b = out[4 * h + 1], c = out[4 * h + 2], d = out[4 * h + 3];
-            const c32 s0 = cadd_exact(a, c), s1 = csub_exact(a, c), s2 = cadd_exact(b, d), s3 = csub_exact(b, d);
+            const c32 s0 = __fadd2_rn(a, c), s1 = __fadd2_rn(a, mk(-c.x, -c.y)), s2 = __fadd2_rn(b, d);
+            const c32 s3 = __fadd2_rn(b, mk(-d.x, -d.y));
             const c32 r3 = DIR < 0 ? mk(s3.y, -s3.x) : mk(-s3.y, s3.x);    // -j / +j times (b - d)
-            out[4 * h] = cadd_exact(s0, s2);
-            out[4 * h + 2] = csub_exact(s0, s2);
-            out[4 * h + 1] = cadd_exact(s1, r3);
-            out[4 * h + 3] = csub_exact(s1, r3);
+            out[4 * h] = __fadd2_rn(s0, s2);
+            out[4 * h + 2] = __fadd2_rn(s0, mk(-s2.x, -s2.y));
+            out[4 * h + 1] = __fadd2_rn(s1, r3);
+            out[4 * h + 3] = __fadd2_rn(s1, mk(-r3.x, -r3.y));
         }
     } else {
 #pragma unroll
         for (int h = 0; h < 4; h++) {
             const c32 a = out[2 * h], b = out[2 * h + 1];
-            out[2 * h] = cadd_exact(a, b);
-            out[2 * h + 1] = csub_exact(a, b);
+            out[2 * h] = __fadd2_rn(a, b);
+            out[2 * h + 1] = __fadd2_rn(a, mk(-b.x, -b.y));
         }
     }
 }
@@ -333,7 +345,10 @@ __global__ void __launch_bounds__(256, PRUNED ? 2 : 3) k_angle_mag(const c32 *__
         dif_passes<LOG2NA, -1, Gm::WARP_SYNC, true>(rows + lr_t * RS, t, T, o);
         float v[8];
 #pragma unroll
-        for (int c = 0; c < 8; c++) v[c] = __fadd_rn(__fmul_rn(o[c].x, o[c].x), __fmul_rn(o[c].y, o[c].y));
+        for (int c = 0; c < 8; c++) {       // re*re + im*im, each product rounded (VOLK's generic kernel)
+            const c32 sq = __fmul2_rn(o[c], o[c]);
+            v[c] = __fadd_rn(sq.x, sq.y);
+        }
         if (map) {
             float *mrow = map + ((long long)cpi * Nr + n0 + lr_t) * NA;
 #pragma unroll
