@@ -26,7 +26,7 @@
 #include "jrc_staged.cuh"
 
 #ifndef JRC_STORE_MODE
-#define JRC_STORE_MODE 0   // 0: LDS.128 + STG.128 from the staging tiles; 1: per-warp cp.async.bulk (A/B build)
+#define JRC_STORE_MODE 0   // 0: LDS.128 + STG.128 from the staging tiles; A/B builds: 1 per-warp cp.async.bulk, 2 direct STG.32
 #endif
 
 namespace jrc {
@@ -151,7 +151,7 @@ __global__ void __launch_bounds__(256, 2) k_fused64x8(const FusedParams P)
     // range pass 2: task q = 32 half + lane + 64 i;                 twiddle W_Nr^{k0 q} from tw2t
     // angle pass:   task (n, b);                                    twiddle (-1)^p w_Na^{p (b + IA*rot)}
     const int q0 = lane % IR;
-    const int b = lane % IA, g = lane / IA, rot = g;
+    const int b = lane % IA, g = lane / IA, rot = (JRC_STORE_MODE == 2) ? 0 : g;
     c32 tw1[8];
     AngleTw tw3;
 #pragma unroll
@@ -338,6 +338,14 @@ __global__ void __launch_bounds__(256, 2) k_fused64x8(const FusedParams P)
                 if (WRITE_MAP) {
                     // conflict-free scalar st.shared of the strided bins, then the warp streams its two
                     // 1 KiB tiles (G whole map rows each, contiguous in HBM) out as 4 x 512 B
+#if JRC_STORE_MODE == 2
+                    {   // A/B: no staging -- every warp store writes G x IA/8 full 32-byte sectors
+                        float *d0 = reinterpret_cast<float *>(map_w + it * (TILE / 4)) + g * NA + b;
+#pragma unroll
+                        for (int a = 0; a < 8; a++) { __stcs(d0 + IA * a, v[a].x); __stcs(d0 + Q * NA + IA * a, v[a].y); }
+                    }
+                    continue;
+#endif
 #if JRC_STORE_MODE == 1
                     // A/B: the two tiles leave through the bulk-copy engine instead of LDS.128 + STG.128
                     if (elect_one()) bulk_wait_read0();   // the previous iteration's copies have read the tiles
