@@ -419,3 +419,77 @@ def test_target_simulator_is_bit_exact(jrc, orc, n):
     base = orc.target_simulator(x, [12.0], [0.0], [1.0], [10.0], pos, 125000000, 24e9, False, -10.0, False)
     ratio = o1[0][np.abs(base[0]) > 1e-9] / base[0][np.abs(base[0]) > 1e-9]
     assert np.allclose(np.abs(ratio), 1.0, atol=1e-4) and np.allclose(ratio, ratio[0], atol=1e-3)
+
+
+def test_tc_kernel_variant_matches_oracle(jrc, orc, monkeypatch):
+    """The tensor-core form (JRC_FUSED_KERNEL=tc, jrc_tc.cuh: angle DFT as a 3xTF32 tcgen05 GEMM with TMEM
+    accumulators) is opt-in; it must satisfy the north-star tolerance and find the same peaks."""
+    monkeypatch.setenv("JRC_FUSED_KERNEL", "tc")
+    for name in ("C1", "C2"):
+        cfg = CFGS[name]
+        est = est_for(cfg)
+        rx, tx, _ = scene(cfg, 64, seed=19, n_targets=2, amp_db_span=12.0, tx_per_cpi=True)
+        ch = gpu_chain(jrc, cfg, est)
+        m, d = ch.run_host(rx, tx)
+        assert ch.last_path == jrc.PATH_FUSED and ch.launch_count >= 3      # chan_est + tc + finalize
+        mo, _, do = oracle(orc, rx, tx, cfg, est)
+        peak = mo.reshape(64, -1).max(axis=1)
+        assert (np.abs(m - mo).reshape(64, -1).max(axis=1) / peak).max() <= 1e-4
+        ok = top2_margin(mo) > 1e-3
+        assert ok.sum() >= 56
+        assert np.array_equal(d["range_idx"][ok], do["range_idx"][ok])
+        assert np.array_equal(d["angle_idx"][ok], do["angle_idx"][ok])
+
+
+@pytest.mark.parametrize("name", ["C2", "C3s"])
+def test_degenerate_inputs(jrc, orc, name):
+    """Empty batch, all-zero CPIs and NaN CPIs on the fused (C2) and the tiled (C3s) path: no launch for an empty
+    batch; a zero map keeps the scan's initial peak (0, 0) like the reference (strict '>' never fires) and is
+    gated out; a NaN CPI is reported with the -1 sentinel and no detection, and does not disturb its neighbours."""
+    cfg = CFGS[name]
+    est = est_for(cfg)
+    ch = gpu_chain(jrc, cfg, est)
+    rx, tx, _ = scene(cfg, 6, seed=23, tx_per_cpi=True)
+    l0 = ch.launch_count
+    m, d = ch.run_host(rx[:0], tx[:0])
+    assert m.shape[0] == 0 and d.shape[0] == 0 and ch.launch_count == l0
+    rx[1] = 0
+    rx[3] = np.nan
+    m, d = ch.run_host(rx, tx)
+    mo, _, do = oracle(orc, rx, tx, cfg, est)
+    good = [0, 2, 4, 5]
+    assert np.array_equal(d["range_idx"][good], do["range_idx"][good]) and np.array_equal(d["angle_idx"][good], do["angle_idx"][good])
+    assert np.array_equal(d["flags"][good], do["flags"][good]) and d["flags"][good].all()
+    assert not m[1].any() and (d["range_idx"][1], d["angle_idx"][1], d["flags"][1]) == (0, 0, 0)
+    assert (do["range_idx"][1], do["angle_idx"][1], do["flags"][1]) == (0, 0, 0)
+    assert np.isnan(m[3]).all() and d["flags"][3] == 0 and d["range_idx"][3] == -1 and do["flags"][3] == 0
+
+
+def test_tiled_path_with_background_removal_and_requests(jrc, orc):
+    """Tiled path: per-CPI TX frames, the background ring in front of the range FFT, explicit path requests."""
+    cfg = CFGS["C3s"]
+    est = est_for(cfg)
+    n = 10
+    rx, tx, _ = scene(cfg, n, seed=29, n_targets=2, amp_db_span=6.0, tx_per_cpi=True)
+    ch = gpu_chain(jrc, cfg, est, background_removal=True, background_recording=True, record_len=3)
+    m, d = ch.run_host(rx, tx)
+    assert ch.last_path == jrc.PATH_TILED
+    rad = orc.Radar(cfg["N"], cfg["T"], cfg["R"], cfg["S"], 0, True, True, 3, cfg["IR"], False)
+    V = cfg["T"] * cfg["R"]
+    for c in range(n):
+        pad = rad.work(list(tx[c].reshape(cfg["T"], -1)), list(rx[c].reshape(cfg["R"], -1)))
+        mo = orc.mag_squared(orc.fft_vcc(orc.matrix_transpose(orc.fft_vcc(pad, False, False), V, cfg["IA"]), True, True))
+        assert np.abs(m[c] - mo).max() <= 1e-5 * mo.max() + 1e-3, c
+    import torch
+    rc = jrc.radar_chain(cfg["N"], cfg["T"], cfg["R"], cfg["S"], cfg["IR"], cfg["IA"], estimator=est)
+    drx, dtx = torch.from_numpy(rx).cuda(), torch.from_numpy(tx).cuda()
+    m1, d1 = rc.run(drx, dtx, path=jrc.PATH_TILED)
+    m2, d2 = rc.run(drx, dtx, path=jrc.PATH_STAGED)
+    rc.sync()
+    assert (m1 - m2).abs().max().item() <= 1e-5 * m2.max().item()
+    with pytest.raises(jrc.JrcError):
+        rc.run(drx, dtx, path=jrc.PATH_FUSED)            # no fused specialisation for 32 channels
+    rc2 = jrc.radar_chain(32, 2, 2, 3, 2, 4, estimator=synth.default_estimator_params(32, 4, 2, 4))   # 64 x 16 map
+    rx2, tx2, _ = scene(CFGS["odd"], 4, seed=1)
+    with pytest.raises(jrc.JrcError):
+        rc2.run(torch.from_numpy(rx2).cuda(), torch.from_numpy(tx2).cuda(), path=jrc.PATH_TILED)   # Na = 16 < 64
