@@ -105,6 +105,7 @@ struct jrc_chain {
     int64_t launches = 0;
     int fused_ctas_per_sm = 0;
     c32 *d_tw1g = nullptr, *d_tw2g = nullptr;   // slice-streaming kernel twiddle tables
+    int zero_copy = 1;                          // latency mode: kernel reads/writes pinned host memory directly (JRC_ZEROCOPY=0 disables)
     int det_mode = 1;                           // 1: in-kernel estimator (faster on B200); 0 (JRC_DET=map): key + k_map_finalize when the map is written
     float *d_bblob = nullptr;                   // tensor-core kernel: swizzled [Bhi | Blo] angle-DFT operand
     int stream_mode = 0;                        // map-producing kernel: 0 k_fused64x8, 1 k_stream64x8, 2 k_tc64x8 (JRC_FUSED_KERNEL)
@@ -169,6 +170,7 @@ extern "C" jrc_status jrc_chain_create(const jrc_chain_cfg *cfg, jrc_chain **out
     }
     h->pin_a.pinned = h->pin_b.pinned = true;
     if (const char *e = getenv("JRC_DET")) h->det_mode = !strcmp(e, "map") ? 0 : 1;
+    if (const char *e = getenv("JRC_ZEROCOPY")) h->zero_copy = atoi(e) != 0;
     if (const char *e = getenv("JRC_FUSED_KERNEL"))   // A/B switch for measurements: cta | stream | tc
         h->stream_mode = !strcmp(e, "stream") ? 1 : (!strcmp(e, "tc") ? 2 : 0);
     const size_t vn = (size_t)h->V * cfg->fft_len;
@@ -910,6 +912,28 @@ extern "C" jrc_status jrc_chain_run_host(jrc_chain *h, const jrc_c32 *rx_host, c
             memcpy((c32 *)h->pin_a.p + (size_t)n_cpi * rx_cpi, src_tx, txn * sizeof(c32));
             src_rx = (const c32 *)h->pin_a.p;
             src_tx = src_rx + (size_t)n_cpi * rx_cpi;
+        }
+        float *dst_map0 = map_host;
+        jrc_det *dst_dets0 = dets_host;
+        if (!direct) {
+            dst_map0 = map_host ? (float *)h->pin_b.p : nullptr;
+            dst_dets0 = dets_host ? (jrc_det *)((char *)h->pin_b.p + (map_host ? (size_t)chunk * map_cpi * sizeof(float) : 0)) : nullptr;
+        }
+        if (h->zero_copy && n_cpi <= 4) {
+            // A few CPIs: the copies cost more than the kernel.  Pinned host memory is device-accessible (unified
+            // addressing): the kernel prefetches the symbols over PCIe itself and streams map and records
+            // straight into the host buffers while it computes -- one launch, one synchronisation.
+            jrc_port_layout zrx{(const jrc_c32 *)src_rx, (int64_t)rx_cpi, (int64_t)c.n_sym * c.fft_len};
+            jrc_port_layout ztx{(const jrc_c32 *)src_tx, tx_shared ? 0 : (int64_t)tx_cpi, (int64_t)c.n_sym * c.fft_len};
+            st = jrc_chain_run_batch(h, zrx, ztx, n_cpi, cpi0, dst_map0, nullptr, dst_dets0, JRC_PATH_AUTO);
+            h->cfg = saved;
+            if (st != JRC_OK) return st;
+            CU(cudaStreamSynchronize(h->stream));
+            if (!direct) {
+                if (map_host) memcpy(map_host, dst_map0, (size_t)n_cpi * map_cpi * sizeof(float));
+                if (dets_host) memcpy(dets_host, dst_dets0, (size_t)n_cpi * sizeof(jrc_det));
+            }
+            return JRC_OK;
         }
         cudaError_t e = cudaMemcpyAsync(d_rx, src_rx, (size_t)n_cpi * rx_cpi * sizeof(c32), cudaMemcpyHostToDevice, h->stream);
         if (e == cudaSuccess) e = cudaMemcpyAsync(d_tx, src_tx, txn * sizeof(c32), cudaMemcpyHostToDevice, h->stream);
