@@ -864,6 +864,15 @@ static bool host_ptr_is_pinned(const void *p)
     if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
     return a.type == cudaMemoryTypeHost;
 }
+// device-side alias of a pinned host pointer (unified addressing: normally the pointer itself), nullptr when the
+// memory is not mapped into the device's address space
+static void *host_dev_alias(const void *p)
+{
+    if (!p) return nullptr;
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return a.type == cudaMemoryTypeHost ? a.devicePointer : nullptr;
+}
 static bool ptr_is_device(const void *p)
 {
     cudaPointerAttributes a;
@@ -919,13 +928,16 @@ extern "C" jrc_status jrc_chain_run_host(jrc_chain *h, const jrc_c32 *rx_host, c
             dst_map0 = map_host ? (float *)h->pin_b.p : nullptr;
             dst_dets0 = dets_host ? (jrc_det *)((char *)h->pin_b.p + (map_host ? (size_t)chunk * map_cpi * sizeof(float) : 0)) : nullptr;
         }
-        if (h->zero_copy && n_cpi <= 4) {
+        const c32 *z_rx = (const c32 *)host_dev_alias(src_rx), *z_tx = (const c32 *)host_dev_alias(src_tx);
+        float *z_map = (float *)host_dev_alias(dst_map0);
+        jrc_det *z_dets = (jrc_det *)host_dev_alias(dst_dets0);
+        if (h->zero_copy && n_cpi <= 4 && z_rx && z_tx && (!map_host || z_map) && (!dets_host || z_dets)) {
             // A few CPIs: the copies cost more than the kernel.  Pinned host memory is device-accessible (unified
             // addressing): the kernel prefetches the symbols over PCIe itself and streams map and records
             // straight into the host buffers while it computes -- one launch, one synchronisation.
-            jrc_port_layout zrx{(const jrc_c32 *)src_rx, (int64_t)rx_cpi, (int64_t)c.n_sym * c.fft_len};
-            jrc_port_layout ztx{(const jrc_c32 *)src_tx, tx_shared ? 0 : (int64_t)tx_cpi, (int64_t)c.n_sym * c.fft_len};
-            st = jrc_chain_run_batch(h, zrx, ztx, n_cpi, cpi0, dst_map0, nullptr, dst_dets0, JRC_PATH_AUTO);
+            jrc_port_layout zrx{(const jrc_c32 *)z_rx, (int64_t)rx_cpi, (int64_t)c.n_sym * c.fft_len};
+            jrc_port_layout ztx{(const jrc_c32 *)z_tx, tx_shared ? 0 : (int64_t)tx_cpi, (int64_t)c.n_sym * c.fft_len};
+            st = jrc_chain_run_batch(h, zrx, ztx, n_cpi, cpi0, z_map, nullptr, z_dets, JRC_PATH_AUTO);
             h->cfg = saved;
             if (st != JRC_OK) return st;
             CU(cudaStreamSynchronize(h->stream));
