@@ -98,7 +98,7 @@ struct jrc_chain {
     c32 *d_ring = nullptr, *d_temp = nullptr;
     int ring_size = 0, ring_head = 0;
     // scratch
-    GrowBuf sH, sY, sC, sKeys, sDet, sIn[2], sMap[2], sDets[2], sMisc, sMisc2;
+    GrowBuf sH, sY, sC, sKeys, sDet, sIn[2], sMap[2], sDets[2], sMisc, sMisc2, sStage[8];
     GrowBuf pin_a, pin_b;
     std::map<std::pair<int, int>, c32 *> twiddles;   // (n, forward) -> device table
     int last_path = 0;
@@ -194,6 +194,7 @@ extern "C" void jrc_chain_destroy(jrc_chain *h)
     GrowBuf *bufs[] = {&h->sH, &h->sY, &h->sC, &h->sKeys, &h->sDet, &h->sIn[0], &h->sIn[1], &h->sMap[0], &h->sMap[1],
                        &h->sDets[0], &h->sDets[1], &h->sMisc, &h->sMisc2, &h->pin_a, &h->pin_b};
     for (GrowBuf *b : bufs) b->release();
+    for (GrowBuf &b : h->sStage) b.release();
     for (auto &kv : h->twiddles_full) cudaFree(kv.second);
     for (auto &kv : h->dft_tabs) cudaFree(kv.second);
     if (h->d_angle_bins) cudaFree(h->d_angle_bins);
@@ -1039,15 +1040,21 @@ struct Staging {   // maps caller pointers onto device memory for the duration o
     jrc_chain *h;
     struct Out { void *host; void *dev; size_t bytes; };
     std::vector<Out> outs;
-    std::vector<void *> temps;
+    int slot = 0;      // grow-only staging buffers of the handle: no allocation on the per-work() path
     explicit Staging(jrc_chain *hh) : h(hh) {}
-    ~Staging() { for (void *p : temps) cudaFree(p); }
+    jrc_status take(size_t bytes, void **d)
+    {
+        if (slot >= (int)(sizeof(h->sStage) / sizeof(h->sStage[0]))) return fail(JRC_ERR_STATE, "too many staged buffers in one call");
+        GrowBuf &b = h->sStage[slot++];
+        ST(b.need(bytes ? bytes : 1));
+        *d = b.p;
+        return JRC_OK;
+    }
     jrc_status in(const void *p, size_t bytes, const void **dev)
     {
         if (ptr_is_device(p)) { *dev = p; return JRC_OK; }
         void *d = nullptr;
-        CU(cudaMalloc(&d, bytes ? bytes : 1));
-        temps.push_back(d);
+        ST(take(bytes, &d));
         CU(cudaMemcpyAsync(d, p, bytes, cudaMemcpyHostToDevice, h->stream));
         *dev = d;
         return JRC_OK;
@@ -1056,8 +1063,7 @@ struct Staging {   // maps caller pointers onto device memory for the duration o
     {
         if (ptr_is_device(p)) { *dev = p; return JRC_OK; }
         void *d = nullptr;
-        CU(cudaMalloc(&d, bytes ? bytes : 1));
-        temps.push_back(d);
+        ST(take(bytes, &d));
         outs.push_back({p, d, bytes});
         *dev = d;
         return JRC_OK;
