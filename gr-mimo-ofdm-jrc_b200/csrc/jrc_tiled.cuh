@@ -33,11 +33,11 @@ namespace jrc {
 __device__ __host__ __forceinline__ constexpr int fpad(int i) { return i + (i >> 3); }
 
 // frequency whose result the DIF passes (radix 8, ..., 8, then 4 or 2) leave at position p
+// (a permutation of bit fields: dif_freq(a | b) = dif_freq(a) | dif_freq(b) for disjoint a, b)
 template <int LOG2N>
-__device__ __forceinline__ int dif_freq(int p)
+__device__ __host__ __forceinline__ constexpr int dif_freq(int p)
 {
     int f = 0, shift = 0, rem = LOG2N;
-#pragma unroll
     for (; rem >= 3; rem -= 3) { f |= ((p >> (rem - 3)) & 7) << shift; shift += 3; }
     if (rem > 0) f |= (p & ((1 << rem) - 1)) << shift;
     return f;
@@ -72,7 +72,8 @@ struct DifTw {
     c32 w[TiledGeom<LOG2N>::NTW > 0 ? TiledGeom<LOG2N>::NTW : 1][7];
     // j0: index of this thread in the first pass (the caller's choice when that pass is pruned), t: index
     // within the row for the other passes
-    __device__ __forceinline__ void load(const c32 *__restrict__ tw, int j0, int t)
+    // alt0: the first-pass factors carry the sign (-1)^j0 (input modulation that moves the output by N/2: fftshift)
+    __device__ __forceinline__ void load(const c32 *__restrict__ tw, int j0, int t, bool alt0 = false)
     {
 #pragma unroll
         for (int i = 0; i < TiledGeom<LOG2N>::NTW; i++) {
@@ -82,6 +83,7 @@ struct DifTw {
 #pragma unroll
             for (int k = 1; k < 8; k++) {
                 c32 v = __ldg(tw + q * k);
+                if (i == 0 && alt0 && (j0 & 1)) v = mk(-v.x, -v.y);
                 asm volatile("" : "+f"(v.x), "+f"(v.y));   // keep it in registers: ptxas would re-load it inside the tile loop
                 w[i][k - 1] = v;
             }
@@ -102,7 +104,8 @@ struct DifTwS {
         return n;
     }
     // fills the table (all threads of the CTA, followed by the caller's __syncthreads) and points at this thread's rows
-    __device__ __forceinline__ void init(c32 *table, const c32 *__restrict__ tw, int j0, int t, int tid, int nthreads)
+    __device__ __forceinline__ void init(c32 *table, const c32 *__restrict__ tw, int j0, int t, int tid, int nthreads,
+                                         bool alt0 = false)
     {
         int off = 0;
 #pragma unroll
@@ -110,7 +113,9 @@ struct DifTwS {
             const int nj = 1 << (LOG2N - 3 * i - 3);
             for (int e = tid; e < 7 * nj; e += nthreads) {
                 const int j = e / 7, k = e % 7 + 1;
-                table[off + e] = __ldg(tw + (j << (3 * i)) * k);
+                c32 v = __ldg(tw + (j << (3 * i)) * k);
+                if (i == 0 && alt0 && (j & 1)) v = mk(-v.x, -v.y);
+                table[off + e] = v;
             }
             const int j = i == 0 ? j0 : (t & (nj - 1));
             p[i] = table + off + 7 * j;
@@ -123,21 +128,22 @@ struct DifTwS {
 // First pass when only inputs j < N/8 can be non-zero: u[k] = x_j * w_N^{j k}, written to the 8 places
 // the full pass would write.  (r, j) of this thread is the caller's choice (coalesced HBM reads).
 template <int LOG2N, class TW>
-__device__ __forceinline__ void dif_first_pruned(c32 *x, int j, c32 xj, const TW &T)
+__device__ __forceinline__ void dif_first_pruned(c32 *x, int j, c32 xj, const TW &T, bool neg0 = false)
 {
     constexpr int s = 1 << (LOG2N - 3);
     c32 *xb = x + fpad(j);
-    xb[0] = xj;
+    xb[0] = neg0 ? mk(-xj.x, -xj.y) : xj;
 #pragma unroll
     for (int k = 1; k < 8; k++) xb[fpad_step(k, s)] = cmul_fma(xj, T.get(0, k));
 }
 
 // First pass in general, fed from HBM as well: u[m] = x[j + m N/8] (zero beyond n_in), DFT-8, twiddle, store.
 template <int LOG2N, int DIR, class TW>
-__device__ __forceinline__ void dif_first_full(c32 *x, int j, c32 (&u)[8], const TW &T)
+__device__ __forceinline__ void dif_first_full(c32 *x, int j, c32 (&u)[8], const TW &T, bool neg0 = false)
 {
     constexpr int s = 1 << (LOG2N - 3);
     JRC_FFT8<DIR>(u);
+    if (neg0) u[0] = mk(-u[0].x, -u[0].y);
 #pragma unroll
     for (int k = 1; k < 8; k++) u[k] = cmul_fma(u[k], T.get(0, k));
     c32 *xb = x + fpad(j);
@@ -244,9 +250,9 @@ __global__ void __launch_bounds__(TiledGeom<LOG2N>::THREADS) k_fft8_rows(const c
         c32 o[8];
         dif_passes<LOG2N, DIR, Gm::WARP_SYNC, true>(xrow, t, T, o);
         if (row < rows) {
-            c32 *orow = out + row * N;
+            c32 *orow = out + row * N + dif_freq<LOG2N>(8 * t);      // + dif_freq(c): immediates
 #pragma unroll
-            for (int c = 0; c < 8; c++) orow[dif_freq<LOG2N>(8 * t + c)] = o[c];
+            for (int c = 0; c < 8; c++) orow[dif_freq<LOG2N>(c)] = o[c];
         }
         __syncthreads();
     }
@@ -272,28 +278,33 @@ __global__ void __launch_bounds__(256, PRUNED ? 2 : 3) k_angle_mag(const c32 *__
     c32 *sm = reinterpret_cast<c32 *>(smem_raw_t);          // two tile buffers: one CTA barrier per tile
     const int tid = threadIdx.x, lane = tid & 31;
     const int lr_t = tid / TPR, t = tid % TPR;
-    // output: position 8t + c holds frequency f = dif_freq; after the fftshift it is angle bin (f + NA/2) mod NA
-    int obin[8];
-#pragma unroll
-    for (int c = 0; c < 8; c++) obin[c] = (dif_freq<LOG2NA>(8 * t + c) + NA / 2) & (NA - 1);
+    // The output fftshift is an input modulation: channel p enters as (-1)^p y[p] (its sign folded into the first
+    // pass's twiddles), so position 8t + c of the last pass holds angle bin dif_freq(8t) + dif_freq(c) directly.
+    const int obin0 = dif_freq<LOG2NA>(8 * t);
     // every CTA takes a contiguous run of tiles, so the running maximum is folded into keys[] once per CPI
     const long long n_tiles = (long long)n_cpi << log2_tiles_per_cpi;
     const long long tile_begin = n_tiles * blockIdx.x / gridDim.x, tile_end = n_tiles * (blockIdx.x + 1) / gridDim.x;
     const int tpc_mask = (1 << log2_tiles_per_cpi) - 1;
-    // PRUNED (V <= NA/8): (range bin r fastest, channel p) per thread -> coalesced reads, first pass on the fly,
-    // the input of the next tile fetched one iteration ahead
+    // thread (range bin r fastest, channel / first-pass index pp): coalesced reads, first pass on the fly
     const int pr = tid % RPC, pp = tid / RPC;
+    const bool neg0 = pp & 1;
     typename std::conditional<PRUNED, DifTw<LOG2NA>, DifTwS<LOG2NA>>::type T;
     if constexpr (PRUNED) {
-        T.load(tw, pp, t);
+        T.load(tw, pp, t, true);
     } else {
-        T.init(sm + 2 * RPC * RS, tw, pp, t, tid, 256);     // table behind the two tile buffers
+        T.init(sm + 2 * RPC * RS, tw, pp, t, tid, 256, true);     // table behind the two tile buffers
         __syncthreads();
     }
-    auto fetch = [&](long long tile) {
-        const long long cpi = tile >> log2_tiles_per_cpi;
-        const int n0 = ((int)tile & tpc_mask) * RPC;
-        return (tile < tile_end && pp < V) ? Y[(cpi * V + pp) * Nr + n0 + pr] : mk(0.f, 0.f);
+    // input pointer of tile ft for this thread, advanced tile by tile (+RPC range bins, next CPI at the wrap)
+    long long ft = tile_begin;
+    const c32 *fp = Y + ((tile_begin >> log2_tiles_per_cpi) * V + pp) * Nr + ((int)tile_begin & tpc_mask) * RPC + pr;
+    const long long cpi_jump = (long long)(V - 1) * Nr;
+    auto fetch_next = [&]() {        // PRUNED: the single non-zero input of the next tile not fetched yet
+        const c32 v = (ft < tile_end && pp < V) ? *fp : mk(0.f, 0.f);
+        ft++;
+        fp += RPC;
+        if (((int)ft & tpc_mask) == 0) fp += cpi_jump;
+        return v;
     };
     auto flush = [&](int cpi, float best, int best_row) {
         if (!keys) return;
@@ -310,10 +321,12 @@ __global__ void __launch_bounds__(256, PRUNED ? 2 : 3) k_angle_mag(const c32 *__
     constexpr int PF = 2;                           // tiles fetched ahead (one is not enough: measured 0.31 -> 0.23 ms)
     c32 xq[PF];
 #pragma unroll
-    for (int i = 0; i < PF; i++) xq[i] = PRUNED ? fetch(tile_begin + i) : mk(0.f, 0.f);
+    for (int i = 0; i < PF; i++) xq[i] = PRUNED ? fetch_next() : mk(0.f, 0.f);
     float best = -1.f;
     int best_row = 0, cur_cpi = (int)(tile_begin >> log2_tiles_per_cpi);
     int buf = 0;
+    // map rows are contiguous across tiles and CPIs: row of (tile, lr_t) = tile * RPC + lr_t
+    float *mp = map ? map + (tile_begin * RPC + lr_t) * NA + obin0 : nullptr;
     for (long long tile = tile_begin; tile < tile_end; tile++, buf ^= 1) {
         const int cpi = (int)(tile >> log2_tiles_per_cpi), n0 = ((int)tile & tpc_mask) * RPC;
         if (cpi != cur_cpi) {
@@ -326,19 +339,22 @@ __global__ void __launch_bounds__(256, PRUNED ? 2 : 3) k_angle_mag(const c32 *__
             const c32 xj = xq[0];
 #pragma unroll
             for (int i = 0; i + 1 < PF; i++) xq[i] = xq[i + 1];
-            xq[PF - 1] = fetch(tile + PF);
-            dif_first_pruned<LOG2NA>(rows + pr * RS, pp, xj, T);
+            xq[PF - 1] = fetch_next();
+            dif_first_pruned<LOG2NA>(rows + pr * RS, pp, xj, T, neg0);
         } else {
             // transposing load: thread (range bin r fastest, j) reads channels j + m NA/8 -- per channel RPC consecutive
-            // range bins, contiguous in HBM -- and runs the first pass on them
-            const c32 *Yc = Y + (long long)cpi * V * Nr + n0 + pr;
+            // range bins, contiguous in HBM -- and runs the first pass on them (NA/8 is even: one sign for all eight)
+            const c32 *Yc = fp;
             c32 u[8];
 #pragma unroll
             for (int m = 0; m < 8; m++) {
                 const int p = pp + m * TPR;
-                u[m] = p < V ? Yc[(long long)p * Nr] : mk(0.f, 0.f);   // angle zero-pad
+                u[m] = p < V ? Yc[(long long)m * TPR * Nr] : mk(0.f, 0.f);   // angle zero-pad
             }
-            dif_first_full<LOG2NA, -1>(rows + pr * RS, pp, u, T);
+            ft++;
+            fp += RPC;
+            if (((int)ft & tpc_mask) == 0) fp += cpi_jump;
+            dif_first_full<LOG2NA, -1>(rows + pr * RS, pp, u, T, neg0);
         }
         __syncthreads();
         c32 o[8];
@@ -350,9 +366,9 @@ __global__ void __launch_bounds__(256, PRUNED ? 2 : 3) k_angle_mag(const c32 *__
             v[c] = __fadd_rn(sq.x, sq.y);
         }
         if (map) {
-            float *mrow = map + ((long long)cpi * Nr + n0 + lr_t) * NA;
 #pragma unroll
-            for (int c = 0; c < 8; c++) __stcs(mrow + obin[c], v[c]);
+            for (int c = 0; c < 8; c++) __stcs(mp + dif_freq<LOG2NA>(c), v[c]);
+            mp += RPC * NA;
         }
         const float m8 = fmaxf(fmaxf(fmaxf(v[0], v[1]), fmaxf(v[2], v[3])), fmaxf(fmaxf(v[4], v[5]), fmaxf(v[6], v[7])));
         if (m8 > best) { best = m8; best_row = n0 + lr_t; }     // rows ascend within a CPI: the first maximum stays
