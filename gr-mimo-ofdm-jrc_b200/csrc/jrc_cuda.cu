@@ -932,7 +932,8 @@ extern "C" jrc_status jrc_chain_run_host(jrc_chain *h, const jrc_c32 *rx_host, c
         const c32 *z_rx = (const c32 *)host_dev_alias(src_rx), *z_tx = (const c32 *)host_dev_alias(src_tx);
         float *z_map = (float *)host_dev_alias(dst_map0);
         jrc_det *z_dets = (jrc_det *)host_dev_alias(dst_dets0);
-        if (h->zero_copy && n_cpi <= 4 && z_rx && z_tx && (!map_host || z_map) && (!dets_host || z_dets)) {
+        // (fused kernel only: the tiled and staged paths re-read their outputs)
+        if (h->zero_copy && n_cpi <= 4 && fused_config_ok(h) && z_rx && z_tx && (!map_host || z_map) && (!dets_host || z_dets)) {
             // A few CPIs: the copies cost more than the kernel.  Pinned host memory is device-accessible (unified
             // addressing): the kernel prefetches the symbols over PCIe itself and streams map and records
             // straight into the host buffers while it computes -- one launch, one synchronisation.
