@@ -360,6 +360,11 @@ TILED_CFGS = {
     "n64r4": (dict(T=2, R=4, S=2, N=64, IR=4, IA=8), 40, 2),          # 256 x 64, not a k_fused64x8 shape
     "wide": (dict(T=8, R=8, S=2, N=64, IR=2, IA=8), 16, 2),           # 128 x 512: radix 8.8.2 / 8.8.8
     "n2048a": (dict(T=4, R=4, S=2, N=512, IR=16, IA=128), 2, 2),      # 8192 x 2048: the largest supported FFTs
+    "r64": (dict(T=2, R=2, S=2, N=64, IR=1, IA=16), 32, 1),           # 64 x 64: shortest range FFT, no zero-pad
+    "r1k": (dict(T=4, R=4, S=2, N=128, IR=8, IA=32), 8, 2),           # 1024 x 512: radix 8.8.8.2 pruned / 8.8.8 pruned
+    "r2k": (dict(T=8, R=8, S=2, N=256, IR=8, IA=8), 4, 3),            # 2048 x 512: 8.8.8.4 pruned, 64 channels
+    "a1k": (dict(T=16, R=16, S=1, N=64, IR=2, IA=4), 4, 2),           # 128 x 1024 from 256 channels: angle 8.8.8.2 unpruned
+    "a512": (dict(T=8, R=16, S=1, N=64, IR=4, IA=4), 4, 2),           # 256 x 512 from 128 channels: angle 8.8.8 unpruned
 }
 
 
