@@ -267,7 +267,10 @@ __global__ void __launch_bounds__(TiledGeom<LOG2N>::THREADS) k_fft8_rows(const c
 // Twiddles: registers (2 CTAs per SM) when the first pass is pruned, shared memory (3 CTAs per SM) otherwise --
 // measured on configs[2] (registers 0.234 ms vs shared 0.250 ms) and configs[4] (0.160 ms vs 0.134 ms).
 template <int LOG2NA, bool PRUNED>
-__global__ void __launch_bounds__(256, PRUNED ? 2 : 3) k_angle_mag(const c32 *__restrict__ Y, int V, int Nr, int log2_tiles_per_cpi, int n_cpi,
+#ifndef JRC_ANGLE_CTAS
+#define JRC_ANGLE_CTAS 2     // resident CTAs per SM asked of ptxas for the pruned form (A/B: 3, 4)
+#endif
+__global__ void __launch_bounds__(256, PRUNED ? JRC_ANGLE_CTAS : 3) k_angle_mag(const c32 *__restrict__ Y, int V, int Nr, int log2_tiles_per_cpi, int n_cpi,
                                                       float *__restrict__ map, unsigned long long *__restrict__ keys,
                                                       const c32 *__restrict__ tw)
 {
