@@ -2,7 +2,7 @@
 headline bench is bench.py).  configs[2] (4x8, 256 sc, 4096x256) and configs[4] (8x16, 2048 sc)
 have no fused specialisation yet and run on the staged kernels."""
 import json, os, sys
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "gr-mimo-ofdm-jrc_b200", "python"))
 import numpy as np, torch
 import mimo_ofdm_jrc as jrc

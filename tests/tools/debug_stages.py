@@ -1,6 +1,6 @@
 """GPU debug helper: compares every staged kernel with the oracle and reports the first mismatch."""
 import os, sys
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "gr-mimo-ofdm-jrc_b200", "python"))
 import numpy as np
 import mimo_ofdm_jrc as jrc
