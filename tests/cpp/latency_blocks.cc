@@ -1,0 +1,67 @@
+// BASELINE configs[3]: streaming latency mode -- one CPI per work() call of the fused radar_chain block, driven through
+// the runtime stand-in exactly as the scheduler drives a tagged-stream block (pageable stream buffers, length tags,
+// message port).  Prints p50 / p99 of the per-call wall time as one JSON line.
+//   build/latency_blocks [n_calls]
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <numeric>
+#include <random>
+#include <vector>
+
+#include <mimo_ofdm_jrc/radar_chain.h>
+
+using namespace gr;
+using namespace gr::mimo_ofdm_jrc;
+typedef std::vector<gr_complex> cvec;
+
+int main(int argc, char **argv)
+{
+    const int n_calls = argc > 1 ? std::atoi(argv[1]) : 10000;
+    std::mt19937 rng(1);
+    std::normal_distribution<float> nd(0.f, 1.f);
+    std::printf("{");
+    const int cfgs[2][2] = {{8, 16}, {16, 8}};     // shipped 512 x 128, configs[1] 1024 x 64
+    for (int ci = 0; ci < 2; ci++) {
+        const int N = 64, T = 4, R = 2, S = 4, pre = 5, IR = cfgs[ci][0], IA = cfgs[ci][1], V = 8, Nr = N * IR, Na = V * IA, items = pre + S;
+        std::vector<float> rb(Nr), ab(Na);
+        for (int i = 0; i < Nr; i++) rb[i] = 76.8f * i / (Nr - 1);
+        for (int i = 0; i < Na; i++) ab[i] = (float)(std::asin(2.0 * (i - Na / 2) / Na) * 180.0 / M_PI);
+        auto blk = radar_chain::make(N, T, R, S, pre, false, false, 8, IR, IA, false, rb, ab, 2.4f, 28.955f, 15.f, 0.f, "/tmp/jrc_lat_log.csv", false);
+        std::vector<cvec> tx(T, cvec((size_t)items * N)), rx(R, cvec((size_t)items * N));
+        for (auto &v : tx) for (auto &z : v) z = gr_complex(nd(rng) > 0 ? 1.f : -1.f, 0.f);
+        for (int r = 0; r < R; r++)
+            for (int s = 0; s < items; s++)
+                for (int k = 0; k < N; k++) {
+                    gr_complex acc = 0;
+                    for (int t = 0; t < T; t++) acc += tx[t][(size_t)s * N + k] * std::polar(1.0f, (float)(-2 * M_PI * 0.13 * k + 0.9 * (t + T * r)));
+                    rx[r][(size_t)s * N + k] = acc + gr_complex(0.05f * nd(rng), 0.05f * nd(rng));
+                }
+        std::vector<float> map((size_t)Nr * Na);
+        std::vector<double> us;
+        us.reserve(n_calls);
+        uint64_t rd = 0;
+        for (int it = 0; it < n_calls + 200; it++) {
+            std::vector<shim::input_t> in(T + R);
+            for (int t = 0; t < T; t++) { in[t].items = tx[t].data(); in[t].n_items = items; }
+            for (int r = 0; r < R; r++) { in[T + r].items = rx[r].data(); in[T + r].n_items = items; }
+            in[0].tags.push_back(shim::make_tag(rd, "packet_len", pmt::from_long(items)));
+            in[T].tags.push_back(shim::make_tag(rd, "packet_len", pmt::from_long(items)));
+            rd += items;
+            auto t0 = std::chrono::steady_clock::now();
+            auto res = shim::run_once(*blk, in, {{map.data(), Nr}});
+            auto t1 = std::chrono::steady_clock::now();
+            if (res.produced != Nr) { std::fprintf(stderr, "radar_chain produced %d items\n", res.produced); return 1; }
+            if (it >= 200) us.push_back(std::chrono::duration<double, std::micro>(t1 - t0).count());
+            blk->shim_published["params"].clear();
+        }
+        std::sort(us.begin(), us.end());
+        std::printf("%s\"radar_chain block %dx%d, 1 CPI per work(), pageable buffers\": {\"calls\": %d, \"p50_us\": %.2f, \"p99_us\": %.2f, \"mean_us\": %.2f}",
+                    ci ? ", " : "", Nr, Na, n_calls, us[us.size() / 2], us[(size_t)(us.size() * 0.99)],
+                    std::accumulate(us.begin(), us.end(), 0.0) / us.size());
+    }
+    std::printf("}\n");
+    return 0;
+}

@@ -24,7 +24,8 @@ def _built():
 def test_wrapper_library_exports_the_reference_factories():
     assert _built(), "run `python -c 'import __graft_entry__ as g; g.build()'` first"
     out = subprocess.run(["nm", "-DC", LIB], capture_output=True, text=True, check=True).stdout
-    for blk in ("mimo_ofdm_radar", "matrix_transpose", "range_angle_estimator", "fft_peak_detect", "zero_pad", "radar_chain"):
+    for blk in ("mimo_ofdm_radar", "matrix_transpose", "range_angle_estimator", "fft_peak_detect", "zero_pad", "radar_chain",
+                "ofdm_cyclic_prefix_remover", "target_simulator"):
         assert f"gr::mimo_ofdm_jrc::{blk}::make(" in out, blk
     ctypes.CDLL(os.path.join(PKG, "libjrc_cuda.so"))
     ctypes.CDLL(LIB)
@@ -45,3 +46,17 @@ def test_cpp_blocks_against_oracle():
     r = subprocess.run([EXE], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-4000:] + r.stderr[-2000:]
     assert "ALL BLOCK TESTS PASSED" in r.stdout
+
+
+@pytest.mark.gpu
+def test_streaming_latency_harness_runs():
+    """configs[3]: the fused block driven one CPI per general_work() call (tests/cpp/latency_blocks.cc)."""
+    import json
+    exe = os.path.join(PKG, "build", "latency_blocks")
+    assert os.path.exists(exe)
+    r = subprocess.run([exe, "300"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    res = json.loads(r.stdout)
+    assert len(res) == 2
+    for v in res.values():
+        assert v["calls"] == 300 and 0 < v["p50_us"] <= v["p99_us"] < 5000
