@@ -141,6 +141,10 @@ JRC_API int64_t    jrc_chain_launch_count(const jrc_chain *h);
 /* Same chain with HOST buffers (packed layout rx[n_cpi][n_rx][n_sym][fft_len],
  * tx[n_cpi or 1][n_tx][n_sym][fft_len], i.e. n_pre symbols already stripped):
  * pinned double-buffered H2D -> kernels -> D2H, synchronous on return.
+ * Up to 4 CPIs in front of the fused kernel take the latency path instead: the
+ * kernel reads the (pinned, device-mapped) host symbols and writes map and
+ * records straight into host memory -- no copies, one launch (pageable caller
+ * buffers go through the handle's pinned staging buffers).
  * map_host / dets_host may be NULL.                                           */
 JRC_API jrc_status jrc_chain_run_host(jrc_chain *h, const jrc_c32 *rx_host, const jrc_c32 *tx_host,
                                       int32_t tx_shared, int32_t n_cpi, int32_t cpi0,
