@@ -15,6 +15,19 @@ BLOCKS = ["mimo_ofdm_radar", "matrix_transpose", "range_angle_estimator", "fft_p
           "ofdm_cyclic_prefix_remover", "target_simulator"]
 
 
+def _generate():
+    """The .block.yml files are build products of grc/gen_grc.py (table-driven): regenerate when missing."""
+    if not glob.glob(os.path.join(OURS, "*.block.yml")):
+        import importlib.util
+        spec = importlib.util.spec_from_file_location("gen_grc", os.path.join(OURS, "gen_grc.py"))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        mod.main()
+
+
+_generate()
+
+
 def norm(s):
     return re.sub(r"\s+", "", s)
 
