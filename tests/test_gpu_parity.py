@@ -518,3 +518,23 @@ def test_tiled_path_chunks_long_batches(jrc, orc):
     _, _, do = oracle(orc, rx[idx], tx, cfg, est)
     assert np.array_equal(d["range_idx"][idx], do["range_idx"]) and np.array_equal(d["angle_idx"][idx], do["angle_idx"])
     assert np.array_equal(d["cpi"], 1000 + np.arange(n)) and (d["flags"] & 1).all()
+
+
+def test_tiled_linearity_and_shard_consistency(jrc):
+    """Size-independent properties of the tiled path at BASELINE configs[2] size: |chain(2x)|^2 = 4 |chain(x)|^2 exactly
+    (power-of-two scaling commutes with every rounding), and processing a batch as two shards (the multi-GPU split)
+    gives the same bits as processing it whole."""
+    cfg = CFGS["C3"]
+    est = est_for(cfg)
+    n = 6
+    rx, tx, _ = scene(cfg, n, seed=37, n_targets=3, amp_db_span=10.0)
+    ch = gpu_chain(jrc, cfg, est)
+    m1, d1 = ch.run_host(rx, tx)
+    assert ch.last_path == jrc.PATH_TILED
+    m2, d2 = ch.run_host(rx * np.float32(2), tx)
+    assert np.array_equal(m2, m1 * np.float32(4))
+    assert np.array_equal(d1["range_idx"], d2["range_idx"]) and np.array_equal(d1["angle_idx"], d2["angle_idx"])
+    ma, da = ch.run_host(rx[:2], tx, cpi0=0)
+    mb, db = ch.run_host(rx[2:], tx, cpi0=2)
+    assert np.array_equal(np.concatenate([ma, mb]), m1)
+    assert np.array_equal(np.concatenate([da, db]), d1)
