@@ -1,9 +1,10 @@
 // jrc_tc.cuh -- the fused radar chain with the angle DFT on the 5th-generation tensor cores.
 //
 // BASELINE.json allows tensor cores "only if ncu shows the small-N angle DFT performs better when
-// expressed as a complex GEMM".  It does: the SIMT kernels (jrc_fused.cuh, jrc_stream.cuh) are bound by
-// FP32 issue -- 104 FMA-pipe cycles per 256 map elements in the angle pass, 0.20 ms per 4096 CPIs even
-// without the map store -- while HBM needs 0.15-0.17 ms (profiles/README.md).  Here the angle pass
+// expressed as a complex GEMM".  This opt-in variant (JRC_FUSED_KERNEL=tc) is the experiment: correct (parity
+// tests), but measured slower than the SIMT kernel of jrc_fused.cuh (0.26 ms + two helper kernels against
+// 0.226 ms per 4096 CPIs) because its A tiles are staged in shared memory; scripts/ubench/tc_angle_stage.cu
+// shows the form that does win (A operand in tensor memory).  Here the angle pass
 //     M[n][i] = sum_p (-1)^p e^{-j 2 pi p i / Na} y[p][n]
 // is the real GEMM  D[128 rows n][2 Na] = A[128][16] * B[2 Na][16]^T  per tile of 128 range bins, issued
 // as tcgen05.mma kind::tf32 with the accumulator in TMEM, in 3xTF32 form for float32-class accuracy:
