@@ -1,5 +1,6 @@
 // jrc_stream.cuh -- "slice-streaming" form of the fused radar chain for the 64-subcarrier /
-// 8-virtual-channel family: the map-producing hot path.
+// 8-virtual-channel family: an opt-in A/B kernel (JRC_FUSED_KERNEL=stream); measured 14.7 M CPI/s on configs[1]
+// against 18 M for k_fused64x8 (profiles/README.md), kept because its footprint does not grow with the zero-pad.
 //
 // Same arithmetic as k_fused64x8 (jrc_fused.cuh: three passes of "twiddle 8 inputs, DFT-8"), but
 // organised so that a WARP, not a CTA, is the unit of execution and no CTA barrier exists:
