@@ -11,7 +11,10 @@
 #include <cstdlib>
 #include <cuda_runtime.h>
 
-constexpr int GROUPS = 3, THREADS = 128 * GROUPS, ROWB = 272;      // staging row: 256 B + 16 B pad (conflict-free STS.128)
+#ifndef NGROUPS
+#define NGROUPS 3
+#endif
+constexpr int GROUPS = NGROUPS, THREADS = 128 * GROUPS, ROWB = 272;      // staging row: 256 B + 16 B pad (conflict-free STS.128)
 constexpr int G_Y = 128 * 64, G_STG = 128 * ROWB, G_SIZE = ((G_Y + G_STG + 1023) / 1024) * 1024;
 constexpr int OFF_G = 16384, SMEM = OFF_G + GROUPS * G_SIZE + 1024;
 
