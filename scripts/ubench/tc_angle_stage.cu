@@ -35,6 +35,11 @@ __device__ __forceinline__ uint32_t make_idesc_tf32(int M, int N)
                    "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),      \
                    "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])                                                              \
                  : "r"(taddr))
+#define LD16(taddr, v)                                                                                                             \
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"          \
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),   \
+                   "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])                                    \
+                 : "r"(taddr))
 #define ST32(taddr, v)                                                                                                             \
     asm volatile("tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "                                                                   \
                  "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};" \
@@ -43,7 +48,10 @@ __device__ __forceinline__ uint32_t make_idesc_tf32(int M, int N)
                    "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]),            \
                    "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31]) : "memory")
 
-__global__ void __launch_bounds__(THREADS, 1) k_tc_angle(const float *Bblob, float *map, float *maxout, int n_tiles)
+#ifndef MAXREG_THREADS
+#define MAXREG_THREADS THREADS
+#endif
+__global__ void __launch_bounds__(MAXREG_THREADS, 1) k_tc_angle(const float *Bblob, float *map, float *maxout, int n_tiles)
 {
     extern __shared__ unsigned char smem_dyn[];
     unsigned char *base = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
@@ -116,14 +124,23 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_angle(const float *Bblob, flo
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         // 6: epilogue, two halves of 32 bins: Re columns [h*32, +32), Im columns [64 + h*32, +32)
         float4 *srow = reinterpret_cast<float4 *>(stg + r * ROWB);
+#ifndef CHUNK16
+#define CHUNK16 0
+#endif
 #pragma unroll
-        for (int h = 0; h < 2; h++) {
+        for (int h = 0; h < (CHUNK16 ? 4 : 2); h++) {
+#if CHUNK16
+            uint32_t re[16], im[16];                        // 16 bins per step: fits 128 registers per thread
+            LD16(tmem_d + lane_off + (uint32_t)(h * 16), re);
+            LD16(tmem_d + lane_off + (uint32_t)(64 + h * 16), im);
+#else
             uint32_t re[32], im[32];
             LD32(tmem_d + lane_off + (uint32_t)(h * 32), re);
             LD32(tmem_d + lane_off + (uint32_t)(64 + h * 32), im);
+#endif
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-            for (int j = 0; j < 8; j++) {
+            for (int j = 0; j < (CHUNK16 ? 4 : 8); j++) {
                 float2 o[2];
 #pragma unroll
                 for (int q = 0; q < 2; q++) {
@@ -132,7 +149,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_angle(const float *Bblob, flo
                     o[q] = __ffma2_rn(ii, ii, __fmul2_rn(rr, rr));
                 }
                 best = fmaxf(best, fmaxf(fmaxf(o[0].x, o[0].y), fmaxf(o[1].x, o[1].y)));
-                srow[h * 8 + j] = make_float4(o[0].x, o[0].y, o[1].x, o[1].y);
+                srow[h * (CHUNK16 ? 4 : 8) + j] = make_float4(o[0].x, o[0].y, o[1].x, o[1].y);
             }
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
