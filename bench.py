@@ -219,7 +219,7 @@ def run_ours(args):
     counts = [B] * world                       # contiguous equal shards: no size exchange needed
     # two detection buffers per rank: the gather of step k overlaps the kernel of step k+1
     ddets = [ddet, torch.zeros_like(ddet)] if world > 1 else [ddet]
-    gbufs = [[torch.empty_like(ddet) for _ in range(world)] for _ in range(2)] if (world > 1 and rank == 0) else [None, None]
+    gbufs = [torch.empty((world * B, 32), dtype=torch.uint8, device=dev) for _ in range(2)] if (world > 1 and rank == 0) else [None, None]
     pending = [None, None]
 
     def step(k=0):
@@ -229,7 +229,7 @@ def run_ours(args):
             pending[slot] = None
         rc.run(rx, tx, map_out=dmap, dets_out=ddets[slot], path=jrc.PATH_FUSED, sync_inputs=False)
         if world > 1:
-            pending[slot], _ = shard.gather_detections(ddets[slot], dst=0, counts=counts, bufs=gbufs[slot], async_op=True)
+            pending[slot], _ = shard.gather_detections(ddets[slot], dst=0, counts=counts, out=gbufs[slot], async_op=True)
 
     def drain():
         for i in range(2):

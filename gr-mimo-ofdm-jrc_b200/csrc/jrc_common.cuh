@@ -217,6 +217,13 @@ __device__ __forceinline__ c32 cispi_ratio(int num, int den)
     return mk(c, s);
 }
 
+// 10*log10(peak/noise) as the reference evaluates it (lib/range_angle_estimator_impl.cc:227): float division, log10f, float product.  log10 is taken
+// in double and rounded once, which is what a correctly rounded log10f returns.
+__device__ __forceinline__ float snr_db_of(float peak, float noise)
+{
+    return __fmul_rn(10.f, (float)log10((double)__fdiv_rn(peak, noise)));
+}
+
 __device__ __forceinline__ unsigned long long pack_key(float v, unsigned idx)
 {
     // v >= 0 and not NaN: float bits are monotonic; ties -> the smaller index wins

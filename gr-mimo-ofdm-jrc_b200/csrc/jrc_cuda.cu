@@ -5,7 +5,9 @@
 #include "jrc_cuda.h"
 
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>
 
+#include <atomic>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -17,9 +19,8 @@
 
 #include "jrc_fused.cuh"
 #include "jrc_tiled.cuh"
-#include "jrc_stream.cuh"
-#include "jrc_tc.cuh"
 #include "jrc_staged.cuh"
+#include "jrc_exact.cuh"
 
 using namespace jrc;
 
@@ -52,8 +53,16 @@ static jrc_status fail(jrc_status st, const char *fmt, ...)
         if (s_ != JRC_OK) return s_;             \
     } while (0)
 
+// NVTX ranges around the stages of a call (visible in Nsight Systems; no-ops without a tool attached)
+struct NvtxRange {
+    explicit NvtxRange(const char *name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+    NvtxRange(const NvtxRange &) = delete;
+    NvtxRange &operator=(const NvtxRange &) = delete;
+};
+
 extern "C" const char *jrc_last_error(void) { return g_err.c_str(); }
-extern "C" int32_t jrc_abi_version(void) { return 1; }
+extern "C" int32_t jrc_abi_version(void) { return 2; }
 
 // ---------------------------------------------------------------------------
 // handle
@@ -79,8 +88,12 @@ struct GrowBuf {   // grow-only device / pinned-host buffer
     }
 };
 
+enum { JRC_STREAM_DEPTH = 4 };
+struct jrc_stream_state;
+
 struct jrc_chain {
     jrc_chain_cfg cfg;
+    jrc_stream_state *sstate = nullptr;         // jrc_chain_submit / jrc_chain_wait slots, created on first use
     int V = 0, Nr = 0, Na = 0;
     int sm_count = 0;
     cudaStream_t stream = nullptr, s_h2d = nullptr, s_d2h = nullptr;
@@ -98,17 +111,16 @@ struct jrc_chain {
     c32 *d_ring = nullptr, *d_temp = nullptr;
     int ring_size = 0, ring_head = 0;
     // scratch
-    GrowBuf sH, sY, sC, sKeys, sDet, sIn[2], sMap[2], sDets[2], sMisc, sMisc2, sStage[8];
+    GrowBuf sH, sY, sC, sKeys, sSec, sDet, sIn[2], sMap[2], sDets[2], sMisc, sMisc2, sStage[8];
+    GrowBuf sFix, sExact;                        // marked-CPI list (FixCtl + int[n]) and range-spectra scratch of k_est_exact
+    int exact_grid = 0;
     GrowBuf pin_a, pin_b;
     std::map<std::pair<int, int>, c32 *> twiddles;   // (n, forward) -> device table
     int last_path = 0;
     int64_t launches = 0;
     int fused_ctas_per_sm = 0;
-    c32 *d_tw1g = nullptr, *d_tw2g = nullptr;   // slice-streaming kernel twiddle tables
     int zero_copy = 1;                          // latency mode: kernel reads/writes pinned host memory directly (JRC_ZEROCOPY=0 disables)
-    int det_mode = 1;                           // 1: in-kernel estimator (faster on B200); 0 (JRC_DET=map): key + k_map_finalize when the map is written
-    float *d_bblob = nullptr;                   // tensor-core kernel: swizzled [Bhi | Blo] angle-DFT operand
-    int stream_mode = 0;                        // map-producing kernel: 0 k_fused64x8, 1 k_stream64x8, 2 k_tc64x8 (JRC_FUSED_KERNEL)
+    std::atomic<int> bg_recording{0};           // set_background_record may come from another thread (GUI / RPC callback)
 };
 
 static bool is_pow2(int n) { return n > 0 && (n & (n - 1)) == 0; }
@@ -135,28 +147,14 @@ static jrc_status get_twiddles(jrc_chain *h, int n, int forward, const c32 **out
     return JRC_OK;
 }
 
-extern "C" jrc_status jrc_chain_create(const jrc_chain_cfg *cfg, jrc_chain **out)
-{
-    if (!cfg || !out) return fail(JRC_ERR_INVALID, "null argument");
-    *out = nullptr;
-    int ndev = 0;
-    cudaError_t e = cudaGetDeviceCount(&ndev);
-    if (e != cudaSuccess || ndev == 0)
-        return fail(JRC_ERR_NO_DEVICE, "no CUDA device (%s); this library has no CPU path",
-                    e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
-    if (cfg->device < 0 || cfg->device >= ndev) return fail(JRC_ERR_INVALID, "device %d out of range (%d devices)", cfg->device, ndev);
-    if (!is_pow2(cfg->fft_len)) return fail(JRC_ERR_INVALID, "fft_len must be a power of two");
-    if (cfg->n_tx < 1 || cfg->n_rx < 1 || cfg->n_sym < 1 || cfg->n_pre < 0) return fail(JRC_ERR_INVALID, "bad antenna/symbol counts");
-    if (cfg->interp_range < 1 || cfg->interp_angle < 1) return fail(JRC_ERR_INVALID, "interp factors must be >= 1");
-    const long long Nr = (long long)cfg->fft_len * cfg->interp_range, Na = (long long)cfg->n_tx * cfg->n_rx * cfg->interp_angle;
-    if (!is_pow2((int)Nr) || !is_pow2((int)Na) || Nr > 16384 || Na > 16384)
-        return fail(JRC_ERR_INVALID, "Nr=%lld / Na=%lld must be powers of two <= 16384", Nr, Na);
-    if (cfg->background_removal && cfg->record_len < 0) return fail(JRC_ERR_INVALID, "record_len < 0");
+extern "C" void jrc_chain_destroy(jrc_chain *h);
+static void stream_state_destroy(jrc_chain *h);
 
-    CU(cudaSetDevice(cfg->device));
-    jrc_chain *h = new jrc_chain();
+static jrc_status chain_init(jrc_chain *h, const jrc_chain_cfg *cfg, int Nr, int Na)
+{
     h->cfg = *cfg;
-    h->V = cfg->n_tx * cfg->n_rx; h->Nr = (int)Nr; h->Na = (int)Na;
+    h->bg_recording = cfg->background_recording;
+    h->V = cfg->n_tx * cfg->n_rx; h->Nr = Nr; h->Na = Na;
     cudaDeviceProp prop;
     CU(cudaGetDeviceProperties(&prop, cfg->device));
     h->sm_count = prop.multiProcessorCount;
@@ -169,10 +167,7 @@ extern "C" jrc_status jrc_chain_create(const jrc_chain_cfg *cfg, jrc_chain **out
         CU(cudaEventCreateWithFlags(&h->ev_out[i], cudaEventDisableTiming));
     }
     h->pin_a.pinned = h->pin_b.pinned = true;
-    if (const char *e = getenv("JRC_DET")) h->det_mode = !strcmp(e, "map") ? 0 : 1;
     if (const char *e = getenv("JRC_ZEROCOPY")) h->zero_copy = atoi(e) != 0;
-    if (const char *e = getenv("JRC_FUSED_KERNEL"))   // A/B switch for measurements: cta | stream | tc
-        h->stream_mode = !strcmp(e, "stream") ? 1 : (!strcmp(e, "tc") ? 2 : 0);
     const size_t vn = (size_t)h->V * cfg->fft_len;
     CU(cudaMalloc(&h->d_temp, vn * sizeof(c32)));
     CU(cudaMemsetAsync(h->d_temp, 0, vn * sizeof(c32), h->stream));
@@ -181,6 +176,37 @@ extern "C" jrc_status jrc_chain_create(const jrc_chain_cfg *cfg, jrc_chain **out
         CU(cudaMemsetAsync(h->d_ring, 0, vn * sizeof(c32) * (size_t)cfg->record_len, h->stream));
     }
     CU(cudaStreamSynchronize(h->stream));
+    return JRC_OK;
+}
+
+extern "C" jrc_status jrc_chain_create(const jrc_chain_cfg *cfg, jrc_chain **out)
+{
+    if (!cfg || !out) return fail(JRC_ERR_INVALID, "null argument");
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(JRC_ERR_NO_DEVICE, "no CUDA device (%s); this library has no CPU path",
+                    e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+    if (cfg->device < 0 || cfg->device >= ndev) return fail(JRC_ERR_INVALID, "device %d out of range (%d devices)", cfg->device, ndev);
+    if (cfg->fft_len < 1) return fail(JRC_ERR_INVALID, "fft_len must be positive");
+    if (cfg->n_tx < 1 || cfg->n_rx < 1 || cfg->n_sym < 1 || cfg->n_pre < 0) return fail(JRC_ERR_INVALID, "bad antenna/symbol counts");
+    if (cfg->interp_range < 1 || cfg->interp_angle < 1) return fail(JRC_ERR_INVALID, "interp factors must be >= 1");
+    // (power-of-two sizes are a requirement of the FFT chains, checked where a chain runs: the per-block calls
+    //  -- conj-MAC, transpose, estimator, ... -- take any antenna count, like the reference blocks)
+    const long long Nr = (long long)cfg->fft_len * cfg->interp_range, Na = (long long)cfg->n_tx * cfg->n_rx * cfg->interp_angle;
+    if (Nr > (1 << 24) || Na > (1 << 24)) return fail(JRC_ERR_INVALID, "Nr=%lld / Na=%lld too large", Nr, Na);
+    if (cfg->background_removal && cfg->record_len < 0) return fail(JRC_ERR_INVALID, "record_len < 0");
+
+    CU(cudaSetDevice(cfg->device));
+    jrc_chain *h = new jrc_chain();
+    jrc_status st = chain_init(h, cfg, (int)Nr, (int)Na);
+    if (st != JRC_OK) {              // release whatever was created (the message of the failure is kept)
+        const std::string msg = g_err;
+        jrc_chain_destroy(h);
+        g_err = msg;
+        return st;
+    }
     *out = h;
     return JRC_OK;
 }
@@ -190,8 +216,9 @@ extern "C" void jrc_chain_destroy(jrc_chain *h)
     if (!h) return;
     cudaSetDevice(h->cfg.device);
     cudaDeviceSynchronize();
+    stream_state_destroy(h);
     for (auto &kv : h->twiddles) cudaFree(kv.second);
-    GrowBuf *bufs[] = {&h->sH, &h->sY, &h->sC, &h->sKeys, &h->sDet, &h->sIn[0], &h->sIn[1], &h->sMap[0], &h->sMap[1],
+    GrowBuf *bufs[] = {&h->sH, &h->sY, &h->sC, &h->sKeys, &h->sSec, &h->sFix, &h->sExact, &h->sDet, &h->sIn[0], &h->sIn[1], &h->sMap[0], &h->sMap[1],
                        &h->sDets[0], &h->sDets[1], &h->sMisc, &h->sMisc2, &h->pin_a, &h->pin_b};
     for (GrowBuf *b : bufs) b->release();
     for (GrowBuf &b : h->sStage) b.release();
@@ -200,9 +227,6 @@ extern "C" void jrc_chain_destroy(jrc_chain *h)
     if (h->d_angle_bins) cudaFree(h->d_angle_bins);
     if (h->d_win_tab) cudaFree(h->d_win_tab);
     if (h->d_g_tab) cudaFree(h->d_g_tab);
-    if (h->d_bblob) cudaFree(h->d_bblob);
-    if (h->d_tw1g) cudaFree(h->d_tw1g);
-    if (h->d_tw2g) cudaFree(h->d_tw2g);
     if (h->d_ring) cudaFree(h->d_ring);
     if (h->d_temp) cudaFree(h->d_temp);
     for (int i = 0; i < 2; i++) {
@@ -266,7 +290,7 @@ extern "C" jrc_status jrc_chain_set_thresholds(jrc_chain *h, float snr_threshold
 extern "C" jrc_status jrc_chain_set_background_record(jrc_chain *h, int32_t on)
 {
     if (!h) return fail(JRC_ERR_INVALID, "null handle");
-    h->cfg.background_recording = on ? 1 : 0;
+    h->bg_recording.store(on ? 1 : 0);      // read once per batch by launch_chan_est
     return JRC_OK;
 }
 extern "C" jrc_status jrc_chain_reset_background(jrc_chain *h)
@@ -379,7 +403,7 @@ static jrc_status launch_fft8_rows_t(jrc_chain *h, const c32 *in, long long in_s
 
 template <int LOG2NA>
 static jrc_status launch_angle_mag_t(jrc_chain *h, const c32 *Y, int V, int Nr, int n_cpi, float *map,
-                                     unsigned long long *keys, const c32 *tw)
+                                     unsigned long long *keys, unsigned *sec, const c32 *tw)
 {
     using Gm = TiledGeom<LOG2NA>;
     auto kern = (V <= Gm::N / 8) ? k_angle_mag<LOG2NA, true> : k_angle_mag<LOG2NA, false>;
@@ -390,7 +414,7 @@ static jrc_status launch_angle_mag_t(jrc_chain *h, const c32 *Y, int V, int Nr, 
     if (per_sm < 1) return fail(JRC_ERR_INVALID, "angle kernel does not fit");
     long long grid = (long long)n_cpi * (Nr / Gm::RPC), cap = (long long)h->sm_count * per_sm;
     if (grid > cap) grid = cap;
-    kern<<<(unsigned)grid, 256, smem, h->stream>>>(Y, V, Nr, ilog2(Nr / Gm::RPC), n_cpi, map, keys, tw);
+    kern<<<(unsigned)grid, 256, smem, h->stream>>>(Y, V, Nr, ilog2(Nr / Gm::RPC), n_cpi, map, keys, sec, tw);
     CU(cudaGetLastError());
     h->launches++;
     return JRC_OK;
@@ -418,12 +442,12 @@ static jrc_status launch_fft8_rows(jrc_chain *h, const c32 *in, long long in_str
 }
 
 static jrc_status launch_angle_mag(jrc_chain *h, const c32 *Y, int V, int Nr, int Na, int n_cpi, float *map,
-                                   unsigned long long *keys)
+                                   unsigned long long *keys, unsigned *sec)
 {
     const c32 *tw = nullptr;
     ST(get_twiddles_full(h, Na, 1, &tw));
     switch (ilog2(Na)) {
-#define JRC_CASE(l) case l: return launch_angle_mag_t<l>(h, Y, V, Nr, n_cpi, map, keys, tw);
+#define JRC_CASE(l) case l: return launch_angle_mag_t<l>(h, Y, V, Nr, n_cpi, map, keys, sec, tw);
         JRC_CASE(6) JRC_CASE(7) JRC_CASE(8) JRC_CASE(9) JRC_CASE(10) JRC_CASE(11)
 #undef JRC_CASE
     }
@@ -454,22 +478,23 @@ static jrc_status launch_estimate(jrc_chain *h, const c32 *cmap, int n_inputs, i
 }
 
 // channel estimates for a batch -> d_H [n_cpi][V][N]  (+ background ring update)
-static jrc_status launch_chan_est(jrc_chain *h, PortDev rx, PortDev tx, int n_cpi, c32 *d_H)
+static jrc_status launch_chan_est(jrc_chain *h, PortDev rx, PortDev tx, int n_cpi, c32 *d_H, int n_pre)
 {
     const jrc_chain_cfg &c = h->cfg;
+    const int recording = h->bg_recording.load();
     long long total = (long long)n_cpi * h->V * c.fft_len;
     if (c.n_tx % 4 == 0 && c.n_rx % 4 == 0)     // large arrays: 4 x 4 antenna blocks per thread
         k_chan_est_tile<4, 4><<<grid_for(total / 16, 256, h->sm_count), 256, 0, h->stream>>>(
-            rx, tx, n_cpi, c.fft_len, c.n_tx, c.n_rx, c.n_sym, c.n_pre, c.tx_interleave, d_H);
+            rx, tx, n_cpi, c.fft_len, c.n_tx, c.n_rx, c.n_sym, n_pre, c.tx_interleave, d_H);
     else
         k_chan_est<<<grid_for(total, 256, h->sm_count), 256, 0, h->stream>>>(rx, tx, n_cpi, c.fft_len, c.n_tx, c.n_rx, c.n_sym,
-                                                                           c.n_pre, c.tx_interleave, d_H);
+                                                                           n_pre, c.tx_interleave, d_H);
     CU(cudaGetLastError());
     h->launches++;
-    if (c.background_removal || c.background_recording) {
+    if (c.background_removal || recording) {
         int VN = h->V * c.fft_len;
         k_background<<<(VN + 127) / 128, 128, 0, h->stream>>>(d_H, n_cpi, VN, h->d_ring, h->d_temp, c.record_len,
-                                                            h->ring_size, h->ring_head, c.background_recording,
+                                                            h->ring_size, h->ring_head, recording,
                                                             c.background_removal);
         CU(cudaGetLastError());
         h->launches++;
@@ -487,15 +512,21 @@ static jrc_status launch_chan_est(jrc_chain *h, PortDev rx, PortDev tx, int n_cp
 // fused path dispatch
 // ---------------------------------------------------------------------------
 template <int IR, int IA, bool FROM_H>
-static jrc_status launch_fused_t(jrc_chain *h, const FusedParams &P)
+static jrc_status launch_fused_t(jrc_chain *h, const FusedParams &P, bool *supported)
 {
     using Gm = FusedGeom<IR, IA>;
     size_t smem = Gm::smem_bytes(P.T, P.R, P.S, FROM_H);
     auto kern = P.map ? k_fused64x8<IR, IA, FROM_H, true> : k_fused64x8<IR, IA, FROM_H, false>;
+    int dev_smem = 0;
+    CU(cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->cfg.device));
+    if (smem > (size_t)dev_smem) {     // many LTF symbols: the symbol buffer does not fit next to the spectra
+        *supported = false;
+        return JRC_OK;
+    }
     CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, smem));
-    if (per_sm < 1) return fail(JRC_ERR_INVALID, "fused kernel does not fit (smem %zu bytes)", smem);
+    if (per_sm < 1) { *supported = false; return JRC_OK; }
     h->fused_ctas_per_sm = per_sm;
     long long grid = (long long)h->sm_count * per_sm;
     if (grid > P.n_cpi) grid = P.n_cpi;
@@ -510,7 +541,7 @@ static jrc_status launch_fused(jrc_chain *h, const FusedParams &P, bool *support
 {
     const int IR = h->cfg.interp_range, IA = h->cfg.interp_angle;
     *supported = true;
-#define JRC_FUSED_CASE(ir, ia) if (IR == ir && IA == ia) return launch_fused_t<ir, ia, FROM_H>(h, P);
+#define JRC_FUSED_CASE(ir, ia) if (IR == ir && IA == ia) return launch_fused_t<ir, ia, FROM_H>(h, P, supported);
     JRC_FUSED_CASE(8, 16)    // shipped flowgraph: 512 x 128 map
     JRC_FUSED_CASE(16, 8)    // BASELINE configs[1]: 1024 x 64 map
     JRC_FUSED_CASE(8, 8)
@@ -520,151 +551,48 @@ static jrc_status launch_fused(jrc_chain *h, const FusedParams &P, bool *support
     return JRC_OK;
 }
 
-
 // ---------------------------------------------------------------------------
-// slice-streaming path (jrc_stream.cuh): k_chan_est -> k_stream64x8 -> k_stream_finalize
+// k_est_exact (jrc_exact.cuh): redoes the marked records of a batch in the staged arithmetic
 // ---------------------------------------------------------------------------
-static jrc_status stream_tables(jrc_chain *h)
+static jrc_status fix_buffers(jrc_chain *h, int n_cpi, FixCtl **ctl, int **list)
 {
-    if (h->d_tw1g) return JRC_OK;
-    const int IR = h->cfg.interp_range, NR = h->Nr, Q = NR / 8;
-    std::vector<c32> t1((size_t)IR * 8), t2((size_t)IR * 64);
-    for (int q0 = 0; q0 < IR; q0++)
-        for (int k = 0; k < 8; k++) {
-            double a = 2.0 * M_PI * (double)((k * q0) % Q) / (double)Q;
-            t1[q0 * 8 + k].x = (float)cos(a); t1[q0 * 8 + k].y = (float)sin(a);
-            for (int m0 = 0; m0 < 8; m0++) {
-                double a2 = 2.0 * M_PI * (double)((k * (q0 + IR * m0)) % NR) / (double)NR;
-                t2[(q0 * 8 + k) * 8 + m0].x = (float)cos(a2); t2[(q0 * 8 + k) * 8 + m0].y = (float)sin(a2);
-            }
-        }
-    CU(cudaMalloc(&h->d_tw1g, t1.size() * sizeof(c32)));
-    CU(cudaMalloc(&h->d_tw2g, t2.size() * sizeof(c32)));
-    CU(cudaMemcpyAsync(h->d_tw1g, t1.data(), t1.size() * sizeof(c32), cudaMemcpyHostToDevice, h->stream));
-    CU(cudaMemcpyAsync(h->d_tw2g, t2.data(), t2.size() * sizeof(c32), cudaMemcpyHostToDevice, h->stream));
-    CU(cudaStreamSynchronize(h->stream));
+    const size_t need = 16 + sizeof(int) * (size_t)n_cpi;
+    if (need > h->sFix.cap) {
+        ST(h->sFix.need(need));
+        CU(cudaMemsetAsync(h->sFix.p, 0, 16, h->stream));      // k_est_exact re-arms it after every batch
+    }
+    *ctl = (FixCtl *)h->sFix.p;
+    *list = (int *)((char *)h->sFix.p + 16);
     return JRC_OK;
 }
 
-template <int IR, int IA>
-static jrc_status launch_stream_t(jrc_chain *h, const StreamParams &P)
+static jrc_status launch_exact(jrc_chain *h, PortDev rx, PortDev tx, const c32 *H, int n_pre, int cpi0, const float *map,
+                               DetDev *dets, const EstParams &est)
 {
-    using Gm = StreamGeom<IR, IA>;
-    constexpr int WPC = 4, SPU = (IR >= 2) ? 2 : 1;
-    auto kern = k_stream64x8<IR, IA, SPU, WPC>;
-    const size_t smem = (size_t)WPC * Gm::WARP_SMEM;
-    CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int per_sm = 0;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, WPC * 32, smem));
-    if (per_sm < 1) return fail(JRC_ERR_INVALID, "stream kernel does not fit (smem %zu bytes)", smem);
-    h->fused_ctas_per_sm = per_sm;
-    const long long units = (long long)P.n_cpi * (IR / SPU);
-    long long grid = (long long)h->sm_count * per_sm;
-    if (grid * WPC > units) grid = (units + WPC - 1) / WPC;
-    kern<<<(unsigned)grid, WPC * 32, smem, h->stream>>>(P);
+    const jrc_chain_cfg &c = h->cfg;
+    ExactParams P;
+    memset(&P, 0, sizeof(P));
+    P.rx = rx; P.tx = tx; P.H = H;
+    P.N = c.fft_len; P.T = c.n_tx; P.R = c.n_rx; P.S = c.n_sym; P.n_pre = n_pre; P.tx_interleave = c.tx_interleave;
+    P.V = h->V; P.Nr = h->Nr; P.Na = h->Na; P.log2Nr = ilog2(h->Nr); P.log2Na = ilog2(h->Na);
+    ST(get_twiddles(h, h->Nr, 0, &P.tw_r));
+    ST(get_twiddles(h, h->Na, 1, &P.tw_a));
+    P.est = est; P.dets = dets; P.map = map; P.cpi0 = cpi0;
+    P.ctl = (FixCtl *)h->sFix.p;
+    P.list = (const int *)((char *)h->sFix.p + 16);
+    const int big = h->Nr > h->Na ? h->Nr : h->Na;
+    P.buf_elems = big > 8192 ? big : 8192;
+    const size_t smem = (size_t)P.buf_elems * sizeof(c32);
+    if (!h->exact_grid) {
+        CU(cudaFuncSetAttribute(k_est_exact, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        h->exact_grid = 32;
+    }
+    ST(h->sExact.need((size_t)h->exact_grid * h->V * h->Nr * sizeof(c32)));
+    P.scratch = (c32 *)h->sExact.p;
+    k_est_exact<<<h->exact_grid, 256, smem, h->stream>>>(P);
     CU(cudaGetLastError());
     h->launches++;
-    if (P.dets) {
-        auto fin = k_stream_finalize<IR, IA, WPC>;
-        CU(cudaFuncSetAttribute(fin, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        fin<<<(unsigned)((P.n_cpi + WPC - 1) / WPC), WPC * 32, smem, h->stream>>>(P);
-        CU(cudaGetLastError());
-        h->launches++;
-    }
     return JRC_OK;
-}
-
-static jrc_status launch_stream(jrc_chain *h, const StreamParams &P)
-{
-    const int IR = h->cfg.interp_range, IA = h->cfg.interp_angle;
-#define JRC_STREAM_CASE(ir, ia) if (IR == ir && IA == ia) return launch_stream_t<ir, ia>(h, P);
-    JRC_STREAM_CASE(8, 16)
-    JRC_STREAM_CASE(16, 8)
-    JRC_STREAM_CASE(8, 8)
-    JRC_STREAM_CASE(16, 16)
-#undef JRC_STREAM_CASE
-    return fail(JRC_ERR_INVALID, "no stream kernel for this configuration");
-}
-
-// ---------------------------------------------------------------------------
-// tensor-core path (jrc_tc.cuh): k_chan_est -> k_tc64x8 -> k_tc_finalize
-// ---------------------------------------------------------------------------
-static float tf32_hi(float x)
-{
-    uint32_t u;
-    memcpy(&u, &x, 4);
-    u &= 0xFFFFE000u;
-    memcpy(&x, &u, 4);
-    return x;
-}
-
-static jrc_status tc_operand(jrc_chain *h)
-{
-    if (h->d_bblob) return JRC_OK;
-    const int NA = h->Na, N = 2 * NA;
-    std::vector<float> img((size_t)N * 32, 0.f);
-    for (int i = 0; i < NA; i++)
-        for (int p = 0; p < 8; p++) {
-            // D[p][i] = (-1)^p e^{-j 2 pi p i / NA}: the angle DFT with its output fftshift folded in
-            const double a = -2.0 * M_PI * (double)((p * i) % NA) / (double)NA, sg = (p & 1) ? -1.0 : 1.0;
-            const double dr = sg * cos(a), di = sg * sin(a);
-            const double rows[2][2] = {{dr, -di}, {di, dr}};   // Re row: (yr, yi) -> dr, -di;  Im row: di, dr
-            for (int ri = 0; ri < 2; ri++)
-                for (int c = 0; c < 2; c++) {
-                    const int j = 2 * i + ri, k = 2 * p + c;
-                    const float full = (float)rows[ri][c], hi = tf32_hi(full), lo = tf32_hi(full - hi);
-                    auto at = [&](int kk) { return (size_t)(j >> 3) * 256 + (j & 7) * 32 + ((((kk >> 2) ^ (j & 7)) << 2) + (kk & 3)); };
-                    img[at(k)] = hi;
-                    img[at(16 + k)] = lo;
-                }
-        }
-    CU(cudaMalloc(&h->d_bblob, img.size() * sizeof(float)));
-    CU(cudaMemcpyAsync(h->d_bblob, img.data(), img.size() * sizeof(float), cudaMemcpyHostToDevice, h->stream));
-    CU(cudaStreamSynchronize(h->stream));
-    return JRC_OK;
-}
-
-template <int IR, int IA>
-static jrc_status launch_tc_t(jrc_chain *h, const TcParams &P)
-{
-    using Gm = TcGeom<IR, IA>;
-    auto kern = k_tc64x8<IR, IA>;
-    // a TMEM kernel gets one CTA per SM; the CTA holds Gm::GROUPS independent 4-warp groups
-    const size_t smem = Gm::SMEM;
-    CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int per_sm = 1;
-    h->fused_ctas_per_sm = per_sm;
-    const long long units = (long long)P.n_cpi * (IR / 2);
-    long long grid = (long long)h->sm_count * per_sm;
-    if (grid * Gm::GROUPS > units) grid = (units + Gm::GROUPS - 1) / Gm::GROUPS;
-    kern<<<(unsigned)grid, Gm::THREADS, smem, h->stream>>>(P);
-    CU(cudaGetLastError());
-    h->launches++;
-    if (P.dets) {
-        k_map_finalize<<<(unsigned)P.n_cpi, 128, (size_t)Gm::NA * sizeof(float), h->stream>>>(
-            P.map, P.keys, P.n_cpi, Gm::NR, Gm::NA, P.est, P.dets, P.cpi0);
-        CU(cudaGetLastError());
-        h->launches++;
-    }
-    return JRC_OK;
-}
-
-static bool tc_config_ok(const jrc_chain *h)
-{
-    const int IR = h->cfg.interp_range, IA = h->cfg.interp_angle;
-    return h->cfg.fft_len == 64 && h->V == 8 && ((IR == 16 && IA == 8) || (IR == 8 && IA == 16) || (IR == 8 && IA == 8) || (IR == 16 && IA == 16));
-}
-
-static jrc_status launch_tc(jrc_chain *h, const TcParams &P)
-{
-    const int IR = h->cfg.interp_range, IA = h->cfg.interp_angle;
-#define JRC_TC_CASE(ir, ia) if (IR == ir && IA == ia) return launch_tc_t<ir, ia>(h, P);
-    JRC_TC_CASE(16, 8)
-    JRC_TC_CASE(8, 16)
-    JRC_TC_CASE(8, 8)
-    JRC_TC_CASE(16, 16)
-#undef JRC_TC_CASE
-    return fail(JRC_ERR_INVALID, "no tensor-core kernel for this configuration");
 }
 
 static bool fused_config_ok(const jrc_chain *h)
@@ -676,8 +604,10 @@ static bool fused_config_ok(const jrc_chain *h)
 
 static bool aligned16(const void *p) { return ((uintptr_t)p & 15u) == 0; }
 
-extern "C" jrc_status jrc_chain_run_batch(jrc_chain *h, jrc_port_layout rx, jrc_port_layout tx, int32_t n_cpi,
-                                           int32_t cpi0, float *map, jrc_c32 *cmap, jrc_det *dets, int32_t path)
+// n_pre: symbols to skip in front of every antenna row (cfg.n_pre for GNU Radio packets, 0 for the packed host layout).
+// defer_exact: do not launch k_est_exact; the caller looks at the DET_PENDING marks itself (latency path).
+static jrc_status run_batch_impl(jrc_chain *h, jrc_port_layout rx, jrc_port_layout tx, int32_t n_cpi, int32_t cpi0,
+                                 float *map, jrc_c32 *cmap, jrc_det *dets, int32_t path, int n_pre, bool defer_exact)
 {
     if (!h) return fail(JRC_ERR_INVALID, "null handle");
     if (n_cpi < 0) return fail(JRC_ERR_INVALID, "n_cpi < 0");
@@ -687,9 +617,13 @@ extern "C" jrc_status jrc_chain_run_batch(jrc_chain *h, jrc_port_layout rx, jrc_
     CU(cudaSetDevice(h->cfg.device));
     const jrc_chain_cfg &c = h->cfg;
     const int N = c.fft_len, V = h->V, Nr = h->Nr, Na = h->Na;
+    if (!is_pow2(N) || !is_pow2(Nr) || !is_pow2(Na) || Nr > 16384 || Na > 16384)
+        return fail(JRC_ERR_INVALID, "the FFT chain needs power-of-two fft_len / Nr=%d / Na=%d <= 16384", Nr, Na);
     PortDev drx{(const c32 *)rx.base, rx.cpi_stride, rx.ant_stride};
     PortDev dtx{(const c32 *)tx.base, tx.cpi_stride, tx.ant_stride};
     const bool bg = c.background_removal != 0;
+    const bool recording = h->bg_recording.load() != 0;
+    NvtxRange nv_batch("jrc_chain_run_batch");
 
     bool want_fused = (path == JRC_PATH_AUTO || path == JRC_PATH_FUSED) && fused_config_ok(h) && cmap == nullptr;
     if (want_fused && !bg) {
@@ -702,81 +636,44 @@ extern "C" jrc_status jrc_chain_run_batch(jrc_chain *h, jrc_port_layout rx, jrc_
     if (path == JRC_PATH_FUSED && !want_fused)
         return fail(JRC_ERR_INVALID, "fused path requested but this configuration/layout has no fused kernel");
 
-    if (want_fused && map && h->stream_mode == 2 && tc_config_ok(h)) {
-        // tensor-core hot path: channel estimates (+ background ring) -> range passes + tcgen05 angle DFT
-        ST(stream_tables(h));
-        ST(tc_operand(h));
-        ST(h->sH.need((size_t)n_cpi * V * N * sizeof(c32)));
-        ST(launch_chan_est(h, drx, dtx, n_cpi, (c32 *)h->sH.p));
-        TcParams TP;
-        memset(&TP, 0, sizeof(TP));
-        TP.H = (const c32 *)h->sH.p; TP.n_cpi = n_cpi; TP.cpi0 = cpi0; TP.map = map;
-        TP.tw1g = h->d_tw1g; TP.tw2g = h->d_tw2g; TP.bblob = h->d_bblob;
-        if (dets) {
-            ST(est_params(h, Nr, Na, &TP.est));
-            ST(h->sKeys.need(sizeof(unsigned long long) * (size_t)n_cpi));
-            CU(cudaMemsetAsync(h->sKeys.p, 0, sizeof(unsigned long long) * (size_t)n_cpi, h->stream));
-            TP.keys = (unsigned long long *)h->sKeys.p;
-            TP.dets = (DetDev *)dets;
-        }
-        ST(launch_tc(h, TP));
-        h->last_path = JRC_PATH_FUSED;
-        return JRC_OK;
+    EstParams EP;
+    FixCtl *fix_ctl = nullptr;
+    int *fix_list = nullptr;
+    if (dets) {
+        ST(est_params(h, Nr, Na, &EP));
+        ST(fix_buffers(h, n_cpi, &fix_ctl, &fix_list));
     }
-    if (want_fused && map && h->stream_mode == 1) {
-        // map-producing hot path: channel estimates (+ background ring) -> slice-streaming kernel
-        ST(stream_tables(h));
-        ST(h->sH.need((size_t)n_cpi * V * N * sizeof(c32)));
-        ST(launch_chan_est(h, drx, dtx, n_cpi, (c32 *)h->sH.p));
-        StreamParams SP;
-        memset(&SP, 0, sizeof(SP));
-        SP.H = (const c32 *)h->sH.p; SP.n_cpi = n_cpi; SP.cpi0 = cpi0; SP.map = map;
-        SP.tw1g = h->d_tw1g; SP.tw2g = h->d_tw2g;
-        if (dets) {
-            ST(est_params(h, Nr, Na, &SP.est));
-            ST(h->sKeys.need(sizeof(unsigned long long) * (size_t)n_cpi));
-            CU(cudaMemsetAsync(h->sKeys.p, 0, sizeof(unsigned long long) * (size_t)n_cpi, h->stream));
-            SP.keys = (unsigned long long *)h->sKeys.p;
-            SP.dets = (DetDev *)dets;
-        }
-        ST(launch_stream(h, SP));
-        h->last_path = JRC_PATH_FUSED;
-        return JRC_OK;
-    }
+
     if (want_fused) {
+        NvtxRange nv("fused: k_fused64x8");
         FusedParams P;
         memset(&P, 0, sizeof(P));
         P.rx = drx; P.tx = dtx; P.n_cpi = n_cpi; P.cpi0 = cpi0;
-        P.T = c.n_tx; P.R = c.n_rx; P.S = c.n_sym; P.n_pre = c.n_pre; P.tx_interleave = c.tx_interleave;
+        P.T = c.n_tx; P.R = c.n_rx; P.S = c.n_sym; P.n_pre = n_pre; P.tx_interleave = c.tx_interleave;
         P.map = map; P.dets = (DetDev *)dets;
         if (dets) {
-            ST(est_params(h, Nr, Na, &P.est));
+            P.est = EP;
             P.win_tab = h->d_win_tab; P.g_tab = h->d_g_tab;
-        }
-        const bool map_backed = dets && map && h->det_mode == 0;   // detections from key + map after the kernel
-        if (map_backed) {
-            ST(h->sKeys.need(sizeof(unsigned long long) * (size_t)n_cpi));
-            CU(cudaMemsetAsync(h->sKeys.p, 0, sizeof(unsigned long long) * (size_t)n_cpi, h->stream));
-            P.keys = (unsigned long long *)h->sKeys.p;
-            P.dets = nullptr;
+            P.fix_ctl = fix_ctl; P.fix_list = fix_list;
         }
         bool ok = false;
-        if (bg || c.background_recording) {
+        const c32 *Hsrc = nullptr;
+        if (bg || recording) {
             // background path: raw estimates -> ring update/subtraction -> fused kernel from H
             ST(h->sH.need((size_t)n_cpi * V * N * sizeof(c32)));
-            ST(launch_chan_est(h, drx, dtx, n_cpi, (c32 *)h->sH.p));
-            P.H = (const c32 *)h->sH.p;
+            ST(launch_chan_est(h, drx, dtx, n_cpi, (c32 *)h->sH.p, n_pre));
+            P.H = Hsrc = (const c32 *)h->sH.p;
             ST(launch_fused<true>(h, P, &ok));
         } else {
             ST(launch_fused<false>(h, P, &ok));
         }
-        if (ok && map_backed) {
-            k_map_finalize<<<(unsigned)n_cpi, 128, (size_t)Na * sizeof(float), h->stream>>>(
-                map, (const unsigned long long *)h->sKeys.p, n_cpi, Nr, Na, P.est, (DetDev *)dets, cpi0);
-            CU(cudaGetLastError());
-            h->launches++;
+        if (ok) {
+            h->last_path = JRC_PATH_FUSED;
+            if (dets && !defer_exact) ST(launch_exact(h, drx, dtx, Hsrc, n_pre, cpi0, map, (DetDev *)dets, EP));
+            return JRC_OK;
         }
-        if (ok) { h->last_path = JRC_PATH_FUSED; return JRC_OK; }
+        if (path == JRC_PATH_FUSED)
+            return fail(JRC_ERR_INVALID, "fused kernel does not fit this configuration (n_sym = %d symbols in shared memory)", c.n_sym);
     }
 
     // ---- tiled path: configurations without a fused specialisation -------------
@@ -785,6 +682,7 @@ extern "C" jrc_status jrc_chain_run_batch(jrc_chain *h, jrc_port_layout rx, jrc_
     if (path == JRC_PATH_TILED && !want_tiled)
         return fail(JRC_ERR_INVALID, "tiled path requested but this configuration has no tiled kernel");
     if (want_tiled) {
+        NvtxRange nv("tiled: chan_est + range FFT + angle FFT");
         h->last_path = JRC_PATH_TILED;
         const size_t per = ((size_t)V * N + (size_t)V * Nr) * sizeof(c32) + (map ? 0 : (size_t)Nr * Na * sizeof(float));
         int chunk = (int)(((size_t)1 << 30) / per);
@@ -793,10 +691,9 @@ extern "C" jrc_status jrc_chain_run_batch(jrc_chain *h, jrc_port_layout rx, jrc_
         ST(h->sH.need((size_t)chunk * V * N * sizeof(c32)));
         ST(h->sY.need((size_t)chunk * V * Nr * sizeof(c32)));
         if (!map) ST(h->sC.need((size_t)chunk * Nr * Na * sizeof(float)));
-        EstParams EP;
         if (dets) {
-            ST(est_params(h, Nr, Na, &EP));
             ST(h->sKeys.need(sizeof(unsigned long long) * (size_t)chunk));
+            ST(h->sSec.need(sizeof(unsigned) * (size_t)chunk));
         }
         for (int c0 = 0; c0 < n_cpi; c0 += chunk) {
             const int nc = n_cpi - c0 < chunk ? n_cpi - c0 : chunk;
@@ -806,21 +703,28 @@ extern "C" jrc_status jrc_chain_run_batch(jrc_chain *h, jrc_port_layout rx, jrc_
             c32 *dH = (c32 *)h->sH.p, *dY = (c32 *)h->sY.p;
             float *dM = map ? map + (size_t)c0 * Nr * Na : (float *)h->sC.p;
             unsigned long long *dK = dets ? (unsigned long long *)h->sKeys.p : nullptr;
-            ST(launch_chan_est(h, crx, ctx, nc, dH));
+            unsigned *dS = dets ? (unsigned *)h->sSec.p : nullptr;
+            ST(launch_chan_est(h, crx, ctx, nc, dH, n_pre));
             ST(launch_fft8_rows(h, dH, N, N, dY, Nr, (long long)nc * V));
-            if (dK) CU(cudaMemsetAsync(dK, 0, sizeof(unsigned long long) * (size_t)nc, h->stream));
-            ST(launch_angle_mag(h, dY, V, Nr, Na, nc, dM, dK));
+            if (dK) {
+                CU(cudaMemsetAsync(dK, 0, sizeof(unsigned long long) * (size_t)nc, h->stream));
+                CU(cudaMemsetAsync(dS, 0, sizeof(unsigned) * (size_t)nc, h->stream));
+            }
+            ST(launch_angle_mag(h, dY, V, Nr, Na, nc, dM, dK, dS));
             if (dets) {
                 k_map_finalize<<<(unsigned)nc, 128, (size_t)Na * sizeof(float), h->stream>>>(
-                    dM, dK, nc, Nr, Na, EP, (DetDev *)dets + c0, cpi0 + c0);
+                    dM, dK, dS, nc, Nr, Na, EP, (DetDev *)dets + c0, cpi0 + c0, fix_ctl, fix_list);
                 CU(cudaGetLastError());
                 h->launches++;
+                // (the channel estimates of the chunk are still in dH: background removal included)
+                ST(launch_exact(h, crx, ctx, dH, n_pre, cpi0 + c0, dM, (DetDev *)dets + c0, EP));
             }
         }
         return JRC_OK;
     }
 
     // ---- staged path: one kernel per reference block, chunked over CPIs ------
+    NvtxRange nv("staged: one kernel per reference block");
     h->last_path = JRC_PATH_STAGED;
     const size_t per_cpi = ((size_t)V * N + (size_t)V * Nr + (cmap ? 0 : (size_t)Nr * Na)) * sizeof(c32);
     const size_t budget = (size_t)1 << 30;
@@ -838,7 +742,7 @@ extern "C" jrc_status jrc_chain_run_batch(jrc_chain *h, jrc_port_layout rx, jrc_
         ctx.base += (long long)c0 * tx.cpi_stride;
         c32 *dH = (c32 *)h->sH.p, *dY = (c32 *)h->sY.p;
         c32 *dC = cmap ? (c32 *)cmap + (size_t)c0 * Nr * Na : (c32 *)h->sC.p;
-        ST(launch_chan_est(h, crx, ctx, nc, dH));
+        ST(launch_chan_est(h, crx, ctx, nc, dH, n_pre));
         // fft_vcc #A: backward, no shift; the zero-padded tail is implied by n_in = N
         ST(launch_fft_rows(h, dH, N, N, dY, Nr, (long long)nc * V, 0, 0));
         // matrix_transpose + fft_vcc #B (forward, shift).  The transpose is materialised
@@ -854,6 +758,13 @@ extern "C" jrc_status jrc_chain_run_batch(jrc_chain *h, jrc_port_layout rx, jrc_
         if (dets) ST(launch_estimate(h, dC, Nr, Na, nc, cpi0 + c0, (DetDev *)dets + c0));
     }
     return JRC_OK;
+}
+
+extern "C" jrc_status jrc_chain_run_batch(jrc_chain *h, jrc_port_layout rx, jrc_port_layout tx, int32_t n_cpi,
+                                           int32_t cpi0, float *map, jrc_c32 *cmap, jrc_det *dets, int32_t path)
+{
+    if (!h) return fail(JRC_ERR_INVALID, "null handle");
+    return run_batch_impl(h, rx, tx, n_cpi, cpi0, map, cmap, dets, path, h->cfg.n_pre, false);
 }
 
 // ---------------------------------------------------------------------------
@@ -881,6 +792,251 @@ static bool ptr_is_device(const void *p)
     return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
 }
 
+// The final scalar of lib/range_angle_estimator_impl.cc:227,234 with the HOST libm, like jrc_estimate2d: what a block
+// publishes has the bit pattern the reference's own expression gives on this record's peak and noise power.  A record
+// whose device-side gate was within the margin was redone in the reference's order before (jrc_exact.cuh).
+static void finish_records_host(const jrc_chain *h, jrc_det *d, int n)
+{
+    for (int i = 0; i < n; i++) {
+        if (d[i].range_idx < 0) continue;
+        d[i].snr_db = 10 * std::log10(d[i].peak_power / d[i].noise_power);
+        const uint32_t pass = (d[i].snr_db >= h->snr_thr && d[i].peak_power >= h->pow_thr) ? JRC_DET_PASSED : 0u;
+        d[i].flags = pass | (d[i].flags & JRC_DET_EXACT);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// streaming: jrc_chain_submit / jrc_chain_wait (BASELINE configs[3]).  Up to JRC_STREAM_DEPTH submissions are in
+// flight, each on the stream of its slot, so CPI k+1's input transfer and kernel overlap CPI k's output transfer.
+// ---------------------------------------------------------------------------
+struct StreamSlot {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t done = nullptr;
+    GrowBuf in, map, dets, pin_in, pin_out, fix, exact;
+    bool busy = false, deferred = false;
+    int64_t ticket = 0;
+    int n_cpi = 0, cpi0 = 0, tx_shared = 0;
+    float *map_host = nullptr, *map_stage = nullptr;         // caller buffer / pinned staging copy (nullptr: written in place)
+    jrc_det *dets_host = nullptr, *dets_final = nullptr;     // caller buffer / where the records land (pinned)
+    const c32 *z_rx = nullptr, *z_tx = nullptr;              // device aliases of the (pinned) inputs, deferred exact pass
+    float *z_map = nullptr;
+    jrc_det *z_dets = nullptr;
+};
+
+struct jrc_stream_state {
+    StreamSlot slot[JRC_STREAM_DEPTH];
+    int64_t next_ticket = 1;
+    bool ready = false;
+};
+
+static jrc_status stream_state(jrc_chain *h, jrc_stream_state **out)
+{
+    if (!h->sstate) h->sstate = new jrc_stream_state();
+    jrc_stream_state *S = h->sstate;
+    if (!S->ready) {
+        for (StreamSlot &sl : S->slot) {
+            CU(cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking));
+            CU(cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming));
+            sl.pin_in.pinned = sl.pin_out.pinned = true;
+        }
+        S->ready = true;
+    }
+    *out = S;
+    return JRC_OK;
+}
+
+static void stream_state_destroy(jrc_chain *h)
+{
+    if (!h->sstate) return;
+    for (StreamSlot &sl : h->sstate->slot) {
+        if (sl.stream) { cudaStreamSynchronize(sl.stream); cudaStreamDestroy(sl.stream); }
+        if (sl.done) cudaEventDestroy(sl.done);
+        GrowBuf *bufs[] = {&sl.in, &sl.map, &sl.dets, &sl.pin_in, &sl.pin_out, &sl.fix, &sl.exact};
+        for (GrowBuf *b : bufs) b->release();
+    }
+    delete h->sstate;
+    h->sstate = nullptr;
+}
+
+// runs fn with the slot's stream and marked-CPI list in place of the handle's
+template <class F>
+static jrc_status on_slot(jrc_chain *h, StreamSlot &sl, F fn)
+{
+    std::swap(h->stream, sl.stream);
+    std::swap(h->sFix, sl.fix);
+    std::swap(h->sExact, sl.exact);
+    jrc_status st = fn();
+    std::swap(h->stream, sl.stream);
+    std::swap(h->sFix, sl.fix);
+    std::swap(h->sExact, sl.exact);
+    return st;
+}
+
+extern "C" jrc_status jrc_chain_submit(jrc_chain *h, const jrc_c32 *rx_host, const jrc_c32 *tx_host, int32_t tx_shared,
+                                        int32_t n_cpi, int32_t cpi0, float *map_host, jrc_det *dets_host, int64_t *ticket)
+{
+    if (!h || !rx_host || !tx_host || !ticket) return fail(JRC_ERR_INVALID, "null argument");
+    if (n_cpi <= 0) return fail(JRC_ERR_INVALID, "n_cpi must be positive");
+    if (dets_host && !h->est_set) return fail(JRC_ERR_STATE, "dets requested but jrc_chain_set_estimator has not been called");
+    CU(cudaSetDevice(h->cfg.device));
+    jrc_stream_state *S = nullptr;
+    ST(stream_state(h, &S));
+    StreamSlot *slp = nullptr;
+    for (StreamSlot &c : S->slot) if (!c.busy) { slp = &c; break; }
+    if (!slp) return fail(JRC_ERR_STATE, "%d submissions in flight: jrc_chain_wait first", (int)JRC_STREAM_DEPTH);
+    StreamSlot &sl = *slp;
+    const jrc_chain_cfg &c = h->cfg;
+    NvtxRange nv("jrc_chain_submit");
+    // the background ring buffer evolves frame by frame (lib/mimo_ofdm_radar_impl.cc:276-300): with it, submissions
+    // run one after the other
+    const bool bgp = c.background_removal || h->bg_recording.load();
+    if (bgp)
+        for (StreamSlot &o : S->slot)
+            if (o.busy) CU(cudaEventSynchronize(o.done));
+    const size_t rx_cpi = (size_t)c.n_rx * c.n_sym * c.fft_len, tx_cpi = (size_t)c.n_tx * c.n_sym * c.fft_len;
+    const size_t map_cpi = (size_t)h->Nr * h->Na;
+    const size_t txn = tx_shared ? tx_cpi : (size_t)n_cpi * tx_cpi;
+    const size_t rx_bytes = (size_t)n_cpi * rx_cpi * sizeof(c32), tx_bytes = txn * sizeof(c32);
+    const size_t map_bytes = (size_t)n_cpi * map_cpi * sizeof(float), det_bytes = (size_t)n_cpi * sizeof(jrc_det);
+
+    // inputs: pinned caller memory is used in place, pageable memory goes through the slot's pinned buffer
+    const c32 *src_rx = (const c32 *)rx_host, *src_tx = (const c32 *)tx_host;
+    if (!(host_ptr_is_pinned(rx_host) && host_ptr_is_pinned(tx_host))) {
+        ST(sl.pin_in.need(rx_bytes + tx_bytes));
+        memcpy(sl.pin_in.p, rx_host, rx_bytes);
+        memcpy((char *)sl.pin_in.p + rx_bytes, tx_host, tx_bytes);
+        src_rx = (const c32 *)sl.pin_in.p;
+        src_tx = (const c32 *)((char *)sl.pin_in.p + rx_bytes);
+    }
+    // outputs: likewise
+    float *dst_map = map_host;
+    jrc_det *dst_dets = dets_host;
+    const bool map_direct = !map_host || host_ptr_is_pinned(map_host), dets_direct = !dets_host || host_ptr_is_pinned(dets_host);
+    if (!map_direct || !dets_direct) {
+        ST(sl.pin_out.need((map_direct ? 0 : map_bytes) + (dets_direct ? 0 : det_bytes)));
+        if (!map_direct) dst_map = (float *)sl.pin_out.p;
+        if (!dets_direct) dst_dets = (jrc_det *)((char *)sl.pin_out.p + (map_direct ? 0 : map_bytes));
+    }
+    sl.n_cpi = n_cpi; sl.cpi0 = cpi0; sl.tx_shared = tx_shared;
+    sl.map_host = map_host; sl.map_stage = map_direct ? nullptr : dst_map;
+    sl.dets_host = dets_host; sl.dets_final = dst_dets;
+    sl.deferred = false;
+
+    const c32 *z_rx = (const c32 *)host_dev_alias(src_rx), *z_tx = (const c32 *)host_dev_alias(src_tx);
+    float *z_map = (float *)host_dev_alias(dst_map);
+    jrc_det *z_dets = (jrc_det *)host_dev_alias(dst_dets);
+    const long long ant = (long long)c.n_sym * c.fft_len;
+    jrc_status st;
+    if (h->zero_copy && n_cpi <= 4 && fused_config_ok(h) && z_rx && z_tx && (!map_host || z_map) && (!dets_host || z_dets)) {
+        // A few CPIs: the copies cost more than the kernel.  Pinned host memory is device-accessible (unified
+        // addressing): the kernel prefetches the symbols over PCIe itself and streams map and records straight into
+        // host memory while it computes -- one launch.  Marked records (jrc_exact.cuh) are looked at in wait().
+        jrc_port_layout zrx{(const jrc_c32 *)z_rx, (int64_t)rx_cpi, ant};
+        jrc_port_layout ztx{(const jrc_c32 *)z_tx, tx_shared ? 0 : (int64_t)tx_cpi, ant};
+        sl.z_rx = z_rx; sl.z_tx = z_tx; sl.z_map = z_map; sl.z_dets = z_dets;
+        sl.deferred = dets_host != nullptr && !bgp;
+        st = on_slot(h, sl, [&]() { return run_batch_impl(h, zrx, ztx, n_cpi, cpi0, z_map, nullptr, z_dets, JRC_PATH_AUTO, 0, sl.deferred); });
+    } else {
+        ST(sl.in.need(rx_bytes + tx_bytes));
+        if (map_host) ST(sl.map.need(map_bytes));
+        if (dets_host) ST(sl.dets.need(det_bytes));
+        c32 *d_rx = (c32 *)sl.in.p, *d_tx = (c32 *)((char *)sl.in.p + rx_bytes);
+        float *d_map = map_host ? (float *)sl.map.p : nullptr;
+        jrc_det *d_dets = dets_host ? (jrc_det *)sl.dets.p : nullptr;
+        CU(cudaMemcpyAsync(d_rx, src_rx, rx_bytes, cudaMemcpyHostToDevice, sl.stream));
+        CU(cudaMemcpyAsync(d_tx, src_tx, tx_bytes, cudaMemcpyHostToDevice, sl.stream));
+        jrc_port_layout lrx{(const jrc_c32 *)d_rx, (int64_t)rx_cpi, ant};
+        jrc_port_layout ltx{(const jrc_c32 *)d_tx, tx_shared ? 0 : (int64_t)tx_cpi, ant};
+        st = on_slot(h, sl, [&]() { return run_batch_impl(h, lrx, ltx, n_cpi, cpi0, d_map, nullptr, d_dets, JRC_PATH_AUTO, 0, false); });
+        if (st == JRC_OK && map_host) CU(cudaMemcpyAsync(dst_map, d_map, map_bytes, cudaMemcpyDeviceToHost, sl.stream));
+        if (st == JRC_OK && dets_host) CU(cudaMemcpyAsync(dst_dets, d_dets, det_bytes, cudaMemcpyDeviceToHost, sl.stream));
+    }
+    if (st != JRC_OK) return st;
+    CU(cudaEventRecord(sl.done, sl.stream));
+    sl.busy = true;
+    sl.ticket = S->next_ticket++;
+    *ticket = sl.ticket;
+    return JRC_OK;
+}
+
+// pinned host memory for callers without a CUDA toolchain of their own (GNU Radio blocks, ctypes)
+extern "C" jrc_status jrc_pinned_alloc(size_t bytes, void **out)
+{
+    if (!out) return fail(JRC_ERR_INVALID, "null argument");
+    *out = nullptr;
+    CU(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocPortable | cudaHostAllocMapped));
+    return JRC_OK;
+}
+extern "C" jrc_status jrc_pinned_free(void *p)
+{
+    if (p) CU(cudaFreeHost(p));
+    return JRC_OK;
+}
+// page-locks an existing buffer (a GNU Radio stream buffer, a NumPy array) so that submit / run_host use it in place
+extern "C" jrc_status jrc_host_register(void *p, size_t bytes)
+{
+    if (!p || !bytes) return fail(JRC_ERR_INVALID, "null argument");
+    CU(cudaHostRegister(p, bytes, cudaHostRegisterPortable | cudaHostRegisterMapped));
+    return JRC_OK;
+}
+extern "C" jrc_status jrc_host_unregister(void *p)
+{
+    if (!p) return fail(JRC_ERR_INVALID, "null argument");
+    CU(cudaHostUnregister(p));
+    return JRC_OK;
+}
+
+static StreamSlot *find_ticket(jrc_chain *h, int64_t ticket)
+{
+    if (!h->sstate) return nullptr;
+    for (StreamSlot &c : h->sstate->slot) if (c.busy && c.ticket == ticket) return &c;
+    return nullptr;
+}
+
+extern "C" jrc_status jrc_chain_poll(jrc_chain *h, int64_t ticket, int32_t *done)
+{
+    if (!h || !done) return fail(JRC_ERR_INVALID, "null argument");
+    StreamSlot *sl = find_ticket(h, ticket);
+    if (!sl) return fail(JRC_ERR_INVALID, "unknown ticket %lld", (long long)ticket);
+    cudaError_t e = cudaEventQuery(sl->done);
+    if (e != cudaSuccess && e != cudaErrorNotReady) return fail(JRC_ERR_CUDA, "cudaEventQuery: %s", cudaGetErrorString(e));
+    *done = e == cudaSuccess;
+    return JRC_OK;
+}
+
+extern "C" jrc_status jrc_chain_wait(jrc_chain *h, int64_t ticket)
+{
+    if (!h) return fail(JRC_ERR_INVALID, "null handle");
+    StreamSlot *slp = find_ticket(h, ticket);
+    if (!slp) return fail(JRC_ERR_INVALID, "unknown ticket %lld", (long long)ticket);
+    StreamSlot &sl = *slp;
+    CU(cudaSetDevice(h->cfg.device));
+    NvtxRange nv("jrc_chain_wait");
+    sl.busy = false;                       // whatever happens below, the slot is free again
+    CU(cudaEventSynchronize(sl.done));
+    const jrc_chain_cfg &c = h->cfg;
+    if (sl.dets_final) {
+        if (sl.deferred) {
+            // marked records (jrc_exact.cuh) are rare: the reference-order pass is only launched when one is there
+            bool marked = false;
+            for (int i = 0; i < sl.n_cpi; i++) marked |= (sl.dets_final[i].flags & DET_PENDING) != 0;
+            if (marked) {
+                EstParams EP;
+                ST(est_params(h, h->Nr, h->Na, &EP));
+                const long long ant = (long long)c.n_sym * c.fft_len;
+                PortDev prx{sl.z_rx, (long long)c.n_rx * ant, ant};
+                PortDev ptx{sl.z_tx, sl.tx_shared ? 0 : (long long)c.n_tx * ant, ant};
+                ST(on_slot(h, sl, [&]() { return launch_exact(h, prx, ptx, nullptr, 0, sl.cpi0, sl.z_map, (DetDev *)sl.z_dets, EP); }));
+                CU(cudaStreamSynchronize(sl.stream));
+            }
+        }
+        finish_records_host(h, sl.dets_final, sl.n_cpi);
+        if (sl.dets_final != sl.dets_host) memcpy(sl.dets_host, sl.dets_final, (size_t)sl.n_cpi * sizeof(jrc_det));
+    }
+    if (sl.map_stage) memcpy(sl.map_host, sl.map_stage, (size_t)sl.n_cpi * h->Nr * h->Na * sizeof(float));
+    return JRC_OK;
+}
+
 extern "C" jrc_status jrc_chain_run_host(jrc_chain *h, const jrc_c32 *rx_host, const jrc_c32 *tx_host, int32_t tx_shared,
                                           int32_t n_cpi, int32_t cpi0, float *map_host, jrc_det *dets_host)
 {
@@ -895,6 +1051,15 @@ extern "C" jrc_status jrc_chain_run_host(jrc_chain *h, const jrc_c32 *rx_host, c
     int chunk = (int)(((size_t)128 << 20) / (map_cpi * sizeof(float)));
     if (chunk < 1) chunk = 1;
     if (chunk > n_cpi) chunk = n_cpi;
+    if (n_cpi <= chunk) {
+        // one chunk (typically one CPI per work() call): submit + wait on one slot
+        if (h->sstate)
+            for (StreamSlot &sl : h->sstate->slot)
+                if (sl.busy) return fail(JRC_ERR_STATE, "jrc_chain_run_host while submissions are in flight");
+        int64_t ticket = 0;
+        ST(jrc_chain_submit(h, rx_host, tx_host, tx_shared, n_cpi, cpi0, map_host, dets_host, &ticket));
+        return jrc_chain_wait(h, ticket);
+    }
     const bool direct = host_ptr_is_pinned(rx_host) && host_ptr_is_pinned(tx_host) &&
                         (!map_host || host_ptr_is_pinned(map_host)) && (!dets_host || host_ptr_is_pinned(dets_host));
     const size_t in_bytes = (rx_cpi + (tx_shared ? 0 : tx_cpi)) * sizeof(c32);
@@ -907,73 +1072,8 @@ extern "C" jrc_status jrc_chain_run_host(jrc_chain *h, const jrc_c32 *rx_host, c
         ST(h->pin_a.need((size_t)chunk * in_bytes + tx_cpi * sizeof(c32)));
         ST(h->pin_b.need((size_t)chunk * (map_host ? map_cpi * sizeof(float) : 0) + (size_t)chunk * sizeof(jrc_det)));
     }
-    // jrc_chain_run_batch ignores n_pre here: the host layout is already stripped
-    jrc_chain_cfg saved = h->cfg;
-    h->cfg.n_pre = 0;
     jrc_status st = JRC_OK;
-    if (n_cpi <= chunk) {
-        // streaming / latency mode (one chunk, typically one CPI per work() call): a single stream,
-        // no cross-stream events -- copy in, kernels, copy out, one synchronisation
-        c32 *d_rx = (c32 *)h->sIn[0].p, *d_tx = d_rx + (size_t)chunk * rx_cpi;
-        const c32 *src_rx = (const c32 *)rx_host, *src_tx = (const c32 *)tx_host;
-        const size_t txn = tx_shared ? tx_cpi : (size_t)n_cpi * tx_cpi;
-        if (!direct) {
-            memcpy(h->pin_a.p, src_rx, (size_t)n_cpi * rx_cpi * sizeof(c32));
-            memcpy((c32 *)h->pin_a.p + (size_t)n_cpi * rx_cpi, src_tx, txn * sizeof(c32));
-            src_rx = (const c32 *)h->pin_a.p;
-            src_tx = src_rx + (size_t)n_cpi * rx_cpi;
-        }
-        float *dst_map0 = map_host;
-        jrc_det *dst_dets0 = dets_host;
-        if (!direct) {
-            dst_map0 = map_host ? (float *)h->pin_b.p : nullptr;
-            dst_dets0 = dets_host ? (jrc_det *)((char *)h->pin_b.p + (map_host ? (size_t)chunk * map_cpi * sizeof(float) : 0)) : nullptr;
-        }
-        const c32 *z_rx = (const c32 *)host_dev_alias(src_rx), *z_tx = (const c32 *)host_dev_alias(src_tx);
-        float *z_map = (float *)host_dev_alias(dst_map0);
-        jrc_det *z_dets = (jrc_det *)host_dev_alias(dst_dets0);
-        // (fused kernel only: the tiled and staged paths re-read their outputs)
-        if (h->zero_copy && n_cpi <= 4 && fused_config_ok(h) && z_rx && z_tx && (!map_host || z_map) && (!dets_host || z_dets)) {
-            // A few CPIs: the copies cost more than the kernel.  Pinned host memory is device-accessible (unified
-            // addressing): the kernel prefetches the symbols over PCIe itself and streams map and records
-            // straight into the host buffers while it computes -- one launch, one synchronisation.
-            jrc_port_layout zrx{(const jrc_c32 *)z_rx, (int64_t)rx_cpi, (int64_t)c.n_sym * c.fft_len};
-            jrc_port_layout ztx{(const jrc_c32 *)z_tx, tx_shared ? 0 : (int64_t)tx_cpi, (int64_t)c.n_sym * c.fft_len};
-            st = jrc_chain_run_batch(h, zrx, ztx, n_cpi, cpi0, z_map, nullptr, z_dets, JRC_PATH_AUTO);
-            h->cfg = saved;
-            if (st != JRC_OK) return st;
-            CU(cudaStreamSynchronize(h->stream));
-            if (!direct) {
-                if (map_host) memcpy(map_host, dst_map0, (size_t)n_cpi * map_cpi * sizeof(float));
-                if (dets_host) memcpy(dets_host, dst_dets0, (size_t)n_cpi * sizeof(jrc_det));
-            }
-            return JRC_OK;
-        }
-        cudaError_t e = cudaMemcpyAsync(d_rx, src_rx, (size_t)n_cpi * rx_cpi * sizeof(c32), cudaMemcpyHostToDevice, h->stream);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(d_tx, src_tx, txn * sizeof(c32), cudaMemcpyHostToDevice, h->stream);
-        if (e != cudaSuccess) { h->cfg = saved; return fail(JRC_ERR_CUDA, "H2D: %s", cudaGetErrorString(e)); }
-        jrc_port_layout lrx{(const jrc_c32 *)d_rx, (int64_t)rx_cpi, (int64_t)c.n_sym * c.fft_len};
-        jrc_port_layout ltx{(const jrc_c32 *)d_tx, tx_shared ? 0 : (int64_t)tx_cpi, (int64_t)c.n_sym * c.fft_len};
-        float *d_map = map_host ? (float *)h->sMap[0].p : nullptr;
-        jrc_det *d_dets = dets_host ? (jrc_det *)h->sDets[0].p : nullptr;
-        st = jrc_chain_run_batch(h, lrx, ltx, n_cpi, cpi0, d_map, nullptr, d_dets, JRC_PATH_AUTO);
-        h->cfg = saved;
-        if (st != JRC_OK) return st;
-        float *dst_map = map_host;
-        jrc_det *dst_dets = dets_host;
-        if (!direct) {
-            dst_map = map_host ? (float *)h->pin_b.p : nullptr;
-            dst_dets = dets_host ? (jrc_det *)((char *)h->pin_b.p + (map_host ? (size_t)chunk * map_cpi * sizeof(float) : 0)) : nullptr;
-        }
-        if (map_host) CU(cudaMemcpyAsync(dst_map, d_map, (size_t)n_cpi * map_cpi * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
-        if (dets_host) CU(cudaMemcpyAsync(dst_dets, d_dets, (size_t)n_cpi * sizeof(jrc_det), cudaMemcpyDeviceToHost, h->stream));
-        CU(cudaStreamSynchronize(h->stream));
-        if (!direct) {
-            if (map_host) memcpy(map_host, dst_map, (size_t)n_cpi * map_cpi * sizeof(float));
-            if (dets_host) memcpy(dets_host, dst_dets, (size_t)n_cpi * sizeof(jrc_det));
-        }
-        return JRC_OK;
-    }
+    NvtxRange nv_host("jrc_chain_run_host (pipelined chunks)");
     int idx = 0;
     for (int c0 = 0; c0 < n_cpi && st == JRC_OK; c0 += chunk, idx++) {
         const int nc = n_cpi - c0 < chunk ? n_cpi - c0 : chunk;
@@ -1005,7 +1105,7 @@ extern "C" jrc_status jrc_chain_run_host(jrc_chain *h, const jrc_c32 *rx_host, c
         jrc_port_layout ltx{(const jrc_c32 *)d_tx, tx_shared ? 0 : (int64_t)tx_cpi, (int64_t)c.n_sym * c.fft_len};
         float *d_map = map_host ? (float *)h->sMap[s].p : nullptr;
         jrc_det *d_dets = dets_host ? (jrc_det *)h->sDets[s].p : nullptr;
-        st = jrc_chain_run_batch(h, lrx, ltx, nc, cpi0 + c0, d_map, nullptr, d_dets, JRC_PATH_AUTO);
+        st = run_batch_impl(h, lrx, ltx, nc, cpi0 + c0, d_map, nullptr, d_dets, JRC_PATH_AUTO, 0, false);
         if (st != JRC_OK) break;
         e = cudaEventRecord(h->ev_comp[s], h->stream);
         if (e == cudaSuccess) e = cudaStreamWaitEvent(h->s_d2h, h->ev_comp[s], 0);
@@ -1023,14 +1123,14 @@ extern "C" jrc_status jrc_chain_run_host(jrc_chain *h, const jrc_c32 *rx_host, c
         if (e == cudaSuccess && !direct) {
             e = cudaStreamSynchronize(h->s_d2h);
             if (e == cudaSuccess && map_host) memcpy(map_host + (size_t)c0 * map_cpi, dst_map, (size_t)nc * map_cpi * sizeof(float));
-            if (e == cudaSuccess && dets_host) memcpy(dets_host + c0, dst_dets, (size_t)nc * sizeof(jrc_det));
+            if (e == cudaSuccess && dets_host) { finish_records_host(h, dst_dets, nc); memcpy(dets_host + c0, dst_dets, (size_t)nc * sizeof(jrc_det)); }
         }
         if (e != cudaSuccess) { st = fail(JRC_ERR_CUDA, "pipeline D2H: %s", cudaGetErrorString(e)); break; }
     }
-    h->cfg = saved;
     cudaError_t e1 = cudaStreamSynchronize(h->s_h2d), e2 = cudaStreamSynchronize(h->stream), e3 = cudaStreamSynchronize(h->s_d2h);
     if (st == JRC_OK && (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess))
         st = fail(JRC_ERR_CUDA, "pipeline sync: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : (e2 != cudaSuccess ? e2 : e3)));
+    if (st == JRC_OK && dets_host && direct) finish_records_host(h, dets_host, n_cpi);
     return st;
 }
 
@@ -1098,7 +1198,7 @@ extern "C" jrc_status jrc_radar_estimate(jrc_chain *h, const jrc_c32 *const *tx,
     PortDev dtx{blk, 0, (long long)frame}, drx{blk + (size_t)c.n_tx * frame, 0, (long long)frame};
     ST(h->sH.need((size_t)V * N * sizeof(c32)));
     c32 *dH = (c32 *)h->sH.p;
-    ST(launch_chan_est(h, drx, dtx, 1, dH));
+    ST(launch_chan_est(h, drx, dtx, 1, dH, c.n_pre));
     void *dout = nullptr;
     ST(sg.out(out, (size_t)V * Nr * sizeof(c32), &dout));
     k_pad_rows<<<grid_for((long long)V * Nr, 256, h->sm_count), 256, 0, h->stream>>>(dH, (c32 *)dout, V, N, Nr);

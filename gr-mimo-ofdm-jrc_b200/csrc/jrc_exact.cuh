@@ -1,0 +1,265 @@
+// jrc_exact.cuh -- the reference-order resolution of range_angle_estimator decisions
+// (lib/range_angle_estimator_impl.cc:137-151 arg-max, :209-227 noise window, :234 gate).
+//
+// The fused and tiled kernels take their decisions on their own float32 map, which differs from the
+// staged (oracle-order) arithmetic by FFT rounding (~3e-7 of the map peak).  Wherever such a difference
+// could change a published DECISION they do not decide; they mark the record and k_est_exact redoes the
+// estimator for that CPI in the staged kernels' arithmetic (radix2_rows of jrc_staged.cuh, ref_pow_abs2,
+// the sequential float += double window sum), so that
+//   * peak indices and the gate flag of EVERY record equal the staged path's / the CPU oracle's, and
+//   * a record whose decision was redone (DET_EXACT) is bit-identical to the staged path's in every field.
+// Marks (DetDev::flags):
+//   DET_PENDING  set by the fast kernel, cleared here
+//   DET_AMB      a second map element lies within EPS_AMB of the maximum: the arg-max is redone on the
+//                candidates (taken from the fast |.|^2 map when there is one, else from a full scan)
+//   DET_GATE     snr_db / peak_power lie within the error bound of the fast noise estimate of a threshold:
+//                the window sum is redone in the reference's order
+// One CTA per marked CPI; the marked CPIs of a batch come as a device list (FixCtl).  Rare by construction
+// (~1e-4 of the CPIs of a random scene), so clarity beats speed here.
+#pragma once
+#include "jrc_common.cuh"
+#include "jrc_staged.cuh"
+
+namespace jrc {
+
+constexpr unsigned DET_PASSED = 1u, DET_EXACT = 2u;
+constexpr unsigned DET_PENDING = 0x80000000u, DET_AMB = 0x40000000u, DET_GATE = 0x20000000u;
+// relative power margin inside which two map elements are "the same height": measured map error 3e-7 of the
+// peak on either element, plus the two roundings of pow(abs(z),2)
+constexpr float EPS_AMB = 4e-6f;
+
+struct FixCtl { int count; int done; };
+
+// Is the gate decision (:234) safe on the fast path's values?  noise carries the error of the fast window sum against
+// the reference's sequential float accumulation (<= n_noise * 2^-24 relative, the worst case of recursive summation of
+// positive terms), the FFT rounding of the window samples (each within 3e-7 of the map PEAK amplitude) and of the peak.
+__device__ __forceinline__ bool gate_is_marginal(float peak, float noise, float snr_db, int n_noise, float snr_thr, float pow_thr)
+{
+    const float rel = (float)n_noise * 5.9604645e-8f + 4e-6f * sqrtf(__fdiv_rn(peak, noise)) + 1e-5f;
+    const float margin_db = 4.3429448f * rel + 2e-6f * fabsf(snr_db) + 2e-6f * fabsf(snr_thr);
+    const bool near_snr = fabsf(snr_db - snr_thr) <= margin_db;            // NaN / inf: false
+    const bool near_pow = fabsf(peak - pow_thr) <= 1e-5f * fabsf(peak);
+    return near_snr || near_pow;
+}
+
+// fast kernels: append a marked CPI (index within the batch) to the list
+__device__ __forceinline__ void fix_push(FixCtl *ctl, int *list, int cpi)
+{
+    list[atomicAdd(&ctl->count, 1)] = cpi;
+}
+
+struct ExactParams {
+    PortDev rx, tx;          // symbols (H == nullptr)
+    const c32 *H;            // or channel estimates [n_cpi][V][N] (background path)
+    int N, T, R, S, n_pre, tx_interleave, V, Nr, Na, log2Nr, log2Na;
+    const c32 *tw_r, *tw_a;  // radix-2 tables [n/2]: inverse Nr, forward Na (get_twiddles)
+    EstParams est;
+    DetDev *dets;
+    const float *map;        // fast |.|^2 map [n_cpi][Nr][Na] or nullptr
+    int cpi0;
+    const int *list;
+    FixCtl *ctl;
+    c32 *scratch;            // [gridDim.x][V][Nr] range spectra
+    int buf_elems;           // dynamic shared memory, in c32 (>= max(Nr, Na))
+};
+
+constexpr int EXACT_MAX_CAND = 64;
+
+__global__ void __launch_bounds__(256) k_est_exact(const ExactParams P)
+{
+    extern __shared__ c32 sm[];
+    __shared__ float chunk[1024];
+    __shared__ unsigned long long s_red[8];
+    __shared__ int s_cand[EXACT_MAX_CAND], s_ncand, s_rows[EXACT_MAX_CAND], s_wrows[EXACT_MAX_CAND];
+    __shared__ float s_noise;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int count = *reinterpret_cast<volatile int *>(&P.ctl->count);
+    const int N = P.N, V = P.V, Nr = P.Nr, Na = P.Na;
+    c32 *Y = P.scratch + (size_t)blockIdx.x * V * Nr;
+
+    auto block_max = [&](unsigned long long key) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            unsigned long long other = __shfl_xor_sync(0xffffffffu, key, o);
+            key = other > key ? other : key;
+        }
+        __syncthreads();
+        if (lane == 0) s_red[warp] = key;
+        __syncthreads();
+        key = s_red[0];
+#pragma unroll
+        for (int w = 1; w < 8; w++) key = s_red[w] > key ? s_red[w] : key;
+        return key;
+    };
+    // angle FFT (fft_vcc #B: forward, shift) of map rows rows[0..nrows) into sm, row lr at sm + lr*Na, natural
+    // (shifted) order is read through ang()
+    auto angle_rows = [&](const int *rows_idx, int row_first, int nrows, bool consecutive) {
+        for (int e = tid; e < nrows * Na; e += 256) {
+            const int lr = e / Na, i = e % Na;
+            const int n = consecutive ? row_first + lr : rows_idx[lr];
+            const unsigned rev = __brev((unsigned)i) >> (32 - P.log2Na);
+            sm[lr * Na + rev] = i < V ? Y[(size_t)i * Nr + n] : mk(0.f, 0.f);     // matrix_transpose + angle zero-pad
+        }
+        __syncthreads();
+        radix2_rows(sm, Na, nrows, P.tw_a);
+    };
+    auto ang = [&](int lr, int i) { return sm[lr * Na + ((i + (Na + 1) / 2) % Na)]; };
+
+    for (int it = blockIdx.x; it < count; it += gridDim.x) {
+        const int c = P.list[it];
+        const DetDev d0 = P.dets[c];
+        // ---- range spectra of all channels, staged arithmetic: conj-MAC (:250-274), zero-pad, fft_vcc #A ----
+        const int rp = max(1, min(V, P.buf_elems / Nr));
+        for (int p0 = 0; p0 < V; p0 += rp) {
+            const int np = min(rp, V - p0);
+            for (int e = tid; e < np * Nr; e += 256) {
+                const int lr = e / Nr, i = e % Nr, p = p0 + lr;
+                c32 v = mk(0.f, 0.f);
+                if (i < N) {
+                    if (P.H) v = P.H[((size_t)c * V + p) * N + i];
+                    else {
+                        int r, t;
+                        if (P.tx_interleave) { t = p / P.R; r = p % P.R; } else { r = p / P.T; t = p % P.T; }
+                        const c32 *prx = P.rx.base + c * P.rx.cpi_stride + r * P.rx.ant_stride + (long long)P.n_pre * N + i;
+                        const c32 *ptx = P.tx.base + c * P.tx.cpi_stride + t * P.tx.ant_stride + (long long)P.n_pre * N + i;
+                        for (int s = 0; s < P.S; s++) {
+                            const c32 a = prx[(long long)s * N], b = ptx[(long long)s * N];
+                            v = cadd_exact(v, cmul_exact(a, mk(b.x, -b.y)));
+                        }
+                    }
+                }
+                sm[lr * Nr + (__brev((unsigned)i) >> (32 - P.log2Nr))] = v;
+            }
+            __syncthreads();
+            radix2_rows(sm, Nr, np, P.tw_r);
+            for (int e = tid; e < np * Nr; e += 256) Y[(size_t)(p0 + e / Nr) * Nr + e % Nr] = sm[e];
+            __syncthreads();
+        }
+        const int rpa = max(1, P.buf_elems / Na);
+
+        // ---- arg-max (:137-151): first maximum of (float)pow(abs(z),2) in row-major order ----
+        unsigned long long key = 0ull;
+        if (tid == 0) s_ncand = 0;
+        __syncthreads();
+        bool full_scan = (d0.flags & DET_AMB) && (P.map == nullptr || d0.range_idx < 0);
+        if ((d0.flags & DET_AMB) && !full_scan) {
+            // candidates: every element of the fast map within 2*EPS_AMB of its maximum
+            const float *mc = P.map + (size_t)c * Nr * Na;
+            const float thr = __fmul_rn(mc[(size_t)d0.range_idx * Na + d0.angle_idx], 1.f - 2.f * EPS_AMB);
+            const long long tot = (long long)Nr * Na;
+            for (long long e = (long long)tid * 4; e < tot; e += 256 * 4) {
+                const float4 v = __ldcs(reinterpret_cast<const float4 *>(mc + e));
+                const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int k = 0; k < 4; k++)
+                    if (vv[k] >= thr) {
+                        const int slot = atomicAdd(&s_ncand, 1);
+                        if (slot < EXACT_MAX_CAND) s_cand[slot] = (int)(e + k);
+                    }
+            }
+            __syncthreads();
+            if (s_ncand > EXACT_MAX_CAND || s_ncand == 0) full_scan = true;      // block-uniform
+        }
+        if (full_scan) {
+            for (int n0 = 0; n0 < Nr; n0 += rpa) {
+                const int nr = min(rpa, Nr - n0);
+                angle_rows(nullptr, n0, nr, true);
+                for (int e = tid; e < nr * Na; e += 256) {
+                    const int lr = e / Na, i = e % Na;
+                    const float pw = (float)ref_pow_abs2(ang(lr, i));
+                    if (pw == pw) {
+                        const unsigned long long k2 = pack_key(pw, (unsigned)((n0 + lr) * Na + i));
+                        key = k2 > key ? k2 : key;
+                    }
+                }
+                __syncthreads();
+            }
+        } else {
+            // one row per candidate (the unmarked arg-max is a single candidate: the fast path's own peak)
+            const int nc = (d0.flags & DET_AMB) ? s_ncand : 1;
+            for (int c0 = 0; c0 < nc; c0 += rpa) {
+                const int nr = min(rpa, nc - c0);
+                if (tid < nr) s_rows[tid] = ((d0.flags & DET_AMB) ? s_cand[c0 + tid] : d0.range_idx * Na + d0.angle_idx) / Na;
+                __syncthreads();
+                angle_rows(s_rows, 0, nr, false);
+                if (tid < nr) {
+                    const int lin = (d0.flags & DET_AMB) ? s_cand[c0 + tid] : d0.range_idx * Na + d0.angle_idx;
+                    const float pw = (float)ref_pow_abs2(ang(tid, lin % Na));
+                    if (pw == pw) key = pack_key(pw, (unsigned)lin);
+                }
+                __syncthreads();
+            }
+        }
+        key = block_max(key);
+        if (key == 0ull) {       // NaN-only map: nothing wins the strict '>' scan
+            if (tid == 0) {
+                DetDev d; d.range_idx = -1; d.angle_idx = -1; d.peak_power = -1.f;
+                d.noise_power = __int_as_float(0x7fc00000); d.snr_db = d.noise_power;
+                d.n_noise = 0; d.flags = DET_EXACT; d.cpi = P.cpi0 + c;
+                P.dets[c] = d;
+            }
+            continue;
+        }
+        const unsigned lin = 0xFFFFFFFFu - (unsigned)(key & 0xFFFFFFFFull);
+        const int nstar = (int)(lin / (unsigned)Na), istar = (int)(lin % (unsigned)Na);
+        const float peak = __uint_as_float((unsigned)(key >> 32));
+        if (!(d0.flags & DET_GATE) && nstar == d0.range_idx && istar == d0.angle_idx) {
+            // the candidates' order is the fast path's: its window, noise estimate and (safe) gate decision stand
+            if (tid == 0) P.dets[c].flags = d0.flags & DET_PASSED;
+            continue;
+        }
+
+        // ---- noise window (:152-227) in the reference's order ----
+        const NoiseWin w = noise_window(P.est, nstar, istar);
+        const int ncols = w.end_a - w.start_a, nrows = w.end_r - w.start_r;
+        const int total = (ncols > 0 && nrows > 0) ? nrows * ncols : 0;
+        if (tid == 0) s_noise = 0.f;
+        __syncthreads();
+        if (total > 0) {
+            for (int r0 = 0; r0 < nrows; r0 += min(rpa, EXACT_MAX_CAND)) {
+                const int nr = min(min(rpa, EXACT_MAX_CAND), nrows - r0);
+                if (tid < nr) { const int ir = w.start_r + r0 + tid; s_wrows[tid] = ((ir % Nr) + Nr) % Nr; }
+                __syncthreads();
+                angle_rows(s_wrows, 0, nr, false);
+                for (int lr = 0; lr < nr; lr++)
+                    for (int cb = 0; cb < ncols; cb += 1024) {
+                        const int cnt = min(1024, ncols - cb);
+                        for (int j = tid; j < cnt; j += 256) {
+                            const int ia = w.start_a + cb + j, a_idx = ((ia % Na) + Na) % Na;
+                            chunk[j] = ref_abs(ang(lr, a_idx));
+                        }
+                        __syncthreads();
+                        if (tid == 0) {
+                            float acc = s_noise;
+                            for (int j = 0; j < cnt; j++) {
+                                const double a = (double)chunk[j];
+                                acc = (float)((double)acc + a * a);          // :217 float += double
+                            }
+                            s_noise = acc;
+                        }
+                        __syncthreads();
+                    }
+            }
+        }
+        if (tid == 0) {
+            DetDev d;
+            d.range_idx = nstar; d.angle_idx = istar; d.peak_power = peak; d.n_noise = total;
+            d.noise_power = __fdiv_rn(s_noise, (float)total);                                   // :226
+            d.snr_db = snr_db_of(d.peak_power, d.noise_power);                                  // :227
+            d.flags = ((d.snr_db >= P.est.snr_threshold && d.peak_power >= P.est.power_threshold) ? DET_PASSED : 0u) | DET_EXACT;
+            d.cpi = P.cpi0 + c;
+            P.dets[c] = d;
+        }
+        __syncthreads();
+    }
+    // the last CTA to finish re-arms the list for the next batch
+    __shared__ bool s_last;
+    if (tid == 0) {
+        __threadfence();
+        s_last = atomicAdd(&P.ctl->done, 1) == (int)gridDim.x - 1;
+    }
+    __syncthreads();
+    if (s_last && tid == 0) { P.ctl->count = 0; P.ctl->done = 0; __threadfence(); }
+}
+
+}  // namespace jrc

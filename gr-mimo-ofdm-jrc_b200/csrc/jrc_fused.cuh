@@ -24,10 +24,7 @@
 #pragma once
 #include "jrc_common.cuh"
 #include "jrc_staged.cuh"
-
-#ifndef JRC_STORE_MODE
-#define JRC_STORE_MODE 0   // 0: LDS.128 + STG.128 from the staging tiles; A/B builds: 1 per-warp cp.async.bulk, 2 direct STG.32
-#endif
+#include "jrc_exact.cuh"
 
 namespace jrc {
 
@@ -38,7 +35,8 @@ struct FusedParams {
     int T, R, S, n_pre, tx_interleave;
     float *map;                // [n_cpi][NR][NA] or nullptr
     DetDev *dets;              // [n_cpi] or nullptr (in-kernel estimator)
-    unsigned long long *keys;  // [n_cpi] zeroed, or nullptr: per-CPI arg-max key for k_map_finalize instead of dets
+    FixCtl *fix_ctl;           // records whose decision k_est_exact has to redo (jrc_exact.cuh)
+    int *fix_list;
     EstParams est;
     const int2 *win_tab;       // [NA] k_est_tables
     const double2 *g_tab;      // [NA][8]
@@ -75,22 +73,6 @@ __device__ __forceinline__ void cp_async16(void *sdst, const void *gsrc)
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
-// per-warp bulk (TMA) store of a staging tile, issued by one elected lane
-__device__ __forceinline__ bool elect_one()
-{
-    unsigned p;
-    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(p));
-    return p != 0;
-}
-__device__ __forceinline__ void bulk_s2g(void *gdst, const void *ssrc, unsigned bytes)
-{
-    unsigned sa = (unsigned)__cvta_generic_to_shared(ssrc);
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(sa), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-
 // Angle twiddles of one thread, duplicated into both halves of a register pair.
 struct AngleTw { float2 r[8], i[8]; };   // (re,re), (im,im); index 0 unused
 
@@ -151,7 +133,7 @@ __global__ void __launch_bounds__(256, 2) k_fused64x8(const FusedParams P)
     // range pass 2: task q = 32 half + lane + 64 i;                 twiddle W_Nr^{k0 q} from tw2t
     // angle pass:   task (n, b);                                    twiddle (-1)^p w_Na^{p (b + IA*rot)}
     const int q0 = lane % IR;
-    const int b = lane % IA, g = lane / IA, rot = (JRC_STORE_MODE == 2) ? 0 : g;
+    const int b = lane % IA, g = lane / IA, rot = g;
     c32 tw1[8];
     AngleTw tw3;
 #pragma unroll
@@ -204,6 +186,7 @@ __global__ void __launch_bounds__(256, 2) k_fused64x8(const FusedParams P)
     // runs after the next CPI's barrier (A) instead of costing a barrier of its own.
     // Lag d is accumulated by warp pair part(d): 0 -> {0}, 1 -> {1,7}, 2 -> {2,6}, 3 -> {3,4,5}.
     bool pending = false;
+    bool amb_prev = false;   // block-uniform: a second group maximum lies within EPS_AMB of the CPI's maximum
     auto finalize = [&]() {
         if (tid < 8) {
             const int d = tid;
@@ -227,9 +210,14 @@ __global__ void __launch_bounds__(256, 2) k_fused64x8(const FusedParams P)
                 dd.peak_power = __int_as_float(sint[6]);
                 dd.n_noise = total;
                 dd.noise_power = __fdiv_rn(total > 0 ? (float)s : 0.f, (float)total);
-                dd.snr_db = __fmul_rn(10.f, log10f(__fdiv_rn(dd.peak_power, dd.noise_power)));
-                dd.flags = (dd.snr_db >= est.snr_threshold && dd.peak_power >= est.power_threshold) ? 1u : 0u;
+                dd.snr_db = snr_db_of(dd.peak_power, dd.noise_power);
+                dd.flags = (dd.snr_db >= est.snr_threshold && dd.peak_power >= est.power_threshold) ? DET_PASSED : 0u;
+                // decisions that FFT rounding could turn are not taken here (jrc_exact.cuh)
+                if (amb_prev || sint[5]) dd.flags |= DET_PENDING | DET_AMB;
+                if (gate_is_marginal(dd.peak_power, dd.noise_power, dd.snr_db, total, est.snr_threshold, est.power_threshold))
+                    dd.flags |= DET_PENDING | DET_GATE;
                 dd.cpi = P.cpi0 + sint[7];
+                if (dd.flags & DET_PENDING) fix_push(P.fix_ctl, P.fix_list, sint[7]);
                 P.dets[sint[7]] = dd;
             }
         }
@@ -318,6 +306,7 @@ __global__ void __launch_bounds__(256, 2) k_fused64x8(const FusedParams P)
 
         // ---- stage 4: angle pass + |.|^2 + store + running max ---------------
         float best0 = -1.f, best1 = -1.f;   // rows of tile 0 all precede those of tile 1
+        float sec = -1.f;                   // largest group maximum of this thread that is not best0 / best1
         int bit0 = 0, bit1 = 0;
         const int jp = warp >> 1;
         const int qw = (warp & 1) * (Q / 2);             // first q of this warp
@@ -333,35 +322,12 @@ __global__ void __launch_bounds__(256, 2) k_fused64x8(const FusedParams P)
                                        fmaxf(fmaxf(v[4].x, v[5].x), fmaxf(v[6].x, v[7].x)));
                 const float m1 = fmaxf(fmaxf(fmaxf(v[0].y, v[1].y), fmaxf(v[2].y, v[3].y)),
                                        fmaxf(fmaxf(v[4].y, v[5].y), fmaxf(v[6].y, v[7].y)));
+                sec = fmaxf(sec, fmaxf(fminf(m0, best0), fminf(m1, best1)));
                 if (m0 > best0) { best0 = m0; bit0 = it; }
                 if (m1 > best1) { best1 = m1; bit1 = it; }
                 if (WRITE_MAP) {
                     // conflict-free scalar st.shared of the strided bins, then the warp streams its two
                     // 1 KiB tiles (G whole map rows each, contiguous in HBM) out as 4 x 512 B
-#if JRC_STORE_MODE == 2
-                    {   // A/B: no staging -- every warp store writes G x IA/8 full 32-byte sectors
-                        float *d0 = reinterpret_cast<float *>(map_w + it * (TILE / 4)) + g * NA + b;
-#pragma unroll
-                        for (int a = 0; a < 8; a++) { __stcs(d0 + IA * a, v[a].x); __stcs(d0 + Q * NA + IA * a, v[a].y); }
-                    }
-                    continue;
-#endif
-#if JRC_STORE_MODE == 1
-                    // A/B: the two tiles leave through the bulk-copy engine instead of LDS.128 + STG.128
-                    if (elect_one()) bulk_wait_read0();   // the previous iteration's copies have read the tiles
-                    __syncwarp();
-#pragma unroll
-                    for (int a = 0; a < 8; a++) { sp[a][0] = v[a].x; sp[a][TILE] = v[a].y; }
-                    fence_proxy_async_smem();
-                    __syncwarp();
-                    if (elect_one()) {
-                        float *dstb = reinterpret_cast<float *>(map_w + it * (TILE / 4));
-                        bulk_s2g(dstb, wstg, TILE * 4);
-                        bulk_s2g(dstb + Q * NA, wstg + TILE, TILE * 4);
-                        bulk_commit();
-                    }
-                    continue;
-#endif
 #pragma unroll
                     for (int a = 0; a < 8; a++) { sp[a][0] = v[a].x; sp[a][TILE] = v[a].y; }
                     __syncwarp();
@@ -382,28 +348,33 @@ __global__ void __launch_bounds__(256, 2) k_fused64x8(const FusedParams P)
 
         // ---- stage 5: range_angle_estimator ----------------------------------
         pending = false;
-        const bool in_kernel_est = P.dets && !P.keys;
-        if (P.keys || P.dets) {
+        const bool in_kernel_est = P.dets != nullptr;
+        if (in_kernel_est) {
             unsigned long long key = best >= 0.f ? pack_key(best, (unsigned)best_row) : 0ull;
+            float b2 = fmaxf(sec, fminf(best0, best1));      // runner-up among this thread's group maxima
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {
-                unsigned long long other = __shfl_xor_sync(0xffffffffu, key, o);
+                const unsigned long long other = __shfl_xor_sync(0xffffffffu, key, o);
+                const float o2 = __shfl_xor_sync(0xffffffffu, b2, o);
+                const float v1 = __uint_as_float((unsigned)(key >> 32)), v1o = __uint_as_float((unsigned)(other >> 32));
+                // keys are distinct unless both are 0: the loser of (key, other) is a runner-up candidate
+                b2 = fmaxf(fmaxf(b2, o2), (key && other) ? fminf(v1, v1o) : -1.f);
                 key = other > key ? other : key;
             }
-            if (P.keys) {
-                // map-backed detection: fold this CTA's maximum into the CPI's 64-bit key;
-                // k_map_finalize turns key + map into the record after the kernel
-                if (lane == 0 && key) atomicMax(P.keys + cpi, key);
-            } else if (lane == 0) {
-                red[warp] = key;
-            }
+            if (lane == 0) { red[warp] = key; sint[8 + warp] = __float_as_int(b2); }
         }
         if (!FROM_H) cp_async_wait_all();
         __syncthreads();   // (E) block maximum; the next CPI's symbols are visible to every thread
         if (in_kernel_est) {
             unsigned long long key = red[0];
+            float g2 = __int_as_float(sint[8]);
 #pragma unroll
-            for (int w = 1; w < 8; w++) key = red[w] > key ? red[w] : key;
+            for (int w = 1; w < 8; w++) {
+                const unsigned long long kw = red[w];
+                g2 = fmaxf(fmaxf(g2, __int_as_float(sint[8 + w])),
+                           (key && kw) ? fminf(__uint_as_float((unsigned)(key >> 32)), __uint_as_float((unsigned)(kw >> 32))) : -1.f);
+                key = kw > key ? kw : key;
+            }
             if (key == 0ull) {   // NaN-only input: nothing can win the strict '>' scan
                 if (tid == 0) {
                     DetDev d; d.range_idx = -1; d.angle_idx = -1; d.peak_power = -1.f;
@@ -414,6 +385,8 @@ __global__ void __launch_bounds__(256, 2) k_fused64x8(const FusedParams P)
             } else {
                 const float gmax = __uint_as_float((unsigned)(key >> 32));
                 const int nstar = (int)(0xFFFFFFFFu - (unsigned)(key & 0xFFFFFFFFull));
+                const float thr_amb = __fmul_rn(gmax, 1.f - EPS_AMB);
+                amb_prev = g2 >= thr_amb;
                 // Noise window (lib/range_angle_estimator_impl.cc:197-226) without evaluating its samples:
                 //   sum_{r,c} |sum_p y[p][r] w^{p c'}|^2 = ncols*A[0] + 2 Re sum_{d=1..7} g[d] A[d],
                 //   A[d] = sum_r sum_q y[q+d][r] conj(y[q][r]),  g[d] = sum_c w^{d c'},  c' = c + Na/2,
@@ -485,7 +458,7 @@ __global__ void __launch_bounds__(256, 2) k_fused64x8(const FusedParams P)
                 const int sq = nstar % Q, sm1 = nstar / Q;
                 if (warp == (sm1 >> 1) * 2 + (sq >= Q / 2)) {
                     // the lanes that own row nstar re-evaluate it and pick the first bin == gmax
-                    int icand = 0x7fffffff;
+                    int icand = 0x7fffffff, ncand = 0;
                     c32 zc = mk(0.f, 0.f);
                     if (g == sq % G) {
                         float2 re[8], im[8], v[8];
@@ -495,14 +468,19 @@ __global__ void __launch_bounds__(256, 2) k_fused64x8(const FusedParams P)
                         for (int a = 0; a < 8; a++) {
                             const int i = b + IA * ((a + rot) & 7);
                             const float va = odd ? v[a].y : v[a].x;
+                            ncand += va >= thr_amb;
                             if (va == gmax && i < icand) { icand = i; zc = odd ? mk(re[a].y, im[a].y) : mk(re[a].x, im[a].x); }
                         }
                     }
                     int imin = icand;
 #pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) imin = min(imin, __shfl_xor_sync(0xffffffffu, imin, o));
+                    for (int o = 16; o > 0; o >>= 1) {
+                        imin = min(imin, __shfl_xor_sync(0xffffffffu, imin, o));
+                        ncand += __shfl_xor_sync(0xffffffffu, ncand, o);
+                    }
                     if (icand == imin) {   // exactly one lane (bins are distinct); imin is always found
                         sint[0] = nstar; sint[1] = imin & (NA - 1);
+                        sint[5] = ncand > 1;       // several bins of the winning row within EPS_AMB
                         sint[6] = __float_as_int((float)ref_pow_abs2(zc));
                         sint[7] = cpi;
                     }
@@ -511,9 +489,6 @@ __global__ void __launch_bounds__(256, 2) k_fused64x8(const FusedParams P)
             }
         }
     }
-#if JRC_STORE_MODE == 1
-    if (elect_one()) bulk_wait_read0();   // the CTA's shared memory must outlive the bulk copies that read it
-#endif
     if (pending) {
         __syncthreads();
         finalize();

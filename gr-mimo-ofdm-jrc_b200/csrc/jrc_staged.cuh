@@ -144,6 +144,28 @@ __global__ void k_pad_rows(const c32 *__restrict__ H, c32 *__restrict__ out, lon
 // input is zero: this is how the range zero-pad is never materialised) and writes
 // n samples at out + r*n.  rows_per_cta rows share a CTA when n is small.
 // ---------------------------------------------------------------------------
+// butterflies of `rows` n-point transforms that sit bit-reversed in shared memory (row r at sm + r*n); every
+// thread of the CTA takes part.  Shared by k_fft_rows and the reference-order estimator (jrc_exact.cuh): the
+// float operation order below IS the oracle's.
+__device__ __forceinline__ void radix2_rows(c32 *sm, int n, int rows, const c32 *__restrict__ tw)
+{
+    const int nbf = rows * (n >> 1);
+    for (int len = 2; len <= n; len <<= 1) {
+        const int half = len >> 1, step = n / len;
+        for (int b = threadIdx.x; b < nbf; b += blockDim.x) {
+            int lr = b / (n >> 1), bb = b % (n >> 1);
+            int grp = bb / half, j = bb % half;
+            int i0 = lr * n + grp * len + j, i1 = i0 + half;
+            c32 w = tw[j * step];
+            c32 u = sm[i0];
+            c32 v = cmul_exact(sm[i1], w);
+            sm[i0] = cadd_exact(u, v);
+            sm[i1] = csub_exact(u, v);
+        }
+        __syncthreads();
+    }
+}
+
 __global__ void k_fft_rows(const c32 *in, long long in_stride, int n_in,   // in may alias out (in place)
                            c32 *out, int n, int log2n, long long rows, int rows_per_cta,
                            int forward, int shift, const c32 *__restrict__ tw /* [n/2] */)
@@ -164,21 +186,7 @@ __global__ void k_fft_rows(const c32 *in, long long in_stride, int n_in,   // in
         sm[lr * n + rev] = v;
     }
     __syncthreads();
-    const int nbf = rows_per_cta * (n >> 1);
-    for (int len = 2; len <= n; len <<= 1) {
-        const int half = len >> 1, step = n / len;
-        for (int b = threadIdx.x; b < nbf; b += blockDim.x) {
-            int lr = b / (n >> 1), bb = b % (n >> 1);
-            int grp = bb / half, j = bb % half;
-            int i0 = lr * n + grp * len + j, i1 = i0 + half;
-            c32 w = tw[j * step];
-            c32 u = sm[i0];
-            c32 v = cmul_exact(sm[i1], w);
-            sm[i0] = cadd_exact(u, v);
-            sm[i1] = csub_exact(u, v);
-        }
-        __syncthreads();
-    }
+    radix2_rows(sm, n, rows_per_cta, tw);
     for (int e = threadIdx.x; e < tot; e += blockDim.x) {
         int lr = e / n, i = e % n;
         long long row = row0 + lr;
@@ -397,8 +405,8 @@ __global__ void k_est_tables(EstParams P, int2 *__restrict__ win, double2 *__res
 
 // pass 2: one CTA per map.  The window powers are evaluated in parallel, but the
 // float accumulation runs in the reference's order on one thread (:211-221) so the
-// noise power is bit-identical.  snr/flags are finalised here with device log10f;
-// host-side callers that need the reference's libm bit pattern recompute them.
+// noise power is bit-identical.  snr/flags are finalised here (snr_db_of: log10 in double, rounded once);
+// host-side callers that need the host libm's bit pattern recompute them.
 __global__ void k_est_finalize(const c32 *__restrict__ map, long long per_mat, int n_inputs, int vlen,
                                const unsigned long long *__restrict__ keys, EstParams P,
                                DetDev *__restrict__ dets, int cpi0)
@@ -456,89 +464,13 @@ __global__ void k_est_finalize(const c32 *__restrict__ map, long long per_mat, i
         d.peak_power = __uint_as_float((unsigned)(key >> 32));
         d.n_noise = (int)total;
         d.noise_power = __fdiv_rn(s_noise, (float)d.n_noise);            // :226
-        d.snr_db = __fmul_rn(10.f, log10f(__fdiv_rn(d.peak_power, d.noise_power)));   // :227
+        d.snr_db = snr_db_of(d.peak_power, d.noise_power);                            // :227
         d.flags = (d.snr_db >= P.snr_threshold && d.peak_power >= P.power_threshold) ? 1u : 0u;   // :234
         d.cpi = cpi0 + (int)mat;
         dets[mat] = d;
     }
 }
 
-
-// ---------------------------------------------------------------------------
-// Detection record from a per-CPI arg-max key and the |.|^2 map (used behind the fused kernels when the
-// map is written anyway): key = (map value bits << 32) | (0xFFFFFFFF - range bin n), the earliest row
-// among equal values.  One CTA per CPI: first bin of row n that holds the value, noise window
-// (lib/range_angle_estimator_impl.cc:152-227) read back from the map, SNR gate (:234).
-// ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) k_map_finalize(const float *__restrict__ map, const unsigned long long *__restrict__ keys,
-                                                      int n_cpi, int NR, int NA, EstParams P, DetDev *__restrict__ dets, int cpi0)
-{
-    extern __shared__ float s_abins[];     // angle_bins copy: the window geometry's binary search stays on chip
-    __shared__ int s_istar[4];
-    __shared__ double s_acc[4];
-    for (int i = threadIdx.x; i < NA; i += blockDim.x) s_abins[i] = P.angle_bins[i];
-    __syncthreads();
-    EstParams est = P;
-    est.angle_bins = s_abins;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int cpi = blockIdx.x;            // one CTA per CPI: the window reads are latency bound, 128 lanes keep 1024 in flight
-    if (cpi >= n_cpi) return;
-    const unsigned long long key = keys[cpi];
-    if (key == 0ull) {   // NaN-only input: nothing can win the strict '>' scan
-        if (tid == 0) {
-            DetDev d; d.range_idx = -1; d.angle_idx = -1; d.peak_power = -1.f;
-            d.noise_power = __int_as_float(0x7fc00000); d.snr_db = d.noise_power;
-            d.n_noise = 0; d.flags = 0; d.cpi = cpi0 + cpi;
-            dets[cpi] = d;
-        }
-        return;
-    }
-    const float peak = __uint_as_float((unsigned)(key >> 32));
-    const int nstar = (int)(0xFFFFFFFFu - (unsigned)(key & 0xFFFFFFFFull));
-    const float *map_c = map + (long long)cpi * NR * NA;
-    int istar = 0x7fffffff;
-    for (int i = tid; i < NA; i += 128)
-        if (__ldcg(map_c + (long long)nstar * NA + i) == peak && i < istar) istar = i;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) istar = min(istar, __shfl_xor_sync(0xffffffffu, istar, o));
-    if (lane == 0) s_istar[warp] = istar;
-    __syncthreads();
-    istar = min(min(s_istar[0], s_istar[1]), min(s_istar[2], s_istar[3]));
-    if (istar == 0x7fffffff) istar = 0;      // cannot happen: the key was built from this row
-    const NoiseWin w = noise_window(est, nstar, istar);
-    const int ncols = w.end_a - w.start_a, nrows = w.end_r - w.start_r;
-    const int total = (ncols > 0 && nrows > 0) ? nrows * ncols : 0;
-    double acc = 0.0;
-    for (int j0 = tid; j0 < total; j0 += 128 * 8) {      // 8 independent loads in flight per lane
-        float v[8];
-#pragma unroll
-        for (int q = 0; q < 8; q++) {
-            const int j = j0 + 128 * q;
-            v[q] = 0.f;
-            if (j < total) {
-                const int ir = w.start_r + j / ncols, ia = w.start_a + j % ncols;
-                const int r_idx = ((ir % NR) + NR) % NR, a_idx = ((ia % NA) + NA) % NA;
-                v[q] = __ldcg(map_c + (long long)r_idx * NA + a_idx);
-            }
-        }
-#pragma unroll
-        for (int q = 0; q < 8; q++) acc += (double)v[q];
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if (lane == 0) s_acc[warp] = acc;
-    __syncthreads();
-    if (tid == 0) {
-        acc = (s_acc[0] + s_acc[1]) + (s_acc[2] + s_acc[3]);
-        DetDev d;
-        d.range_idx = nstar; d.angle_idx = istar; d.peak_power = peak; d.n_noise = total;
-        d.noise_power = __fdiv_rn((float)acc, (float)total);
-        d.snr_db = __fmul_rn(10.f, log10f(__fdiv_rn(d.peak_power, d.noise_power)));
-        d.flags = (d.snr_db >= P.snr_threshold && d.peak_power >= P.power_threshold) ? 1u : 0u;
-        d.cpi = cpi0 + cpi;
-        dets[cpi] = d;
-    }
-}
 
 // ---------------------------------------------------------------------------
 // fft_peak_detect  (lib/fft_peak_detect_impl.cc:88-95): first maximum of abs(in[p])

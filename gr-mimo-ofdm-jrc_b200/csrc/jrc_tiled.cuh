@@ -27,6 +27,7 @@
 #include <type_traits>
 #include "jrc_common.cuh"
 #include "jrc_staged.cuh"
+#include "jrc_exact.cuh"
 
 namespace jrc {
 
@@ -263,6 +264,9 @@ __global__ void __launch_bounds__(TiledGeom<LOG2N>::THREADS) k_fft8_rows(const c
 //   Y   [n_cpi][V][Nr]   range spectra
 //   map [n_cpi][Nr][NA]  |.|^2, angle bin fastest, fftshifted
 //   keys[n_cpi]          (map value bits << 32) | (0xFFFFFFFF - range bin): atomicMax, zeroed by the host
+//   sec[n_cpi]           bits of the largest group maximum that is NOT the CPI's maximum (every key that loses an
+//                        exchange, and every warp's runner-up): k_map_finalize marks the record when it lies within
+//                        EPS_AMB of the maximum (jrc_exact.cuh).  Zeroed by the host.
 // ---------------------------------------------------------------------------
 // Twiddles: registers (2 CTAs per SM) when the first pass is pruned, shared memory (3 CTAs per SM) otherwise --
 // measured on configs[2] (registers 0.234 ms vs shared 0.250 ms) and configs[4] (0.160 ms vs 0.134 ms).
@@ -272,7 +276,7 @@ template <int LOG2NA, bool PRUNED>
 #endif
 __global__ void __launch_bounds__(256, PRUNED ? JRC_ANGLE_CTAS : 3) k_angle_mag(const c32 *__restrict__ Y, int V, int Nr, int log2_tiles_per_cpi, int n_cpi,
                                                       float *__restrict__ map, unsigned long long *__restrict__ keys,
-                                                      const c32 *__restrict__ tw)
+                                                      unsigned *__restrict__ sec, const c32 *__restrict__ tw)
 {
     using Gm = TiledGeom<LOG2NA>;
     constexpr int NA = Gm::N, RPC = Gm::RPC, RS = Gm::RS, TPR = Gm::TPR;
@@ -309,23 +313,41 @@ __global__ void __launch_bounds__(256, PRUNED ? JRC_ANGLE_CTAS : 3) k_angle_mag(
         if (((int)ft & tpc_mask) == 0) fp += cpi_jump;
         return v;
     };
-    auto flush = [&](int cpi, float best, int best_row) {
+    auto flush = [&](int cpi, float best, int best_row, float sec_t) {
         if (!keys) return;
         unsigned long long key = best >= 0.f ? pack_key(best, (unsigned)best_row) : 0ull;
+        float b2 = sec_t;
 #pragma unroll
         for (int o2 = 16; o2 > 0; o2 >>= 1) {
-            unsigned long long other = __shfl_xor_sync(0xffffffffu, key, o2);
+            const unsigned long long other = __shfl_xor_sync(0xffffffffu, key, o2);
+            const float ob2 = __shfl_xor_sync(0xffffffffu, b2, o2);
+            b2 = fmaxf(fmaxf(b2, ob2), (key && other) ? fminf(__uint_as_float((unsigned)(key >> 32)), __uint_as_float((unsigned)(other >> 32))) : -1.f);
             key = other > key ? other : key;
         }
-        // most candidates lose against the running maximum: a plain read filters them before the
-        // (same-address, hence serialised) atomic
-        if (lane == 0 && key && key > *reinterpret_cast<volatile unsigned long long *>(keys + cpi)) atomicMax(keys + cpi, key);
+        if (lane == 0 && key) {
+            // most candidates lose against the running maximum: a plain read filters them before the (same-address,
+            // hence serialised) atomic.  Whoever loses an exchange is folded into sec[] when it could still matter
+            // (the running maximum only grows).
+            const unsigned long long cur = *reinterpret_cast<volatile unsigned long long *>(keys + cpi);
+            unsigned long long top = cur;
+            float loser = -1.f;
+            if (key > cur) {
+                const unsigned long long old = atomicMax(keys + cpi, key);
+                top = old > key ? old : key;
+                const unsigned long long lo = old > key ? key : old;
+                if (lo) loser = __uint_as_float((unsigned)(lo >> 32));
+            } else {
+                loser = __uint_as_float((unsigned)(key >> 32));
+            }
+            loser = fmaxf(loser, b2);
+            if (loser >= __uint_as_float((unsigned)(top >> 32)) * (1.f - 2.f * EPS_AMB)) atomicMax(sec + cpi, __float_as_uint(loser));
+        }
     };
     constexpr int PF = 2;                           // tiles fetched ahead (one is not enough: measured 0.31 -> 0.23 ms)
     c32 xq[PF];
 #pragma unroll
     for (int i = 0; i < PF; i++) xq[i] = PRUNED ? fetch_next() : mk(0.f, 0.f);
-    float best = -1.f;
+    float best = -1.f, sec_t = -1.f;
     int best_row = 0, cur_cpi = (int)(tile_begin >> log2_tiles_per_cpi);
     int buf = 0;
     // map rows are contiguous across tiles and CPIs: row of (tile, lr_t) = tile * RPC + lr_t
@@ -333,8 +355,8 @@ __global__ void __launch_bounds__(256, PRUNED ? JRC_ANGLE_CTAS : 3) k_angle_mag(
     for (long long tile = tile_begin; tile < tile_end; tile++, buf ^= 1) {
         const int cpi = (int)(tile >> log2_tiles_per_cpi), n0 = ((int)tile & tpc_mask) * RPC;
         if (cpi != cur_cpi) {
-            flush(cur_cpi, best, best_row);
-            best = -1.f;
+            flush(cur_cpi, best, best_row, sec_t);
+            best = sec_t = -1.f;
             cur_cpi = cpi;
         }
         c32 *rows = sm + buf * (RPC * RS);
@@ -374,9 +396,101 @@ __global__ void __launch_bounds__(256, PRUNED ? JRC_ANGLE_CTAS : 3) k_angle_mag(
             mp += RPC * NA;
         }
         const float m8 = fmaxf(fmaxf(fmaxf(v[0], v[1]), fmaxf(v[2], v[3])), fmaxf(fmaxf(v[4], v[5]), fmaxf(v[6], v[7])));
+        sec_t = fmaxf(sec_t, fminf(m8, best));
         if (m8 > best) { best = m8; best_row = n0 + lr_t; }     // rows ascend within a CPI: the first maximum stays
     }
-    if (tile_begin < tile_end) flush(cur_cpi, best, best_row);
+    if (tile_begin < tile_end) flush(cur_cpi, best, best_row, sec_t);
 }
+
+// ---------------------------------------------------------------------------
+// Detection record from a per-CPI arg-max key and the |.|^2 map (used behind the fused kernels when the
+// map is written anyway): key = (map value bits << 32) | (0xFFFFFFFF - range bin n), the earliest row
+// among equal values.  One CTA per CPI: first bin of row n that holds the value, noise window
+// (lib/range_angle_estimator_impl.cc:152-227) read back from the map, SNR gate (:234).
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_map_finalize(const float *__restrict__ map, const unsigned long long *__restrict__ keys,
+                                                      const unsigned *__restrict__ sec, int n_cpi, int NR, int NA, EstParams P,
+                                                      DetDev *__restrict__ dets, int cpi0, FixCtl *fix_ctl, int *fix_list)
+{
+    extern __shared__ float s_abins[];     // angle_bins copy: the window geometry's binary search stays on chip
+    __shared__ int s_istar[4], s_ncand[4];
+    __shared__ double s_acc[4];
+    for (int i = threadIdx.x; i < NA; i += blockDim.x) s_abins[i] = P.angle_bins[i];
+    __syncthreads();
+    EstParams est = P;
+    est.angle_bins = s_abins;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int cpi = blockIdx.x;            // one CTA per CPI: the window reads are latency bound, 128 lanes keep 1024 in flight
+    if (cpi >= n_cpi) return;
+    const unsigned long long key = keys[cpi];
+    if (key == 0ull) {   // NaN-only input: nothing can win the strict '>' scan
+        if (tid == 0) {
+            DetDev d; d.range_idx = -1; d.angle_idx = -1; d.peak_power = -1.f;
+            d.noise_power = __int_as_float(0x7fc00000); d.snr_db = d.noise_power;
+            d.n_noise = 0; d.flags = 0; d.cpi = cpi0 + cpi;
+            dets[cpi] = d;
+        }
+        return;
+    }
+    const float peak = __uint_as_float((unsigned)(key >> 32));
+    const int nstar = (int)(0xFFFFFFFFu - (unsigned)(key & 0xFFFFFFFFull));
+    const float *map_c = map + (long long)cpi * NR * NA;
+    const float thr_amb = __fmul_rn(peak, 1.f - EPS_AMB);
+    int istar = 0x7fffffff, ncand = 0;
+    for (int i = tid; i < NA; i += 128) {
+        const float v = __ldcg(map_c + (long long)nstar * NA + i);
+        if (v == peak && i < istar) istar = i;
+        ncand += v >= thr_amb;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        istar = min(istar, __shfl_xor_sync(0xffffffffu, istar, o));
+        ncand += __shfl_xor_sync(0xffffffffu, ncand, o);
+    }
+    if (lane == 0) { s_istar[warp] = istar; s_ncand[warp] = ncand; }
+    __syncthreads();
+    istar = min(min(s_istar[0], s_istar[1]), min(s_istar[2], s_istar[3]));
+    ncand = s_ncand[0] + s_ncand[1] + s_ncand[2] + s_ncand[3];
+    if (istar == 0x7fffffff) istar = 0;      // cannot happen: the key was built from this row
+    const NoiseWin w = noise_window(est, nstar, istar);
+    const int ncols = w.end_a - w.start_a, nrows = w.end_r - w.start_r;
+    const int total = (ncols > 0 && nrows > 0) ? nrows * ncols : 0;
+    double acc = 0.0;
+    for (int j0 = tid; j0 < total; j0 += 128 * 8) {      // 8 independent loads in flight per lane
+        float v[8];
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+            const int j = j0 + 128 * q;
+            v[q] = 0.f;
+            if (j < total) {
+                const int ir = w.start_r + j / ncols, ia = w.start_a + j % ncols;
+                const int r_idx = ((ir % NR) + NR) % NR, a_idx = ((ia % NA) + NA) % NA;
+                v[q] = __ldcg(map_c + (long long)r_idx * NA + a_idx);
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < 8; q++) acc += (double)v[q];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) s_acc[warp] = acc;
+    __syncthreads();
+    if (tid == 0) {
+        acc = (s_acc[0] + s_acc[1]) + (s_acc[2] + s_acc[3]);
+        DetDev d;
+        d.range_idx = nstar; d.angle_idx = istar; d.peak_power = peak; d.n_noise = total;
+        d.noise_power = __fdiv_rn((float)acc, (float)total);
+        d.snr_db = snr_db_of(d.peak_power, d.noise_power);
+        d.flags = (d.snr_db >= P.snr_threshold && d.peak_power >= P.power_threshold) ? DET_PASSED : 0u;
+        // decisions that FFT rounding could turn are not taken here (jrc_exact.cuh)
+        if (ncand > 1 || __uint_as_float(sec[cpi]) >= thr_amb) d.flags |= DET_PENDING | DET_AMB;
+        if (gate_is_marginal(d.peak_power, d.noise_power, d.snr_db, total, P.snr_threshold, P.power_threshold))
+            d.flags |= DET_PENDING | DET_GATE;
+        d.cpi = cpi0 + cpi;
+        dets[cpi] = d;
+        if (d.flags & DET_PENDING) fix_push(fix_ctl, fix_list, cpi);
+    }
+}
+
 
 }  // namespace jrc

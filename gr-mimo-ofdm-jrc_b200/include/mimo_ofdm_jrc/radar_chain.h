@@ -30,6 +30,9 @@ public:
     virtual void set_snr_threshold(float snr_threshold) = 0;
     virtual void set_power_threshold(float power_threshold) = 0;
     virtual void set_stats_record(bool stats_record) = 0;
+    // frames in flight (1: every call is synchronous; up to 4: a call submits its frame and publishes the oldest
+    // finished one -- jrc_chain_submit / jrc_chain_wait).  Also settable with JRC_PIPELINE=<depth>.
+    virtual void set_pipeline_depth(int depth) = 0;
 };
 
 }  // namespace mimo_ofdm_jrc

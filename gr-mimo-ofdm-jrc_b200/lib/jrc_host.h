@@ -6,6 +6,8 @@
 #include <jrc_cuda.h>
 
 #include <chrono>
+#include <cstdlib>
+#include <mutex>
 #include <cstdint>
 #include <ctime>
 #include <fstream>
@@ -33,11 +35,19 @@ class chain_handle
 
 public:
     chain_handle() {}
-    explicit chain_handle(const jrc_chain_cfg &cfg, const char *who) { check(jrc_chain_create(&cfg, &d_h), who); }
+    explicit chain_handle(const jrc_chain_cfg &cfg, const char *who) { open(cfg, who); }
     chain_handle(const chain_handle &) = delete;
     chain_handle &operator=(const chain_handle &) = delete;
     ~chain_handle() { jrc_chain_destroy(d_h); }
-    void open(const jrc_chain_cfg &cfg, const char *who) { jrc_chain_destroy(d_h); d_h = nullptr; check(jrc_chain_create(&cfg, &d_h), who); }
+    // The make() signatures of the reference have no device argument: the CUDA device of a block comes from the
+    // environment (JRC_DEVICE=<ordinal>, default 0), one flowgraph process per GPU.
+    void open(jrc_chain_cfg cfg, const char *who)
+    {
+        jrc_chain_destroy(d_h);
+        d_h = nullptr;
+        if (const char *e = std::getenv("JRC_DEVICE")) cfg.device = std::atoi(e);
+        check(jrc_chain_create(&cfg, &d_h), who);
+    }
     jrc_chain *get() const { return d_h; }
 };
 

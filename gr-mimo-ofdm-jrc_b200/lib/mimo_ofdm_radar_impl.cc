@@ -35,7 +35,7 @@ mimo_ofdm_radar_impl::mimo_ofdm_radar_impl(int fft_len, int N_tx, int N_rx, int 
     cfg.fft_len = fft_len; cfg.n_tx = N_tx; cfg.n_rx = N_rx; cfg.n_sym = N_sym; cfg.n_pre = N_pre;
     cfg.interp_range = interp_factor; cfg.interp_angle = 1; cfg.tx_interleave = enable_tx_interleave;
     cfg.background_removal = background_removal; cfg.background_recording = background_recording;
-    cfg.record_len = record_len; cfg.device = 0;
+    cfg.record_len = record_len;
     d_chain.open(cfg, "MIMO OFDM RADAR");
     set_tag_propagation_policy(TPP_DONT);
     set_output_multiple(N_tx * N_rx);   // one call emits all virtual channels of a frame
@@ -43,6 +43,7 @@ mimo_ofdm_radar_impl::mimo_ofdm_radar_impl(int fft_len, int N_tx, int N_rx, int 
 
 void mimo_ofdm_radar_impl::set_background_record(bool background_recording)
 {
+    std::lock_guard<std::mutex> guard(d_lock);
     std::cout << "[MIMO OFDM RADAR] Background recording set to  " << background_recording << std::endl;
     host::check(jrc_chain_set_background_record(d_chain.get(), background_recording), "MIMO OFDM RADAR");
 }
@@ -50,6 +51,7 @@ void mimo_ofdm_radar_impl::set_background_record(bool background_recording)
 void mimo_ofdm_radar_impl::capture_radar_data(bool capture_sig)
 {
     if (!capture_sig) return;
+    std::lock_guard<std::mutex> guard(d_lock);
     // one line per capture: "HH:MM:SS.mmm, N_tx, N_rx, fft_len:" then the estimate, ';' separated,
     // ";\n" terminated (the Eigen IOFormat of lib/mimo_ofdm_radar_impl.cc:352-369)
     std::ofstream f(d_radar_chan_file, std::ofstream::app);
@@ -62,9 +64,18 @@ void mimo_ofdm_radar_impl::capture_radar_data(bool capture_sig)
     std::cout << "[MIMO OFDM RADAR] Radar image captured!" << std::endl;
 }
 
+// One call needs one whole frame on every port.  The reference keeps gr::block's default (1:1) forecast and reads
+// past the items it was given when a frame is split over two calls; asking the scheduler for the frame up front makes
+// the WAIT branch below (nothing consumed, nothing produced) the exception instead of a way to stall.
+void mimo_ofdm_radar_impl::forecast(int /*noutput_items*/, gr_vector_int &ninput_items_required)
+{
+    for (auto &n : ninput_items_required) n = d_N_pre + d_N_sym;
+}
+
 int mimo_ofdm_radar_impl::general_work(int noutput_items, gr_vector_int &ninput_items,
                                        gr_vector_const_void_star &input_items, gr_vector_void_star &output_items)
 {
+    std::lock_guard<std::mutex> guard(d_lock);
     const int V = d_N_tx * d_N_rx;
     host::frame_plan plan = host::plan_frame(*this, d_N_tx, ninput_items, d_N_pre + d_N_sym);
     switch (plan.action) {

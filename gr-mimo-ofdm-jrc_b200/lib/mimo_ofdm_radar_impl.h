@@ -12,6 +12,7 @@ class mimo_ofdm_radar_impl : public mimo_ofdm_radar
     const bool d_debug;
     host::chain_handle d_chain;
     std::vector<gr_complex> d_chan_est;   // last radar_chan_est, host copy for capture_radar_data
+    std::mutex d_lock;                    // the GRC callbacks run on another thread than general_work()
 
 public:
     mimo_ofdm_radar_impl(int fft_len, int N_tx, int N_rx, int N_sym, int N_pre, bool background_removal,
@@ -19,6 +20,7 @@ public:
                          const std::string &radar_chan_file, const std::string &len_tag_key, bool debug);
     void set_background_record(bool background_recording) override;
     void capture_radar_data(bool capture_sig) override;
+    void forecast(int noutput_items, gr_vector_int &ninput_items_required) override;
     int general_work(int noutput_items, gr_vector_int &ninput_items, gr_vector_const_void_star &input_items,
                      gr_vector_void_star &output_items) override;
 };

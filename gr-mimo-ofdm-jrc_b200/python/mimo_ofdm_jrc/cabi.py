@@ -18,6 +18,7 @@ LIB_PATH = os.environ.get("JRC_CUDA_LIB") or os.path.join(PKG_ROOT, "libjrc_cuda
 
 JRC_OK, JRC_ERR_INVALID, JRC_ERR_CUDA, JRC_ERR_NO_DEVICE, JRC_ERR_STATE = 0, 1, 2, 3, 4
 PATH_AUTO, PATH_FUSED, PATH_STAGED, PATH_TILED = 0, 1, 2, 3
+DET_PASSED, DET_EXACT = 1, 2          # jrc_det.flags (include/jrc_cuda.h)
 
 
 class JrcError(RuntimeError):
@@ -51,7 +52,8 @@ EXPORTS = [
     "jrc_chain_set_background_record", "jrc_chain_reset_background", "jrc_chain_run_batch",
     "jrc_chain_last_path", "jrc_chain_launch_count", "jrc_chain_run_host", "jrc_radar_estimate",
     "jrc_fft_vcc", "jrc_transpose_pad", "jrc_mag_squared", "jrc_target_sim", "jrc_nlog10", "jrc_estimate2d", "jrc_peak1d", "jrc_zero_pad",
-    "jrc_cp_remove", "jrc_ofdm_demod",
+    "jrc_cp_remove", "jrc_ofdm_demod", "jrc_chain_submit", "jrc_chain_poll", "jrc_chain_wait",
+    "jrc_pinned_alloc", "jrc_pinned_free", "jrc_host_register", "jrc_host_unregister",
 ]
 
 _lib = None
@@ -95,6 +97,13 @@ def load():
     lib.jrc_zero_pad.argtypes = [vp, vp, i32, u32, u32, u64, vp]
     lib.jrc_cp_remove.argtypes = [vp, vp, i32, i32, i32, vp]
     lib.jrc_ofdm_demod.argtypes = [vp, vp, i32, i32, i32, vp]
+    lib.jrc_chain_submit.argtypes = [vp, vp, vp, i32, i32, i32, vp, vp, C.POINTER(i64)]
+    lib.jrc_chain_poll.argtypes = [vp, i64, C.POINTER(i32)]
+    lib.jrc_chain_wait.argtypes = [vp, i64]
+    lib.jrc_pinned_alloc.argtypes = [sz, C.POINTER(vp)]
+    lib.jrc_pinned_free.argtypes = [vp]
+    lib.jrc_host_register.argtypes = [vp, sz]
+    lib.jrc_host_unregister.argtypes = [vp]
     for name in EXPORTS:
         fn = getattr(lib, name)
         if name not in ("jrc_last_error", "jrc_abi_version", "jrc_chain_destroy", "jrc_chain_stream",
@@ -184,6 +193,21 @@ class Chain:
     def run_host_ptr(self, rx_ptr, tx_ptr, tx_shared, n_cpi, cpi0=0, map_ptr=None, dets_ptr=None):
         check(load().jrc_chain_run_host(self._h, rx_ptr, tx_ptr, int(bool(tx_shared)), n_cpi, cpi0,
                                         map_ptr, dets_ptr))
+
+    # -- streaming form: up to 4 submissions in flight ------------------------
+    def submit_ptr(self, rx_ptr, tx_ptr, tx_shared, n_cpi, cpi0=0, map_ptr=None, dets_ptr=None):
+        t = C.c_int64()
+        check(load().jrc_chain_submit(self._h, rx_ptr, tx_ptr, int(bool(tx_shared)), n_cpi, cpi0, map_ptr, dets_ptr,
+                                      C.byref(t)))
+        return t.value
+
+    def poll(self, ticket):
+        d = C.c_int32()
+        check(load().jrc_chain_poll(self._h, ticket, C.byref(d)))
+        return bool(d.value)
+
+    def wait(self, ticket):
+        check(load().jrc_chain_wait(self._h, ticket))
 
     def run_host(self, rx: np.ndarray, tx: np.ndarray, want_map=True, want_dets=True, cpi0=0):
         """rx [n_cpi][R][S][N] complex64, tx [n_cpi or 1][T][S][N] complex64 (NumPy, host)."""

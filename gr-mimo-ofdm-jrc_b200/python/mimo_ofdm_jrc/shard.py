@@ -19,44 +19,51 @@ def shard_range(n_cpi: int, rank: int, world: int):
     return lo, lo + base + (1 if rank < rem else 0)
 
 
-def gather_detections(dets, dst: int = 0, group=None, counts=None, bufs=None, async_op=False):
+def gather_detections(dets, dst: int = 0, group=None, counts=None, out=None, async_op=False):
     """dets: uint8 tensor [n_local][32] (device tensor under NCCL, CPU tensor under gloo).
-    Returns on rank dst the concatenation over ranks in rank order (ragged shards allowed),
-    None elsewhere.
+    Returns on rank dst ONE tensor [sum(counts)][32]: the records of all ranks in rank order (ragged shards
+    allowed); None on the other ranks.
 
-    counts: per-rank record counts when the caller already knows them (contiguous shards of a known
-    batch: shard_range) -- skips the size exchange and its host synchronisation, so the gather is
-    a single asynchronous NCCL call on the current stream.  bufs: optional preallocated receive
-    buffers on rank dst (list of world tensors [max(counts)][32]) to keep the step allocation-free.
-    async_op=True (needs counts): returns (work, result) without making the current stream wait for
-    the collective, so the next step's kernel overlaps the gather; call work.wait() before the
-    records (or the send buffer) are touched again."""
+    counts: per-rank record counts when the caller already knows them (contiguous shards of a known batch:
+    shard_range) -- skips the size exchange and its host synchronisation, so the gather is a single asynchronous
+    NCCL call on the current stream.  out: optional preallocated receive tensor [world * max(counts)][32] on
+    rank dst (keeps the step allocation-free; with equal shards the result IS this tensor).
+    async_op=True (needs counts and equal shard sizes, checked before anything is launched): returns
+    (work, result) without making the current stream wait for the collective; call work.wait() before the records
+    (or the send buffer) are touched again."""
     import torch
     import torch.distributed as dist
 
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
     if world == 1:
-        return dets
+        return (None, dets) if async_op else dets
+    if async_op:
+        if counts is None:
+            raise ValueError("async gather needs the per-rank counts")
+        if len(set(counts)) != 1:
+            raise ValueError("async gather needs equal shard sizes")      # raised on EVERY rank, before the collective
     if counts is None:
         n_local = torch.tensor([dets.shape[0]], dtype=torch.int64, device=dets.device)
         cts = [torch.zeros_like(n_local) for _ in range(world)]
         dist.all_gather(cts, n_local, group=group)
         counts = [int(c.item()) for c in cts]
+    if len(counts) != world:
+        raise ValueError("counts must have one entry per rank")
     n_max = max(counts)
     padded = dets
     if dets.shape[0] < n_max:
         padded = torch.zeros((n_max, dets.shape[1]), dtype=dets.dtype, device=dets.device)
         padded[: dets.shape[0]] = dets
-    if rank == dst and bufs is None:
-        bufs = [torch.empty_like(padded) for _ in range(world)]
-    work = dist.gather(padded.contiguous(), bufs if rank == dst else None, dst=dst, group=group, async_op=async_op)
-    if rank != dst:
-        res = None
-    elif all(c == n_max for c in counts):
-        res = bufs             # equal shards: the per-rank blocks, in rank order, no copy
-    else:
-        if async_op:
-            raise ValueError("async gather needs equal shard sizes")
-        res = torch.cat([b[:c] for b, c in zip(bufs, counts)], dim=0)
+    bufs = None
+    if rank == dst:
+        if out is None:
+            out = torch.empty((world * n_max, dets.shape[1]), dtype=dets.dtype, device=dets.device)
+        if out.shape[0] != world * n_max:
+            raise ValueError("out must be [world * max(counts)][32]")
+        bufs = [out[r * n_max:(r + 1) * n_max] for r in range(world)]      # views: the gather fills `out` in place
+    work = dist.gather(padded.contiguous(), bufs, dst=dst, group=group, async_op=async_op)
+    res = None
+    if rank == dst:
+        res = out if all(c == n_max for c in counts) else torch.cat([b[:c] for b, c in zip(bufs, counts)], dim=0)
     return (work, res) if async_op else res

@@ -72,11 +72,17 @@ typedef struct {
     float    noise_power;   /* mean of pow(abs(z),2) over the noise window    */
     float    snr_db;        /* 10*log10(peak/noise)                           */
     int32_t  n_noise;       /* n_noise_samples                                */
-    uint32_t flags;         /* bit0: snr >= snr_threshold && peak >= power_threshold (:234) */
+    uint32_t flags;         /* JRC_DET_PASSED | JRC_DET_EXACT                 */
     int32_t  cpi;           /* sequence number: cpi0 + index in the batch     */
 } jrc_det;
 
-#define JRC_DET_PASSED 1u
+#define JRC_DET_PASSED 1u   /* snr >= snr_threshold && peak >= power_threshold (:234): the "params" message goes out */
+/* The fused and tiled kernels decide on their own float32 map, which differs from the reference-order (staged)
+ * arithmetic by FFT rounding (~3e-7 of the map peak).  A record whose arg-max or gate lies inside that margin is
+ * redone in the reference's order (the staged kernels' float operations, the sequential window sum): the peak
+ * indices and JRC_DET_PASSED of EVERY record equal the staged path's, and a record carrying JRC_DET_EXACT is
+ * bit-identical to it in every field.                                            */
+#define JRC_DET_EXACT 2u
 
 /* fft_peak_detect outputs (lib/fft_peak_detect_impl.cc:98-107); k == -1: no
  * sample passed the threshold (the reference then leaves its outputs unwritten). */
@@ -149,6 +155,27 @@ JRC_API int64_t    jrc_chain_launch_count(const jrc_chain *h);
 JRC_API jrc_status jrc_chain_run_host(jrc_chain *h, const jrc_c32 *rx_host, const jrc_c32 *tx_host,
                                       int32_t tx_shared, int32_t n_cpi, int32_t cpi0,
                                       float *map_host, jrc_det *dets_host);
+
+/* Streaming form of jrc_chain_run_host (BASELINE configs[3], "pinned-host double-buffering"): submit enqueues the
+ * chain for n_cpi CPIs and returns at once; up to 4 submissions are in flight, each on its own stream, so the input
+ * transfer and kernel of CPI k+1 overlap the output transfer of CPI k.  The buffers must stay valid until
+ * jrc_chain_wait(ticket) returns (which also finalises the records); pageable buffers are staged through pinned
+ * memory of the handle, pinned ones (cudaHostAlloc / cudaHostRegister, e.g. a registered GNU Radio stream buffer)
+ * are read and written in place.  jrc_chain_poll is the non-blocking test.  This is the scheduler hand-off of
+ * lib/mimo_ofdm_radar_impl.cc:131-340 made asynchronous: general_work() submits frame k and publishes frame k-1. */
+JRC_API jrc_status jrc_chain_submit(jrc_chain *h, const jrc_c32 *rx_host, const jrc_c32 *tx_host,
+                                    int32_t tx_shared, int32_t n_cpi, int32_t cpi0,
+                                    float *map_host, jrc_det *dets_host, int64_t *ticket);
+JRC_API jrc_status jrc_chain_poll(jrc_chain *h, int64_t ticket, int32_t *done);
+JRC_API jrc_status jrc_chain_wait(jrc_chain *h, int64_t ticket);
+
+/* Page-locked host memory for callers that do not link the CUDA runtime themselves: allocate (jrc_pinned_alloc) or
+ * page-lock an existing buffer (jrc_host_register, e.g. the stream buffers a block sees in start()).  Pinned buffers
+ * are what makes jrc_chain_run_host / jrc_chain_submit copy-free.                                         */
+JRC_API jrc_status jrc_pinned_alloc(size_t bytes, void **out);
+JRC_API jrc_status jrc_pinned_free(void *p);
+JRC_API jrc_status jrc_host_register(void *p, size_t bytes);
+JRC_API jrc_status jrc_host_unregister(void *p);
 
 /* ---- per-block stage calls (exact per-block semantics; pointers may be host
  * or device, detected with cudaPointerGetAttributes; host buffers are staged

@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol(jrc):
     for name in declared_symbols():
         assert hasattr(lib, name), name
     lib.jrc_abi_version.restype = ctypes.c_int32
-    assert lib.jrc_abi_version() == 1
+    assert lib.jrc_abi_version() == 2
 
 
 def test_no_cpu_fallback_without_a_device(jrc):

@@ -1,9 +1,11 @@
 """GPU parity tests (run on the B200 box): the CUDA path through the C ABI against the CPU
 oracle on identical seeded inputs.
 
-Bars: byte/index work and every per-block stage call bit-exact; the fused chain's maps within
-1e-4 of the map peak (BASELINE.json north_star), its peak indices exact on every CPI whose
-oracle top-1/top-2 margin exceeds the float32 FFT error."""
+Bars: byte/index work and every per-block stage call bit-exact; the fused and tiled chains' maps within
+1e-4 of the map peak (BASELINE.json north_star); their detection lists -- peak range/angle indices, the size of
+the noise window and the gate flag -- IDENTICAL to the oracle's on every CPI, no exclusions: a decision that FFT
+rounding could turn is redone in the reference's order (csrc/jrc_exact.cuh), and such a record (DET_EXACT) is
+bit-identical to the oracle's in every field."""
 import numpy as np
 import pytest
 
@@ -48,6 +50,23 @@ def oracle(orc, rx, tx, cfg, est, **kw):
     return orc.chain_batch(rx, tx, cfg["N"], cfg["T"], cfg["R"], cfg["S"], cfg["IR"], cfg["IA"], est, **kw)
 
 
+def check_detections(jrc, d, do, what, rtol_peak=5e-6):
+    """Detection lists equal on EVERY CPI; records redone in the reference's order equal in every bit."""
+    n = len(do)
+    for f in ("range_idx", "angle_idx", "n_noise"):
+        assert np.array_equal(d[f], do[f]), (what, f, np.flatnonzero(d[f] != do[f])[:8])
+    assert np.array_equal(d["flags"] & jrc.DET_PASSED, do["flags"] & 1), (what, "gate")
+    ex = (d["flags"] & jrc.DET_EXACT) != 0
+    for f in ("peak_power", "noise_power", "snr_db"):
+        assert np.array_equal(d[f][ex], do[f][ex], equal_nan=True), (what, f, "DET_EXACT records")
+    ok = ~ex & (do["range_idx"] >= 0)
+    np.testing.assert_allclose(d["peak_power"][ok], do["peak_power"][ok], rtol=rtol_peak)
+    np.testing.assert_allclose(d["noise_power"][ok], do["noise_power"][ok], rtol=2e-5)
+    np.testing.assert_allclose(d["snr_db"][ok], do["snr_db"][ok], atol=1e-4)
+    print(f"[{what}] {n} CPIs: detection lists identical; {int(ex.sum())} redone in the reference's order")
+    return int(ex.sum())
+
+
 def top2_margin(m):
     flat = np.partition(m.reshape(m.shape[0], -1), -2, axis=1)
     return (flat[:, -1] - flat[:, -2]) / flat[:, -1]
@@ -66,16 +85,8 @@ def test_fused_chain_vs_oracle(jrc, orc, name):
     err = np.abs(m - mo).reshape(96, -1).max(axis=1) / peak
     assert err.max() <= 1e-4, err.max()               # north_star tolerance
     assert err.max() <= 5e-6, err.max()               # what float32 should actually deliver
-    ok = top2_margin(mo) > 1e-5
-    assert ok.sum() >= 90
-    assert np.array_equal(d["range_idx"][ok], do["range_idx"][ok])
-    assert np.array_equal(d["angle_idx"][ok], do["angle_idx"][ok])
-    assert np.array_equal(d["n_noise"][ok], do["n_noise"][ok])
     assert np.array_equal(d["cpi"], np.arange(96))
-    np.testing.assert_allclose(d["peak_power"][ok], do["peak_power"][ok], rtol=5e-6)
-    np.testing.assert_allclose(d["noise_power"][ok], do["noise_power"][ok], rtol=2e-4)
-    np.testing.assert_allclose(d["snr_db"][ok], do["snr_db"][ok], atol=2e-3)
-    assert np.array_equal(d["flags"][ok], do["flags"][ok])
+    check_detections(jrc, d, do, f"fused {name}")
 
 
 @pytest.mark.parametrize("name", list(CFGS))
@@ -127,8 +138,8 @@ def test_fused_equals_staged_detections_large_batch(jrc):
     pk = m2.reshape(n, -1).max(dim=1).values
     err = ((m1 - m2).abs().reshape(n, -1).max(dim=1).values / pk).max().item()
     assert err <= 5e-6, err
-    same = (d1["range_idx"] == d2["range_idx"]) & (d1["angle_idx"] == d2["angle_idx"])
-    assert same.mean() > 0.999
+    n_exact = check_detections(jrc, d1, d2, "fused vs staged, 4096 CPIs of configs[1]")
+    assert n_exact <= 16, n_exact                     # the reference-order pass is the exception (expected ~1e-4 .. 1e-3 of the CPIs)
     exp = np.array([synth.expected_peak(r[i, 0], a[i, 0], 64, 16, 8, 8) for i in range(n)])
     close = (np.abs(d1["range_idx"] - exp[:, 0]) <= 1) & (np.abs(d1["angle_idx"] - exp[:, 1]) <= 1)
     assert close.mean() > 0.99
@@ -169,8 +180,8 @@ def test_fused_background_removal_matches_block_sequence(jrc, orc):
         mo = orc.mag_squared(cm)
         assert np.abs(m[c] - mo).max() <= 1e-5 * mo.max() + 1e-3, c
         do = orc.range_angle_estimate(cm, **est)
-        if top2_margin(mo[None])[0] > 1e-4:
-            assert (d[c]["range_idx"], d[c]["angle_idx"]) == (do["range_idx"], do["angle_idx"])
+        assert (d[c]["range_idx"], d[c]["angle_idx"]) == (do["range_idx"], do["angle_idx"]), c
+        assert (d[c]["flags"] & jrc.DET_PASSED) == (do["flags"] & 1), c
 
 
 @pytest.mark.parametrize("name", ["C1", "C3s", "odd"])
@@ -317,28 +328,6 @@ def test_fused_chain_vs_reference_golden_vectors(jrc, path):
     assert np.array_equal(d2["range_idx"], g["range_idx"]) and np.array_equal(d2["peak_power"], g["peak_power"])
 
 
-def test_stream_kernel_variant_matches_oracle(jrc, orc, monkeypatch):
-    """The slice-streaming form of the fused chain (JRC_FUSED_KERNEL=stream, jrc_stream.cuh) is an
-    independent third GPU implementation; it must satisfy the same parity bars."""
-    monkeypatch.setenv("JRC_FUSED_KERNEL", "stream")
-    for name in ("C1", "C2"):
-        cfg = CFGS[name]
-        est = est_for(cfg)
-        rx, tx, _ = scene(cfg, 64, seed=17, n_targets=2, amp_db_span=12.0, tx_per_cpi=True)
-        ch = gpu_chain(jrc, cfg, est)
-        m, d = ch.run_host(rx, tx)
-        assert ch.last_path == jrc.PATH_FUSED and ch.launch_count >= 3      # chan_est + stream + finalize
-        mo, _, do = oracle(orc, rx, tx, cfg, est)
-        peak = mo.reshape(64, -1).max(axis=1)
-        assert (np.abs(m - mo).reshape(64, -1).max(axis=1) / peak).max() <= 5e-6
-        ok = top2_margin(mo) > 1e-5
-        assert np.array_equal(d["range_idx"][ok], do["range_idx"][ok])
-        assert np.array_equal(d["angle_idx"][ok], do["angle_idx"][ok])
-        np.testing.assert_allclose(d["peak_power"][ok], do["peak_power"][ok], rtol=5e-6)
-        np.testing.assert_allclose(d["noise_power"][ok], do["noise_power"][ok], rtol=2e-4)
-        assert np.array_equal(d["flags"][ok], do["flags"][ok])
-
-
 def test_ofdm_demod_front_end(jrc, orc):
     """cyclic-prefix removal (+ the RX OFDM FFT) in front of the radar path."""
     rng = np.random.default_rng(31)
@@ -384,19 +373,63 @@ def test_tiled_chain_vs_oracle(jrc, orc, name):
     err = np.abs(m - mo).reshape(n, -1).max(axis=1) / peak
     assert err.max() <= 1e-4, err.max()               # north_star tolerance
     assert err.max() <= 1e-5, err.max()               # what float32 should actually deliver
-    ok = top2_margin(mo) > 1e-5
-    assert ok.sum() >= n - 2
-    for f in ("range_idx", "angle_idx", "n_noise"):
-        assert np.array_equal(d[f][ok], do[f][ok]), f
     assert np.array_equal(d["cpi"], np.arange(n))
-    np.testing.assert_allclose(d["peak_power"][ok], do["peak_power"][ok], rtol=1e-5)
-    np.testing.assert_allclose(d["noise_power"][ok], do["noise_power"][ok], rtol=2e-4)
-    np.testing.assert_allclose(d["snr_db"][ok], do["snr_db"][ok], atol=2e-3)
-    assert np.array_equal(d["flags"][ok], do["flags"][ok])
+    check_detections(jrc, d, do, f"tiled {name}", rtol_peak=1e-5)
     # detections without a caller-provided map use the handle's scratch map
     _, d2 = ch.run_host(rx, tx, want_map=False)
     for f in ("range_idx", "angle_idx", "peak_power", "noise_power", "flags"):
         assert np.array_equal(d2[f], d[f]), f
+
+
+def test_gate_decision_at_the_threshold(jrc, orc):
+    """SNR thresholds placed within +-1e-4 dB of a CPI's own SNR (and exactly on it): the fused and tiled paths take the
+    oracle's gate decision, because a gate inside the error bound of the fast noise estimate is redone with the
+    reference's sequential window sum (DET_EXACT)."""
+    for name, n in (("C2", 8), ("C1", 4), ("C3s", 4)):
+        cfg = CFGS[name]
+        est = est_for(cfg)
+        rx, tx, _ = scene(cfg, n, seed=41, n_targets=2, amp_db_span=6.0, snr_db=10.0, tx_per_cpi=True)
+        _, _, do0 = oracle(orc, rx, tx, cfg, est)
+        ch = gpu_chain(jrc, cfg, est)
+        n_exact = 0
+        for j in range(n):
+            for delta in (-1e-4, -2e-5, -1e-6, 0.0, 1e-6, 2e-5, 1e-4):
+                thr = np.float32(np.float64(do0["snr_db"][j]) + delta)
+                est_j = dict(est, snr_threshold=thr)
+                ch.set_thresholds(thr, est["power_threshold"])
+                _, d = ch.run_host(rx, tx)
+                _, _, do = oracle(orc, rx, tx, cfg, est_j)
+                assert np.array_equal(d["flags"] & jrc.DET_PASSED, do["flags"] & 1), (name, j, delta)
+                if abs(delta) <= 2e-5:            # well inside every configuration's error bound: redone, hence identical bits
+                    assert d["flags"][j] & jrc.DET_EXACT, (name, j, delta)
+                    for f in ("range_idx", "angle_idx", "peak_power", "noise_power", "snr_db", "n_noise"):
+                        assert d[f][j] == do[f][j], (name, j, delta, f)
+                n_exact += int(((d["flags"] & jrc.DET_EXACT) != 0).sum())
+        # a threshold far from every SNR leaves the fast path's records alone
+        ch.set_thresholds(np.float32(-50.0), est["power_threshold"])
+        _, d = ch.run_host(rx, tx)
+        assert ((d["flags"] & jrc.DET_EXACT) != 0).sum() <= 1 and (d["flags"] & jrc.DET_PASSED).all()
+        print(f"[gate {name}] {n_exact} records redone over {7 * n} threshold placements")
+
+
+def test_exact_ties_in_the_map(jrc, orc):
+    """Two targets whose echoes are mirror images give (near-)equal map maxima: the arg-max is taken in the reference's
+    order on the candidates, first maximum in row-major order wins, on both the fused and the tiled path."""
+    for name in ("C2", "C3s"):
+        cfg = CFGS[name]
+        est = est_for(cfg)
+        tx = synth.tx_symbols(cfg["T"], cfg["S"], cfg["N"])
+        n = 12
+        rng = np.random.default_rng(5)
+        r = np.stack([rng.uniform(5, 30, n), rng.uniform(40, 60, n)], axis=1)
+        a = np.stack([rng.uniform(-40, 40, n), rng.uniform(-40, 40, n)], axis=1)
+        amp = np.ones((n, 2))
+        amp[n // 2:, 1] = 1.0 + 1e-6 * rng.standard_normal(n - n // 2)       # equal and almost equal heights
+        rx = synth.rx_symbols(tx, cfg["R"], r, a, amp)
+        ch = gpu_chain(jrc, cfg, est)
+        _, d = ch.run_host(rx, tx)
+        _, _, do = oracle(orc, rx, tx, cfg, est)
+        check_detections(jrc, d, do, f"ties {name}", rtol_peak=1e-5)
 
 
 @pytest.mark.parametrize("n", [1040, 1024, 250])
@@ -424,26 +457,6 @@ def test_target_simulator_is_bit_exact(jrc, orc, n):
     base = orc.target_simulator(x, [12.0], [0.0], [1.0], [10.0], pos, 125000000, 24e9, False, -10.0, False)
     ratio = o1[0][np.abs(base[0]) > 1e-9] / base[0][np.abs(base[0]) > 1e-9]
     assert np.allclose(np.abs(ratio), 1.0, atol=1e-4) and np.allclose(ratio, ratio[0], atol=1e-3)
-
-
-def test_tc_kernel_variant_matches_oracle(jrc, orc, monkeypatch):
-    """The tensor-core form (JRC_FUSED_KERNEL=tc, jrc_tc.cuh: angle DFT as a 3xTF32 tcgen05 GEMM with TMEM
-    accumulators) is opt-in; it must satisfy the north-star tolerance and find the same peaks."""
-    monkeypatch.setenv("JRC_FUSED_KERNEL", "tc")
-    for name in ("C1", "C2"):
-        cfg = CFGS[name]
-        est = est_for(cfg)
-        rx, tx, _ = scene(cfg, 64, seed=19, n_targets=2, amp_db_span=12.0, tx_per_cpi=True)
-        ch = gpu_chain(jrc, cfg, est)
-        m, d = ch.run_host(rx, tx)
-        assert ch.last_path == jrc.PATH_FUSED and ch.launch_count >= 3      # chan_est + tc + finalize
-        mo, _, do = oracle(orc, rx, tx, cfg, est)
-        peak = mo.reshape(64, -1).max(axis=1)
-        assert (np.abs(m - mo).reshape(64, -1).max(axis=1) / peak).max() <= 1e-4
-        ok = top2_margin(mo) > 1e-3
-        assert ok.sum() >= 56
-        assert np.array_equal(d["range_idx"][ok], do["range_idx"][ok])
-        assert np.array_equal(d["angle_idx"][ok], do["angle_idx"][ok])
 
 
 @pytest.mark.parametrize("name", ["C2", "C3s"])

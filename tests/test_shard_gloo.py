@@ -45,11 +45,29 @@ WORKER = textwrap.dedent("""
         print("GATHER_OK")
     else:
         assert out is None
-    # equal shards with known counts: no size exchange, per-rank blocks returned in rank order
+    # equal shards with known counts (n_cpi % world == 0, e.g. 4096 CPIs on 2/4/8 GPUs): no size exchange, and the SAME
+    # return type as the ragged case -- one [world * n][32] tensor in rank order
     e = torch.full((5, 32), rank, dtype=torch.uint8)
     out = shard.gather_detections(e, dst=0, counts=[5] * world)
     if rank == 0:
-        assert len(out) == world and all(int(b[0, 0]) == r for r, b in enumerate(out))
+        assert isinstance(out, torch.Tensor) and tuple(out.shape) == (5 * world, 32)
+        assert all(int(out[5 * r, 0]) == r for r in range(world))
+        assert out.numpy().view(DET_DTYPE).reshape(-1).size == 5 * world
+    else:
+        assert out is None
+    # preallocated receive tensor, asynchronous form
+    recv = torch.empty((5 * world, 32), dtype=torch.uint8) if rank == 0 else None
+    work, out = shard.gather_detections(e, dst=0, counts=[5] * world, out=recv, async_op=True)
+    work.wait()
+    if rank == 0:
+        assert out is recv and all(int(recv[5 * r, 0]) == r for r in range(world))
+    # an asynchronous ragged gather is refused on every rank BEFORE any collective is issued
+    try:
+        shard.gather_detections(e, dst=0, counts=[5, 4], async_op=True)
+        raise SystemExit("ragged async gather was accepted")
+    except ValueError:
+        pass
+    dist.barrier()                      # still in step: nobody is stuck in a half-issued collective
     dist.barrier(); dist.destroy_process_group()
 """)
 
