@@ -250,6 +250,22 @@ extern "C" jrc_status jrc_chain_sync(jrc_chain *h)
 extern "C" int32_t jrc_chain_last_path(const jrc_chain *h) { return h ? h->last_path : 0; }
 extern "C" int64_t jrc_chain_launch_count(const jrc_chain *h) { return h ? h->launches : 0; }
 
+// statistics of the reference-order pass (csrc/jrc_exact.cuh) since the handle was created:
+// out[0] records marked by the fast kernels, out[1] records redone by k_est_exact, out[2] arg-max ties resolved inside
+// the fused kernel.  Synchronises the handle's stream.
+extern "C" jrc_status jrc_chain_exact_stats(jrc_chain *h, int64_t *out)
+{
+    if (!h || !out) return fail(JRC_ERR_INVALID, "null argument");
+    out[0] = out[1] = out[2] = 0;
+    if (!h->sFix.p) return JRC_OK;
+    CU(cudaSetDevice(h->cfg.device));
+    FixCtl c;
+    CU(cudaStreamSynchronize(h->stream));
+    CU(cudaMemcpy(&c, h->sFix.p, sizeof(c), cudaMemcpyDeviceToHost));
+    out[0] = c.n_marked; out[1] = c.n_redone; out[2] = c.n_inkernel;
+    return JRC_OK;
+}
+
 extern "C" jrc_status jrc_chain_set_estimator(jrc_chain *h, const float *range_bins, int32_t n_range,
                                                const float *angle_bins, int32_t n_angle,
                                                float noise_discard_range_m, float noise_discard_angle_deg,
@@ -556,13 +572,13 @@ static jrc_status launch_fused(jrc_chain *h, const FusedParams &P, bool *support
 // ---------------------------------------------------------------------------
 static jrc_status fix_buffers(jrc_chain *h, int n_cpi, FixCtl **ctl, int **list)
 {
-    const size_t need = 16 + sizeof(int) * (size_t)n_cpi;
+    const size_t need = 32 + sizeof(int) * (size_t)n_cpi;
     if (need > h->sFix.cap) {
         ST(h->sFix.need(need));
-        CU(cudaMemsetAsync(h->sFix.p, 0, 16, h->stream));      // k_est_exact re-arms it after every batch
+        CU(cudaMemsetAsync(h->sFix.p, 0, sizeof(FixCtl), h->stream));      // k_est_exact re-arms it after every batch
     }
     *ctl = (FixCtl *)h->sFix.p;
-    *list = (int *)((char *)h->sFix.p + 16);
+    *list = (int *)((char *)h->sFix.p + 32);
     return JRC_OK;
 }
 
@@ -579,7 +595,7 @@ static jrc_status launch_exact(jrc_chain *h, PortDev rx, PortDev tx, const c32 *
     ST(get_twiddles(h, h->Na, 1, &P.tw_a));
     P.est = est; P.dets = dets; P.map = map; P.cpi0 = cpi0;
     P.ctl = (FixCtl *)h->sFix.p;
-    P.list = (const int *)((char *)h->sFix.p + 16);
+    P.list = (const int *)((char *)h->sFix.p + 32);
     const int big = h->Nr > h->Na ? h->Nr : h->Na;
     P.buf_elems = big > 8192 ? big : 8192;
     const size_t smem = (size_t)P.buf_elems * sizeof(c32);
@@ -655,6 +671,8 @@ static jrc_status run_batch_impl(jrc_chain *h, jrc_port_layout rx, jrc_port_layo
             P.est = EP;
             P.win_tab = h->d_win_tab; P.g_tab = h->d_g_tab;
             P.fix_ctl = fix_ctl; P.fix_list = fix_list;
+            ST(get_twiddles(h, Nr, 0, &P.tw_r));
+            ST(get_twiddles(h, Na, 1, &P.tw_a));
         }
         bool ok = false;
         const c32 *Hsrc = nullptr;

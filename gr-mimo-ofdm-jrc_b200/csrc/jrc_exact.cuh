@@ -28,7 +28,53 @@ constexpr unsigned DET_PENDING = 0x80000000u, DET_AMB = 0x40000000u, DET_GATE = 
 // peak on either element, plus the two roundings of pow(abs(z),2)
 constexpr float EPS_AMB = 4e-6f;
 
-struct FixCtl { int count; int done; };
+struct FixCtl { int count; int done; int n_marked, n_redone, n_inkernel, pad; };   // the last three: running totals (statistics)
+
+// ---------------------------------------------------------------------------
+// ONE output bin of the staged radix-2 DIT FFT (radix2_rows) of a zero-padded input, without the transform.
+// With n_in = 2^m non-zero inputs in front of n - n_in zeros, the first log2(n / n_in) butterfly levels only copy
+// (u +- w*0 = u exactly), and bin o of the rest is a pairwise reduction of the bit-reversed inputs A[k] = x[rev_m(k)]
+// with ONE twiddle and ONE sign per level:
+//     level l = log2(n/n_in) + s, s = 0..m-1:   A'[k] = A[2k] +- w_l * A[2k+1],
+//     w_l = tw[(o mod 2^l) * n / 2^(l+1)],  sign = bit l of o
+// -- the same float operations, in the same order, as the transform performs on the way to that bin (checked bin by
+// bin against the CPU oracle's FFT: tests/test_oracle_kat.py::test_single_bin_dit).  n_in - 1 complex MACs instead of
+// (n/2) log2 n butterflies: what lets a kernel re-decide an ambiguous arg-max in the reference's arithmetic.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ c32 dit_level(c32 u, c32 v, const c32 *__restrict__ tw, int log2n, int l, int o)
+{
+    const c32 w = tw[(o & ((1 << l) - 1)) << (log2n - l - 1)];
+    const c32 t = cmul_exact(v, w);
+    return ((o >> l) & 1) ? csub_exact(u, t) : cadd_exact(u, t);
+}
+// 64 inputs, one warp: lane holds the leaves A[2 lane] = x[rev6(2 lane)] and A[2 lane + 1]; result in lane 0
+__device__ __forceinline__ c32 dit_bin_warp64(c32 a0, c32 a1, int log2n, const c32 *__restrict__ tw, int o)
+{
+    const int l0 = log2n - 6;
+    c32 val = dit_level(a0, a1, tw, log2n, l0, o);
+#pragma unroll
+    for (int s = 1; s < 6; s++) {
+        c32 other;
+        other.x = __shfl_down_sync(0xffffffffu, val.x, 1 << (s - 1));
+        other.y = __shfl_down_sync(0xffffffffu, val.y, 1 << (s - 1));
+        val = dit_level(val, other, tw, log2n, l0 + s, o);
+    }
+    return val;
+}
+// 8 inputs in natural order, one thread
+__device__ __forceinline__ c32 dit_bin8(const c32 (&x)[8], int log2n, const c32 *__restrict__ tw, int o)
+{
+    const int l0 = log2n - 3;
+    c32 A[4], B[2];
+    // A[k] = x[rev3(k)]: (0,4) (2,6) (1,5) (3,7)
+    A[0] = dit_level(x[0], x[4], tw, log2n, l0, o);
+    A[1] = dit_level(x[2], x[6], tw, log2n, l0, o);
+    A[2] = dit_level(x[1], x[5], tw, log2n, l0, o);
+    A[3] = dit_level(x[3], x[7], tw, log2n, l0, o);
+    B[0] = dit_level(A[0], A[1], tw, log2n, l0 + 1, o);
+    B[1] = dit_level(A[2], A[3], tw, log2n, l0 + 1, o);
+    return dit_level(B[0], B[1], tw, log2n, l0 + 2, o);
+}
 
 // Is the gate decision (:234) safe on the fast path's values?  noise carries the error of the fast window sum against
 // the reference's sequential float accumulation (<= n_noise * 2^-24 relative, the worst case of recursive summation of
@@ -46,6 +92,7 @@ __device__ __forceinline__ bool gate_is_marginal(float peak, float noise, float 
 __device__ __forceinline__ void fix_push(FixCtl *ctl, int *list, int cpi)
 {
     list[atomicAdd(&ctl->count, 1)] = cpi;
+    atomicAdd(&ctl->n_marked, 1);
 }
 
 struct ExactParams {
@@ -249,6 +296,7 @@ __global__ void __launch_bounds__(256) k_est_exact(const ExactParams P)
             d.flags = ((d.snr_db >= P.est.snr_threshold && d.peak_power >= P.est.power_threshold) ? DET_PASSED : 0u) | DET_EXACT;
             d.cpi = P.cpi0 + c;
             P.dets[c] = d;
+            atomicAdd(&P.ctl->n_redone, 1);
         }
         __syncthreads();
     }

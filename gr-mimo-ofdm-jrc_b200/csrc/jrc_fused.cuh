@@ -38,6 +38,7 @@ struct FusedParams {
     FixCtl *fix_ctl;           // records whose decision k_est_exact has to redo (jrc_exact.cuh)
     int *fix_list;
     EstParams est;
+    const c32 *tw_r, *tw_a;    // the staged FFTs' twiddle tables [n/2] (inverse NR, forward NA): in-kernel arg-max resolution
     const int2 *win_tab;       // [NA] k_est_tables
     const double2 *g_tab;      // [NA][8]
 };
@@ -384,9 +385,69 @@ __global__ void __launch_bounds__(256, 2) k_fused64x8(const FusedParams P)
                 }
             } else {
                 const float gmax = __uint_as_float((unsigned)(key >> 32));
-                const int nstar = (int)(0xFFFFFFFFu - (unsigned)(key & 0xFFFFFFFFull));
+                const int nstar_fast = (int)(0xFFFFFFFFu - (unsigned)(key & 0xFFFFFFFFull));
                 const float thr_amb = __fmul_rn(gmax, 1.f - EPS_AMB);
-                amb_prev = g2 >= thr_amb;
+                const bool amb = g2 >= thr_amb;          // block-uniform
+                bool resolved = false;
+                if (amb) {
+                    // Rare (~1e-4 of the CPIs): another map element is within the FFT rounding of the maximum, so the
+                    // fast map cannot say which one the reference's scan (:137-151) would keep.  Collect the candidates
+                    // (one more angle pass, no stores), evaluate each in the STAGED arithmetic (dit_bin_*: the same float
+                    // operations as the radix-2 transforms of the staged path) and let the reference's rule decide.
+                    constexpr int MAXC = 24;
+                    int *cand = reinterpret_cast<int *>(redA);                       // [0] count, [1 ..] linear map indices
+                    c32 *ycand = reinterpret_cast<c32 *>(redA + 16);                 // [8] range spectra of a candidate's row
+                    if (tid == 0) cand[0] = 0;
+                    __syncthreads();
+                    for (int it = 0; it < PITERS; it++) {
+                        float2 re[8], im[8], v[8];
+                        angle_pair(ys, NR, Q, jp * Q + qw + g + it * G, tw3, re, im, v);
+#pragma unroll
+                        for (int a = 0; a < 8; a++) {
+                            const int i = b + IA * ((a + rot) & 7), r = row0 + g + it * G;
+                            if (v[a].x >= thr_amb) { const int sl = atomicAdd(cand, 1); if (sl < MAXC) cand[1 + sl] = r * NA + i; }
+                            if (v[a].y >= thr_amb) { const int sl = atomicAdd(cand, 1); if (sl < MAXC) cand[1 + sl] = (r + Q) * NA + i; }
+                        }
+                    }
+                    __syncthreads();
+                    const int nc = cand[0];
+                    if (nc >= 1 && nc <= MAXC) {
+                        unsigned long long kb = 0ull;
+                        for (int c = 0; c < nc; c++) {
+                            const int lin = cand[1 + c], n = lin / NA, i = lin % NA;
+                            {   // warp w: bin n of the range IFFT of channel w
+                                const int k0 = (int)(__brev((unsigned)(2 * lane)) >> 26), k1 = (int)(__brev((unsigned)(2 * lane + 1)) >> 26);
+                                const float4 h0 = Hs[(warp >> 1) * 64 + k0], h1 = Hs[(warp >> 1) * 64 + k1];
+                                const c32 a0 = (warp & 1) ? mk(h0.z, h0.w) : mk(h0.x, h0.y);
+                                const c32 a1 = (warp & 1) ? mk(h1.z, h1.w) : mk(h1.x, h1.y);
+                                const c32 yv = dit_bin_warp64(a0, a1, 6 + (31 - __clz(IR)), P.tw_r, n);
+                                if (lane == 0) ycand[warp] = yv;
+                            }
+                            __syncthreads();
+                            if (tid == 0) {     // bin i of the shifted angle FFT across the 8 channels
+                                c32 yy[8];
+#pragma unroll
+                                for (int p = 0; p < 8; p++) yy[p] = ycand[p];
+                                const c32 z = dit_bin8(yy, 3 + (31 - __clz(IA)), P.tw_a, (i + NA / 2) & (NA - 1));
+                                const float pw = (float)ref_pow_abs2(z);
+                                if (pw == pw) { const unsigned long long k2 = pack_key(pw, (unsigned)lin); kb = k2 > kb ? k2 : kb; }
+                            }
+                            __syncthreads();
+                        }
+                        if (tid == 0) {
+                            const unsigned lin = 0xFFFFFFFFu - (unsigned)(kb & 0xFFFFFFFFull);
+                            sint[0] = (int)(lin / (unsigned)NA); sint[1] = (int)(lin % (unsigned)NA);
+                            sint[5] = kb == 0ull;                                       // (NaN candidates only: leave it to k_est_exact)
+                            sint[6] = (int)(unsigned)(kb >> 32);
+                            sint[7] = cpi;
+                            atomicAdd(&P.fix_ctl->n_inkernel, 1);
+                        }
+                        __syncthreads();
+                        resolved = true;
+                    }
+                }
+                amb_prev = amb && !resolved;
+                const int nstar = resolved ? sint[0] : nstar_fast;
                 // Noise window (lib/range_angle_estimator_impl.cc:197-226) without evaluating its samples:
                 //   sum_{r,c} |sum_p y[p][r] w^{p c'}|^2 = ncols*A[0] + 2 Re sum_{d=1..7} g[d] A[d],
                 //   A[d] = sum_r sum_q y[q+d][r] conj(y[q][r]),  g[d] = sum_c w^{d c'},  c' = c + Na/2,
@@ -456,7 +517,7 @@ __global__ void __launch_bounds__(256, 2) k_fused64x8(const FusedParams P)
                     }
                 }
                 const int sq = nstar % Q, sm1 = nstar / Q;
-                if (warp == (sm1 >> 1) * 2 + (sq >= Q / 2)) {
+                if (!resolved && warp == (sm1 >> 1) * 2 + (sq >= Q / 2)) {
                     // the lanes that own row nstar re-evaluate it and pick the first bin == gmax
                     int icand = 0x7fffffff, ncand = 0;
                     c32 zc = mk(0.f, 0.f);

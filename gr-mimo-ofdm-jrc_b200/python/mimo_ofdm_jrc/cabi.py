@@ -53,7 +53,7 @@ EXPORTS = [
     "jrc_chain_last_path", "jrc_chain_launch_count", "jrc_chain_run_host", "jrc_radar_estimate",
     "jrc_fft_vcc", "jrc_transpose_pad", "jrc_mag_squared", "jrc_target_sim", "jrc_nlog10", "jrc_estimate2d", "jrc_peak1d", "jrc_zero_pad",
     "jrc_cp_remove", "jrc_ofdm_demod", "jrc_chain_submit", "jrc_chain_poll", "jrc_chain_wait",
-    "jrc_pinned_alloc", "jrc_pinned_free", "jrc_host_register", "jrc_host_unregister",
+    "jrc_pinned_alloc", "jrc_pinned_free", "jrc_host_register", "jrc_host_unregister", "jrc_chain_exact_stats",
 ]
 
 _lib = None
@@ -104,6 +104,7 @@ def load():
     lib.jrc_pinned_free.argtypes = [vp]
     lib.jrc_host_register.argtypes = [vp, sz]
     lib.jrc_host_unregister.argtypes = [vp]
+    lib.jrc_chain_exact_stats.argtypes = [vp, C.POINTER(i64)]
     for name in EXPORTS:
         fn = getattr(lib, name)
         if name not in ("jrc_last_error", "jrc_abi_version", "jrc_chain_destroy", "jrc_chain_stream",
@@ -193,6 +194,12 @@ class Chain:
     def run_host_ptr(self, rx_ptr, tx_ptr, tx_shared, n_cpi, cpi0=0, map_ptr=None, dets_ptr=None):
         check(load().jrc_chain_run_host(self._h, rx_ptr, tx_ptr, int(bool(tx_shared)), n_cpi, cpi0,
                                         map_ptr, dets_ptr))
+
+    def exact_stats(self):
+        """(marked, redone by k_est_exact, ties settled in the fused kernel) since the handle was created."""
+        out = (C.c_int64 * 3)()
+        check(load().jrc_chain_exact_stats(self._h, out))
+        return {"marked": out[0], "redone": out[1], "ties_in_kernel": out[2]}
 
     # -- streaming form: up to 4 submissions in flight ------------------------
     def submit_ptr(self, rx_ptr, tx_ptr, tx_shared, n_cpi, cpi0=0, map_ptr=None, dets_ptr=None):

@@ -156,6 +156,11 @@ JRC_API jrc_status jrc_chain_run_host(jrc_chain *h, const jrc_c32 *rx_host, cons
                                       int32_t tx_shared, int32_t n_cpi, int32_t cpi0,
                                       float *map_host, jrc_det *dets_host);
 
+/* Running totals of the reference-order pass behind JRC_DET_EXACT since the handle was created: out[0] records the
+ * fast kernels marked, out[1] records redone in the reference's order, out[2] arg-max ties settled inside the fused
+ * kernel.  Synchronises the handle.                                                                       */
+JRC_API jrc_status jrc_chain_exact_stats(jrc_chain *h, int64_t *out);
+
 /* Streaming form of jrc_chain_run_host (BASELINE configs[3], "pinned-host double-buffering"): submit enqueues the
  * chain for n_cpi CPIs and returns at once; up to 4 submissions are in flight, each on its own stream, so the input
  * transfer and kernel of CPI k+1 overlap the output transfer of CPI k.  The buffers must stay valid until

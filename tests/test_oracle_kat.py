@@ -202,3 +202,42 @@ def test_zero_pad_and_cp_remove(orc):
     assert pads.size == 247
     z = orc.cp_remove(x, 2, 64, 16)
     assert np.array_equal(z[0], x[16:80]) and np.array_equal(z[1], x[96:160])
+
+
+def test_single_bin_dit(orc):
+    """csrc/jrc_exact.cuh dit_bin_*: ONE bin of the oracle's radix-2 FFT of a zero-padded input as a pairwise reduction
+    of the bit-reversed inputs with one twiddle and one sign per level.  NumPy model of exactly that recipe (float32
+    products and sums rounded one by one) against the oracle's transform, every bin, identical bits."""
+    f32 = np.float32
+
+    def cmul(a, b):
+        ar, ai, br, bi = f32(a.real), f32(a.imag), f32(b.real), f32(b.imag)
+        return complex(f32(f32(ar * br) - f32(ai * bi)), f32(f32(ar * bi) + f32(ai * br)))
+
+    def cadd(a, b, sgn):
+        return complex(f32(f32(a.real) + sgn * f32(b.real)), f32(f32(a.imag) + sgn * f32(b.imag)))
+
+    def rev(k, bits):
+        return int(format(k, f"0{bits}b")[::-1], 2) if bits else 0
+
+    def dit_bin(x, n, tw, o):
+        m, ln = len(x).bit_length() - 1, n.bit_length() - 1
+        A = [complex(x[rev(k, m)]) for k in range(len(x))]
+        for s in range(m):
+            lvl = ln - m + s
+            w = complex(tw[(o & ((1 << lvl) - 1)) * (n >> (lvl + 1))])
+            sgn = f32(-1.0) if (o >> lvl) & 1 else f32(1.0)
+            A = [cadd(A[2 * k], cmul(A[2 * k + 1], w), sgn) for k in range(len(A) // 2)]
+        return np.complex64(A[0])
+
+    rng = np.random.default_rng(0)
+    for n_in, n, fwd in ((64, 1024, False), (8, 64, True), (64, 512, False), (8, 128, True), (32, 256, True)):
+        x = (rng.standard_normal(n_in) + 1j * rng.standard_normal(n_in)).astype(np.complex64)
+        xp = np.zeros(n, np.complex64)
+        xp[:n_in] = x
+        ref = orc.fft_vcc(xp[None], fwd, fwd)[0]              # the angle FFT runs with shift=True, the range IFFT without
+        a = (-1.0 if fwd else 1.0) * 2.0 * np.pi * np.arange(n // 2) / n
+        tw = (np.cos(a).astype(f32) + 1j * np.sin(a).astype(f32)).astype(np.complex64)
+        for i in range(0, n, 1 if n <= 128 else 7):
+            o = (i + n // 2) % n if fwd else i
+            assert dit_bin(x, n, tw, o).view(np.uint64) == ref[i].view(np.uint64), (n_in, n, i)
