@@ -8,14 +8,23 @@ One step = one pass of the fused chain (mimo_ofdm_radar -> range IFFT -> transpo
 -> |.|^2 -> range_angle_estimator) over one batch of BASELINE configs[1]: 64 subcarriers,
 4 TX x 2 RX = 8 virtual channels, 4 LTF symbols, range zero-pad 1024, angle zero-pad 64,
 4096 CPIs per GPU.  CPIs are independent, so N GPUs each process their own 4096-CPI shard
-(weak scaling) and only the 32-byte detection records are gathered to rank 0 over NCCL.
+(weak scaling); the 32-byte detection records of all K steps are gathered to rank 0 over NCCL once,
+after the last step.
 
-Prints ONE JSON line (rank 0).  `--impl reference` times the CPU restatement of the reference
-chain (oracle/) on the host cores for the same metric and configuration.
+Prints ONE JSON line (rank 0).  Besides the contract's keys it carries
+  configs   the other BASELINE configurations (configs[0] shipped flowgraph, configs[2], configs[4]) event-timed in
+            the same process: CPI/s, kernels, fraction of the HBM roofline
+  latency   configs[3]: one CPI per general_work() of the radar_chain block through the runtime stand-in
+            (tests/cpp/latency_blocks.cc): p50/p99 per call, sustained CPI/s with the submit/wait pipeline
+  sweep_c5  (--gpus N) the configs[4] sweep of 65 536 CPIs sharded over the N ranks
+`--impl reference` times the reference's own CPU chain (oracle/_ref) on the host cores for the same metric,
+configuration and batch.
 """
 import argparse
+import hashlib
 import json
 import os
+import subprocess
 import sys
 import threading
 import time
@@ -31,6 +40,12 @@ CFG = dict(T=4, R=2, S=4, N=64, IR=16, IA=8)          # BASELINE configs[1]
 WORKLOAD = ("configs[1]: 64 subcarriers, 4TX x 2RX = 8 virtual channels, 4 LTF symbols, range zero-pad 1024, "
             "angle zero-pad 64, batch of 4096 CPIs per GPU per step, per-CPI TX symbols")
 METRIC, UNIT = "range-angle CPIs/s", "CPI/s"
+OTHER_CONFIGS = {
+    "configs[0] shipped flowgraph 4x2, 64 sc, 512x128": dict(T=4, R=2, S=4, N=64, IR=8, IA=16, n=4096, targets=1,
+                                                             kernels=["k_fused64x8<8,16>", "k_est_exact"]),
+    "configs[2] 4x8, 256 sc, 4096x256, 5 targets": dict(T=4, R=8, S=4, N=256, IR=16, IA=8, n=128, targets=5, kernels=None),
+    "configs[4] 8x16, 2048 sc, 2048x128": dict(T=8, R=16, S=8, N=2048, IR=1, IA=1, n=64, targets=3, kernels=None),
+}
 
 
 def b_alg_per_cpi(c):
@@ -38,15 +53,46 @@ def b_alg_per_cpi(c):
     return (c["T"] + c["R"]) * c["S"] * c["N"] * 8 + (c["N"] * c["IR"]) * (c["T"] * c["R"] * c["IA"]) * 4 + 32
 
 
-def make_inputs(batch, seed):
+def config_dict(batch, world):
+    """The same dict on both arms (the driver compares them)."""
+    Nr, Na = CFG["N"] * CFG["IR"], CFG["T"] * CFG["R"] * CFG["IA"]
+    return {"workload": WORKLOAD, "batch_per_gpu": batch, "map": [Nr, Na],
+            "l2": "per-step working set (1.0 GiB map + 48 MiB symbols) exceeds the 126 MB L2; no flush needed",
+            "parallelism": f"cpi-shard x{world}, detections gathered to rank 0 after the last step" if world > 1 else "single GPU"}
+
+
+def make_inputs(batch, seed, cfg=CFG, targets=2, span=10.0):
     from mimo_ofdm_jrc import synth
     rng = np.random.default_rng(seed)
-    tx = synth.tx_symbols(CFG["T"], CFG["S"], CFG["N"])
-    r, a, amp = synth.random_scene(rng, batch, 2, CFG["N"], amp_db_span=10.0)
-    rx = synth.rx_symbols(tx, CFG["R"], r, a, amp, snr_db=20.0, rng=rng)
-    txb = np.ascontiguousarray(np.broadcast_to(tx, (batch,) + tx.shape))
-    est = synth.default_estimator_params(CFG["N"], CFG["T"] * CFG["R"], CFG["IR"], CFG["IA"])
+    tx = synth.tx_symbols(cfg["T"], cfg["S"], cfg["N"])
+    r, a, amp = synth.random_scene(rng, batch, targets, cfg["N"], amp_db_span=span if targets > 1 else 0.0)
+    rx = synth.rx_symbols(tx, cfg["R"], r, a, amp, snr_db=20.0, rng=rng, chunk=512 if cfg["N"] <= 64 else 16)
+    txb = np.ascontiguousarray(np.broadcast_to(tx, (batch,) + tx.shape)) if cfg is CFG else tx
+    est = synth.default_estimator_params(cfg["N"], cfg["T"] * cfg["R"], cfg["IR"], cfg["IA"])
     return rx, txb, est
+
+
+def source_hash():
+    """Hash of the kernel sources: profiles/ncu_traffic.json is only quoted for the code it was measured on."""
+    h = hashlib.sha256()
+    d = os.path.join(ROOT, "gr-mimo-ofdm-jrc_b200", "csrc")
+    for f in sorted(os.listdir(d)):
+        if f.endswith((".cu", ".cuh")):
+            h.update(open(os.path.join(d, f), "rb").read())
+    return h.hexdigest()[:16]
+
+
+def bind_rank_to_cores(local, world):
+    """One disjoint block of host cores per rank, BEFORE any pinned allocation (first touch decides the NUMA node of
+    the staging buffers)."""
+    try:
+        cores = sorted(os.sched_getaffinity(0))
+        per = max(1, len(cores) // max(1, world))
+        mine = cores[local * per:(local + 1) * per] or cores
+        os.sched_setaffinity(0, mine)
+        return mine
+    except Exception:  # noqa: BLE001
+        return None
 
 
 # --------------------------------------------------------------------------------------
@@ -84,7 +130,7 @@ class ClockSampler:
                 self.power.append(nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
             except Exception:  # noqa: BLE001
                 pass
-            time.sleep(0.002)
+            time.sleep(0.001)
 
     def start(self):
         if self.ok:
@@ -103,7 +149,7 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------------------------
-# CPU arm: the oracle restatement of the reference chain on the host cores
+# CPU arm: the reference's own block sources (oracle/_ref) on the host cores
 # --------------------------------------------------------------------------------------
 REF_LIB = os.path.join(ROOT, "oracle", "_ref", "libjrc_ref.so")
 
@@ -130,6 +176,7 @@ def cpu_chain_rate(n_threads, per_thread, repeats=1, warm=0):
                                         C.c_void_p, C.c_void_p, C.c_void_p]
     Nr, Na = CFG["N"] * CFG["IR"], CFG["T"] * CFG["R"] * CFG["IA"]
     rb, ab = orc.f32(est["range_bins"]), orc.f32(est["angle_bins"])
+    maps = [np.empty((per_thread, Nr, Na), np.float32) for _ in range(n_threads)]
 
     def work(i):
         sl = slice(i * per_thread, (i + 1) * per_thread)
@@ -140,9 +187,8 @@ def cpu_chain_rate(n_threads, per_thread, repeats=1, warm=0):
                          est["noise_discard_range_m"], est["noise_discard_angle_deg"], est["snr_threshold"],
                          est["power_threshold"])
         a, b = np.ascontiguousarray(rx[sl]), np.ascontiguousarray(tx[sl])
-        m = np.empty((per_thread, Nr, Na), np.float32)
         d = np.zeros(per_thread, orc.DET_DTYPE)
-        ref.ref_chain_batch(C.byref(c), a.ctypes.data, b.ctypes.data, 0, per_thread, 0, m.ctypes.data, None, d.ctypes.data)
+        ref.ref_chain_batch(C.byref(c), a.ctypes.data, b.ctypes.data, 0, per_thread, 0, maps[i].ctypes.data, None, d.ctypes.data)
 
     times = []
     with ThreadPoolExecutor(n_threads) as ex:
@@ -154,23 +200,52 @@ def cpu_chain_rate(n_threads, per_thread, repeats=1, warm=0):
     return n_threads * per_thread * len(times) / sum(times), times
 
 
+def fft_sanity(n_cpi=64):
+    """BASELINE.md section 2's sanity point: the two FFT stages of the chain (V range IFFTs of Nr, Nr angle FFTs of Na per
+    CPI) on ONE core with pocketfft complex64 (scipy.fft) and with the oracle's radix-2 FFT the CPU arm uses for the two
+    stock GNU Radio FFT blocks -- how pessimistic that stand-in is against an optimised library."""
+    try:
+        import scipy.fft as sfft
+        from oracle import orc
+    except Exception as e:  # noqa: BLE001
+        return {"unavailable": repr(e)}
+    V, Nr, Na = CFG["T"] * CFG["R"], CFG["N"] * CFG["IR"], CFG["T"] * CFG["R"] * CFG["IA"]
+    rng = np.random.default_rng(0)
+    a = (rng.standard_normal((n_cpi * V, Nr)) + 1j * rng.standard_normal((n_cpi * V, Nr))).astype(np.complex64)
+    b = (rng.standard_normal((n_cpi * Nr, Na)) + 1j * rng.standard_normal((n_cpi * Nr, Na))).astype(np.complex64)
+    res = {}
+    for name, f in (("pocketfft_c64", lambda x, fwd: (sfft.fft if fwd else sfft.ifft)(x, axis=-1, workers=1)),
+                    ("oracle_radix2", lambda x, fwd: orc.fft_vcc(x, fwd, False))):
+        f(a[:V], False)
+        t0 = time.perf_counter()
+        f(a, False)
+        f(b, True)
+        res[name + "_cpi_per_s_one_core"] = n_cpi / (time.perf_counter() - t0)
+    res["oracle_fft_slowdown_vs_pocketfft"] = res["pocketfft_c64_cpi_per_s_one_core"] / res["oracle_radix2_cpi_per_s_one_core"]
+    res["what"] = "FFT stages only; the CPU arm's chain spends ~60 % of its time in the oracle FFT"
+    return res
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     cores = os.cpu_count() or 1
-    r1, _ = cpu_chain_rate(1, 4)                                   # calibrate: CPIs/s on one thread
-    per_thread = max(1, min(64, int(r1 * 1.0)))                     # ~1 s of work per thread per step
+    per_thread = max(1, args.batch // cores)                       # the same batch as the GPU arm, split over the cores
+    batch = per_thread * cores
     rate, times = cpu_chain_rate(cores, per_thread, repeats=args.steps, warm=args.warmup)
-    sample = f"{cores * per_thread} CPIs per step ({per_thread} per thread x {cores} threads) of the same workload"
+    sample = f"{batch} CPIs per step ({per_thread} per thread x {cores} threads): the GPU arm's batch of the same workload"
     out = {"impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
            "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean(times)), "higher_is_better": True,
            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-           "config": {"workload": WORKLOAD, "note": "reference chain on the host cores: the reference's own block sources "
-                      "(oracle/_ref) when built, else the oracle restatement; no GNU Radio scheduler, float32 radix-2 FFT "
-                      "instead of gr-fft/FFTW (neither is installable here)"},
+           "config": config_dict(args.batch, world),
+           "note": "reference chain on the host cores: the reference's own block sources (oracle/_ref) when built, else the "
+                   "oracle restatement; no GNU Radio scheduler, float32 radix-2 FFT instead of gr-fft/FFTW (neither is "
+                   "installable here; see cpu_baseline.fft_sanity)",
            "complex_msps": rate * CFG["R"] * CFG["S"] * CFG["N"] / 1e6,
-           "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": cpu_kind(), "sample": sample},
+           "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": cpu_kind(), "sample": sample,
+                            "fft_sanity": fft_sanity()},
            "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(out), flush=True)
 
@@ -178,15 +253,69 @@ def run_reference(args):
 # --------------------------------------------------------------------------------------
 # GPU arm
 # --------------------------------------------------------------------------------------
+def time_config(jrc, torch, name, c, dev, peak_gbs, reps):
+    """One of the other BASELINE configurations: whole-chain CPI/s over a resident batch, event-timed."""
+    cfg = {k: c[k] for k in ("T", "R", "S", "N", "IR", "IA")}
+    n = c["n"]
+    rx_h, tx_h, est = make_inputs(n, seed=5, cfg=cfg, targets=c["targets"], span=15.0)
+    rc = jrc.radar_chain(cfg["N"], cfg["T"], cfg["R"], cfg["S"], cfg["IR"], cfg["IA"], device=dev.index, estimator=est)
+    drx, dtx = torch.from_numpy(rx_h).to(dev), torch.from_numpy(tx_h).to(dev)
+    dmap = torch.empty((n, rc.Nr, rc.Na), dtype=torch.float32, device=dev)
+    ddet = torch.zeros((n, 32), dtype=torch.uint8, device=dev)
+    ext = torch.cuda.ExternalStream(rc.chain.stream, device=dev)
+    torch.cuda.synchronize()
+    l0 = None
+    with torch.cuda.stream(ext):
+        for _ in range(3):
+            rc.run(drx, dtx, map_out=dmap, dets_out=ddet, sync_inputs=False)
+        l0 = rc.chain.launch_count
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(ext)
+        for _ in range(reps):
+            rc.run(drx, dtx, map_out=dmap, dets_out=ddet, sync_inputs=False)
+        e1.record(ext)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    launches = (rc.chain.launch_count - l0) // reps
+    d = rc.dets_to_numpy(ddet)
+    rate = n / (ms * 1e-3)
+    path = {jrc.PATH_FUSED: "fused", jrc.PATH_TILED: "tiled", jrc.PATH_STAGED: "staged"}[rc.chain.last_path]
+    alg = b_alg_per_cpi(cfg)
+    out = {"path": path, "cpis_per_call": n, "ms_per_call": ms, "cpi_per_s": rate, "launches_per_call": int(launches),
+           "complex_msps": rate * cfg["R"] * cfg["S"] * cfg["N"] / 1e6, "map": [rc.Nr, rc.Na],
+           "algorithmic_bytes_per_cpi": alg, "achieved_gbs": rate * alg / 1e9, "roofline_frac": rate * alg / 1e9 / peak_gbs,
+           "gate_pass_fraction": float((d["flags"] & 1).mean()), "exact_pass": rc.chain.exact_stats(),
+           "kernels": c["kernels"] or (["k_chan_est(_tile)", "k_fft8_rows", "k_angle_mag", "k_map_finalize", "k_est_exact"]
+                                       if path == "tiled" else None)}
+    del drx, dtx, dmap, ddet, rc
+    torch.cuda.empty_cache()
+    return out
+
+
+def latency_mode():
+    """configs[3] through the C++ block harness (built by build()); its JSON is passed through."""
+    exe = os.path.join(ROOT, "gr-mimo-ofdm-jrc_b200", "build", "latency_blocks")
+    if not os.path.exists(exe):
+        return {"unavailable": "build/latency_blocks not built"}
+    try:
+        r = subprocess.run([exe, "4000"], capture_output=True, text=True, timeout=300)
+        if r.returncode != 0:
+            return {"unavailable": (r.stderr or r.stdout)[-300:]}
+        return json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("{")][-1])
+    except Exception as e:  # noqa: BLE001
+        return {"unavailable": repr(e)}
+
+
 def run_ours(args):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    cores_bound = bind_rank_to_cores(local, world) if world > 1 else None
     import torch
     import torch.distributed as dist
     import mimo_ofdm_jrc as jrc
     from mimo_ofdm_jrc import shard
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
     torch.cuda.set_device(local)
@@ -205,6 +334,13 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    def sum_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
     B, K, W = args.batch, args.steps, max(3, args.warmup)
     rx_h, tx_h, est = make_inputs(B, seed=100 + rank)
     rc = jrc.radar_chain(CFG["N"], CFG["T"], CFG["R"], CFG["S"], CFG["IR"], CFG["IA"], device=local, estimator=est)
@@ -212,35 +348,23 @@ def run_ours(args):
     rx = torch.from_numpy(rx_h).to(dev)
     tx = torch.from_numpy(tx_h).to(dev)
     dmap = torch.empty((B, Nr, Na), dtype=torch.float32, device=dev)
-    ddet = torch.zeros((B, 32), dtype=torch.uint8, device=dev)
+    # the records of ALL K steps stay on the GPU and are gathered once, after the last step
+    ddet_all = torch.zeros((K, B, 32), dtype=torch.uint8, device=dev)
+    gath = torch.empty((world * K * B, 32), dtype=torch.uint8, device=dev) if (world > 1 and rank == 0) else None
     ext = torch.cuda.ExternalStream(rc.chain.stream, device=dev)
     torch.cuda.synchronize()
 
-    counts = [B] * world                       # contiguous equal shards: no size exchange needed
-    # two detection buffers per rank: the gather of step k overlaps the kernel of step k+1
-    ddets = [ddet, torch.zeros_like(ddet)] if world > 1 else [ddet]
-    gbufs = [torch.empty((world * B, 32), dtype=torch.uint8, device=dev) for _ in range(2)] if (world > 1 and rank == 0) else [None, None]
-    pending = [None, None]
+    def step(k):
+        rc.run(rx, tx, map_out=dmap, dets_out=ddet_all[k % K], path=jrc.PATH_FUSED, sync_inputs=False)
 
-    def step(k=0):
-        slot = k & 1 if world > 1 else 0
-        if pending[slot] is not None:
-            pending[slot].wait()               # the gather that last read this buffer
-            pending[slot] = None
-        rc.run(rx, tx, map_out=dmap, dets_out=ddets[slot], path=jrc.PATH_FUSED, sync_inputs=False)
+    def gather_all():
         if world > 1:
-            pending[slot], _ = shard.gather_detections(ddets[slot], dst=0, counts=counts, out=gbufs[slot], async_op=True)
-
-    def drain():
-        for i in range(2):
-            if pending[i] is not None:
-                pending[i].wait()
-                pending[i] = None
+            shard.gather_detections(ddet_all.view(K * B, 32), dst=0, counts=[K * B] * world, out=gath)
 
     with torch.cuda.stream(ext):
         for k in range(W):
             step(k)
-        drain()
+        gather_all()
     torch.cuda.synchronize()
     launches0 = rc.chain.launch_count
     sampler = ClockSampler(local) if rank == 0 else None
@@ -256,15 +380,39 @@ def run_ours(args):
             ev[k][0].record(ext)
             step(k)
             ev[k][1].record(ext)
-        drain()
+        gather_all()
         e1.record(ext)
     torch.cuda.synchronize()
-    clocks = sampler.stop() if sampler else None
-    barrier()
-    elapsed_ms = max_over_ranks(e0.elapsed_time(e1))
-    kern_ms = float(np.mean([a.elapsed_time(b) for a, b in ev]))
+    elapsed_local = e0.elapsed_time(e1)
     launches = rc.chain.launch_count - launches0
+    # the timed region of a short run is a few milliseconds: keep the same kernel running until the clock record
+    # holds enough samples (NOT part of the timed value)
+    if sampler:
+        t_end = time.perf_counter() + 0.25
+        with torch.cuda.stream(ext):
+            while time.perf_counter() < t_end:
+                for k in range(8):
+                    step(k)
+                ext.synchronize()
+    clocks = sampler.stop() if sampler else None
+    if clocks is not None:
+        clocks["note"] = "sampled over the timed region and 0.25 s of the same step right after it"
+    barrier()
+    elapsed_ms = max_over_ranks(elapsed_local)
+    step_ms = float(np.mean([a.elapsed_time(b) for a, b in ev]))
     value = world * B * K / (elapsed_ms * 1e-3)
+    exact_stats = rc.chain.exact_stats()
+
+    # ---- dominant kernel alone: k_fused64x8 without the (tiny) reference-order pass behind it ----
+    with torch.cuda.stream(ext):
+        k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        nk = max(5, min(K, 50))
+        k0.record(ext)
+        for _ in range(nk):
+            rc.run(rx, tx, map_out=dmap, want_dets=False, path=jrc.PATH_FUSED, sync_inputs=False)
+        k1.record(ext)
+    torch.cuda.synchronize()
+    map_only_ms = k0.elapsed_time(k1) / nk
 
     # ---- end to end through the host-buffer C-ABI call (pinned host memory) ----
     e2e = None
@@ -290,31 +438,95 @@ def run_ours(args):
             torch.cuda.synchronize()
             dt = max_over_ranks(time.perf_counter() - t0)
             res[with_map] = world * B * Ke / dt
+        # the ceiling of that path: a plain pinned D2H copy of the same 1 GiB, all ranks at once
+        barrier()
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        pmap.copy_(dmap, non_blocking=True)
+        torch.cuda.synchronize()
+        barrier()
+        c0.record()
+        for _ in range(3):
+            pmap.copy_(dmap, non_blocking=True)
+        c1.record()
+        torch.cuda.synchronize()
+        d2h_gbs_rank = 3 * dmap.numel() * 4 / (c0.elapsed_time(c1) * 1e-3) / 1e9
+        d2h_gbs_all = sum_over_ranks(d2h_gbs_rank)
         h2d = int(rx_h.nbytes + tx_h.nbytes)
-        e2e = {"value": res[True], "unit": UNIT, "h2d_bytes_per_step": h2d,
-               "d2h_bytes_per_step": int(B * Nr * Na * 4 + B * 32), "steps": Ke,
+        d2h = int(B * Nr * Na * 4 + B * 32)
+        e2e = {"value": res[True], "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": Ke,
                "what": "jrc_chain_run_host: pinned host symbols in, |.|^2 map + detection records out",
+               "d2h_ceiling_gbs": d2h_gbs_all, "d2h_ceiling_what": "plain pinned cudaMemcpyAsync D2H of the same map, all ranks at once, sum over ranks",
+               "pcie_frac": (res[True] / world) * (d2h / B) * world / 1e9 / d2h_gbs_all,
+               "host_cores_per_rank": len(cores_bound) if cores_bound else None,
                "detections_only": {"value": res[False], "unit": UNIT, "h2d_bytes_per_step": h2d,
                                    "d2h_bytes_per_step": int(B * 32)}}
         del prx, ptx, pmap, pdet
 
     # ---- sanity: the timed output is the real thing --------------------------------
-    d = rc.dets_to_numpy(ddet)
+    d = rc.dets_to_numpy(ddet_all[(K - 1) % K])
     assert (d["flags"] & 1).mean() > 0.9 and d["range_idx"].max() < Nr and d["angle_idx"].max() < Na
+    if gath is not None:
+        g = gath.cpu().numpy().view(jrc.DET_DTYPE).reshape(world, K, B)
+        assert np.array_equal(g[0, K - 1]["range_idx"], d["range_idx"])
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:  # noqa: BLE001
+        pass
+    peak_gbs, peak_src = (peaks["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)") if "hbm_gbs" in peaks \
+        else (6650.0, "fallback (B200_PROFILING.md)")
+
+    # ---- configs[4] sweep: 65 536 CPIs sharded over the ranks (north_star) ----
+    sweep = None
+    if world > 1 or args.sweep:
+        c5 = OTHER_CONFIGS["configs[4] 8x16, 2048 sc, 2048x128"]
+        cfg5 = {k: c5[k] for k in ("T", "R", "S", "N", "IR", "IA")}
+        total = 65536
+        lo, hi = shard.shard_range(total, rank, world)
+        nblk = 64
+        rx5_h, tx5_h, est5 = make_inputs(nblk, seed=7 + rank, cfg=cfg5, targets=3, span=15.0)
+        rc5 = jrc.radar_chain(cfg5["N"], cfg5["T"], cfg5["R"], cfg5["S"], cfg5["IR"], cfg5["IA"], device=local, estimator=est5)
+        rx5, tx5 = torch.from_numpy(rx5_h).to(dev), torch.from_numpy(tx5_h).to(dev)
+        m5 = torch.empty((nblk, rc5.Nr, rc5.Na), dtype=torch.float32, device=dev)
+        d5 = torch.zeros((hi - lo, 32), dtype=torch.uint8, device=dev)
+        g5 = torch.empty((world * ((total + world - 1) // world), 32), dtype=torch.uint8, device=dev) if (world > 1 and rank == 0) else None
+        ext5 = torch.cuda.ExternalStream(rc5.chain.stream, device=dev)
+        with torch.cuda.stream(ext5):
+            rc5.run(rx5, tx5, map_out=m5, dets_out=d5[:nblk], sync_inputs=False)
+        torch.cuda.synchronize()
+        barrier()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(ext5):
+            s0.record(ext5)
+            for c0 in range(0, hi - lo, nblk):
+                nc = min(nblk, hi - lo - c0)
+                rc5.run(rx5[:nc], tx5, map_out=m5[:nc], dets_out=d5[c0:c0 + nc], cpi0=lo + c0, sync_inputs=False)
+            if world > 1:
+                shard.gather_detections(d5, dst=0, counts=[shard.shard_range(total, r, world)[1] - shard.shard_range(total, r, world)[0]
+                                                           for r in range(world)], out=g5)
+            s1.record(ext5)
+        torch.cuda.synchronize()
+        ms5 = max_over_ranks(s0.elapsed_time(s1))
+        sweep = {"workload": "configs[4]: 2048 subcarriers, 8 x 16 virtual array, 65536 CPIs sharded over the ranks, detection records "
+                             "gathered to rank 0 over NCCL; every rank re-processes a resident block of 64 synthetic CPIs (the 192 GiB of "
+                             "symbols do not fit)", "n_gpus": world, "cpis": total, "ms": ms5, "cpi_per_s": total / (ms5 * 1e-3),
+                 "complex_gsps": total / (ms5 * 1e-3) * cfg5["R"] * cfg5["S"] * cfg5["N"] / 1e9,
+                 "roofline_frac_per_gpu": total / (ms5 * 1e-3) * b_alg_per_cpi(cfg5) / 1e9 / peak_gbs / world}
+        del rx5, tx5, m5, d5, rc5
+        torch.cuda.empty_cache()
 
     if rank == 0:
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except Exception:  # noqa: BLE001
-            pass
-        peak_gbs, peak_src = (peaks["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)") if "hbm_gbs" in peaks \
-            else (6650.0, "fallback (B200_PROFILING.md)")
         alg_bytes = b_alg_per_cpi(CFG) * B
+        kern_ms = map_only_ms
         achieved = alg_bytes / (kern_ms * 1e-3) / 1e9
-        traffic = None
+        traffic, traffic_note = None, None
         try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))["k_fused64x8"]["dram_bytes_per_launch"]
+            tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))["k_fused64x8"]
+            if tj.get("source_hash") == source_hash():
+                traffic = tj["dram_bytes_per_launch"]
+            else:
+                traffic_note = "profiles/ncu_traffic.json was captured on other kernel sources (hash mismatch): not quoted"
         except Exception:  # noqa: BLE001
             pass
         cpu = None
@@ -326,19 +538,25 @@ def run_ours(args):
             cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": cpu_kind(),
                    "sample": f"{cores * per_thread} CPIs of the same workload ({per_thread} per thread x {cores} threads); "
                              "kind reference = the reference's block sources (oracle/_ref) + float32 radix-2 FFT for the "
-                             "two stock GNU Radio FFT blocks", "single_thread": r1}
+                             "two stock GNU Radio FFT blocks", "single_thread": r1, "fft_sanity": fft_sanity()}
+        configs, latency = None, None
+        if world == 1 and not args.no_configs:
+            configs = {name: time_config(jrc, torch, name, c, dev, peak_gbs, reps=10) for name, c in OTHER_CONFIGS.items()}
+            latency = latency_mode()
         out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
                "ms_per_step": elapsed_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                "dtype": "f32", "data": "synthetic",
-               "config": {"workload": WORKLOAD, "batch_per_gpu": B, "map": [Nr, Na],
-                          "l2": "per-step working set (1.0 GiB map + 48 MiB symbols) exceeds the 126 MB L2; no flush needed",
-                          "parallelism": f"cpi-shard x{world}, detections gathered to rank 0" if world > 1 else "single GPU"},
+               "config": config_dict(B, world),
                "complex_msps": value * CFG["R"] * CFG["S"] * CFG["N"] / 1e6,
                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
-                            "frac": achieved / peak_gbs, "traffic": traffic, "peak_source": peak_src,
-                            "kernel": "k_fused64x8<16,8>", "kernel_ms": kern_ms,
+                            "frac": achieved / peak_gbs, "traffic": traffic, "traffic_note": traffic_note, "peak_source": peak_src,
+                            "kernel": "k_fused64x8<16,8>", "kernel_ms": kern_ms, "step_ms_events": step_ms,
+                            "kernel_ms_what": "k_fused64x8 launched alone (map, no records), CUDA events on its stream; step_ms_events "
+                                              "= the timed step (same kernel with the in-kernel estimator + the k_est_exact launch behind it)",
                             "algorithmic_bytes_per_launch": alg_bytes},
-               "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks}
+               "exact_pass": exact_stats,
+               "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+               "configs": configs, "latency": latency, "sweep_c5": sweep}
         print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -353,9 +571,10 @@ def main():
     ap.add_argument("--batch", type=int, default=4096)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-configs", action="store_true")
+    ap.add_argument("--sweep", action="store_true", help="run the configs[4] 65536-CPI sweep on one GPU as well")
     args = ap.parse_args()
     if args.gpus > 1 and "WORLD_SIZE" not in os.environ:      # plain `python bench.py --gpus N`: relaunch under torchrun
-        import subprocess
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
                "--master-addr", "127.0.0.1", "--master-port", "29517", os.path.abspath(__file__)] + sys.argv[1:]
         raise SystemExit(subprocess.call(cmd))
