@@ -605,8 +605,16 @@ static jrc_status launch_exact(jrc_chain *h, PortDev rx, PortDev tx, const c32 *
     }
     ST(h->sExact.need((size_t)h->exact_grid * h->V * h->Nr * sizeof(c32)));
     P.scratch = (c32 *)h->sExact.p;
-    k_est_exact<<<h->exact_grid, 256, smem, h->stream>>>(P);
-    CU(cudaGetLastError());
+    // programmatic dependent launch: the grid is staged while the kernel in front of it drains (it waits for that
+    // kernel's memory with griddepcontrol.wait), so an empty marked-CPI list costs no launch gap
+    cudaLaunchConfig_t lc;
+    memset(&lc, 0, sizeof(lc));
+    lc.gridDim = dim3((unsigned)h->exact_grid); lc.blockDim = dim3(256); lc.dynamicSmemBytes = smem; lc.stream = h->stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    lc.attrs = at; lc.numAttrs = 1;
+    CU(cudaLaunchKernelEx(&lc, k_est_exact, P));
     h->launches++;
     return JRC_OK;
 }

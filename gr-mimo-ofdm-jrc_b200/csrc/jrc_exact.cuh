@@ -120,6 +120,7 @@ __global__ void __launch_bounds__(256) k_est_exact(const ExactParams P)
     __shared__ int s_cand[EXACT_MAX_CAND], s_ncand, s_rows[EXACT_MAX_CAND], s_wrows[EXACT_MAX_CAND];
     __shared__ float s_noise;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    asm volatile("griddepcontrol.wait;" ::: "memory");     // launched programmatically behind the kernel that fills the list
     const int count = *reinterpret_cast<volatile int *>(&P.ctl->count);
     const int N = P.N, V = P.V, Nr = P.Nr, Na = P.Na;
     c32 *Y = P.scratch + (size_t)blockIdx.x * V * Nr;
