@@ -19,6 +19,7 @@
 
 #include "jrc_fused.cuh"
 #include "jrc_tiled.cuh"
+#include "jrc_slice.cuh"
 #include "jrc_staged.cuh"
 #include "jrc_exact.cuh"
 
@@ -445,6 +446,30 @@ static bool tiled_config_ok(const jrc_chain *h)
     return h->Nr % rpc == 0;
 }
 
+// k_slice256 (jrc_slice.cuh): range IFFT + transpose + angle FFT + |.|^2 + arg-max in one kernel
+static bool slice_config_ok(const jrc_chain *h)
+{
+    static const bool off = getenv("JRC_NO_SLICE") != nullptr;     // A/B switch for measurements
+    return !off && h->cfg.fft_len == 256 && h->Na == 256 && h->V <= 32 && h->cfg.interp_range >= 2 && h->cfg.interp_range % 2 == 0 &&
+           h->Nr <= 16384;
+}
+
+static jrc_status launch_slice(jrc_chain *h, const c32 *H, int n_cpi, float *map, unsigned long long *keys, unsigned *sec)
+{
+    SliceParams P;
+    memset(&P, 0, sizeof(P));
+    P.H = H; P.V = h->V; P.IR = h->cfg.interp_range; P.n_cpi = n_cpi; P.map = map; P.keys = keys; P.sec = sec;
+    ST(get_twiddles_full(h, h->Nr, 0, &P.tw_range));
+    ST(get_twiddles_full(h, 256, 1, &P.tw256));
+    CU(cudaFuncSetAttribute(k_slice256, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SliceGeom::SMEM));
+    long long grid = (long long)n_cpi * (P.IR / 2);
+    if (grid > h->sm_count) grid = h->sm_count;
+    k_slice256<<<(unsigned)grid, SliceGeom::THREADS, SliceGeom::SMEM, h->stream>>>(P);
+    CU(cudaGetLastError());
+    h->launches++;
+    return JRC_OK;
+}
+
 static jrc_status launch_fft8_rows(jrc_chain *h, const c32 *in, long long in_stride, int n_in, c32 *out, int n, long long rows)
 {
     const c32 *tw = nullptr;
@@ -710,12 +735,13 @@ static jrc_status run_batch_impl(jrc_chain *h, jrc_port_layout rx, jrc_port_layo
     if (want_tiled) {
         NvtxRange nv("tiled: chan_est + range FFT + angle FFT");
         h->last_path = JRC_PATH_TILED;
-        const size_t per = ((size_t)V * N + (size_t)V * Nr) * sizeof(c32) + (map ? 0 : (size_t)Nr * Na * sizeof(float));
+        const size_t per = ((size_t)V * N + (slice_config_ok(h) ? 0 : (size_t)V * Nr)) * sizeof(c32) + (map ? 0 : (size_t)Nr * Na * sizeof(float));
         int chunk = (int)(((size_t)1 << 30) / per);
         if (chunk < 1) chunk = 1;
         if (chunk > n_cpi) chunk = n_cpi;
+        const bool slice = slice_config_ok(h);
         ST(h->sH.need((size_t)chunk * V * N * sizeof(c32)));
-        ST(h->sY.need((size_t)chunk * V * Nr * sizeof(c32)));
+        if (!slice) ST(h->sY.need((size_t)chunk * V * Nr * sizeof(c32)));
         if (!map) ST(h->sC.need((size_t)chunk * Nr * Na * sizeof(float)));
         if (dets) {
             ST(h->sKeys.need(sizeof(unsigned long long) * (size_t)chunk));
@@ -731,12 +757,16 @@ static jrc_status run_batch_impl(jrc_chain *h, jrc_port_layout rx, jrc_port_layo
             unsigned long long *dK = dets ? (unsigned long long *)h->sKeys.p : nullptr;
             unsigned *dS = dets ? (unsigned *)h->sSec.p : nullptr;
             ST(launch_chan_est(h, crx, ctx, nc, dH, n_pre));
-            ST(launch_fft8_rows(h, dH, N, N, dY, Nr, (long long)nc * V));
             if (dK) {
                 CU(cudaMemsetAsync(dK, 0, sizeof(unsigned long long) * (size_t)nc, h->stream));
                 CU(cudaMemsetAsync(dS, 0, sizeof(unsigned) * (size_t)nc, h->stream));
             }
-            ST(launch_angle_mag(h, dY, V, Nr, Na, nc, dM, dK, dS));
+            if (slice) {
+                ST(launch_slice(h, dH, nc, dM, dK, dS));
+            } else {
+                ST(launch_fft8_rows(h, dH, N, N, dY, Nr, (long long)nc * V));
+                ST(launch_angle_mag(h, dY, V, Nr, Na, nc, dM, dK, dS));
+            }
             if (dets) {
                 k_map_finalize<<<(unsigned)nc, 128, (size_t)Na * sizeof(float), h->stream>>>(
                     dM, dK, dS, nc, Nr, Na, EP, (DetDev *)dets + c0, cpi0 + c0, fix_ctl, fix_list);
