@@ -19,8 +19,15 @@
 // parts of the same element of both rows -- so each packed FFMA2/FADD2/FMUL2 does useful work in both halves and every
 // shared-memory access is 128 bits wide (about 113 instructions per map row of 256 bins against 195 for the
 // one-row kernels of jrc_tiled.cuh).  Rows of a range transform = the two slices of one channel; rows of an angle
-// transform = the two range bins (n, n+1).  Radix 8.8.4 decimation in frequency, one warp per row pair, __syncwarp
-// between passes; the angle zero-pad (V <= 32 of 256 inputs) prunes the first pass to "copy with a twiddle".
+// transform = the two range bins (n, n+1).  One warp per row pair, __syncwarp between passes.
+//   range: radix 8.8.4 decimation in frequency, in place in the slice-pair buffer.
+//   angle: with only V <= 32 of the 256 inputs non-zero, bin i = b + 8a is
+//              M[b + 8a] = sum_{s<4} w_4^{s k2} [ w_32^{s k1} sum_{m<8} w_8^{m k1} ( (-1)^p w_256^{p b} x_p ) ],   p = s + 4m, a = k1 + 8 k2:
+//          lane (b, s) twiddles its 8 inputs and runs the 8-point DFT in registers, ONE exchange through shared memory
+//          (8 float4 out, 8 in, conflict-free), then lane (b, kq) finishes k1 = kq, kq + 4 with two 4-point DFTs and owns
+//          bins b + 8 kq + 32 w + 64 k2 -- every store instruction of the warp is one full 128-byte line.  The exchange
+//          is what bounds a shared-memory FFT (the LSU moves 128 B per clock): this form moves 88 wavefronts per row
+//          pair where three radix-8/8/4 passes move 170, about the time the packed FP32 work needs (92 clocks).
 // Same float32 arithmetic class as the oracle's radix-2 FFTs, not their rounding (map criterion 1e-4 of the peak).
 #pragma once
 #include "jrc_common.cuh"
@@ -121,16 +128,15 @@ __global__ void __launch_bounds__(SliceGeom::THREADS, 1) k_slice256(const SliceP
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
     const int V = P.V, IR = P.IR, Nr = N * IR;
 
-    // per-lane twiddles, forward sign: pass 1 w_256^{lane k}, pass 2 w_32^{(lane & 3) k}
-    float2 t1r[7], t1i[7], t2r[7], t2i[7];
+    // per-lane twiddles, forward sign, kept for the whole kernel: w_32^{(lane & 3) k} (range pass 2 and the angle stage)
+    float2 t2r[7], t2i[7];
 #pragma unroll
     for (int k = 1; k < 8; k++) {
-        const c32 a = __ldg(P.tw256 + ((lane * k) & 255)), b = __ldg(P.tw256 + ((8 * (lane & 3) * k) & 255));
-        t1r[k - 1] = mk(a.x, a.x); t1i[k - 1] = mk(a.y, a.y);
+        const c32 b = __ldg(P.tw256 + ((8 * (lane & 3) * k) & 255));
         t2r[k - 1] = mk(b.x, b.x); t2i[k - 1] = mk(b.y, b.y);
     }
-    const float sgn = (lane & 1) ? -1.f : 1.f;      // output fftshift of the angle FFT = input modulation (-1)^channel
     float4 *X = Xw + warp * ROW;
+    const int ab = lane >> 2, as = lane & 3;        // angle stage: lane = (b, s) before the exchange, (b, kq) after it
 
     const int units_per_cpi = IR >> 1;
     const long long n_units = (long long)P.n_cpi * units_per_cpi;
@@ -143,6 +149,12 @@ __global__ void __launch_bounds__(SliceGeom::THREADS, 1) k_slice256(const SliceP
         }
         __syncthreads();      // (also: the previous unit's angle stage has finished reading Ys)
         // ---- range stage: channel p -> Ys[p], two slices at once ----
+        float2 t1r[7], t1i[7];                      // pass 1: w_256^{lane k}
+#pragma unroll
+        for (int k = 1; k < 8; k++) {
+            const c32 a = __ldg(P.tw256 + ((lane * k) & 255));
+            t1r[k - 1] = mk(a.x, a.x); t1i[k - 1] = mk(a.y, a.y);
+        }
         for (int p = warp; p < V; p += Gm::WARPS) {
             float4 *Y = Ys + p * PITCH;
             const c32 *Hp = P.H + ((long long)cpi * V + p) * N + lane;
@@ -181,6 +193,13 @@ __global__ void __launch_bounds__(SliceGeom::THREADS, 1) k_slice256(const SliceP
         }
         __syncthreads();
         // ---- angle stage: range positions pos -> map rows (n, n + 1), n = q0 + IR * dif_freq(pos) ----
+        float2 a1r[8], a1i[8];                      // (-1)^p w_256^{p b}, p = s + 4m: the fftshift is the sign
+#pragma unroll
+        for (int m = 0; m < 8; m++) {
+            const c32 a = __ldg(P.tw256 + (((as + 4 * m) * ab) & 255));
+            const float sg = (as & 1) ? -1.f : 1.f;
+            a1r[m] = mk(sg * a.x, sg * a.x); a1i[m] = mk(sg * a.y, sg * a.y);
+        }
         float best = -1.f, sec_t = -1.f;
         int best_row = 0;
         for (int pos = warp; pos < N; pos += Gm::WARPS) {
@@ -188,30 +207,46 @@ __global__ void __launch_bounds__(SliceGeom::THREADS, 1) k_slice256(const SliceP
             const int n = q0 + IR * m;
             float2 re[8], im[8];
             {
-                const float4 x = Ys[lane * PITCH + fpad(pos)];
-                const float2 xr = mk(sgn * x.x, sgn * x.y), xi = mk(sgn * x.z, sgn * x.w);
-                float4 *xb = X + fpad(lane);
-                xb[0] = make_float4(xr.x, xr.y, xi.x, xi.y);
+                const float4 *yp = Ys + as * PITCH + fpad(pos);
 #pragma unroll
-                for (int k = 1; k < 8; k++) {
-                    float2 r = xr, i = xi;
-                    cmul2(r, i, t1r[k - 1], t1i[k - 1]);
-                    xb[fpad_step(k, 32)] = make_float4(r.x, r.y, i.x, i.y);
+                for (int mm = 0; mm < 8; mm++) {          // 4 distinct addresses per load (broadcast over b): one wavefront
+                    const float4 x = yp[4 * mm * PITCH];
+                    re[mm] = mk(x.x, x.y); im[mm] = mk(x.z, x.w);
+                    cmul2(re[mm], im[mm], a1r[mm], a1i[mm]);
                 }
             }
+            fft8s<-1>(re, im);
+#pragma unroll
+            for (int k = 1; k < 8; k++) cmul2(re[k], im[k], t2r[k - 1], t2i[k - 1]);
+            {
+                float4 *ub = X + 36 * ab + 9 * as;        // U[b][s][k1]: pitches 36 / 9 keep the stores AND the loads below conflict-free
+#pragma unroll
+                for (int k = 0; k < 8; k++) ub[k] = make_float4(re[k].x, re[k].y, im[k].x, im[k].y);
+            }
             __syncwarp();
-            dif2_passes23<-1>(X, lane, t2r, t2i, re, im);
+            {
+                const float4 *ub = X + 36 * ab + as;      // k1 = kq + 4w, kq = lane & 3
+#pragma unroll
+                for (int w = 0; w < 2; w++)
+#pragma unroll
+                    for (int sp = 0; sp < 4; sp++) {
+                        const float4 u = ub[9 * sp + 4 * w];
+                        re[4 * w + sp] = mk(u.x, u.y); im[4 * w + sp] = mk(u.z, u.w);
+                    }
+            }
             __syncwarp();      // the row buffer is free for the next position
+            fft4s<-1>(re[0], re[1], re[2], re[3], im[0], im[1], im[2], im[3]);
+            fft4s<-1>(re[4], re[5], re[6], re[7], im[4], im[5], im[6], im[7]);
             float2 v[8];
 #pragma unroll
             for (int c = 0; c < 8; c++) v[c] = __ffma2_rn(im[c], im[c], __fmul2_rn(re[c], re[c]));
             if (P.map) {
-                // position 8 lane + c holds angle bin dif_freq<8>(8 lane + c) = (lane >> 2) + 16 (lane & 3) + 8 (c >> 2) + 64 (c & 3)
-                float *mp = P.map + ((long long)cpi * Nr + n) * NA + (lane >> 2) + 16 * (lane & 3);
+                // v[4w + k2] is angle bin b + 8 kq + 32 w + 64 k2 = lane-contiguous: one 128-byte line per store instruction
+                float *mp = P.map + ((long long)cpi * Nr + n) * NA + ab + 8 * as;
 #pragma unroll
                 for (int c = 0; c < 8; c++) {
-                    __stcs(mp + 8 * (c >> 2) + 64 * (c & 3), v[c].x);
-                    __stcs(mp + NA + 8 * (c >> 2) + 64 * (c & 3), v[c].y);
+                    __stcs(mp + 32 * (c >> 2) + 64 * (c & 3), v[c].x);
+                    __stcs(mp + NA + 32 * (c >> 2) + 64 * (c & 3), v[c].y);
                 }
             }
             const float ma = fmaxf(fmaxf(fmaxf(v[0].x, v[1].x), fmaxf(v[2].x, v[3].x)), fmaxf(fmaxf(v[4].x, v[5].x), fmaxf(v[6].x, v[7].x)));

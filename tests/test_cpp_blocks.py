@@ -57,7 +57,7 @@ def test_streaming_latency_harness_runs():
     r = subprocess.run([exe, "300"], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     res = json.loads(r.stdout)
-    assert len(res) == 4          # per map size: the five separate blocks and the fused block
+    assert len(res) == 6          # per map size: the five separate blocks, the fused block, the pipelined fused block
     for k, v in res.items():
         assert 0 < v["p50_us"] <= v["p99_us"] < 20000, k
         if k.startswith("radar_chain"):
