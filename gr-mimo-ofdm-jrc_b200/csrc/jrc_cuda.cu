@@ -20,6 +20,7 @@
 #include "jrc_fused.cuh"
 #include "jrc_tiled.cuh"
 #include "jrc_slice.cuh"
+#include "jrc_wide.cuh"
 #include "jrc_staged.cuh"
 #include "jrc_exact.cuh"
 
@@ -470,6 +471,40 @@ static jrc_status launch_slice(jrc_chain *h, const c32 *H, int n_cpi, float *map
     return JRC_OK;
 }
 
+// k_wide_mac_angle + k_wide_range_mag (jrc_wide.cuh): 128 virtual channels x 2048 subcarriers without zero-pads
+static bool wide_config_ok(const jrc_chain *h)
+{
+    static const bool off = getenv("JRC_NO_WIDE") != nullptr;      // A/B switch for measurements
+    const jrc_chain_cfg &c = h->cfg;
+    return !off && c.fft_len == 2048 && c.interp_range == 1 && c.interp_angle == 1 && h->V == 128 && c.n_tx % 2 == 0 &&
+           c.n_rx % 4 == 0 && c.n_tx <= 8 && c.n_rx <= 16 && c.n_sym <= 8;
+}
+
+static jrc_status launch_wide(jrc_chain *h, PortDev rx, PortDev tx, const c32 *H, int n_pre, int n_cpi, c32 *G, float *map,
+                              unsigned long long *keys, unsigned *sec)
+{
+    using Gm = WideGeom<11>;
+    const jrc_chain_cfg &c = h->cfg;
+    WideParams P;
+    memset(&P, 0, sizeof(P));
+    P.rx = rx; P.tx = tx; P.H = H; P.T = c.n_tx; P.R = c.n_rx; P.S = c.n_sym; P.n_pre = n_pre; P.tx_interleave = c.tx_interleave;
+    P.n_cpi = n_cpi; P.G = G; P.map = map; P.keys = keys; P.sec = sec;
+    ST(get_twiddles_full(h, 128, 1, &P.tw_a));
+    ST(get_twiddles_full(h, 2048, 0, &P.tw_r));
+    auto ka = k_wide_mac_angle<11>;
+    auto kb = k_wide_range_mag<11>;
+    CU(cudaFuncSetAttribute(ka, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Gm::SMEM_A));
+    CU(cudaFuncSetAttribute(kb, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Gm::SMEM_B));
+    long long ua = (long long)n_cpi * (Gm::N / Gm::KB), ub = (long long)n_cpi * (Gm::V / Gm::AB);
+    long long ga = ua < 2LL * h->sm_count ? ua : 2LL * h->sm_count, gb = ub < h->sm_count ? ub : h->sm_count;
+    ka<<<(unsigned)ga, 256, Gm::SMEM_A, h->stream>>>(P);
+    CU(cudaGetLastError());
+    kb<<<(unsigned)gb, Gm::GR::THREADS, Gm::SMEM_B, h->stream>>>(P);
+    CU(cudaGetLastError());
+    h->launches += 2;
+    return JRC_OK;
+}
+
 static jrc_status launch_fft8_rows(jrc_chain *h, const c32 *in, long long in_stride, int n_in, c32 *out, int n, long long rows)
 {
     const c32 *tw = nullptr;
@@ -735,11 +770,57 @@ static jrc_status run_batch_impl(jrc_chain *h, jrc_port_layout rx, jrc_port_layo
     if (want_tiled) {
         NvtxRange nv("tiled: chan_est + range FFT + angle FFT");
         h->last_path = JRC_PATH_TILED;
-        const size_t per = ((size_t)V * N + (slice_config_ok(h) ? 0 : (size_t)V * Nr)) * sizeof(c32) + (map ? 0 : (size_t)Nr * Na * sizeof(float));
+        const size_t per = (wide_config_ok(h) ? (size_t)4096 : ((size_t)V * N + (slice_config_ok(h) ? 0 : (size_t)V * Nr)) * sizeof(c32)) +
+                           (map ? 0 : (size_t)Nr * Na * sizeof(float));
         int chunk = (int)(((size_t)1 << 30) / per);
         if (chunk < 1) chunk = 1;
         if (chunk > n_cpi) chunk = n_cpi;
         const bool slice = slice_config_ok(h);
+        const bool wide = wide_config_ok(h);
+        // the wide kernels hand G (2 MiB per CPI) from one to the other through the L2: 18 CPIs = 36 MiB per round, and
+        // 18 x 16 angle-bin blocks fill the 148 SMs twice
+        const int wide_round = 18;
+        if (wide) {
+            const bool need_h = bg || recording;
+            if (need_h) ST(h->sH.need((size_t)chunk * V * N * sizeof(c32)));
+            ST(h->sY.need((size_t)wide_round * V * N * sizeof(c32)));
+            if (!map) ST(h->sC.need((size_t)chunk * Nr * Na * sizeof(float)));
+            if (dets) {
+                ST(h->sKeys.need(sizeof(unsigned long long) * (size_t)chunk));
+                ST(h->sSec.need(sizeof(unsigned) * (size_t)chunk));
+            }
+            for (int c0 = 0; c0 < n_cpi; c0 += chunk) {
+                const int nc = n_cpi - c0 < chunk ? n_cpi - c0 : chunk;
+                PortDev crx = drx, ctx = dtx;
+                crx.base += (long long)c0 * rx.cpi_stride;
+                ctx.base += (long long)c0 * tx.cpi_stride;
+                c32 *dH = need_h ? (c32 *)h->sH.p : nullptr;
+                float *dM = map ? map + (size_t)c0 * Nr * Na : (float *)h->sC.p;
+                unsigned long long *dK = dets ? (unsigned long long *)h->sKeys.p : nullptr;
+                unsigned *dS = dets ? (unsigned *)h->sSec.p : nullptr;
+                if (need_h) ST(launch_chan_est(h, crx, ctx, nc, dH, n_pre));      // background ring in front of the transforms
+                if (dK) {
+                    CU(cudaMemsetAsync(dK, 0, sizeof(unsigned long long) * (size_t)nc, h->stream));
+                    CU(cudaMemsetAsync(dS, 0, sizeof(unsigned) * (size_t)nc, h->stream));
+                }
+                for (int r0 = 0; r0 < nc; r0 += wide_round) {
+                    const int nr = nc - r0 < wide_round ? nc - r0 : wide_round;
+                    PortDev rrx = crx, rtx = ctx;
+                    rrx.base += (long long)r0 * rx.cpi_stride;
+                    rtx.base += (long long)r0 * tx.cpi_stride;
+                    ST(launch_wide(h, rrx, rtx, dH ? dH + (size_t)r0 * V * N : nullptr, n_pre, nr, (c32 *)h->sY.p,
+                                   dM + (size_t)r0 * Nr * Na, dK ? dK + r0 : nullptr, dS ? dS + r0 : nullptr));
+                }
+                if (dets) {
+                    k_map_finalize<<<(unsigned)nc, 128, (size_t)Na * sizeof(float), h->stream>>>(
+                        dM, dK, dS, nc, Nr, Na, EP, (DetDev *)dets + c0, cpi0 + c0, fix_ctl, fix_list);
+                    CU(cudaGetLastError());
+                    h->launches++;
+                    ST(launch_exact(h, crx, ctx, dH, n_pre, cpi0 + c0, dM, (DetDev *)dets + c0, EP));
+                }
+            }
+            return JRC_OK;
+        }
         ST(h->sH.need((size_t)chunk * V * N * sizeof(c32)));
         if (!slice) ST(h->sY.need((size_t)chunk * V * Nr * sizeof(c32)));
         if (!map) ST(h->sC.need((size_t)chunk * Nr * Na * sizeof(float)));

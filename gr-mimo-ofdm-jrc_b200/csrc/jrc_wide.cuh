@@ -1,0 +1,247 @@
+// jrc_wide.cuh -- BASELINE configs[4] (8 TX x 16 RX = 128 virtual channels, 2048 subcarriers, no zero-pads: a 2048 x 128
+// map): the chain as TWO kernels that move the symbols, one intermediate and the map -- not the channel estimates
+// (2 MiB per CPI) nor the transposed range spectra (2 MiB per CPI) the block-by-block flow writes and re-reads.
+//
+// The range IFFT (over subcarriers k) and the angle FFT (over virtual channels p) are the two axes of one separable
+// 2-D transform of H[p][k], so they may run in either order.  The channel estimate is local in k -- H[.][k] only needs
+// the 24 antennas' symbols at subcarrier k (lib/mimo_ofdm_radar_impl.cc:250-274) -- hence:
+//
+//   k_wide_mac_angle   per (CPI, block of 16 subcarriers): symbols -> shared memory (cp.async), conj-MAC of all 128
+//                      channels (register tiled: 4 RX x 2 TX per thread), angle FFT + fftshift across the channels for each
+//                      subcarrier (matrix_transpose + fft_vcc #B, lib/matrix_transpose_impl.cc:97-104,
+//                      ...radar_sim.grc:963-985), result G[cpi][angle bin][k] written as whole 128-byte lines.
+//   k_wide_range_mag   per (CPI, block of 8 angle bins): range IFFT over k of 8 rows of G (fft_vcc #A,
+//                      ...radar_sim.grc:940-962), |.|^2 (:637-652), map[n][a] written as 32-byte sectors (the 16 blocks
+//                      of a CPI run side by side, so the L2 sees whole lines), arg-max partials as in k_angle_mag.
+//
+// G (2 MiB per CPI) is produced and consumed chunk by chunk of CPIs small enough to stay in the 126 MB L2.
+// HBM per CPI: 3 MiB symbols + 1 MiB map (+ what the L2 spills of G) against 12 MiB for chan_est -> range -> angle.
+// Float32 arithmetic of the same class as the oracle's radix-2 FFTs, not its rounding or order: the criterion is 1e-4 of
+// the map peak; detection decisions are settled by jrc_exact.cuh.
+#pragma once
+#include "jrc_common.cuh"
+#include "jrc_tiled.cuh"
+#include "jrc_fused.cuh"      // cp_async16
+
+namespace jrc {
+
+struct WideParams {
+    PortDev rx, tx;
+    const c32 *H;               // channel estimates [n_cpi][128][N] instead of symbols (background path), or nullptr
+    int T, R, S, n_pre, tx_interleave, n_cpi;
+    c32 *G;                     // [n_cpi][128][N] angle spectra per subcarrier
+    float *map;                 // [n_cpi][N][128]
+    unsigned long long *keys;
+    unsigned *sec;
+    const c32 *tw_a;            // [128] w_128^i (forward)
+    const c32 *tw_r;            // [N]   W_N^i  (inverse)
+};
+
+template <int LOG2N>
+struct WideGeom {
+    static constexpr int N = 1 << LOG2N, V = 128, KB = 16;           // subcarriers per k_wide_mac_angle unit
+    static constexpr int AB = 8;                                      // angle bins per k_wide_range_mag unit
+    using GA = TiledGeom<7>;                                          // angle FFT rows: 16 threads per row, 16 rows per CTA
+    using GR = TiledGeom<LOG2N>;
+    static constexpr int MAX_ANT = 24, MAX_S = 8;
+    // k_wide_mac_angle: two symbol buffers [(T+R)][S][KB] + H/FFT rows [KB][RS] (the staging of G reuses the rows)
+    static constexpr size_t SMEM_A = (size_t)2 * MAX_ANT * MAX_S * KB * sizeof(c32) + (size_t)KB * GA::RS * sizeof(c32) +
+                                     (size_t)V * (KB + 1) * sizeof(c32);
+    // k_wide_range_mag: AB rows of the transform + |.|^2 staging [N][AB]
+    static constexpr int RROW = fpad(N - 1) + 1 + 8;
+    static constexpr size_t SMEM_B = (size_t)AB * RROW * sizeof(c32) + (size_t)N * AB * sizeof(float);
+};
+
+// ---------------------------------------------------------------------------
+// conj-MAC + angle FFT, one (CPI, 16-subcarrier block) at a time
+// ---------------------------------------------------------------------------
+template <int LOG2N>
+__global__ void __launch_bounds__(256, 2) k_wide_mac_angle(const WideParams P)
+{
+    using Gm = WideGeom<LOG2N>;
+    using GA = typename Gm::GA;
+    constexpr int N = Gm::N, V = Gm::V, KB = Gm::KB, RS = GA::RS;
+    extern __shared__ __align__(16) unsigned char smem_wide[];
+    c32 *sym = reinterpret_cast<c32 *>(smem_wide);                        // [2][(T+R)*S][KB]
+    c32 *rows = sym + 2 * Gm::MAX_ANT * Gm::MAX_S * KB;                   // [KB][RS]: H[.][k] then its angle transform
+    c32 *stg = rows + KB * RS;                                            // [V][KB+1]: G block, angle bin major
+    const int tid = threadIdx.x;
+    const int T = P.T, R = P.R, S = P.S, per = (T + R) * S;               // antenna-symbol rows of KB subcarriers each
+    const int blocks_per_cpi = N / KB;
+    const long long n_units = (long long)P.n_cpi * blocks_per_cpi;
+
+    // angle FFT thread mapping (TiledGeom<7>): row = subcarrier, 16 threads per row
+    const int lr_t = tid / GA::TPR, t = tid % GA::TPR;
+    DifTw<7> Tw;
+    Tw.load(P.tw_a, t, t, true);            // first-pass twiddles carry (-1)^j: output fftshift
+    // conj-MAC thread mapping: subcarrier kk, RX block of 4, TX block of 2 (T = 8: 4 blocks) -> 8 channels x S products
+    const int kk = tid & 15, rb = (tid >> 4) & 3, tb = tid >> 6;
+
+    auto prefetch = [&](long long unit, int buf) {
+        const int cpi = (int)(unit / blocks_per_cpi), k0 = (int)(unit % blocks_per_cpi) * KB;
+        // per antenna-symbol row: KB subcarriers = 128 bytes = 8 chunks of 16 bytes
+        for (int c = tid; c < per * 8; c += 256) {
+            const int row = c >> 3, ch = c & 7, ant = row / S, s = row - ant * S;
+            const c32 *src = (ant < T)
+                ? P.tx.base + (long long)cpi * P.tx.cpi_stride + (long long)ant * P.tx.ant_stride
+                : P.rx.base + (long long)cpi * P.rx.cpi_stride + (long long)(ant - T) * P.rx.ant_stride;
+            cp_async16(sym + ((size_t)buf * per + row) * KB + 2 * ch, src + (long long)(P.n_pre + s) * N + k0 + 2 * ch);
+        }
+        cp_async_commit();
+    };
+
+    long long unit = blockIdx.x;
+    int buf = 0;
+    if (!P.H && unit < n_units) prefetch(unit, 0);
+    for (; unit < n_units; unit += gridDim.x, buf ^= 1) {
+        const int cpi = (int)(unit / blocks_per_cpi), k0 = (int)(unit % blocks_per_cpi) * KB;
+        if (!P.H) {
+            cp_async_wait_all();
+            __syncthreads();                                  // symbols of this unit visible; previous unit's stores done
+            if (unit + gridDim.x < n_units) prefetch(unit + gridDim.x, buf ^ 1);
+            // ---- conj-MAC: H[p][k0 + kk] for r in 4 rb .. +3, t in 2 tb .. +1 ----
+            const c32 *sb = sym + (size_t)buf * per * KB + kk;
+            for (int r0 = 4 * rb; r0 < R; r0 += 16)
+                for (int t0 = 2 * tb; t0 < T; t0 += 8) {
+                    c32 acc[4][2];
+#pragma unroll
+                    for (int i = 0; i < 4; i++) { acc[i][0] = mk(0.f, 0.f); acc[i][1] = mk(0.f, 0.f); }
+                    for (int s = 0; s < S; s++) {
+                        c32 a[4], b[2];
+#pragma unroll
+                        for (int i = 0; i < 4; i++) a[i] = sb[((T + r0 + i) * S + s) * KB];
+#pragma unroll
+                        for (int j = 0; j < 2; j++) b[j] = sb[((t0 + j) * S + s) * KB];
+#pragma unroll
+                        for (int i = 0; i < 4; i++)
+#pragma unroll
+                            for (int j = 0; j < 2; j++) {       // a * conj(b)
+                                acc[i][j].x = __fmaf_rn(a[i].x, b[j].x, __fmaf_rn(a[i].y, b[j].y, acc[i][j].x));
+                                acc[i][j].y = __fmaf_rn(a[i].y, b[j].x, __fmaf_rn(-a[i].x, b[j].y, acc[i][j].y));
+                            }
+                    }
+#pragma unroll
+                    for (int i = 0; i < 4; i++)
+#pragma unroll
+                        for (int j = 0; j < 2; j++) {
+                            const int p = P.tx_interleave ? (t0 + j) * R + (r0 + i) : (r0 + i) * T + (t0 + j);
+                            rows[kk * RS + fpad(p)] = acc[i][j];
+                        }
+                }
+        } else {
+            __syncthreads();
+            for (int e = tid; e < V * KB; e += 256) {
+                const int p = e / KB, k = e % KB;
+                rows[k * RS + fpad(p)] = P.H[((long long)cpi * V + p) * N + k0 + k];
+            }
+        }
+        __syncthreads();
+        // ---- angle FFT across the 128 channels of subcarrier lr_t (radix 8.8.2, fftshift folded in) ----
+        {
+            c32 *xrow = rows + lr_t * RS;
+            c32 u[8];
+#pragma unroll
+            for (int m = 0; m < 8; m++) u[m] = xrow[fpad(t + m * GA::TPR)];
+            __syncthreads();                                  // every thread has its inputs: the row can be overwritten
+            dif_first_full<7, -1>(xrow, t, u, Tw, t & 1);
+            __syncthreads();
+            c32 o[8];
+            dif_passes<7, -1, GA::WARP_SYNC, true>(xrow, t, Tw, o);
+#pragma unroll
+            for (int c = 0; c < 8; c++) stg[dif_freq<7>(8 * t + c) * (KB + 1) + lr_t] = o[c];
+        }
+        __syncthreads();
+        // ---- G[cpi][a][k0 .. k0+15]: one 128-byte line per angle bin ----
+        for (int e = tid; e < V * KB; e += 256) {
+            const int a = e >> 4, k = e & 15;
+            P.G[((long long)cpi * V + a) * N + k0 + k] = stg[a * (KB + 1) + k];
+        }
+    }
+    cp_async_wait_all();
+}
+
+// ---------------------------------------------------------------------------
+// range IFFT + |.|^2 + arg-max partials, one (CPI, 8 angle bins) at a time
+// ---------------------------------------------------------------------------
+template <int LOG2N>
+__global__ void __launch_bounds__(TiledGeom<LOG2N>::THREADS, 1) k_wide_range_mag(const WideParams P)
+{
+    using Gm = WideGeom<LOG2N>;
+    using GR = typename Gm::GR;
+    constexpr int N = Gm::N, V = Gm::V, AB = Gm::AB, RROW = Gm::RROW, TPR = GR::TPR, THREADS = GR::THREADS;
+    static_assert(GR::RPC == 1, "one transform per pass of the CTA");
+    extern __shared__ __align__(16) unsigned char smem_wide[];
+    c32 *rowbuf = reinterpret_cast<c32 *>(smem_wide);                     // [AB][RROW]
+    float *vst = reinterpret_cast<float *>(rowbuf + AB * RROW);           // [N][AB] |.|^2 of the unit, range bin major
+    const int tid = threadIdx.x, lane = tid & 31, t = tid % TPR;
+    DifTw<LOG2N> Tw;
+    Tw.load(P.tw_r, t, t);
+    const int units_per_cpi = V / AB;
+    const long long n_units = (long long)P.n_cpi * units_per_cpi;
+    for (long long unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+        const int cpi = (int)(unit / units_per_cpi), a0 = (int)(unit % units_per_cpi) * AB;
+        const c32 *Gu = P.G + ((long long)cpi * V + a0) * N;
+        // first pass of all AB rows straight from global memory (L2): 8 loads in flight per row and thread
+        for (int r = 0; r < AB; r++) {
+            c32 u[8];
+#pragma unroll
+            for (int m = 0; m < 8; m++) u[m] = __ldcg(Gu + (long long)r * N + t + m * TPR);
+            dif_first_full<LOG2N, 1>(rowbuf + r * RROW, t, u, Tw);
+        }
+        __syncthreads();
+        float best = -1.f, sec_t = -1.f;
+        int best_row = 0;
+        for (int r = 0; r < AB; r++) {
+            c32 o[8];
+            dif_passes<LOG2N, 1, false, true>(rowbuf + r * RROW, t, Tw, o);
+#pragma unroll
+            for (int c = 0; c < 8; c++) {
+                const c32 sq = __fmul2_rn(o[c], o[c]);
+                const float v = __fadd_rn(sq.x, sq.y);
+                const int n = dif_freq<LOG2N>(8 * t + c);
+                vst[n * AB + r] = v;
+                sec_t = fmaxf(sec_t, fminf(v, best));
+                if (v > best || (v == best && n < best_row)) { best = v; best_row = n; }
+            }
+        }
+        __syncthreads();
+        // map[cpi][n][a0 .. a0+7]: one 32-byte sector per range bin
+        if (P.map) {
+            float *mp = P.map + (long long)cpi * N * V + a0;
+            for (int e = tid; e < N * AB / 4; e += THREADS) {
+                const float4 v4 = reinterpret_cast<const float4 *>(vst)[e];
+                const int n = e >> 1, h = e & 1;
+                __stcs(reinterpret_cast<float4 *>(mp + (long long)n * V + 4 * h), v4);
+            }
+        }
+        if (P.keys) {
+            unsigned long long key = best >= 0.f ? pack_key(best, (unsigned)best_row) : 0ull;
+            float b2 = sec_t;
+#pragma unroll
+            for (int o2 = 16; o2 > 0; o2 >>= 1) {
+                const unsigned long long other = __shfl_xor_sync(0xffffffffu, key, o2);
+                const float ob2 = __shfl_xor_sync(0xffffffffu, b2, o2);
+                b2 = fmaxf(fmaxf(b2, ob2), (key && other) ? fminf(__uint_as_float((unsigned)(key >> 32)), __uint_as_float((unsigned)(other >> 32))) : -1.f);
+                key = other > key ? other : key;
+            }
+            if (lane == 0 && key) {
+                const unsigned long long cur = *reinterpret_cast<volatile unsigned long long *>(P.keys + cpi);
+                unsigned long long top = cur;
+                float loser = -1.f;
+                if (key > cur) {
+                    const unsigned long long old = atomicMax(P.keys + cpi, key);
+                    top = old > key ? old : key;
+                    const unsigned long long lo = old > key ? key : old;
+                    if (lo) loser = __uint_as_float((unsigned)(lo >> 32));
+                } else {
+                    loser = __uint_as_float((unsigned)(key >> 32));
+                }
+                loser = fmaxf(loser, b2);
+                if (loser >= __uint_as_float((unsigned)(top >> 32)) * (1.f - 2.f * EPS_AMB)) atomicMax(P.sec + cpi, __float_as_uint(loser));
+            }
+        }
+        __syncthreads();      // vst and the rows are rewritten by the next unit
+    }
+}
+
+}  // namespace jrc
