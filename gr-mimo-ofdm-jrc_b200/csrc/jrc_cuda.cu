@@ -491,12 +491,12 @@ static jrc_status launch_wide(jrc_chain *h, PortDev rx, PortDev tx, const c32 *H
     P.n_cpi = n_cpi; P.G = G; P.map = map; P.keys = keys; P.sec = sec;
     ST(get_twiddles_full(h, 128, 1, &P.tw_a));
     ST(get_twiddles_full(h, 2048, 0, &P.tw_r));
-    auto ka = k_wide_mac_angle<11>;
+    auto ka = c.n_sym == 8 ? k_wide_mac_angle<11, 8> : (c.n_sym == 4 ? k_wide_mac_angle<11, 4> : k_wide_mac_angle<11, 0>);
     auto kb = k_wide_range_mag<11>;
     CU(cudaFuncSetAttribute(ka, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Gm::SMEM_A));
     CU(cudaFuncSetAttribute(kb, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Gm::SMEM_B));
     long long ua = (long long)n_cpi * (Gm::N / Gm::KB), ub = (long long)n_cpi * (Gm::V / Gm::AB);
-    long long ga = ua < 2LL * h->sm_count ? ua : 2LL * h->sm_count, gb = ub < h->sm_count ? ub : h->sm_count;
+    long long ga = ua < 2LL * h->sm_count ? ua : 2LL * h->sm_count, gb = ub < 2LL * h->sm_count ? ub : 2LL * h->sm_count;
     ka<<<(unsigned)ga, 256, Gm::SMEM_A, h->stream>>>(P);
     CU(cudaGetLastError());
     kb<<<(unsigned)gb, Gm::GR::THREADS, Gm::SMEM_B, h->stream>>>(P);

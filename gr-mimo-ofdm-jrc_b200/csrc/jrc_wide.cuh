@@ -10,9 +10,10 @@
 //                      channels (register tiled: 4 RX x 2 TX per thread), angle FFT + fftshift across the channels for each
 //                      subcarrier (matrix_transpose + fft_vcc #B, lib/matrix_transpose_impl.cc:97-104,
 //                      ...radar_sim.grc:963-985), result G[cpi][angle bin][k] written as whole 128-byte lines.
-//   k_wide_range_mag   per (CPI, block of 8 angle bins): range IFFT over k of 8 rows of G (fft_vcc #A,
-//                      ...radar_sim.grc:940-962), |.|^2 (:637-652), map[n][a] written as 32-byte sectors (the 16 blocks
-//                      of a CPI run side by side, so the L2 sees whole lines), arg-max partials as in k_angle_mag.
+//   k_wide_range_mag   per (CPI, block of 4 angle bins): range IFFT over k of 4 rows of G (fft_vcc #A,
+//                      ...radar_sim.grc:940-962), |.|^2 (:637-652); a thread ends up with the same range bins of all four
+//                      rows, so map[n][a0..a0+3] leaves as 16-byte stores straight from registers (the 32 blocks of a CPI
+//                      run side by side: the L2 merges them into whole lines), arg-max partials as in k_angle_mag.
 //
 // G (2 MiB per CPI) is produced and consumed chunk by chunk of CPIs small enough to stay in the 126 MB L2.
 // HBM per CPI: 3 MiB symbols + 1 MiB map (+ what the L2 spills of G) against 12 MiB for chan_est -> range -> angle.
@@ -40,22 +41,22 @@ struct WideParams {
 template <int LOG2N>
 struct WideGeom {
     static constexpr int N = 1 << LOG2N, V = 128, KB = 16;           // subcarriers per k_wide_mac_angle unit
-    static constexpr int AB = 8;                                      // angle bins per k_wide_range_mag unit
+    static constexpr int AB = 4;                                      // angle bins per k_wide_range_mag unit
     using GA = TiledGeom<7>;                                          // angle FFT rows: 16 threads per row, 16 rows per CTA
     using GR = TiledGeom<LOG2N>;
     static constexpr int MAX_ANT = 24, MAX_S = 8;
     // k_wide_mac_angle: two symbol buffers [(T+R)][S][KB] + H/FFT rows [KB][RS] (the staging of G reuses the rows)
     static constexpr size_t SMEM_A = (size_t)2 * MAX_ANT * MAX_S * KB * sizeof(c32) + (size_t)KB * GA::RS * sizeof(c32) +
                                      (size_t)V * (KB + 1) * sizeof(c32);
-    // k_wide_range_mag: AB rows of the transform + |.|^2 staging [N][AB]
+    // k_wide_range_mag: AB rows of the transform
     static constexpr int RROW = fpad(N - 1) + 1 + 8;
-    static constexpr size_t SMEM_B = (size_t)AB * RROW * sizeof(c32) + (size_t)N * AB * sizeof(float);
+    static constexpr size_t SMEM_B = (size_t)AB * RROW * sizeof(c32);
 };
 
 // ---------------------------------------------------------------------------
 // conj-MAC + angle FFT, one (CPI, 16-subcarrier block) at a time
 // ---------------------------------------------------------------------------
-template <int LOG2N>
+template <int LOG2N, int S_CT>      // S_CT: number of LTF symbols when known at compile time (0: run-time)
 __global__ void __launch_bounds__(256, 2) k_wide_mac_angle(const WideParams P)
 {
     using Gm = WideGeom<LOG2N>;
@@ -66,7 +67,7 @@ __global__ void __launch_bounds__(256, 2) k_wide_mac_angle(const WideParams P)
     c32 *rows = sym + 2 * Gm::MAX_ANT * Gm::MAX_S * KB;                   // [KB][RS]: H[.][k] then its angle transform
     c32 *stg = rows + KB * RS;                                            // [V][KB+1]: G block, angle bin major
     const int tid = threadIdx.x;
-    const int T = P.T, R = P.R, S = P.S, per = (T + R) * S;               // antenna-symbol rows of KB subcarriers each
+    const int T = P.T, R = P.R, S = S_CT ? S_CT : P.S, per = (T + R) * S;  // antenna-symbol rows of KB subcarriers each
     const int blocks_per_cpi = N / KB;
     const long long n_units = (long long)P.n_cpi * blocks_per_cpi;
 
@@ -106,12 +107,14 @@ __global__ void __launch_bounds__(256, 2) k_wide_mac_angle(const WideParams P)
                     c32 acc[4][2];
 #pragma unroll
                     for (int i = 0; i < 4; i++) { acc[i][0] = mk(0.f, 0.f); acc[i][1] = mk(0.f, 0.f); }
+                    const c32 *pa = sb + (T + r0) * S * KB, *pb = sb + t0 * S * KB;
+#pragma unroll 4
                     for (int s = 0; s < S; s++) {
                         c32 a[4], b[2];
 #pragma unroll
-                        for (int i = 0; i < 4; i++) a[i] = sb[((T + r0 + i) * S + s) * KB];
+                        for (int i = 0; i < 4; i++) a[i] = pa[(i * S + s) * KB];
 #pragma unroll
-                        for (int j = 0; j < 2; j++) b[j] = sb[((t0 + j) * S + s) * KB];
+                        for (int j = 0; j < 2; j++) b[j] = pb[(j * S + s) * KB];
 #pragma unroll
                         for (int i = 0; i < 4; i++)
 #pragma unroll
@@ -120,13 +123,13 @@ __global__ void __launch_bounds__(256, 2) k_wide_mac_angle(const WideParams P)
                                 acc[i][j].y = __fmaf_rn(a[i].y, b[j].x, __fmaf_rn(-a[i].x, b[j].y, acc[i][j].y));
                             }
                     }
+                    // channel p of (rx r0 + i, tx t0 + j): p0 + i * pi + j * pj  (lib/mimo_ofdm_radar_impl.cc:262-269)
+                    const int pi = P.tx_interleave ? 1 : T, pj = P.tx_interleave ? R : 1, p0 = r0 * pi + t0 * pj;
+                    c32 *hrow = rows + kk * RS;
 #pragma unroll
                     for (int i = 0; i < 4; i++)
 #pragma unroll
-                        for (int j = 0; j < 2; j++) {
-                            const int p = P.tx_interleave ? (t0 + j) * R + (r0 + i) : (r0 + i) * T + (t0 + j);
-                            rows[kk * RS + fpad(p)] = acc[i][j];
-                        }
+                        for (int j = 0; j < 2; j++) hrow[fpad(p0 + i * pi + j * pj)] = acc[i][j];
                 }
         } else {
             __syncthreads();
@@ -164,15 +167,14 @@ __global__ void __launch_bounds__(256, 2) k_wide_mac_angle(const WideParams P)
 // range IFFT + |.|^2 + arg-max partials, one (CPI, 8 angle bins) at a time
 // ---------------------------------------------------------------------------
 template <int LOG2N>
-__global__ void __launch_bounds__(TiledGeom<LOG2N>::THREADS, 1) k_wide_range_mag(const WideParams P)
+__global__ void __launch_bounds__(TiledGeom<LOG2N>::THREADS, 2) k_wide_range_mag(const WideParams P)
 {
     using Gm = WideGeom<LOG2N>;
     using GR = typename Gm::GR;
-    constexpr int N = Gm::N, V = Gm::V, AB = Gm::AB, RROW = Gm::RROW, TPR = GR::TPR, THREADS = GR::THREADS;
+    constexpr int N = Gm::N, V = Gm::V, AB = Gm::AB, RROW = Gm::RROW, TPR = GR::TPR;
     static_assert(GR::RPC == 1, "one transform per pass of the CTA");
     extern __shared__ __align__(16) unsigned char smem_wide[];
     c32 *rowbuf = reinterpret_cast<c32 *>(smem_wide);                     // [AB][RROW]
-    float *vst = reinterpret_cast<float *>(rowbuf + AB * RROW);           // [N][AB] |.|^2 of the unit, range bin major
     const int tid = threadIdx.x, lane = tid & 31, t = tid % TPR;
     DifTw<LOG2N> Tw;
     Tw.load(P.tw_r, t, t);
@@ -182,6 +184,7 @@ __global__ void __launch_bounds__(TiledGeom<LOG2N>::THREADS, 1) k_wide_range_mag
         const int cpi = (int)(unit / units_per_cpi), a0 = (int)(unit % units_per_cpi) * AB;
         const c32 *Gu = P.G + ((long long)cpi * V + a0) * N;
         // first pass of all AB rows straight from global memory (L2): 8 loads in flight per row and thread
+#pragma unroll
         for (int r = 0; r < AB; r++) {
             c32 u[8];
 #pragma unroll
@@ -189,30 +192,32 @@ __global__ void __launch_bounds__(TiledGeom<LOG2N>::THREADS, 1) k_wide_range_mag
             dif_first_full<LOG2N, 1>(rowbuf + r * RROW, t, u, Tw);
         }
         __syncthreads();
-        float best = -1.f, sec_t = -1.f;
-        int best_row = 0;
+        float v[8][AB];                        // |.|^2 at this thread's 8 range bins, all AB angle bins
+#pragma unroll
         for (int r = 0; r < AB; r++) {
             c32 o[8];
             dif_passes<LOG2N, 1, false, true>(rowbuf + r * RROW, t, Tw, o);
 #pragma unroll
             for (int c = 0; c < 8; c++) {
                 const c32 sq = __fmul2_rn(o[c], o[c]);
-                const float v = __fadd_rn(sq.x, sq.y);
-                const int n = dif_freq<LOG2N>(8 * t + c);
-                vst[n * AB + r] = v;
-                sec_t = fmaxf(sec_t, fminf(v, best));
-                if (v > best || (v == best && n < best_row)) { best = v; best_row = n; }
+                v[c][r] = __fadd_rn(sq.x, sq.y);
             }
         }
-        __syncthreads();
-        // map[cpi][n][a0 .. a0+7]: one 32-byte sector per range bin
-        if (P.map) {
-            float *mp = P.map + (long long)cpi * N * V + a0;
-            for (int e = tid; e < N * AB / 4; e += THREADS) {
-                const float4 v4 = reinterpret_cast<const float4 *>(vst)[e];
-                const int n = e >> 1, h = e & 1;
-                __stcs(reinterpret_cast<float4 *>(mp + (long long)n * V + 4 * h), v4);
-            }
+        // map[cpi][n][a0 .. a0+3] straight from registers; running maximum per range bin
+        float best = -1.f, sec_t = -1.f;
+        int best_row = 0;
+        float *mp = P.map ? P.map + (long long)cpi * N * V + a0 : nullptr;
+#pragma unroll
+        for (int c = 0; c < 8; c++) {
+            const int n = dif_freq<LOG2N>(8 * t) + dif_freq<LOG2N>(c);
+            if (mp) __stcs(reinterpret_cast<float4 *>(mp + (long long)n * V), make_float4(v[c][0], v[c][1], v[c][2], v[c][3]));
+            const float hi = fmaxf(fmaxf(v[c][0], v[c][1]), fmaxf(v[c][2], v[c][3]));
+            // runner-up: the second largest of the four, and whatever loses against the running maximum
+            const float lo01 = fminf(v[c][0], v[c][1]), hi01 = fmaxf(v[c][0], v[c][1]);
+            const float lo23 = fminf(v[c][2], v[c][3]), hi23 = fmaxf(v[c][2], v[c][3]);
+            sec_t = fmaxf(sec_t, fmaxf(fminf(hi01, hi23), fmaxf(lo01, lo23)));
+            sec_t = fmaxf(sec_t, fminf(hi, best));
+            if (hi > best || (hi == best && n < best_row)) { best = hi; best_row = n; }
         }
         if (P.keys) {
             unsigned long long key = best >= 0.f ? pack_key(best, (unsigned)best_row) : 0ull;
@@ -240,7 +245,7 @@ __global__ void __launch_bounds__(TiledGeom<LOG2N>::THREADS, 1) k_wide_range_mag
                 if (loser >= __uint_as_float((unsigned)(top >> 32)) * (1.f - 2.f * EPS_AMB)) atomicMax(P.sec + cpi, __float_as_uint(loser));
             }
         }
-        __syncthreads();      // vst and the rows are rewritten by the next unit
+        __syncthreads();      // the rows are rewritten by the next unit
     }
 }
 
