@@ -68,7 +68,7 @@ __global__ void __launch_bounds__(256, 2) k_wide_mac_angle(const WideParams P)
     c32 *stg = rows + KB * RS;                                            // [V][KB+1]: G block, angle bin major
     const int tid = threadIdx.x;
     const int T = P.T, R = P.R, S = S_CT ? S_CT : P.S, per = (T + R) * S;  // antenna-symbol rows of KB subcarriers each
-    const int blocks_per_cpi = N / KB;
+    constexpr int blocks_per_cpi = N / KB;
     const long long n_units = (long long)P.n_cpi * blocks_per_cpi;
 
     // angle FFT thread mapping (TiledGeom<7>): row = subcarrier, 16 threads per row
@@ -78,16 +78,30 @@ __global__ void __launch_bounds__(256, 2) k_wide_mac_angle(const WideParams P)
     // conj-MAC thread mapping: subcarrier kk, RX block of 4, TX block of 2 (T = 8: 4 blocks) -> 8 channels x S products
     const int kk = tid & 15, rb = (tid >> 4) & 3, tb = tid >> 6;
 
-    auto prefetch = [&](long long unit, int buf) {
-        const int cpi = (int)(unit / blocks_per_cpi), k0 = (int)(unit % blocks_per_cpi) * KB;
-        // per antenna-symbol row: KB subcarriers = 128 bytes = 8 chunks of 16 bytes
-        for (int c = tid; c < per * 8; c += 256) {
-            const int row = c >> 3, ch = c & 7, ant = row / S, s = row - ant * S;
-            const c32 *src = (ant < T)
-                ? P.tx.base + (long long)cpi * P.tx.cpi_stride + (long long)ant * P.tx.ant_stride
-                : P.rx.base + (long long)cpi * P.rx.cpi_stride + (long long)(ant - T) * P.rx.ant_stride;
-            cp_async16(sym + ((size_t)buf * per + row) * KB + 2 * ch, src + (long long)(P.n_pre + s) * N + k0 + 2 * ch);
+    // cp.async plan of this thread, fixed for the whole kernel: chunk i = 16 bytes (two subcarriers) of antenna-symbol
+    // row (tid >> 3) + 32 i; only the CPI and the subcarrier block change from unit to unit
+    constexpr int MAXCH = Gm::MAX_ANT * Gm::MAX_S * 8 / 256;
+    const c32 *src0[MAXCH];
+    unsigned is_tx = 0;
+#pragma unroll
+    for (int i = 0; i < MAXCH; i++) {
+        const int row = (tid >> 3) + 32 * i, ch = tid & 7, ant = row / S, sy = row - ant * S;
+        src0[i] = nullptr;
+        if (row < per) {
+            const bool txr = ant < T;
+            src0[i] = (txr ? P.tx.base + (long long)ant * P.tx.ant_stride : P.rx.base + (long long)(ant - T) * P.rx.ant_stride) +
+                      (long long)(P.n_pre + sy) * N + 2 * ch;
+            is_tx |= txr ? (1u << i) : 0u;
         }
+    }
+    auto prefetch = [&](long long unit, int buf) {
+        const long long cpi = unit / blocks_per_cpi;
+        const int k0 = (int)(unit % blocks_per_cpi) * KB;
+        const long long otx = cpi * P.tx.cpi_stride + k0, orx = cpi * P.rx.cpi_stride + k0;
+        c32 *dst = sym + ((size_t)buf * per + (tid >> 3)) * KB + 2 * (tid & 7);
+#pragma unroll
+        for (int i = 0; i < MAXCH; i++)
+            if (src0[i]) cp_async16(dst + 32 * i * KB, src0[i] + ((is_tx >> i) & 1 ? otx : orx));
         cp_async_commit();
     };
 
