@@ -40,7 +40,8 @@ struct WideParams {
 
 template <int LOG2N>
 struct WideGeom {
-    static constexpr int N = 1 << LOG2N, V = 128, KB = 16;           // subcarriers per k_wide_mac_angle unit
+    static constexpr int N = 1 << LOG2N, V = 128, KB = 32;           // subcarriers per k_wide_mac_angle unit
+    static constexpr int TA = 16 * KB;                                // threads of k_wide_mac_angle: 16 per subcarrier
     static constexpr int AB = 4;                                      // angle bins per k_wide_range_mag unit
     using GA = TiledGeom<7>;                                          // angle FFT rows: 16 threads per row, 16 rows per CTA
     using GR = TiledGeom<LOG2N>;
@@ -57,11 +58,11 @@ struct WideGeom {
 // conj-MAC + angle FFT, one (CPI, 16-subcarrier block) at a time
 // ---------------------------------------------------------------------------
 template <int LOG2N, int S_CT>      // S_CT: number of LTF symbols when known at compile time (0: run-time)
-__global__ void __launch_bounds__(256, 2) k_wide_mac_angle(const WideParams P)
+__global__ void __launch_bounds__(WideGeom<LOG2N>::TA, 1) k_wide_mac_angle(const WideParams P)
 {
     using Gm = WideGeom<LOG2N>;
     using GA = typename Gm::GA;
-    constexpr int N = Gm::N, V = Gm::V, KB = Gm::KB, RS = GA::RS;
+    constexpr int N = Gm::N, V = Gm::V, KB = Gm::KB, RS = GA::RS, TA = Gm::TA, CPR = KB / 2;   // CPR: 16-byte chunks per row
     extern __shared__ __align__(16) unsigned char smem_wide[];
     c32 *sym = reinterpret_cast<c32 *>(smem_wide);                        // [2][(T+R)*S][KB]
     c32 *rows = sym + 2 * Gm::MAX_ANT * Gm::MAX_S * KB;                   // [KB][RS]: H[.][k] then its angle transform
@@ -76,16 +77,16 @@ __global__ void __launch_bounds__(256, 2) k_wide_mac_angle(const WideParams P)
     DifTw<7> Tw;
     Tw.load(P.tw_a, t, t, true);            // first-pass twiddles carry (-1)^j: output fftshift
     // conj-MAC thread mapping: subcarrier kk, RX block of 4, TX block of 2 (T = 8: 4 blocks) -> 8 channels x S products
-    const int kk = tid & 15, rb = (tid >> 4) & 3, tb = tid >> 6;
+    const int kk = tid % KB, rb = (tid / KB) & 3, tb = tid / (4 * KB);
 
     // cp.async plan of this thread, fixed for the whole kernel: chunk i = 16 bytes (two subcarriers) of antenna-symbol
-    // row (tid >> 3) + 32 i; only the CPI and the subcarrier block change from unit to unit
-    constexpr int MAXCH = Gm::MAX_ANT * Gm::MAX_S * 8 / 256;
+    // row tid / CPR + (TA / CPR) i; only the CPI and the subcarrier block change from unit to unit
+    constexpr int MAXCH = Gm::MAX_ANT * Gm::MAX_S * CPR / TA, RSTEP = TA / CPR;
     const c32 *src0[MAXCH];
     unsigned is_tx = 0;
 #pragma unroll
     for (int i = 0; i < MAXCH; i++) {
-        const int row = (tid >> 3) + 32 * i, ch = tid & 7, ant = row / S, sy = row - ant * S;
+        const int row = tid / CPR + RSTEP * i, ch = tid % CPR, ant = row / S, sy = row - ant * S;
         src0[i] = nullptr;
         if (row < per) {
             const bool txr = ant < T;
@@ -98,10 +99,10 @@ __global__ void __launch_bounds__(256, 2) k_wide_mac_angle(const WideParams P)
         const long long cpi = unit / blocks_per_cpi;
         const int k0 = (int)(unit % blocks_per_cpi) * KB;
         const long long otx = cpi * P.tx.cpi_stride + k0, orx = cpi * P.rx.cpi_stride + k0;
-        c32 *dst = sym + ((size_t)buf * per + (tid >> 3)) * KB + 2 * (tid & 7);
+        c32 *dst = sym + ((size_t)buf * per + tid / CPR) * KB + 2 * (tid % CPR);
 #pragma unroll
         for (int i = 0; i < MAXCH; i++)
-            if (src0[i]) cp_async16(dst + 32 * i * KB, src0[i] + ((is_tx >> i) & 1 ? otx : orx));
+            if (src0[i]) cp_async16(dst + RSTEP * i * KB, src0[i] + ((is_tx >> i) & 1 ? otx : orx));
         cp_async_commit();
     };
 
@@ -147,7 +148,7 @@ __global__ void __launch_bounds__(256, 2) k_wide_mac_angle(const WideParams P)
                 }
         } else {
             __syncthreads();
-            for (int e = tid; e < V * KB; e += 256) {
+            for (int e = tid; e < V * KB; e += TA) {
                 const int p = e / KB, k = e % KB;
                 rows[k * RS + fpad(p)] = P.H[((long long)cpi * V + p) * N + k0 + k];
             }
@@ -159,8 +160,7 @@ __global__ void __launch_bounds__(256, 2) k_wide_mac_angle(const WideParams P)
             c32 u[8];
 #pragma unroll
             for (int m = 0; m < 8; m++) u[m] = xrow[fpad(t + m * GA::TPR)];
-            __syncthreads();                                  // every thread has its inputs: the row can be overwritten
-            dif_first_full<7, -1>(xrow, t, u, Tw, t & 1);
+            dif_first_full<7, -1>(xrow, t, u, Tw, t & 1);     // in place: a thread writes the eight slots it has read
             __syncthreads();
             c32 o[8];
             dif_passes<7, -1, GA::WARP_SYNC, true>(xrow, t, Tw, o);
@@ -169,8 +169,8 @@ __global__ void __launch_bounds__(256, 2) k_wide_mac_angle(const WideParams P)
         }
         __syncthreads();
         // ---- G[cpi][a][k0 .. k0+15]: one 128-byte line per angle bin ----
-        for (int e = tid; e < V * KB; e += 256) {
-            const int a = e >> 4, k = e & 15;
+        for (int e = tid; e < V * KB; e += TA) {
+            const int a = e / KB, k = e % KB;
             P.G[((long long)cpi * V + a) * N + k0 + k] = stg[a * (KB + 1) + k];
         }
     }
