@@ -14,6 +14,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -121,6 +122,7 @@ struct jrc_chain {
     int last_path = 0;
     int64_t launches = 0;
     int fused_ctas_per_sm = 0;
+    std::map<std::pair<const void *, size_t>, int> occ_cache;   // (kernel, dynamic smem) -> resident CTAs per SM, attribute set
     int zero_copy = 1;                          // latency mode: kernel reads/writes pinned host memory directly (JRC_ZEROCOPY=0 disables)
     std::atomic<int> bg_recording{0};           // set_background_record may come from another thread (GUI / RPC callback)
 };
@@ -593,15 +595,19 @@ static jrc_status launch_fused_t(jrc_chain *h, const FusedParams &P, bool *suppo
     using Gm = FusedGeom<IR, IA>;
     size_t smem = Gm::smem_bytes(P.T, P.R, P.S, FROM_H);
     auto kern = P.map ? k_fused64x8<IR, IA, FROM_H, true> : k_fused64x8<IR, IA, FROM_H, false>;
-    int dev_smem = 0;
-    CU(cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->cfg.device));
-    if (smem > (size_t)dev_smem) {     // many LTF symbols: the symbol buffer does not fit next to the spectra
-        *supported = false;
-        return JRC_OK;
-    }
-    CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, smem));
+    const auto ck = std::make_pair((const void *)kern, smem);
+    auto it = h->occ_cache.find(ck);
+    if (it != h->occ_cache.end()) per_sm = it->second;
+    else {
+        int dev_smem = 0;
+        CU(cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->cfg.device));
+        if (smem <= (size_t)dev_smem) {     // (else: many LTF symbols, the symbol buffer does not fit next to the spectra)
+            CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, smem));
+        }
+        h->occ_cache[ck] = per_sm;
+    }
     if (per_sm < 1) { *supported = false; return JRC_OK; }
     h->fused_ctas_per_sm = per_sm;
     long long grid = (long long)h->sm_count * per_sm;
@@ -907,8 +913,36 @@ extern "C" jrc_status jrc_chain_run_batch(jrc_chain *h, jrc_port_layout rx, jrc_
 // ---------------------------------------------------------------------------
 // host-buffer chain: pinned double-buffered pipeline
 // ---------------------------------------------------------------------------
+// Pinned ranges created through jrc_pinned_alloc / jrc_host_register: looked up without a driver call (the streaming
+// path asks four times per CPI).
+struct PinnedRange { uintptr_t base; size_t len; uintptr_t dev; };
+static std::mutex g_pin_mu;
+static std::vector<PinnedRange> g_pinned;
+static bool pinned_lookup(const void *p, void **dev)
+{
+    const uintptr_t a = (uintptr_t)p;
+    std::lock_guard<std::mutex> g(g_pin_mu);
+    for (const PinnedRange &r : g_pinned)
+        if (a >= r.base && a < r.base + r.len) { if (dev) *dev = (void *)(r.dev + (a - r.base)); return true; }
+    return false;
+}
+static void pinned_add(void *p, size_t len)
+{
+    void *dev = nullptr;
+    if (cudaHostGetDevicePointer(&dev, p, 0) != cudaSuccess) { cudaGetLastError(); dev = p; }
+    std::lock_guard<std::mutex> g(g_pin_mu);
+    g_pinned.push_back({(uintptr_t)p, len, (uintptr_t)dev});
+}
+static void pinned_remove(void *p)
+{
+    std::lock_guard<std::mutex> g(g_pin_mu);
+    for (size_t i = 0; i < g_pinned.size(); i++)
+        if (g_pinned[i].base == (uintptr_t)p) { g_pinned.erase(g_pinned.begin() + i); return; }
+}
+
 static bool host_ptr_is_pinned(const void *p)
 {
+    if (pinned_lookup(p, nullptr)) return true;
     cudaPointerAttributes a;
     if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
     return a.type == cudaMemoryTypeHost;
@@ -918,6 +952,8 @@ static bool host_ptr_is_pinned(const void *p)
 static void *host_dev_alias(const void *p)
 {
     if (!p) return nullptr;
+    void *dev = nullptr;
+    if (pinned_lookup(p, &dev)) return dev;
     cudaPointerAttributes a;
     if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return nullptr; }
     return a.type == cudaMemoryTypeHost ? a.devicePointer : nullptr;
@@ -1102,11 +1138,12 @@ extern "C" jrc_status jrc_pinned_alloc(size_t bytes, void **out)
     if (!out) return fail(JRC_ERR_INVALID, "null argument");
     *out = nullptr;
     CU(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocPortable | cudaHostAllocMapped));
+    pinned_add(*out, bytes ? bytes : 1);
     return JRC_OK;
 }
 extern "C" jrc_status jrc_pinned_free(void *p)
 {
-    if (p) CU(cudaFreeHost(p));
+    if (p) { pinned_remove(p); CU(cudaFreeHost(p)); }
     return JRC_OK;
 }
 // page-locks an existing buffer (a GNU Radio stream buffer, a NumPy array) so that submit / run_host use it in place
@@ -1114,11 +1151,13 @@ extern "C" jrc_status jrc_host_register(void *p, size_t bytes)
 {
     if (!p || !bytes) return fail(JRC_ERR_INVALID, "null argument");
     CU(cudaHostRegister(p, bytes, cudaHostRegisterPortable | cudaHostRegisterMapped));
+    pinned_add(p, bytes);
     return JRC_OK;
 }
 extern "C" jrc_status jrc_host_unregister(void *p)
 {
     if (!p) return fail(JRC_ERR_INVALID, "null argument");
+    pinned_remove(p);
     CU(cudaHostUnregister(p));
     return JRC_OK;
 }
