@@ -224,6 +224,13 @@ __device__ __forceinline__ float snr_db_of(float peak, float noise)
     return __fmul_rn(10.f, (float)log10((double)__fdiv_rn(peak, noise)));
 }
 
+// the fast kernels' form: device log10f (<= 2 ulp).  Their gate decision is only kept when it is further from the
+// threshold than that (gate_is_marginal, jrc_exact.cuh), and host-side callers recompute the published value with libm.
+__device__ __forceinline__ float snr_db_fast(float peak, float noise)
+{
+    return __fmul_rn(10.f, log10f(__fdiv_rn(peak, noise)));
+}
+
 __device__ __forceinline__ unsigned long long pack_key(float v, unsigned idx)
 {
     // v >= 0 and not NaN: float bits are monotonic; ties -> the smaller index wins

@@ -211,7 +211,7 @@ __global__ void __launch_bounds__(256, 2) k_fused64x8(const FusedParams P)
                 dd.peak_power = __int_as_float(sint[6]);
                 dd.n_noise = total;
                 dd.noise_power = __fdiv_rn(total > 0 ? (float)s : 0.f, (float)total);
-                dd.snr_db = snr_db_of(dd.peak_power, dd.noise_power);
+                dd.snr_db = snr_db_fast(dd.peak_power, dd.noise_power);
                 dd.flags = (dd.snr_db >= est.snr_threshold && dd.peak_power >= est.power_threshold) ? DET_PASSED : 0u;
                 // decisions that FFT rounding could turn are not taken here (jrc_exact.cuh)
                 if (amb_prev || sint[5]) dd.flags |= DET_PENDING | DET_AMB;

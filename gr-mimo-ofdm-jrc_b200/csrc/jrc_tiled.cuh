@@ -480,7 +480,7 @@ __global__ void __launch_bounds__(128) k_map_finalize(const float *__restrict__ 
         DetDev d;
         d.range_idx = nstar; d.angle_idx = istar; d.peak_power = peak; d.n_noise = total;
         d.noise_power = __fdiv_rn((float)acc, (float)total);
-        d.snr_db = snr_db_of(d.peak_power, d.noise_power);
+        d.snr_db = snr_db_fast(d.peak_power, d.noise_power);
         d.flags = (d.snr_db >= P.snr_threshold && d.peak_power >= P.power_threshold) ? DET_PASSED : 0u;
         // decisions that FFT rounding could turn are not taken here (jrc_exact.cuh)
         if (ncand > 1 || __uint_as_float(sec[cpi]) >= thr_amb) d.flags |= DET_PENDING | DET_AMB;

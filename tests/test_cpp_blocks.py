@@ -59,6 +59,9 @@ def test_streaming_latency_harness_runs():
     res = json.loads(r.stdout)
     assert len(res) == 6          # per map size: the five separate blocks, the fused block, the pipelined fused block
     for k, v in res.items():
+        if "pipeline" in k:
+            assert 0 < v["latency_p50_us"] <= v["latency_p99_us"] < 20000 and v["sustained_cpi_per_s"] > 1000 and v["cpis"] == 300, k
+            continue
         assert 0 < v["p50_us"] <= v["p99_us"] < 20000, k
         if k.startswith("radar_chain"):
             assert v["calls"] == 300
