@@ -61,7 +61,7 @@ struct FusedGeom {
     static size_t smem_bytes(int T, int R, int S, bool from_h)
     {
         size_t b = (size_t)V * NR * 8 + (size_t)V * NSC * 8 + (size_t)8 * Q * 8 + (size_t)WARPS * 2 * TILE * 4 +
-                   64 + 512 + 64;
+                   64 + 512 + 64 + (size_t)NA * 8 * 8 + (size_t)NA * 8;      // ... + g_tab (float2) + win_tab copies
         if (!from_h) b += (size_t)(T + R) * S * NSC * 8;
         return b;
     }
@@ -121,7 +121,9 @@ __global__ void __launch_bounds__(256, 2) k_fused64x8(const FusedParams P)
     unsigned long long *red = reinterpret_cast<unsigned long long *>(stg + 8 * 2 * TILE);   // [8]
     double *redA = reinterpret_cast<double *>(red + 8);           // [8 warps][8] partial lag sums
     int *sint = reinterpret_cast<int *>(redA + 64);               // [16] scalars
-    c32 *inb = reinterpret_cast<c32 *>(sint + 16);                // [(T+R)][S][64]
+    float2 *gtab = reinterpret_cast<float2 *>(sint + 16);         // [NA][8] window column sums (k_est_tables), float
+    int2 *wtab = reinterpret_cast<int2 *>(gtab + NA * 8);         // [NA]    window columns
+    c32 *inb = reinterpret_cast<c32 *>(wtab + NA);                // [(T+R)][S][64]
 
     const int tid = threadIdx.x, lane = tid & 31;
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // warp-uniform for the compiler
@@ -145,6 +147,12 @@ __global__ void __launch_bounds__(256, 2) k_fused64x8(const FusedParams P)
         tw3.i[j] = mk(t.y, t.y);
     }
     for (int e = tid; e < 8 * Q; e += 256) tw2t[e] = cispi_ratio(2 * (e / Q) * (e % Q), NR);
+    if (P.dets)       // the estimator's tables: the record's last step must not wait for global memory
+        for (int e = tid; e < NA * 8; e += 256) {
+            const double2 gv = P.g_tab[e];
+            gtab[e] = make_float2((float)gv.x, (float)gv.y);
+            if (e < NA) wtab[e] = P.win_tab[e];
+        }
     const EstParams est = P.est;
 
     // channels of this warp pair -> (rx antenna, tx antenna)  (lib/mimo_ofdm_radar_impl.cc:262-269)
@@ -173,8 +181,9 @@ __global__ void __launch_bounds__(256, 2) k_fused64x8(const FusedParams P)
     auto prefetch = [&](int cpi) {
         const int cpa = per_ant >> 1;   // 16-byte chunks per antenna row
         const int total = (P.T + P.R) * cpa;
+        const int sh = (cpa & (cpa - 1)) ? -1 : 31 - __clz(cpa);
         for (int c = tid; c < total; c += 256) {
-            int a = c / cpa, w = c - a * cpa;
+            const int a = sh >= 0 ? (c >> sh) : c / cpa, w = c - a * cpa;
             const c32 *src = (a < P.T)
                 ? P.tx.base + (long long)cpi * P.tx.cpi_stride + (long long)a * P.tx.ant_stride
                 : P.rx.base + (long long)cpi * P.rx.cpi_stride + (long long)(a - P.T) * P.rx.ant_stride;
@@ -196,13 +205,13 @@ __global__ void __launch_bounds__(256, 2) k_fused64x8(const FusedParams P)
             const double *r0 = redA + (2 * part) * 8 + slot, *r1 = r0 + 8;
             const double ar = r0[0] + r1[0], ai = d ? r0[1] + r1[1] : 0.0;
             const int imin = sint[1];
-            const double2 gd = P.g_tab[imin * 8 + d];
-            double contrib = 2.0 * (gd.x * ar - gd.y * ai);
+            const float2 gd = gtab[imin * 8 + d];
+            double contrib = 2.0 * ((double)gd.x * ar - (double)gd.y * ai);
             contrib += __shfl_xor_sync(0xffu, contrib, 4);
             contrib += __shfl_xor_sync(0xffu, contrib, 2);
             contrib += __shfl_xor_sync(0xffu, contrib, 1);
             if (tid == 0) {
-                const int2 wa = P.win_tab[imin];
+                const int2 wa = wtab[imin];
                 const int ncols = wa.y - wa.x, nrows = 2 * est.discard_range_idx;
                 const int total = (ncols > 0 && nrows > 0) ? nrows * ncols : 0;
                 const double s = contrib > 0.0 ? contrib : 0.0;
