@@ -22,6 +22,7 @@
 #include "jrc_tiled.cuh"
 #include "jrc_slice.cuh"
 #include "jrc_wide.cuh"
+#include "jrc_tcfused.cuh"
 #include "jrc_staged.cuh"
 #include "jrc_exact.cuh"
 
@@ -122,6 +123,8 @@ struct jrc_chain {
     int last_path = 0;
     int64_t launches = 0;
     int fused_ctas_per_sm = 0;
+    float *d_bimg = nullptr;                    // k_fused_tc: angle DFT matrix, tf32 hi/lo, swizzled shared-memory image
+    int tc_mode = 0;                            // JRC_TC: 0 off, 1 tensor-core fused kernel where it applies
     std::map<std::pair<const void *, size_t>, int> occ_cache;   // (kernel, dynamic smem) -> resident CTAs per SM, attribute set
     int zero_copy = 1;                          // latency mode: kernel reads/writes pinned host memory directly (JRC_ZEROCOPY=0 disables)
     std::atomic<int> bg_recording{0};           // set_background_record may come from another thread (GUI / RPC callback)
@@ -172,6 +175,7 @@ static jrc_status chain_init(jrc_chain *h, const jrc_chain_cfg *cfg, int Nr, int
     }
     h->pin_a.pinned = h->pin_b.pinned = true;
     if (const char *e = getenv("JRC_ZEROCOPY")) h->zero_copy = atoi(e) != 0;
+    if (const char *e = getenv("JRC_TC")) h->tc_mode = atoi(e);
     const size_t vn = (size_t)h->V * cfg->fft_len;
     CU(cudaMalloc(&h->d_temp, vn * sizeof(c32)));
     CU(cudaMemsetAsync(h->d_temp, 0, vn * sizeof(c32), h->stream));
@@ -231,6 +235,7 @@ extern "C" void jrc_chain_destroy(jrc_chain *h)
     if (h->d_angle_bins) cudaFree(h->d_angle_bins);
     if (h->d_win_tab) cudaFree(h->d_win_tab);
     if (h->d_g_tab) cudaFree(h->d_g_tab);
+    if (h->d_bimg) cudaFree(h->d_bimg);
     if (h->d_ring) cudaFree(h->d_ring);
     if (h->d_temp) cudaFree(h->d_temp);
     for (int i = 0; i < 2; i++) {
@@ -685,6 +690,63 @@ static jrc_status launch_exact(jrc_chain *h, PortDev rx, PortDev tx, const c32 *
     return JRC_OK;
 }
 
+// ---------------------------------------------------------------------------
+// tensor-core fused kernel (jrc_tcfused.cuh)
+// ---------------------------------------------------------------------------
+static float tf32_hi(float x)
+{
+    uint32_t u;
+    memcpy(&u, &x, 4);
+    u &= 0xFFFFE000u;
+    memcpy(&x, &u, 4);
+    return x;
+}
+
+static jrc_status tc_bimg(jrc_chain *h)
+{
+    if (h->d_bimg) return JRC_OK;
+    const int NA = 64, N = 2 * NA;
+    std::vector<float> img((size_t)N * 32, 0.f);
+    for (int i = 0; i < NA; i++)
+        for (int p = 0; p < 8; p++) {
+            // D[p][i] = (-1)^p e^{-j 2 pi p i / NA}: the angle DFT with its output fftshift folded in
+            const double a = -2.0 * M_PI * (double)((p * i) % NA) / (double)NA, sg = (p & 1) ? -1.0 : 1.0;
+            const double dr = sg * cos(a), di = sg * sin(a);
+            const double rows[2][2] = {{dr, -di}, {di, dr}};   // column i (Re): (yr, yi) -> dr, -di;  column NA + i (Im): di, dr
+            for (int ri = 0; ri < 2; ri++)
+                for (int c = 0; c < 2; c++) {
+                    const int j = ri * NA + i, k = 2 * p + c;
+                    const float full = (float)rows[ri][c], hi = tf32_hi(full), lo = tf32_hi(full - hi);
+                    auto at = [&](int kk) { return (size_t)(j >> 3) * 256 + (j & 7) * 32 + ((((kk >> 2) ^ (j & 7)) << 2) + (kk & 3)); };
+                    img[at(k)] = hi;
+                    img[at(16 + k)] = lo;
+                }
+        }
+    CU(cudaMalloc(&h->d_bimg, img.size() * sizeof(float)));
+    CU(cudaMemcpyAsync(h->d_bimg, img.data(), img.size() * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return JRC_OK;
+}
+
+static bool tc_config_ok(const jrc_chain *h)
+{
+    return h->tc_mode && h->cfg.fft_len == 64 && h->V == 8 && h->cfg.interp_angle == 8 &&
+           (h->cfg.interp_range == 16 || h->cfg.interp_range == 8);
+}
+
+template <int IR>
+static jrc_status launch_tc_t(jrc_chain *h, const TcFusedParams &P)
+{
+    using Gm = TcFusedGeom<IR>;
+    const size_t smem = Gm::smem_bytes(P.T, P.R, P.S);
+    CU(cudaFuncSetAttribute(k_fused_tc<IR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int grid = h->sm_count < P.n_cpi ? h->sm_count : P.n_cpi;
+    k_fused_tc<IR><<<grid, Gm::THREADS, smem, h->stream>>>(P);
+    CU(cudaGetLastError());
+    h->launches++;
+    return JRC_OK;
+}
+
 static bool fused_config_ok(const jrc_chain *h)
 {
     const int IR = h->cfg.interp_range, IA = h->cfg.interp_angle;
@@ -734,6 +796,19 @@ static jrc_status run_batch_impl(jrc_chain *h, jrc_port_layout rx, jrc_port_layo
         ST(fix_buffers(h, n_cpi, &fix_ctl, &fix_list));
     }
 
+    if (want_fused && map && !dets && tc_config_ok(h) && n_cpi >= 32 && !bg && !recording &&
+        (size_t)(c.n_tx + c.n_rx) * c.n_sym * 64 * 8 <= 24576) {
+        NvtxRange nv("fused: k_fused_tc");
+        ST(tc_bimg(h));
+        TcFusedParams TP;
+        memset(&TP, 0, sizeof(TP));
+        TP.rx = drx; TP.tx = dtx; TP.n_cpi = n_cpi; TP.cpi0 = cpi0;
+        TP.T = c.n_tx; TP.R = c.n_rx; TP.S = c.n_sym; TP.n_pre = n_pre; TP.tx_interleave = c.tx_interleave;
+        TP.map = map; TP.bimg = h->d_bimg;
+        if (c.interp_range == 16) ST(launch_tc_t<16>(h, TP)); else ST(launch_tc_t<8>(h, TP));
+        h->last_path = JRC_PATH_FUSED;
+        return JRC_OK;
+    }
     if (want_fused) {
         NvtxRange nv("fused: k_fused64x8");
         FusedParams P;
