@@ -22,7 +22,9 @@
 #include "jrc_tiled.cuh"
 #include "jrc_slice.cuh"
 #include "jrc_wide.cuh"
+#ifdef JRC_WITH_TC      // make TC=1: the tensor-core variant of the fused kernel, an experiment that measures slower (profiles/README.md)
 #include "jrc_tcfused.cuh"
+#endif
 #include "jrc_staged.cuh"
 #include "jrc_exact.cuh"
 
@@ -690,6 +692,7 @@ static jrc_status launch_exact(jrc_chain *h, PortDev rx, PortDev tx, const c32 *
     return JRC_OK;
 }
 
+#ifdef JRC_WITH_TC
 // ---------------------------------------------------------------------------
 // tensor-core fused kernel (jrc_tcfused.cuh)
 // ---------------------------------------------------------------------------
@@ -747,6 +750,8 @@ static jrc_status launch_tc_t(jrc_chain *h, const TcFusedParams &P)
     return JRC_OK;
 }
 
+#endif
+
 static bool fused_config_ok(const jrc_chain *h)
 {
     const int IR = h->cfg.interp_range, IA = h->cfg.interp_angle;
@@ -796,8 +801,9 @@ static jrc_status run_batch_impl(jrc_chain *h, jrc_port_layout rx, jrc_port_layo
         ST(fix_buffers(h, n_cpi, &fix_ctl, &fix_list));
     }
 
+#ifdef JRC_WITH_TC
     if (want_fused && map && !dets && tc_config_ok(h) && n_cpi >= 32 && !bg && !recording &&
-        (size_t)(c.n_tx + c.n_rx) * c.n_sym * 64 * 8 <= 24576) {
+        (size_t)(c.n_tx + c.n_rx) * c.n_sym * 64 * 8 <= 15360) {
         NvtxRange nv("fused: k_fused_tc");
         ST(tc_bimg(h));
         TcFusedParams TP;
@@ -805,10 +811,12 @@ static jrc_status run_batch_impl(jrc_chain *h, jrc_port_layout rx, jrc_port_layo
         TP.rx = drx; TP.tx = dtx; TP.n_cpi = n_cpi; TP.cpi0 = cpi0;
         TP.T = c.n_tx; TP.R = c.n_rx; TP.S = c.n_sym; TP.n_pre = n_pre; TP.tx_interleave = c.tx_interleave;
         TP.map = map; TP.bimg = h->d_bimg;
+        if (const char *e = getenv("JRC_TC_DBG")) TP.dbg = atoi(e);
         if (c.interp_range == 16) ST(launch_tc_t<16>(h, TP)); else ST(launch_tc_t<8>(h, TP));
         h->last_path = JRC_PATH_FUSED;
         return JRC_OK;
     }
+#endif
     if (want_fused) {
         NvtxRange nv("fused: k_fused64x8");
         FusedParams P;

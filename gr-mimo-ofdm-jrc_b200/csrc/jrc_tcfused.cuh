@@ -36,6 +36,7 @@ struct TcFusedParams {
     int T, R, S, n_pre, tx_interleave;
     float *map;                // [n_cpi][NR][64]
     const float *bimg;         // [128][32] tf32 [Bhi | Blo] rows of the angle DFT matrix, 128-byte-swizzled image
+    int dbg;                   // measurement switches (JRC_TC_DBG): 1 skip the range passes, 2 skip the map stores
 };
 
 template <int IR>
@@ -43,11 +44,11 @@ struct TcFusedGeom {
     static constexpr int NSC = 64, V = 8, NA = 64;
     static constexpr int NR = NSC * IR, Q = NR / 8, TILES = NR / 128;
     static constexpr int THREADS = 512, PROD = 128, GROUPS = 3;
-    static constexpr int STG_ROW = 80;                                    // 64 B of a map row + 16 B pad: conflict-free STS.128
+    static constexpr int STG_ROW = 272;                                   // a 256-byte map row + 16 B pad: conflict-free STS.128 / LDS.128
     static constexpr int OFF_B = 0;                                       // 16 KiB
     static constexpr int OFF_Y = 16384;                                   // 2 x NR x 64 B
-    static constexpr int OFF_STG = OFF_Y + 2 * NR * 64;                   // GROUPS x 128 x STG_ROW
-    static constexpr int OFF_HS = OFF_STG + GROUPS * 128 * STG_ROW;       // 2 x [4 pairs][64] float4
+    static constexpr int OFF_STG = OFF_Y + 2 * NR * 64;                   // GROUPS x 64 rows x STG_ROW (half a tile at a time)
+    static constexpr int OFF_HS = OFF_STG + GROUPS * 64 * STG_ROW;        // 2 x [4 pairs][64] float4
     static constexpr int OFF_TW = OFF_HS + 2 * 4 * 64 * 16;               // [8][Q] c32
     static constexpr int OFF_IN = OFF_TW + 8 * Q * 8;                     // [(T+R)][S][64] c32
     static size_t smem_bytes(int T, int R, int S) { return (size_t)OFF_IN + (size_t)(T + R) * S * 64 * 8 + 1024; }
@@ -149,8 +150,9 @@ __global__ void __launch_bounds__(512, 1) k_fused_tc(const TcFusedParams P)
         }
         auto prefetch = [&](int cpi) {
             const int cpa = per_ant >> 1, total = (P.T + P.R) * cpa;
+            const int sh = (cpa & (cpa - 1)) ? -1 : 31 - __clz(cpa);
             for (int c = tid; c < total; c += Gm::PROD) {
-                const int a = c / cpa, w = c - a * cpa;
+                const int a = sh >= 0 ? (c >> sh) : c / cpa, w = c - a * cpa;
                 const c32 *src = (a < P.T)
                     ? P.tx.base + (long long)cpi * P.tx.cpi_stride + (long long)a * P.tx.ant_stride
                     : P.rx.base + (long long)cpi * P.rx.cpi_stride + (long long)(a - P.T) * P.rx.ant_stride;
@@ -192,6 +194,7 @@ __global__ void __launch_bounds__(512, 1) k_fused_tc(const TcFusedParams P)
             // the buffer must have been streamed out by crew B (CPI i - 2)
             if (i >= 2) mbar_wait(smem_u32(&mbar_free[b]), ((i >> 1) - 1) & 1);
             // ---- stage 2: range pass 1 (pruned: 8 of Q inputs non-zero), tasks (k0, q0) ----
+            if (!(P.dbg & 1) || i < 2) {
 #pragma unroll
             for (int j = 0; j < (8 * IR) / 32; j++) {
                 const int k0 = (lane + 32 * j) / IR;
@@ -234,6 +237,7 @@ __global__ void __launch_bounds__(512, 1) k_fused_tc(const TcFusedParams P)
                 for (int m1 = 0; m1 < 8; m1++)
                     y[yslot(m1 * Q + q, pair)] = make_float4(u0[m1].x, u0[m1].y, u1[m1].x, u1[m1].y);
             }
+            }
             named_bar(1, Gm::PROD);                      // all four channel pairs of y[b] are written
             if (tid == 0) mbar_arrive(smem_u32(&mbar_full[b]));
         }
@@ -242,7 +246,7 @@ __global__ void __launch_bounds__(512, 1) k_fused_tc(const TcFusedParams P)
         // crew B: group g streams the tiles tg = g, g + 3, ... of this CTA's CPIs (tile tg: CPI tg / TILES)
         // =====================================================================================
         const int g = (warp - 4) >> 2, r = tid & 127;                   // r: row of the tile = TMEM lane
-        unsigned char *stg = base + Gm::OFF_STG + g * (128 * Gm::STG_ROW);
+        unsigned char *stg = base + Gm::OFF_STG + g * (64 * Gm::STG_ROW);
         const uint32_t tmem_d = tmem_slot + (uint32_t)(g * 160), tmem_a = tmem_d + 128u;
         const uint32_t lane_off = (uint32_t)(((tid >> 5) & 3) * 32) << 16;
         const uint32_t mbar = smem_u32(&mbar_mma[g]);
@@ -292,34 +296,43 @@ __global__ void __launch_bounds__(512, 1) k_fused_tc(const TcFusedParams P)
             mbar_wait(mbar, mma_parity);
             mma_parity ^= 1;
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            // epilogue: 16 angle bins at a time -- Re columns [16h, +16), Im columns [64 + 16h, +16)
-            float4 *srow = reinterpret_cast<float4 *>(stg + r * Gm::STG_ROW);
+            // epilogue, half a tile (64 rows = warps 2 half, 2 half + 1 of the group) at a time: the owners of the rows read
+            // their accumulators 16 angle bins at a time -- Re columns [16h, +16), Im columns [64 + 16h, +16) --, form
+            // re^2 + im^2 and stage the map rows; then all 128 threads stream the 16 KiB out as whole 256-byte rows
             float4 *dst = reinterpret_cast<float4 *>(P.map + ((long long)cpi * NR + 128 * t) * NA);
 #pragma unroll 1
-            for (int h = 0; h < 4; h++) {
-                uint32_t re[16], im[16];
-                JRC_TMEM_LD16(tmem_d + lane_off + (uint32_t)(h * 16), re);
-                JRC_TMEM_LD16(tmem_d + lane_off + (uint32_t)(64 + h * 16), im);
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            for (int half = 0; half < 2; half++) {
+                if ((r >> 6) == half) {
+                    float4 *srow = reinterpret_cast<float4 *>(stg + (r & 63) * Gm::STG_ROW);
 #pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    float2 o[2];
+                    for (int h = 0; h < 4; h++) {
+                        uint32_t re[16], im[16];
+                        JRC_TMEM_LD16(tmem_d + lane_off + (uint32_t)(h * 16), re);
+                        JRC_TMEM_LD16(tmem_d + lane_off + (uint32_t)(64 + h * 16), im);
+                        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-                    for (int q = 0; q < 2; q++) {
-                        const float2 rr = make_float2(__uint_as_float(re[4 * j + 2 * q]), __uint_as_float(re[4 * j + 2 * q + 1]));
-                        const float2 ii = make_float2(__uint_as_float(im[4 * j + 2 * q]), __uint_as_float(im[4 * j + 2 * q + 1]));
-                        o[q] = __ffma2_rn(ii, ii, __fmul2_rn(rr, rr));
+                        for (int j = 0; j < 4; j++) {
+                            float2 o[2];
+#pragma unroll
+                            for (int q = 0; q < 2; q++) {
+                                const float2 rr = make_float2(__uint_as_float(re[4 * j + 2 * q]), __uint_as_float(re[4 * j + 2 * q + 1]));
+                                const float2 ii = make_float2(__uint_as_float(im[4 * j + 2 * q]), __uint_as_float(im[4 * j + 2 * q + 1]));
+                                o[q] = __ffma2_rn(ii, ii, __fmul2_rn(rr, rr));
+                            }
+                            srow[4 * h + j] = make_float4(o[0].x, o[0].y, o[1].x, o[1].y);
+                        }
                     }
-                    srow[j] = make_float4(o[0].x, o[0].y, o[1].x, o[1].y);
                 }
                 named_bar(2 + g, 128);
-                // 128 rows x 64 B: four lanes per row, eight rows per store instruction
+                // 64 rows x 256 B, contiguous in the map: 16 lanes per row, two rows per store instruction
+                float4 *d2 = dst + half * (64 * NA / 4);
 #pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    const int e = k * 128 + r, row = e >> 2, ch = e & 3;
-                    __stcs(dst + row * (NA / 4) + h * 4 + ch, *reinterpret_cast<const float4 *>(stg + row * Gm::STG_ROW + ch * 16));
+                for (int k = 0; k < 8; k++) {
+                    const int e = k * 128 + r, row = e >> 4, ch = e & 15;
+                    const float4 vv = *reinterpret_cast<const float4 *>(stg + row * Gm::STG_ROW + ch * 16);
+                    if (!(P.dbg & 2) || vv.x == 123.456f) __stcs(d2 + e, vv);
                 }
-                named_bar(2 + g, 128);                   // the staging rows are rewritten by the next chunk
+                named_bar(2 + g, 128);                   // the staging rows are rewritten by the other half / the next tile
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         }

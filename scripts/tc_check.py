@@ -1,4 +1,6 @@
-"""k_fused_tc against k_fused64x8 on the bench scene: map error, detection lists, time per 4096 CPIs."""
+"""k_fused_tc (experiment build) against k_fused64x8 on the bench scene: map error, time per 4096 CPIs.
+    make -C gr-mimo-ofdm-jrc_b200 libjrc_cuda_tc.so && JRC_CUDA_LIB=$PWD/gr-mimo-ofdm-jrc_b200/libjrc_cuda_tc.so python scripts/tc_check.py
+JRC_TC_DBG=1/2/3: without the range passes / the map stores / both (elimination runs)."""
 import os, sys, json
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "gr-mimo-ofdm-jrc_b200", "python")]
