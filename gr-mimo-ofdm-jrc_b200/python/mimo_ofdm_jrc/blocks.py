@@ -48,7 +48,7 @@ class mimo_ofdm_radar:
         with f:
             now = datetime.datetime.now()
             f.write(f"{now.strftime('%H:%M:%S')}.{now.microsecond // 1000:03d}, {self.N_tx}, {self.N_rx}, {self.fft_len}:")
-            f.write(";".join(f"({z.real:.9g},{z.imag:.9g})" for z in self._chan_est.ravel()))
+            f.write(";".join(f"({z.real:.7g},{z.imag:.7g})" for z in self._chan_est.ravel()))
             f.write(";\n\n")
         print("[MIMO OFDM RADAR] Radar image captured!")
 

@@ -26,6 +26,25 @@ using namespace gr::mimo_ofdm_jrc;
 typedef std::vector<gr_complex> cvec;
 
 // ---------------------------------------------------------------------------------------------
+// the reference block's own capture_radar_data() dump (lib/mimo_ofdm_radar_impl.cc:348-377) of one frame:
+// golden text for the drop-in block's CSV format (tests/golden/make_golden.py)
+// ---------------------------------------------------------------------------------------------
+extern "C" __attribute__((visibility("default")))
+void ref_capture(const orc_c32 *tx, const orc_c32 *rx, int N, int T, int R, int S, int pre, int interleave, const char *path)
+{
+    const int V = T * R, items = pre + S;
+    auto radar = mimo_ofdm_radar::make(N, T, R, S, pre, false, false, 1, 1, interleave, path);
+    cvec pad((size_t)V * N);
+    std::vector<shim::input_t> in(T + R);
+    for (int t = 0; t < T; t++) { in[t].items = tx + (size_t)t * items * N; in[t].n_items = items; }
+    for (int r = 0; r < R; r++) { in[T + r].items = rx + (size_t)r * items * N; in[T + r].n_items = items; }
+    in[0].tags.push_back(shim::make_tag(0, "packet_len", pmt::from_long(items)));
+    in[T].tags.push_back(shim::make_tag(0, "packet_len", pmt::from_long(items)));
+    shim::run_once(*radar, in, {{pad.data(), V}});
+    radar->capture_radar_data(true);
+}
+
+// ---------------------------------------------------------------------------------------------
 // reference chain for one batch (C ABI, same arguments as orc_chain_batch)
 // ---------------------------------------------------------------------------------------------
 static int find_bin(const float *bins, int n, float v)

@@ -4,6 +4,10 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <fstream>
+#include <iterator>
+#include <string>
+#include <cstdlib>
 #include <cstring>
 #include <random>
 
@@ -314,8 +318,41 @@ static void test_fused_block()
     }
 }
 
+// capture_radar_data(): the CSV line of the drop-in block against the line the REFERENCE block wrote for the same frame
+// (tests/golden/c1_capture_line.txt, produced by tests/golden/make_golden.py from the reference's own sources;
+// lib/mimo_ofdm_radar_impl.cc:348-377).  The time stamp in front of the first ", " is the only difference allowed.
+static void test_capture_format(const char *golden_dir)
+{
+    const int N = 64, T = 4, R = 2, S = 4, V = T * R;
+    std::string dir(golden_dir);
+    std::ifstream ff(dir + "/c1_frame0.c64", std::ios::binary), gf(dir + "/c1_capture_line.txt");
+    CHECK(ff.good() && gf.good(), "golden files not found in %s", golden_dir);
+    if (!ff.good() || !gf.good()) return;
+    cvec frame((size_t)(T + R) * S * N);
+    ff.read(reinterpret_cast<char *>(frame.data()), frame.size() * sizeof(gr_complex));
+    std::string golden((std::istreambuf_iterator<char>(gf)), std::istreambuf_iterator<char>());
+    const char *path = "/tmp/jrc_cpp_capture.csv";
+    std::remove(path);
+    auto blk = mimo_ofdm_radar::make(N, T, R, S, 0, false, false, 1, 1, false, path);
+    std::vector<shim::input_t> in(T + R);
+    for (int t = 0; t < T; t++) { in[t].items = frame.data() + (size_t)t * S * N; in[t].n_items = S; }
+    for (int r = 0; r < R; r++) { in[T + r].items = frame.data() + (size_t)(T + r) * S * N; in[T + r].n_items = S; }
+    in[0].tags.push_back(shim::make_tag(0, "packet_len", pmt::from_long(S)));
+    in[T].tags.push_back(shim::make_tag(0, "packet_len", pmt::from_long(S)));
+    cvec out((size_t)V * N);
+    auto res = shim::run_once(*blk, in, {{out.data(), V}});
+    CHECK(res.produced == V, "capture: radar produced %d", res.produced);
+    blk->capture_radar_data(true);
+    std::ifstream cf(path);
+    std::string line((std::istreambuf_iterator<char>(cf)), std::istreambuf_iterator<char>());
+    const size_t cut = line.find(", ");
+    CHECK(cut != std::string::npos && cut == 12, "capture: time stamp HH:MM:SS.mmm expected in front (found at %zu)", cut);
+    CHECK(cut != std::string::npos && line.substr(cut + 2) == golden, "capture: CSV line differs from the reference block's");
+}
+
 int main()
 {
+    if (const char *g = std::getenv("JRC_GOLDEN_DIR")) test_capture_format(g);
     test_radar_block();
     test_chain_of_blocks();
     test_peak_and_pad();

@@ -57,7 +57,31 @@ def main():
                             map_sum=m.reshape(n, -1).astype(np.float64).sum(axis=1),
                             cfg=np.array([cfg[k] for k in ("T", "R", "S", "N", "IR", "IA")]))
         print(name, list(zip(d["range_idx"].tolist(), d["angle_idx"].tolist())))
-
+        if name == "c1_shipped":
+            # the reference block's own capture_radar_data() line for frame 0 (lib/mimo_ofdm_radar_impl.cc:348-377; Eigen's
+            # FullPrecision = 7 significant digits for float, Eigen 3.3), without its time stamp, and the frame as raw
+            # complex64 (tx[T][S][N] then rx[R][S][N]) for the C++ block test
+            frame = os.path.join(HERE, "c1_frame0.c64")
+            t0, r0 = orc.c64(tx), orc.c64(rx[0])
+            np.concatenate([t0.ravel(), r0.ravel()]).astype(np.complex64).tofile(frame)
+            path = "/tmp/jrc_ref_capture.csv"
+            if os.path.exists(path):
+                os.remove(path)
+            # (in a process of its own, ctypes only: with NumPy's bundled runtime libraries loaded, std::put_time inside the
+            #  reference's current_date_time2() crashes)
+            import subprocess
+            code = (
+                "import ctypes as C, sys\n"
+                "buf = open(sys.argv[2], 'rb').read()\n"
+                "lib = C.CDLL(sys.argv[1]); lib.ref_capture.restype = None\n"
+                "lib.ref_capture.argtypes = [C.c_void_p, C.c_void_p] + [C.c_int] * 6 + [C.c_char_p]\n"
+                "T, R, S, N = (int(a) for a in sys.argv[4:8])\n"
+                "b = C.create_string_buffer(buf, len(buf)); a = C.addressof(b)\n"
+                "lib.ref_capture(a, a + 8 * T * S * N, N, T, R, S, 0, 0, sys.argv[3].encode())\n")
+            subprocess.run([sys.executable, "-c", code, os.path.join(ROOT, "oracle", "_ref", "libjrc_ref.so"), frame, path,
+                            str(cfg["T"]), str(cfg["R"]), str(cfg["S"]), str(cfg["N"])], check=True)
+            line = open(path).read()
+            open(os.path.join(HERE, "c1_capture_line.txt"), "w").write(line.split(", ", 1)[1])
 
 if __name__ == "__main__":
     main()

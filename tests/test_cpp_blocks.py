@@ -43,7 +43,8 @@ def test_blocks_refuse_to_run_without_a_gpu():
 @pytest.mark.gpu
 def test_cpp_blocks_against_oracle():
     assert _built()
-    r = subprocess.run([EXE], capture_output=True, text=True, timeout=600)
+    env = dict(os.environ, JRC_GOLDEN_DIR=os.path.join(ROOT, "tests", "golden"))     # + the capture_radar_data() format test
+    r = subprocess.run([EXE], capture_output=True, text=True, timeout=600, env=env)
     assert r.returncode == 0, r.stdout[-4000:] + r.stderr[-2000:]
     assert "ALL BLOCK TESTS PASSED" in r.stdout
 

@@ -554,3 +554,22 @@ def test_tiled_linearity_and_shard_consistency(jrc):
     mb, db = ch.run_host(rx[2:], tx, cpi0=2)
     assert np.array_equal(np.concatenate([ma, mb]), m1)
     assert np.array_equal(np.concatenate([da, db]), d1)
+
+
+def test_capture_radar_data_line_equals_the_reference_blocks(jrc):
+    """mimo_ofdm_radar::capture_radar_data (lib/mimo_ofdm_radar_impl.cc:348-377): the CSV line for the golden frame
+    against the line the reference block itself wrote (tests/golden/c1_capture_line.txt, make_golden.py); only the time
+    stamp differs.  (The C++ block is checked the same way by tests/cpp/test_blocks.cc.)"""
+    gdir = _os.path.join(_os.path.dirname(_os.path.abspath(__file__)), "golden")
+    frame = np.fromfile(_os.path.join(gdir, "c1_frame0.c64"), dtype=np.complex64).reshape(6, 4 * 64)
+    golden = open(_os.path.join(gdir, "c1_capture_line.txt")).read()
+    path = "/tmp/jrc_py_capture.csv"
+    if _os.path.exists(path):
+        _os.remove(path)
+    blk = jrc.mimo_ofdm_radar(64, 4, 2, 4, 0, False, False, 1, 1, False, path)
+    out, tags, consumed = blk.work(list(frame[:4]), list(frame[4:]))
+    assert out is not None
+    blk.capture_radar_data(True)
+    line = open(path).read()
+    stamp, rest = line.split(", ", 1)
+    assert len(stamp) == 12 and rest == golden

@@ -46,3 +46,34 @@ def test_oracle_reproduces_reference_golden_vectors(orc, path):
     exp0 = synth.expected_peak(10.0, 0.0, N, IR, T * R, IA)
     assert (int(g["range_idx"][0]), int(g["angle_idx"][0])) == exp0
     assert len(GOLDEN) >= 2
+
+
+def test_capture_line_golden_is_what_the_reference_block_writes(orc):
+    """tests/golden/c1_capture_line.txt = the reference block's own capture_radar_data() output for the golden frame
+    (regenerated here from /root/reference through oracle/_ref; a process of its own, see make_golden.py), and the values in
+    it are the oracle's channel estimate printed with 7 significant digits."""
+    lib = os.path.join(ROOT, "oracle", "_ref", "libjrc_ref.so")
+    if not os.path.exists(lib):
+        pytest.skip("oracle/_ref not built (no /root/reference here)")
+    import sys
+    gdir = os.path.join(ROOT, "tests", "golden")
+    frame, path = os.path.join(gdir, "c1_frame0.c64"), "/tmp/jrc_ref_capture_test.csv"
+    if os.path.exists(path):
+        os.remove(path)
+    code = ("import ctypes as C, sys\n"
+            "buf = open(sys.argv[2], 'rb').read()\n"
+            "lib = C.CDLL(sys.argv[1]); lib.ref_capture.restype = None\n"
+            "lib.ref_capture.argtypes = [C.c_void_p, C.c_void_p] + [C.c_int] * 6 + [C.c_char_p]\n"
+            "b = C.create_string_buffer(buf, len(buf)); a = C.addressof(b)\n"
+            "lib.ref_capture(a, a + 8 * 4 * 4 * 64, 64, 4, 2, 4, 0, 0, sys.argv[3].encode())\n")
+    subprocess.run([sys.executable, "-c", code, lib, frame, path], check=True, capture_output=True)
+    golden = open(os.path.join(gdir, "c1_capture_line.txt")).read()
+    assert open(path).read().split(", ", 1)[1] == golden
+    # same numbers as the oracle's conj-MAC
+    f = np.fromfile(frame, dtype=np.complex64).reshape(6, 4 * 64)
+    rad = orc.Radar(64, 4, 2, 4, 0, False, False, 1, 1, False)
+    H = rad.work(list(f[:4]), list(f[4:])).ravel()
+    fields = golden.split(":", 1)[1].strip().rstrip(";").split(";")
+    assert golden.startswith("4, 2, 64:") and len(fields) == H.size and golden.endswith(";\n\n")
+    got = np.array([complex(*map(float, x.strip("()").split(","))) for x in fields])
+    assert np.allclose(got.real, H.real, rtol=1e-6, atol=1e-12) and np.allclose(got.imag, H.imag, rtol=1e-6, atol=1e-12)
