@@ -1615,6 +1615,40 @@ extern "C" jrc_status jrc_target_sim(jrc_chain *h, const jrc_c32 *in, int32_t n,
     return sg.finish();
 }
 
+extern "C" jrc_status jrc_scene_synth(jrc_chain *h, const jrc_c32 *tx, int32_t n_cpi, int32_t n_targets, const float *range_m,
+                                       const float *az_deg, const float *amp, double samp_rate, double center_freq,
+                                       float noise_sigma, uint64_t seed, jrc_c32 *rx_dev)
+{
+    if (!h || !tx || !range_m || !az_deg || !amp || !rx_dev) return fail(JRC_ERR_INVALID, "null argument");
+    if (n_cpi < 0 || n_targets < 0) return fail(JRC_ERR_INVALID, "bad sizes");
+    if (n_cpi == 0) return JRC_OK;
+    if (!ptr_is_device(rx_dev)) return fail(JRC_ERR_INVALID, "rx must be device memory");
+    const jrc_chain_cfg &c = h->cfg;
+    if (c.n_tx > 16) return fail(JRC_ERR_INVALID, "at most 16 TX antennas");
+    CU(cudaSetDevice(c.device));
+    NvtxRange nv("jrc_scene_synth");
+    Staging sg(h);
+    const void *dtx = nullptr, *dr = nullptr, *da = nullptr, *dm = nullptr;
+    const size_t np = (size_t)n_cpi * (n_targets > 0 ? n_targets : 1) * sizeof(float);
+    ST(sg.in(tx, (size_t)c.n_tx * c.n_sym * c.fft_len * sizeof(c32), &dtx));
+    ST(sg.in(range_m, np, &dr));
+    ST(sg.in(az_deg, np, &da));
+    ST(sg.in(amp, np, &dm));
+    SceneParams P;
+    memset(&P, 0, sizeof(P));
+    P.tx = (const c32 *)dtx; P.range_m = (const float *)dr; P.az_deg = (const float *)da; P.amp = (const float *)dm;
+    P.n_cpi = n_cpi; P.J = n_targets; P.T = c.n_tx; P.R = c.n_rx; P.S = c.n_sym; P.N = c.fft_len;
+    P.samp_rate = samp_rate; P.center_freq = center_freq; P.noise_sigma = noise_sigma; P.seed = seed; P.rx = (c32 *)rx_dev;
+    const long long total = (long long)n_cpi * c.n_rx * c.fft_len;
+    const int grid = grid_for(total, 256, h->sm_count);
+    if (c.n_tx <= 4) k_scene_synth<4><<<grid, 256, 0, h->stream>>>(P);
+    else if (c.n_tx <= 8) k_scene_synth<8><<<grid, 256, 0, h->stream>>>(P);
+    else k_scene_synth<16><<<grid, 256, 0, h->stream>>>(P);
+    CU(cudaGetLastError());
+    h->launches++;
+    return sg.finish();
+}
+
 extern "C" jrc_status jrc_nlog10(jrc_chain *h, const float *in, float *out, size_t n_items, float n, float k)
 {
     if (!h || !in || !out) return fail(JRC_ERR_INVALID, "null argument");

@@ -370,6 +370,87 @@ __global__ void k_sim_combine(const c32 *__restrict__ res /* [n_rx][n_targets][n
     }
 }
 
+// ---------------------------------------------------------------------------
+// Batched scene synthesis: what target_simulator (lib/target_simulator_impl.cc:177,188,296-303) + the RX OFDM demodulator
+// deliver to the radar block for point targets, evaluated directly in the frequency domain for a whole batch of CPIs:
+//     Y[cpi][r][s][k] = sum_t X[t][s][k] * sum_j a_j exp(-j 2 pi tau_{j,t,r} (f_k + fc)),
+//     tau = (2 R_j - d_{t,r} sin(az_j)) / c,   d_{t,r} = lambda + (t + T r) lambda / 2     (...radar_sim.grc:105-147)
+// plus optional complex Gaussian noise from a counter-based generator.  The delay phase needs float64 (tau * f ~ 1e3
+// cycles).  One thread per (cpi, r, k).  Mirrors mimo_ofdm_jrc.synth.rx_symbols (NumPy float64), which the tests compare
+// it with; it feeds bench.py's configs[4] sweep, whose 128 GiB of RX symbols cannot be kept anywhere.
+// ---------------------------------------------------------------------------
+struct SceneParams {
+    const c32 *tx;            // [T][S][N]
+    const float *range_m, *az_deg, *amp;     // [n_cpi][J]
+    int n_cpi, J, T, R, S, N;
+    double samp_rate, center_freq;
+    float noise_sigma;        // per real component; 0: none
+    unsigned long long seed;
+    c32 *rx;                  // [n_cpi][R][S][N]
+};
+
+__device__ __forceinline__ unsigned long long scene_mix64(unsigned long long z)
+{
+    z += 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+
+template <int TMAX>
+__global__ void __launch_bounds__(256) k_scene_synth(const SceneParams P)
+{
+    const double c_light = 3e8, lam = c_light / P.center_freq;
+    const long long total = (long long)P.n_cpi * P.R * P.N;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const int k = (int)(e % P.N), r = (int)((e / P.N) % P.R);
+        const long long cpi = e / ((long long)P.N * P.R);
+        const double fk = (double)(k - P.N / 2) * P.samp_rate / (double)P.N + P.center_freq;
+        c32 hch[TMAX];
+#pragma unroll
+        for (int t = 0; t < TMAX; t++) hch[t] = mk(0.f, 0.f);
+        for (int j = 0; j < P.J; j++) {
+            const double rg = (double)P.range_m[cpi * P.J + j], a = (double)P.amp[cpi * P.J + j];
+            const double sn = sinpi((double)P.az_deg[cpi * P.J + j] / 180.0);
+#pragma unroll
+            for (int t = 0; t < TMAX; t++) {
+                if (t < P.T) {
+                    const double d = lam + (double)(t + P.T * r) * lam * 0.5;
+                    const double cyc = (2.0 * rg - d * sn) / c_light * fk;
+                    const double fr = cyc - floor(cyc);
+                    double s, c;
+                    sincospi(-2.0 * fr, &s, &c);
+                    hch[t].x += (float)(a * c);
+                    hch[t].y += (float)(a * s);
+                }
+            }
+        }
+        for (int s = 0; s < P.S; s++) {
+            float yr = 0.f, yi = 0.f;
+#pragma unroll
+            for (int t = 0; t < TMAX; t++) {
+                if (t < P.T) {
+                    const c32 x = P.tx[((long long)t * P.S + s) * P.N + k];
+                    yr += x.x * hch[t].x - x.y * hch[t].y;
+                    yi += x.x * hch[t].y + x.y * hch[t].x;
+                }
+            }
+            const long long o = ((cpi * P.R + r) * P.S + s) * P.N + k;
+            if (P.noise_sigma > 0.f) {
+                const unsigned long long hsh = scene_mix64(P.seed ^ (unsigned long long)o * 0xD1342543DE82EF95ull);
+                const float u1 = ((float)(unsigned)(hsh >> 40) + 1.0f) * (1.0f / 16777217.0f);
+                const float u2 = (float)(unsigned)((hsh >> 8) & 0xFFFFFFu) * (1.0f / 16777216.0f);
+                const float rad = P.noise_sigma * sqrtf(-2.0f * logf(u1));
+                float sn2, cs2;
+                sincospif(2.0f * u2, &sn2, &cs2);
+                yr += rad * cs2;
+                yi += rad * sn2;
+            }
+            P.rx[o] = mk(yr, yi);
+        }
+    }
+}
+
 // blocks_nlog10_ff (...radar_sim.grc:725-745, in front of gui_heatmap_plot): n*log10(max(x, 1e-18)) + k
 __global__ void k_nlog10(const float *__restrict__ in, float *__restrict__ out, long long cnt, float n, float k)
 {

@@ -53,7 +53,7 @@ EXPORTS = [
     "jrc_chain_last_path", "jrc_chain_launch_count", "jrc_chain_run_host", "jrc_radar_estimate",
     "jrc_fft_vcc", "jrc_transpose_pad", "jrc_mag_squared", "jrc_target_sim", "jrc_nlog10", "jrc_estimate2d", "jrc_peak1d", "jrc_zero_pad",
     "jrc_cp_remove", "jrc_ofdm_demod", "jrc_chain_submit", "jrc_chain_poll", "jrc_chain_wait",
-    "jrc_pinned_alloc", "jrc_pinned_free", "jrc_host_register", "jrc_host_unregister", "jrc_chain_exact_stats",
+    "jrc_pinned_alloc", "jrc_pinned_free", "jrc_host_register", "jrc_host_unregister", "jrc_chain_exact_stats", "jrc_scene_synth",
 ]
 
 _lib = None
@@ -105,6 +105,7 @@ def load():
     lib.jrc_host_register.argtypes = [vp, sz]
     lib.jrc_host_unregister.argtypes = [vp]
     lib.jrc_chain_exact_stats.argtypes = [vp, C.POINTER(i64)]
+    lib.jrc_scene_synth.argtypes = [vp, vp, i32, i32, vp, vp, vp, C.c_double, C.c_double, f32, u64, vp]
     for name in EXPORTS:
         fn = getattr(lib, name)
         if name not in ("jrc_last_error", "jrc_abi_version", "jrc_chain_destroy", "jrc_chain_stream",
@@ -194,6 +195,17 @@ class Chain:
     def run_host_ptr(self, rx_ptr, tx_ptr, tx_shared, n_cpi, cpi0=0, map_ptr=None, dets_ptr=None):
         check(load().jrc_chain_run_host(self._h, rx_ptr, tx_ptr, int(bool(tx_shared)), n_cpi, cpi0,
                                         map_ptr, dets_ptr))
+
+    def scene_synth_ptr(self, tx, ranges_m, az_deg, amps, rx_ptr, samp_rate=125e6, center_freq=24e9, noise_sigma=0.0, seed=0):
+        """Batched point-target RX symbols on the device (mirror of synth.rx_symbols): tx [T][S][N] complex64 (NumPy), the
+        per-CPI target parameters [n_cpi][J] (NumPy), rx_ptr = device pointer of [n_cpi][R][S][N] complex64."""
+        tx = np.ascontiguousarray(tx, dtype=np.complex64)
+        r = np.ascontiguousarray(np.atleast_2d(ranges_m), dtype=np.float32)
+        a = np.ascontiguousarray(np.atleast_2d(az_deg), dtype=np.float32)
+        m = np.ascontiguousarray(np.atleast_2d(amps), dtype=np.float32)
+        assert r.shape == a.shape == m.shape
+        check(load().jrc_scene_synth(self._h, np_ptr(tx), r.shape[0], r.shape[1], np_ptr(r), np_ptr(a), np_ptr(m),
+                                     float(samp_rate), float(center_freq), float(noise_sigma), int(seed), rx_ptr))
 
     def exact_stats(self):
         """(marked, redone by k_est_exact, ties settled in the fused kernel) since the handle was created."""

@@ -224,6 +224,18 @@ JRC_API jrc_status jrc_target_sim(jrc_chain *h, const jrc_c32 *in, int32_t n,
                                   int32_t self_coupling, float self_coupling_db,
                                   const jrc_c32 *target_phase, int32_t accumulate, jrc_c32 *out);
 
+/* Batched point-target scene on the device: what target_simulator (lib/target_simulator_impl.cc:177,188,296-303) followed
+ * by the RX OFDM demodulator hands to the radar block, evaluated in the frequency domain for n_cpi CPIs at once
+ *     Y[cpi][r][s][k] = sum_t X[t][s][k] sum_j a_j exp(-j 2 pi tau_{j,t,r} (f_k + fc)),  tau = (2 R_j - d_{t,r} sin az_j)/c
+ * with the flowgraph's antenna geometry (...radar_sim.grc:105-147) and optional complex Gaussian noise (sigma per real
+ * component, counter-based generator keyed by seed).  tx [n_tx][n_sym][fft_len] and the per-CPI target parameters
+ * [n_cpi][n_targets] may be host or device memory; rx_dev [n_cpi][n_rx][n_sym][fft_len] is DEVICE memory, ready for
+ * jrc_chain_run_batch.  Generator for simulation sweeps whose inputs do not fit anywhere (BASELINE configs[4]).        */
+JRC_API jrc_status jrc_scene_synth(jrc_chain *h, const jrc_c32 *tx, int32_t n_cpi, int32_t n_targets,
+                                   const float *range_m, const float *az_deg, const float *amp,
+                                   double samp_rate, double center_freq, float noise_sigma, uint64_t seed,
+                                   jrc_c32 *rx_dev);
+
 /* blocks_nlog10_ff between complex_to_mag_squared and gui_heatmap_plot (...radar_sim.grc:725-745,
  * 2170-2179; bypassed in the simulation flowgraph, active in the USRP one):
  * out = n*log10(max(in, 1e-18)) + k                                            */

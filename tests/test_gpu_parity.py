@@ -573,3 +573,27 @@ def test_capture_radar_data_line_equals_the_reference_blocks(jrc):
     line = open(path).read()
     stamp, rest = line.split(", ", 1)
     assert len(stamp) == 12 and rest == golden
+
+
+@pytest.mark.parametrize("name", ["C2", "C5"])
+def test_scene_synthesis_on_device(jrc, name):
+    """jrc_scene_synth (batched point-target RX symbols, the generator of the configs[4] sweep) against the NumPy float64
+    model of the same formula (synth.rx_symbols); the noise it adds has the requested level."""
+    import torch
+    cfg = CFGS[name]
+    n = 6 if name == "C5" else 40
+    rng = np.random.default_rng(77)
+    tx = synth.tx_symbols(cfg["T"], cfg["S"], cfg["N"])
+    r, a, amp = synth.random_scene(rng, n, 3, cfg["N"], amp_db_span=12.0)
+    ref = synth.rx_symbols(tx, cfg["R"], r, a, amp, chunk=8)
+    ch = jrc.Chain(cfg["N"], cfg["T"], cfg["R"], cfg["S"], 0, cfg["IR"], cfg["IA"])
+    rx = torch.empty((n, cfg["R"], cfg["S"], cfg["N"]), dtype=torch.complex64, device="cuda")
+    ch.scene_synth_ptr(tx, r, a, amp, rx.data_ptr())
+    got = rx.cpu().numpy()
+    scale = np.abs(ref).max()
+    assert np.abs(got - ref).max() <= 2e-5 * scale, np.abs(got - ref).max() / scale       # float32 range/azimuth inputs, float32 sums
+    ch.scene_synth_ptr(tx, r, a, amp, rx.data_ptr(), noise_sigma=0.25, seed=5)
+    nz = rx.cpu().numpy() - got
+    assert abs(nz.real.std() - 0.25) < 0.01 and abs(nz.imag.std() - 0.25) < 0.01 and abs(nz.mean()) < 0.01
+    ch.scene_synth_ptr(tx, r, a, amp, rx.data_ptr(), noise_sigma=0.25, seed=6)
+    assert not np.array_equal(rx.cpu().numpy() - got, nz)                                  # another seed, another noise
