@@ -584,8 +584,8 @@ def test_scene_synthesis_on_device(jrc, name):
     n = 6 if name == "C5" else 40
     rng = np.random.default_rng(77)
     tx = synth.tx_symbols(cfg["T"], cfg["S"], cfg["N"])
-    r, a, amp = synth.random_scene(rng, n, 3, cfg["N"], amp_db_span=12.0)
-    ref = synth.rx_symbols(tx, cfg["R"], r, a, amp, chunk=8)
+    r, a, amp = (x.astype(np.float32).astype(np.float64) for x in synth.random_scene(rng, n, 3, cfg["N"], amp_db_span=12.0))
+    ref = synth.rx_symbols(tx, cfg["R"], r, a, amp, chunk=8)          # the C ABI takes the scene as float32
     ch = jrc.Chain(cfg["N"], cfg["T"], cfg["R"], cfg["S"], 0, cfg["IR"], cfg["IA"])
     rx = torch.empty((n, cfg["R"], cfg["S"], cfg["N"]), dtype=torch.complex64, device="cuda")
     ch.scene_synth_ptr(tx, r, a, amp, rx.data_ptr())
