@@ -167,14 +167,9 @@ static jrc_status chain_init(jrc_chain *h, const jrc_chain_cfg *cfg, int Nr, int
     cudaDeviceProp prop;
     CU(cudaGetDeviceProperties(&prop, cfg->device));
     h->sm_count = prop.multiProcessorCount;
+    // one stream per handle; the copy streams and events of the chunked host pipeline are created when it first runs
+    // (the utility handles of the per-block calls never need them)
     CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
-    CU(cudaStreamCreateWithFlags(&h->s_h2d, cudaStreamNonBlocking));
-    CU(cudaStreamCreateWithFlags(&h->s_d2h, cudaStreamNonBlocking));
-    for (int i = 0; i < 2; i++) {
-        CU(cudaEventCreateWithFlags(&h->ev_in[i], cudaEventDisableTiming));
-        CU(cudaEventCreateWithFlags(&h->ev_comp[i], cudaEventDisableTiming));
-        CU(cudaEventCreateWithFlags(&h->ev_out[i], cudaEventDisableTiming));
-    }
     h->pin_a.pinned = h->pin_b.pinned = true;
     if (const char *e = getenv("JRC_ZEROCOPY")) h->zero_copy = atoi(e) != 0;
     if (const char *e = getenv("JRC_TC")) h->tc_mode = atoi(e);
@@ -1330,6 +1325,15 @@ extern "C" jrc_status jrc_chain_run_host(jrc_chain *h, const jrc_c32 *rx_host, c
     if (!direct) {
         ST(h->pin_a.need((size_t)chunk * in_bytes + tx_cpi * sizeof(c32)));
         ST(h->pin_b.need((size_t)chunk * (map_host ? map_cpi * sizeof(float) : 0) + (size_t)chunk * sizeof(jrc_det)));
+    }
+    if (!h->s_h2d) {
+        CU(cudaStreamCreateWithFlags(&h->s_h2d, cudaStreamNonBlocking));
+        CU(cudaStreamCreateWithFlags(&h->s_d2h, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; i++) {
+            CU(cudaEventCreateWithFlags(&h->ev_in[i], cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&h->ev_comp[i], cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&h->ev_out[i], cudaEventDisableTiming));
+        }
     }
     jrc_status st = JRC_OK;
     NvtxRange nv_host("jrc_chain_run_host (pipelined chunks)");
