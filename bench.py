@@ -60,7 +60,7 @@ def config_dict(batch, world):
     Nr, Na = CFG["N"] * CFG["IR"], CFG["T"] * CFG["R"] * CFG["IA"]
     return {"workload": WORKLOAD, "batch_per_gpu": batch, "map": [Nr, Na],
             "l2": "per-step working set (1.0 GiB map + 48 MiB symbols) exceeds the 126 MB L2; no flush needed",
-            "parallelism": f"cpi-shard x{world}, detections gathered to rank 0 after the last step" if world > 1 else "single GPU"}
+            "parallelism": f"cpi-shard x{world}, detection records land on rank 0 over NVLink (peer stores; NCCL for the IPC handle and barriers)" if world > 1 else "single GPU"}
 
 
 def make_inputs(batch, seed, cfg=CFG, targets=2, span=10.0):
@@ -350,17 +350,33 @@ def run_ours(args):
     rx = torch.from_numpy(rx_h).to(dev)
     tx = torch.from_numpy(tx_h).to(dev)
     dmap = torch.empty((B, Nr, Na), dtype=torch.float32, device=dev)
-    # the records of ALL K steps stay on the GPU and are gathered once, after the last step
+    # Detection records of all K steps.  N > 1: the table lives in rank 0's memory and every rank's kernels store their
+    # 32-byte records straight into it over NVLink (shard.PeerRecordTable, CUDA IPC): no collective on the timed path.
+    # JRC_BENCH_GATHER=1 (or a failed IPC mapping) falls back to one NCCL gather after the last step.
     ddet_all = torch.zeros((K, B, 32), dtype=torch.uint8, device=dev)
-    gath = torch.empty((world * K * B, 32), dtype=torch.uint8, device=dev) if (world > 1 and rank == 0) else None
+    table = None
+    if world > 1 and not os.environ.get("JRC_BENCH_GATHER"):
+        ok = torch.ones(1, dtype=torch.int32, device=dev)
+        try:
+            table = shard.PeerRecordTable(K * B, local)
+        except Exception as e:  # noqa: BLE001
+            print(f"rank {rank}: peer record table unavailable ({e}); NCCL gather instead", file=sys.stderr)
+            ok.zero_()
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if int(ok.item()) == 0:
+            table = None
+    gath = torch.empty((world * K * B, 32), dtype=torch.uint8, device=dev) if (world > 1 and rank == 0 and table is None) else None
     ext = torch.cuda.ExternalStream(rc.chain.stream, device=dev)
     torch.cuda.synchronize()
 
     def step(k):
-        rc.run(rx, tx, map_out=dmap, dets_out=ddet_all[k % K], path=jrc.PATH_FUSED, sync_inputs=False)
+        if table is not None:
+            rc.run(rx, tx, map_out=dmap, dets_ptr=table.ptr((k % K) * B), path=jrc.PATH_FUSED, sync_inputs=False)
+        else:
+            rc.run(rx, tx, map_out=dmap, dets_out=ddet_all[k % K], path=jrc.PATH_FUSED, sync_inputs=False)
 
     def gather_all():
-        if world > 1:
+        if world > 1 and table is None:
             shard.gather_detections(ddet_all.view(K * B, 32), dst=0, counts=[K * B] * world, out=gath)
 
     with torch.cuda.stream(ext):
@@ -465,8 +481,17 @@ def run_ours(args):
         del prx, ptx, pmap, pdet
 
     # ---- sanity: the timed output is the real thing --------------------------------
+    if table is not None:
+        table.complete()                 # every rank's stream is synchronised: the table in rank 0's memory is whole
+        recs = table.records()
+        if rank == 0:
+            g = recs.cpu().numpy().view(jrc.DET_DTYPE).reshape(world, K, B)
+            ddet_all.copy_(recs.view(world, K, B, 32)[0])
+            for r_ in range(world):      # every rank's records arrived: CPI ids and the gate
+                assert np.array_equal(g[r_, K - 1]["cpi"], np.arange(B)) and (g[r_, K - 1]["flags"] & 1).mean() > 0.9, r_
     d = rc.dets_to_numpy(ddet_all[(K - 1) % K])
-    assert (d["flags"] & 1).mean() > 0.9 and d["range_idx"].max() < Nr and d["angle_idx"].max() < Na
+    if rank == 0 or table is None:
+        assert (d["flags"] & 1).mean() > 0.9 and d["range_idx"].max() < Nr and d["angle_idx"].max() < Na
     if gath is not None:
         g = gath.cpu().numpy().view(jrc.DET_DTYPE).reshape(world, K, B)
         assert np.array_equal(g[0, K - 1]["range_idx"], d["range_idx"])

@@ -1240,6 +1240,53 @@ extern "C" jrc_status jrc_host_unregister(void *p)
     return JRC_OK;
 }
 
+// ---------------------------------------------------------------------------
+// peer memory for the detection records of a multi-GPU job: the host rank allocates the table, the other ranks map it
+// (CUDA IPC) and their kernels store the 32-byte records straight into it over NVLink
+// ---------------------------------------------------------------------------
+extern "C" jrc_status jrc_dev_alloc(int32_t device, size_t bytes, void **out)
+{
+    if (!out) return fail(JRC_ERR_INVALID, "null argument");
+    *out = nullptr;
+    CU(cudaSetDevice(device));
+    CU(cudaMalloc(out, bytes ? bytes : 1));
+    CU(cudaMemset(*out, 0, bytes ? bytes : 1));
+    return JRC_OK;
+}
+extern "C" jrc_status jrc_dev_free(void *p)
+{
+    if (p) CU(cudaFree(p));
+    return JRC_OK;
+}
+extern "C" jrc_status jrc_dev_copy(void *dst, const void *src, size_t bytes)
+{
+    if (!dst || !src) return fail(JRC_ERR_INVALID, "null argument");
+    CU(cudaMemcpy(dst, src, bytes, cudaMemcpyDefault));
+    return JRC_OK;
+}
+extern "C" jrc_status jrc_ipc_export(void *dev_ptr, void *handle64)
+{
+    if (!dev_ptr || !handle64) return fail(JRC_ERR_INVALID, "null argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    CU(cudaIpcGetMemHandle(reinterpret_cast<cudaIpcMemHandle_t *>(handle64), dev_ptr));
+    return JRC_OK;
+}
+extern "C" jrc_status jrc_ipc_open(const void *handle64, int32_t device, void **out)
+{
+    if (!handle64 || !out) return fail(JRC_ERR_INVALID, "null argument");
+    *out = nullptr;
+    CU(cudaSetDevice(device));
+    cudaIpcMemHandle_t hnd;
+    memcpy(&hnd, handle64, sizeof(hnd));
+    CU(cudaIpcOpenMemHandle(out, hnd, cudaIpcMemLazyEnablePeerAccess));
+    return JRC_OK;
+}
+extern "C" jrc_status jrc_ipc_close(void *p)
+{
+    if (p) CU(cudaIpcCloseMemHandle(p));
+    return JRC_OK;
+}
+
 static StreamSlot *find_ticket(jrc_chain *h, int64_t ticket)
 {
     if (!h->sstate) return nullptr;

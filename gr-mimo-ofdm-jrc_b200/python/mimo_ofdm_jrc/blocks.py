@@ -344,7 +344,9 @@ class radar_chain:
             self.chain.set_estimator(**estimator)
 
     def run(self, rx, tx, want_map=True, want_dets=True, cpi0=0, path=cabi.PATH_AUTO, map_out=None, dets_out=None,
-            sync_inputs=True):
+            sync_inputs=True, dets_ptr=None):
+        """dets_ptr: raw device address for the records instead of a tensor (e.g. a slice of a shard.PeerRecordTable in
+        another GPU's memory)."""
         import torch
         assert rx.is_cuda and tx.is_cuda and rx.dtype == torch.complex64 and tx.dtype == torch.complex64
         assert rx.is_contiguous() and tx.is_contiguous()
@@ -352,7 +354,7 @@ class radar_chain:
         tx_shared = tx.dim() == 3 or (tx.shape[0] == 1 and n_cpi > 1)
         if want_map and map_out is None:
             map_out = torch.empty((n_cpi, self.Nr, self.Na), dtype=torch.float32, device=rx.device)
-        if want_dets and dets_out is None:
+        if want_dets and dets_out is None and dets_ptr is None:
             dets_out = torch.zeros((n_cpi, 32), dtype=torch.uint8, device=rx.device)
         if sync_inputs:
             torch.cuda.current_stream(rx.device).synchronize()     # inputs were produced on torch's stream
@@ -360,7 +362,7 @@ class radar_chain:
                                  tx.data_ptr(), 0 if tx_shared else self.N_tx * self.per_ant, self.per_ant,
                                  n_cpi, cpi0,
                                  map_out.data_ptr() if want_map else None, None,
-                                 dets_out.data_ptr() if want_dets else None, path)
+                                 (dets_ptr if dets_ptr is not None else dets_out.data_ptr()) if want_dets else None, path)
         return map_out if want_map else None, dets_out if want_dets else None
 
     def sync(self):

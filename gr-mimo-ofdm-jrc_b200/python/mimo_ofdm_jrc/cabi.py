@@ -54,6 +54,7 @@ EXPORTS = [
     "jrc_fft_vcc", "jrc_transpose_pad", "jrc_mag_squared", "jrc_target_sim", "jrc_nlog10", "jrc_estimate2d", "jrc_peak1d", "jrc_zero_pad",
     "jrc_cp_remove", "jrc_ofdm_demod", "jrc_chain_submit", "jrc_chain_poll", "jrc_chain_wait",
     "jrc_pinned_alloc", "jrc_pinned_free", "jrc_host_register", "jrc_host_unregister", "jrc_chain_exact_stats", "jrc_scene_synth",
+    "jrc_dev_alloc", "jrc_dev_free", "jrc_dev_copy", "jrc_ipc_export", "jrc_ipc_open", "jrc_ipc_close",
 ]
 
 _lib = None
@@ -106,6 +107,12 @@ def load():
     lib.jrc_host_unregister.argtypes = [vp]
     lib.jrc_chain_exact_stats.argtypes = [vp, C.POINTER(i64)]
     lib.jrc_scene_synth.argtypes = [vp, vp, i32, i32, vp, vp, vp, C.c_double, C.c_double, f32, u64, vp]
+    lib.jrc_dev_alloc.argtypes = [i32, sz, C.POINTER(vp)]
+    lib.jrc_dev_free.argtypes = [vp]
+    lib.jrc_dev_copy.argtypes = [vp, vp, sz]
+    lib.jrc_ipc_export.argtypes = [vp, vp]
+    lib.jrc_ipc_open.argtypes = [vp, i32, C.POINTER(vp)]
+    lib.jrc_ipc_close.argtypes = [vp]
     for name in EXPORTS:
         fn = getattr(lib, name)
         if name not in ("jrc_last_error", "jrc_abi_version", "jrc_chain_destroy", "jrc_chain_stream",

@@ -67,3 +67,59 @@ def gather_detections(dets, dst: int = 0, group=None, counts=None, out=None, asy
     if rank == dst:
         res = out if all(c == n_max for c in counts) else torch.cat([b[:c] for b, c in zip(bufs, counts)], dim=0)
     return (work, res) if async_op else res
+
+
+class PeerRecordTable:
+    """Detection table of a multi-GPU job in the memory of rank `dst`, written by every rank's kernels directly (CUDA IPC
+    mapping, NVLink peer stores) instead of being gathered: `ptr(i)` is the address this rank passes as `dets` for its i-th
+    record; after `complete()` (stream synchronised by the caller, then a barrier) rank `dst` reads `records()`.
+    torch.distributed is only used to hand the 64-byte IPC handle around and for the barrier."""
+
+    def __init__(self, n_per_rank, device, dst=0, group=None):
+        import ctypes as C
+        import torch
+        import torch.distributed as dist
+        from . import cabi
+        self._cabi, self._dist, self._group = cabi, dist, group
+        self.world, self.rank, self.dst = dist.get_world_size(group), dist.get_rank(group), dst
+        self.n, self.device = int(n_per_rank), device
+        lib = cabi.load()
+        self._base = C.c_void_p()
+        self._owner = self.rank == dst
+        h = torch.zeros(64, dtype=torch.uint8, device=torch.device("cuda", device))
+        if self._owner:
+            cabi.check(lib.jrc_dev_alloc(device, self.world * self.n * 32, C.byref(self._base)))
+            raw = (C.c_ubyte * 64)()
+            cabi.check(lib.jrc_ipc_export(self._base, raw))
+            h.copy_(torch.frombuffer(bytearray(raw), dtype=torch.uint8))
+        dist.broadcast(h, src=dst, group=group)
+        if not self._owner:
+            raw = (C.c_ubyte * 64).from_buffer_copy(bytes(h.cpu().numpy().tobytes()))
+            cabi.check(lib.jrc_ipc_open(raw, device, C.byref(self._base)))
+
+    def ptr(self, i=0):
+        return self._base.value + (self.rank * self.n + i) * 32
+
+    def complete(self):
+        self._dist.barrier(group=self._group)
+
+    def records(self):
+        """rank dst: uint8 tensor [world * n][32] (a copy); None elsewhere"""
+        if not self._owner:
+            return None
+        import torch
+        out = torch.empty((self.world * self.n, 32), dtype=torch.uint8, device=torch.device("cuda", self.device))
+        torch.cuda.synchronize(self.device)
+        self._cabi.check(self._cabi.load().jrc_dev_copy(out.data_ptr(), self._base, out.numel()))
+        return out
+
+    def close(self):
+        lib = self._cabi.load()
+        if self._base.value:
+            if self._owner:
+                self._dist.barrier(group=self._group)       # nobody maps it any more
+                lib.jrc_dev_free(self._base)
+            else:
+                lib.jrc_ipc_close(self._base)
+                self._dist.barrier(group=self._group)
+            self._base.value = None

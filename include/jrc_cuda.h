@@ -182,6 +182,19 @@ JRC_API jrc_status jrc_pinned_free(void *p);
 JRC_API jrc_status jrc_host_register(void *p, size_t bytes);
 JRC_API jrc_status jrc_host_unregister(void *p);
 
+/* Multi-GPU detection table without a collective on the critical path: the host rank allocates the table
+ * (jrc_dev_alloc) and exports it (jrc_ipc_export, 64-byte handle passed to the other processes by any means); every other
+ * rank maps it (jrc_ipc_open) and hands its slice as `dets` to jrc_chain_run_batch: the kernels store the 32-byte records
+ * straight into the host rank's memory over NVLink.  After the ranks have synchronised their streams and met at a barrier
+ * the table is complete ("NCCL over NVLink used only to gather detections" -- here the gather is the
+ * producing kernel's own stores).                                                                               */
+JRC_API jrc_status jrc_dev_alloc(int32_t device, size_t bytes, void **out);
+JRC_API jrc_status jrc_dev_free(void *p);
+JRC_API jrc_status jrc_dev_copy(void *dst, const void *src, size_t bytes);      /* synchronous, any direction */
+JRC_API jrc_status jrc_ipc_export(void *dev_ptr, void *handle64);
+JRC_API jrc_status jrc_ipc_open(const void *handle64, int32_t device, void **out);
+JRC_API jrc_status jrc_ipc_close(void *p);
+
 /* ---- per-block stage calls (exact per-block semantics; pointers may be host
  * or device, detected with cudaPointerGetAttributes; host buffers are staged
  * through the handle's pinned memory and the call is synchronous) ------------ */
