@@ -13,6 +13,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <map>
 #include <mutex>
 #include <string>
@@ -158,6 +159,8 @@ static jrc_status get_twiddles(jrc_chain *h, int n, int forward, const c32 **out
 
 extern "C" void jrc_chain_destroy(jrc_chain *h);
 static void stream_state_destroy(jrc_chain *h);
+struct GrowBuf;
+static jrc_status stream_stats(jrc_chain *h, const std::function<jrc_status(const GrowBuf &)> &add);
 
 static jrc_status chain_init(jrc_chain *h, const jrc_chain_cfg *cfg, int Nr, int Na)
 {
@@ -263,12 +266,17 @@ extern "C" jrc_status jrc_chain_exact_stats(jrc_chain *h, int64_t *out)
 {
     if (!h || !out) return fail(JRC_ERR_INVALID, "null argument");
     out[0] = out[1] = out[2] = 0;
-    if (!h->sFix.p) return JRC_OK;
     CU(cudaSetDevice(h->cfg.device));
-    FixCtl c;
     CU(cudaStreamSynchronize(h->stream));
-    CU(cudaMemcpy(&c, h->sFix.p, sizeof(c), cudaMemcpyDeviceToHost));
-    out[0] = c.n_marked; out[1] = c.n_redone; out[2] = c.n_inkernel;
+    auto add = [&](const GrowBuf &b) -> jrc_status {
+        if (!b.p) return JRC_OK;
+        FixCtl c;
+        CU(cudaMemcpy(&c, b.p, sizeof(c), cudaMemcpyDeviceToHost));
+        out[0] += c.n_marked; out[1] += c.n_redone; out[2] += c.n_inkernel;
+        return JRC_OK;
+    };
+    ST(add(h->sFix));
+    ST(stream_stats(h, add));
     return JRC_OK;
 }
 
@@ -1107,6 +1115,16 @@ static void stream_state_destroy(jrc_chain *h)
     }
     delete h->sstate;
     h->sstate = nullptr;
+}
+
+static jrc_status stream_stats(jrc_chain *h, const std::function<jrc_status(const GrowBuf &)> &add)
+{
+    if (!h->sstate) return JRC_OK;
+    for (StreamSlot &sl : h->sstate->slot) {
+        if (sl.stream) CU(cudaStreamSynchronize(sl.stream));
+        ST(add(sl.fix));
+    }
+    return JRC_OK;
 }
 
 // runs fn with the slot's stream and marked-CPI list in place of the handle's
