@@ -989,6 +989,34 @@ static jrc_status run_batch_impl(jrc_chain *h, jrc_port_layout rx, jrc_port_layo
     return JRC_OK;
 }
 
+// ---------------------------------------------------------------------------
+// range-Doppler-angle cube over a burst of CPIs (no counterpart in the reference, whose chain
+// stops at one range-angle map per CPI): complex maps of the burst from the one-kernel-per-block path, then one more
+// fft_vcc (forward, shifted) along slow time for every (range, angle) cell, then |.|^2.
+// ---------------------------------------------------------------------------
+extern "C" jrc_status jrc_chain_run_burst(jrc_chain *h, jrc_port_layout rx, jrc_port_layout tx, int32_t n_burst, float *cube)
+{
+    if (!h || !cube) return fail(JRC_ERR_INVALID, "null argument");
+    if (!is_pow2(n_burst) || n_burst > 16384) return fail(JRC_ERR_INVALID, "the burst length must be a power of two <= 16384");
+    if (!ptr_is_device(cube)) return fail(JRC_ERR_INVALID, "cube must be device memory");
+    CU(cudaSetDevice(h->cfg.device));
+    NvtxRange nv("jrc_chain_run_burst");
+    const size_t cells = (size_t)h->Nr * h->Na;
+    if (cells * (size_t)n_burst > ((size_t)1 << 31)) return fail(JRC_ERR_INVALID, "cube too large");
+    ST(h->sMisc.need(cells * n_burst * sizeof(c32)));        // complex maps [burst][cells]
+    ST(h->sMisc2.need(cells * n_burst * sizeof(c32)));       // slow-time rows [cells][burst]
+    c32 *cm = (c32 *)h->sMisc.p, *st = (c32 *)h->sMisc2.p;
+    ST(run_batch_impl(h, rx, tx, n_burst, 0, nullptr, (jrc_c32 *)cm, nullptr, JRC_PATH_STAGED, h->cfg.n_pre, false));
+    if (cells > (size_t)65535 * 32 * 32) return fail(JRC_ERR_INVALID, "map too large for the slow-time transpose");
+    ST(launch_transpose(h, cm, st, n_burst, (int)cells, n_burst, 1));            // [burst][cells] -> [cells][burst]
+    ST(launch_fft_rows(h, st, n_burst, n_burst, st, n_burst, (long long)cells, 1, 1));
+    const long long n = (long long)cells * n_burst;
+    k_mag_squared<<<grid_for(n, 256, h->sm_count), 256, 0, h->stream>>>(st, cube, n);
+    CU(cudaGetLastError());
+    h->launches++;
+    return JRC_OK;
+}
+
 extern "C" jrc_status jrc_chain_run_batch(jrc_chain *h, jrc_port_layout rx, jrc_port_layout tx, int32_t n_cpi,
                                            int32_t cpi0, float *map, jrc_c32 *cmap, jrc_det *dets, int32_t path)
 {

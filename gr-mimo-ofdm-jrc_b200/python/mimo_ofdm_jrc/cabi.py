@@ -53,7 +53,7 @@ EXPORTS = [
     "jrc_chain_last_path", "jrc_chain_launch_count", "jrc_chain_run_host", "jrc_radar_estimate",
     "jrc_fft_vcc", "jrc_transpose_pad", "jrc_mag_squared", "jrc_target_sim", "jrc_nlog10", "jrc_estimate2d", "jrc_peak1d", "jrc_zero_pad",
     "jrc_cp_remove", "jrc_ofdm_demod", "jrc_chain_submit", "jrc_chain_poll", "jrc_chain_wait",
-    "jrc_pinned_alloc", "jrc_pinned_free", "jrc_host_register", "jrc_host_unregister", "jrc_chain_exact_stats", "jrc_scene_synth",
+    "jrc_pinned_alloc", "jrc_pinned_free", "jrc_host_register", "jrc_host_unregister", "jrc_chain_exact_stats", "jrc_scene_synth", "jrc_chain_run_burst",
     "jrc_dev_alloc", "jrc_dev_free", "jrc_dev_copy", "jrc_ipc_export", "jrc_ipc_open", "jrc_ipc_close",
 ]
 
@@ -107,6 +107,7 @@ def load():
     lib.jrc_host_unregister.argtypes = [vp]
     lib.jrc_chain_exact_stats.argtypes = [vp, C.POINTER(i64)]
     lib.jrc_scene_synth.argtypes = [vp, vp, i32, i32, vp, vp, vp, C.c_double, C.c_double, f32, u64, vp]
+    lib.jrc_chain_run_burst.argtypes = [vp, PortLayout, PortLayout, i32, vp]
     lib.jrc_dev_alloc.argtypes = [i32, sz, C.POINTER(vp)]
     lib.jrc_dev_free.argtypes = [vp]
     lib.jrc_dev_copy.argtypes = [vp, vp, sz]
@@ -197,6 +198,12 @@ class Chain:
         rx = PortLayout(rx_ptr, rx_cpi_stride, rx_ant_stride)
         tx = PortLayout(tx_ptr, tx_cpi_stride, tx_ant_stride)
         check(load().jrc_chain_run_batch(self._h, rx, tx, n_cpi, cpi0, map_ptr, cmap_ptr, dets_ptr, path))
+
+    def run_burst_ptr(self, rx_ptr, rx_cpi_stride, rx_ant_stride, tx_ptr, tx_cpi_stride, tx_ant_stride, n_burst, cube_ptr):
+        """Range-Doppler-angle cube [Nr][Na][n_burst] of a burst of CPIs (device pointers)."""
+        rx = PortLayout(rx_ptr, rx_cpi_stride, rx_ant_stride)
+        tx = PortLayout(tx_ptr, tx_cpi_stride, tx_ant_stride)
+        check(load().jrc_chain_run_burst(self._h, rx, tx, n_burst, cube_ptr))
 
     # -- fused chain, host buffers ------------------------------------------
     def run_host_ptr(self, rx_ptr, tx_ptr, tx_shared, n_cpi, cpi0=0, map_ptr=None, dets_ptr=None):

@@ -139,6 +139,13 @@ enum { JRC_PATH_AUTO = 0, JRC_PATH_FUSED = 1, JRC_PATH_STAGED = 2, JRC_PATH_TILE
 JRC_API jrc_status jrc_chain_run_batch(jrc_chain *h, jrc_port_layout rx, jrc_port_layout tx,
                                        int32_t n_cpi, int32_t cpi0,
                                        float *map, jrc_c32 *cmap, jrc_det *dets, int32_t path);
+/* Range-Doppler-angle cube of a burst of n_burst consecutive CPIs (power of two): the complex range-angle maps of the
+ * burst (one-kernel-per-block path, bit-identical to the CPU restatement) followed by a forward, fftshifted FFT along
+ * slow time for every (range, angle) cell and |.|^2.  Device pointers, asynchronous on the handle's stream.
+ *   cube : [Nr][Na][n_burst] float32, Doppler bin fastest, zero Doppler at n_burst / 2
+ * Not part of the reference (its chain ends at one map per CPI); SURVEY.md 8(f) rank 4.                     */
+JRC_API jrc_status jrc_chain_run_burst(jrc_chain *h, jrc_port_layout rx, jrc_port_layout tx, int32_t n_burst, float *cube);
+
 /* which path the last run_batch took (JRC_PATH_FUSED / JRC_PATH_TILED / JRC_PATH_STAGED) and how
  * many kernels it launched                                                    */
 JRC_API int32_t    jrc_chain_last_path(const jrc_chain *h);

@@ -597,3 +597,35 @@ def test_scene_synthesis_on_device(jrc, name):
     assert abs(nz.real.std() - 0.25) < 0.01 and abs(nz.imag.std() - 0.25) < 0.01 and abs(nz.mean()) < 0.01
     ch.scene_synth_ptr(tx, r, a, amp, rx.data_ptr(), noise_sigma=0.25, seed=6)
     assert not np.array_equal(rx.cpu().numpy() - got, nz)                                  # another seed, another noise
+
+
+def test_range_doppler_angle_cube(jrc, orc):
+    """a burst of CPIs -> range-Doppler-angle cube (jrc_chain_run_burst).  No counterpart in the
+    reference; parity against NumPy float64 on the oracle's complex maps, and a moving point target sits on the analytic
+    Doppler bin."""
+    import torch
+    cfg = dict(T=4, R=2, S=4, N=64, IR=4, IA=4)
+    nb, prf, fc = 32, 20e3, 24e9
+    v = 15.0                                                        # m/s towards the radar
+    fd = 2 * v * fc / 3e8                                           # 2.4 kHz
+    tx = synth.tx_symbols(cfg["T"], cfg["S"], cfg["N"])
+    t = np.arange(nb) / prf
+    rx = synth.rx_symbols(tx, cfg["R"], np.full((nb, 1), 20.0), np.full((nb, 1), 15.0), np.ones((nb, 1)))
+    rx = (rx * np.exp(2j * np.pi * fd * t)[:, None, None, None]).astype(np.complex64)
+    rng = np.random.default_rng(3)
+    rx += (0.01 * (rng.standard_normal(rx.shape) + 1j * rng.standard_normal(rx.shape))).astype(np.complex64)
+    est = est_for(cfg)
+    ch = gpu_chain(jrc, cfg, est)
+    drx, dtx = torch.from_numpy(rx).cuda(), torch.from_numpy(tx).cuda()
+    cube = torch.empty((ch.Nr, ch.Na, nb), dtype=torch.float32, device="cuda")
+    per_ant = cfg["S"] * cfg["N"]
+    torch.cuda.synchronize()
+    ch.run_burst_ptr(drx.data_ptr(), cfg["R"] * per_ant, per_ant, dtx.data_ptr(), 0, per_ant, nb, cube.data_ptr())
+    ch.sync()
+    got = cube.cpu().numpy()
+    _, cm, _ = oracle(orc, rx, tx, cfg, est, want_cmap=True)        # [nb][Nr][Na] complex64, oracle arithmetic
+    ref = np.abs(np.fft.fftshift(np.fft.fft(cm.astype(np.complex128), axis=0), axes=0)) ** 2
+    ref = np.moveaxis(ref, 0, 2)
+    assert np.abs(got - ref).max() <= 2e-5 * ref.max(), np.abs(got - ref).max() / ref.max()
+    n, i, d = np.unravel_index(np.argmax(got), got.shape)
+    assert d == nb // 2 + int(round(fd / prf * nb)) and (n, i) == synth.expected_peak(20.0, 15.0, 64, 4, 8, 4)
