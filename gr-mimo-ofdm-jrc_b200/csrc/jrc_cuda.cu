@@ -989,6 +989,8 @@ static jrc_status run_batch_impl(jrc_chain *h, jrc_port_layout rx, jrc_port_layo
     return JRC_OK;
 }
 
+static bool ptr_is_device(const void *p);
+
 // ---------------------------------------------------------------------------
 // range-Doppler-angle cube over a burst of CPIs (no counterpart in the reference, whose chain
 // stops at one range-angle map per CPI): complex maps of the burst from the one-kernel-per-block path, then one more
