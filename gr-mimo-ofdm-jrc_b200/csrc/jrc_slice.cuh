@@ -21,13 +21,14 @@
 // one-row kernels of jrc_tiled.cuh).  Rows of a range transform = the two slices of one channel; rows of an angle
 // transform = the two range bins (n, n+1).  One warp per row pair, __syncwarp between passes.
 //   range: radix 8.8.4 decimation in frequency, in place in the slice-pair buffer.
-//   angle: with only V <= 32 of the 256 inputs non-zero, bin i = b + 8a is
-//              M[b + 8a] = sum_{s<4} w_4^{s k2} [ w_32^{s k1} sum_{m<8} w_8^{m k1} ( (-1)^p w_256^{p b} x_p ) ],   p = s + 4m, a = k1 + 8 k2:
-//          lane (b, s) twiddles its 8 inputs and runs the 8-point DFT in registers, ONE exchange through shared memory
-//          (8 float4 out, 8 in, conflict-free), then lane (b, kq) finishes k1 = kq, kq + 4 with two 4-point DFTs and owns
-//          bins b + 8 kq + 32 w + 64 k2 -- every store instruction of the warp is one full 128-byte line.  The exchange
-//          is what bounds a shared-memory FFT (the LSU moves 128 B per clock): this form moves 88 wavefronts per row
-//          pair where three radix-8/8/4 passes move 170, about the time the packed FP32 work needs (92 clocks).
+//   angle: with only V <= 32 of the 256 inputs non-zero, bin i = b + 8a is a 32-point DFT of the inputs twiddled by w_256^{pb}:
+//              M[b + 8a] = sum_{s<8} w_8^{s k2} [ w_32^{s k1} sum_{m<4} w_4^{m k1} ( (-1)^p w_256^{p b} x_p ) ],   p = s + 8m, a = k1 + 4 k2.
+//          Lane (bq, s) loads its 4 inputs once, and for b = bq and bq + 4 twiddles them, runs the 4-point DFT in registers and
+//          applies w_32^{s k1}; ONE exchange through shared memory (8 float4 out, 8 in, conflict-free both ways); lane (b, k1)
+//          finishes with one 8-point DFT over s and owns bins lane + 32 k2 -- every store instruction of the warp is one
+//          full 128-byte line.  The exchange is what bounds a shared-memory FFT (the LSU moves 128 B per clock): this form
+//          moves 96 wavefronts per row pair (16 in, 64 exchange, 16 out) where three radix-8/8/4 passes move 170, about the time
+//          the packed FP32 work needs (~80 clocks).
 // Same float32 arithmetic class as the oracle's radix-2 FFTs, not their rounding (map criterion 1e-4 of the peak).
 #pragma once
 #include "jrc_common.cuh"
@@ -128,15 +129,12 @@ __global__ void __launch_bounds__(SliceGeom::THREADS, 1) k_slice256(const SliceP
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
     const int V = P.V, IR = P.IR, Nr = N * IR;
 
-    // per-lane twiddles, forward sign, kept for the whole kernel: w_32^{(lane & 3) k} (range pass 2 and the angle stage)
-    float2 t2r[7], t2i[7];
-#pragma unroll
-    for (int k = 1; k < 8; k++) {
-        const c32 b = __ldg(P.tw256 + ((8 * (lane & 3) * k) & 255));
-        t2r[k - 1] = mk(b.x, b.x); t2i[k - 1] = mk(b.y, b.y);
-    }
     float4 *X = Xw + warp * ROW;
-    const int ab = lane >> 2, as = lane & 3;        // angle stage: lane = (b, s) before the exchange, (b, kq) after it
+    // angle stage: before the exchange lane = (bq, s): inputs p = s + 8m, angle sub-bins b = bq and bq + 4;
+    //              after it     lane = (b, k1) = (lane & 7, lane >> 3)
+    const int abq = lane >> 3, as8 = lane & 7;
+    const int xw0 = ((abq << 2) << 3) + ((as8 + abq) & 7), xw1 = (((abq + 4) << 2) << 3) + ((as8 + abq + 4) & 7);   // U[b][k1][(s + b) & 7]
+    const int xr0 = ((((lane & 7) << 2) | (lane >> 3)) << 3);
 
     const int units_per_cpi = IR >> 1;
     const long long n_units = (long long)P.n_cpi * units_per_cpi;
@@ -149,11 +147,12 @@ __global__ void __launch_bounds__(SliceGeom::THREADS, 1) k_slice256(const SliceP
         }
         __syncthreads();      // (also: the previous unit's angle stage has finished reading Ys)
         // ---- range stage: channel p -> Ys[p], two slices at once ----
-        float2 t1r[7], t1i[7];                      // pass 1: w_256^{lane k}
+        float2 t1r[7], t1i[7], t2r[7], t2i[7];      // pass 1: w_256^{lane k}, pass 2: w_32^{(lane & 3) k}
 #pragma unroll
         for (int k = 1; k < 8; k++) {
-            const c32 a = __ldg(P.tw256 + ((lane * k) & 255));
+            const c32 a = __ldg(P.tw256 + ((lane * k) & 255)), b = __ldg(P.tw256 + ((8 * (lane & 3) * k) & 255));
             t1r[k - 1] = mk(a.x, a.x); t1i[k - 1] = mk(a.y, a.y);
+            t2r[k - 1] = mk(b.x, b.x); t2i[k - 1] = mk(b.y, b.y);
         }
         for (int p = warp; p < V; p += Gm::WARPS) {
             float4 *Y = Ys + p * PITCH;
@@ -193,12 +192,19 @@ __global__ void __launch_bounds__(SliceGeom::THREADS, 1) k_slice256(const SliceP
         }
         __syncthreads();
         // ---- angle stage: range positions pos -> map rows (n, n + 1), n = q0 + IR * dif_freq(pos) ----
-        float2 a1r[8], a1i[8];                      // (-1)^p w_256^{p b}, p = s + 4m: the fftshift is the sign
+        float2 a1r[2][4], a1i[2][4], w2r[3], w2i[3];      // (-1)^p w_256^{p b} (the fftshift is the sign), w_32^{s k1}
 #pragma unroll
-        for (int m = 0; m < 8; m++) {
-            const c32 a = __ldg(P.tw256 + (((as + 4 * m) * ab) & 255));
-            const float sg = (as & 1) ? -1.f : 1.f;
-            a1r[m] = mk(sg * a.x, sg * a.x); a1i[m] = mk(sg * a.y, sg * a.y);
+        for (int bi = 0; bi < 2; bi++)
+#pragma unroll
+            for (int m = 0; m < 4; m++) {
+                const c32 a = __ldg(P.tw256 + (((as8 + 8 * m) * (abq + 4 * bi)) & 255));
+                const float sg = (as8 & 1) ? -1.f : 1.f;
+                a1r[bi][m] = mk(sg * a.x, sg * a.x); a1i[bi][m] = mk(sg * a.y, sg * a.y);
+            }
+#pragma unroll
+        for (int k = 1; k < 4; k++) {
+            const c32 a = __ldg(P.tw256 + ((8 * as8 * k) & 255));
+            w2r[k - 1] = mk(a.x, a.x); w2i[k - 1] = mk(a.y, a.y);
         }
         float best = -1.f, sec_t = -1.f;
         int best_row = 0;
@@ -207,46 +213,47 @@ __global__ void __launch_bounds__(SliceGeom::THREADS, 1) k_slice256(const SliceP
             const int n = q0 + IR * m;
             float2 re[8], im[8];
             {
-                const float4 *yp = Ys + as * PITCH + fpad(pos);
+                const float4 *yp = Ys + as8 * PITCH + fpad(pos);
+                float4 x[4];
 #pragma unroll
-                for (int mm = 0; mm < 8; mm++) {          // 4 distinct addresses per load (broadcast over b): one wavefront
-                    const float4 x = yp[4 * mm * PITCH];
-                    re[mm] = mk(x.x, x.y); im[mm] = mk(x.z, x.w);
-                    cmul2(re[mm], im[mm], a1r[mm], a1i[mm]);
+                for (int mm = 0; mm < 4; mm++) x[mm] = yp[8 * mm * PITCH];      // 8 distinct rows per quarter warp: one wavefront each
+#pragma unroll
+                for (int bi = 0; bi < 2; bi++) {
+                    float2 *r4 = re + 4 * bi, *i4 = im + 4 * bi;
+#pragma unroll
+                    for (int mm = 0; mm < 4; mm++) {
+                        r4[mm] = mk(x[mm].x, x[mm].y); i4[mm] = mk(x[mm].z, x[mm].w);
+                        cmul2(r4[mm], i4[mm], a1r[bi][mm], a1i[bi][mm]);
+                    }
+                    fft4s<-1>(r4[0], r4[1], r4[2], r4[3], i4[0], i4[1], i4[2], i4[3]);
+#pragma unroll
+                    for (int k = 1; k < 4; k++) cmul2(r4[k], i4[k], w2r[k - 1], w2i[k - 1]);
+                    float4 *ub = X + (bi ? xw1 : xw0);
+#pragma unroll
+                    for (int k = 0; k < 4; k++) ub[k << 3] = make_float4(r4[k].x, r4[k].y, i4[k].x, i4[k].y);
                 }
-            }
-            fft8s<-1>(re, im);
-#pragma unroll
-            for (int k = 1; k < 8; k++) cmul2(re[k], im[k], t2r[k - 1], t2i[k - 1]);
-            {
-                float4 *ub = X + 36 * ab + 9 * as;        // U[b][s][k1]: pitches 36 / 9 keep the stores AND the loads below conflict-free
-#pragma unroll
-                for (int k = 0; k < 8; k++) ub[k] = make_float4(re[k].x, re[k].y, im[k].x, im[k].y);
             }
             __syncwarp();
             {
-                const float4 *ub = X + 36 * ab + as;      // k1 = kq + 4w, kq = lane & 3
+                const float4 *ub = X + xr0;
 #pragma unroll
-                for (int w = 0; w < 2; w++)
-#pragma unroll
-                    for (int sp = 0; sp < 4; sp++) {
-                        const float4 u = ub[9 * sp + 4 * w];
-                        re[4 * w + sp] = mk(u.x, u.y); im[4 * w + sp] = mk(u.z, u.w);
-                    }
+                for (int sp = 0; sp < 8; sp++) {
+                    const float4 u = ub[(sp + lane) & 7];
+                    re[sp] = mk(u.x, u.y); im[sp] = mk(u.z, u.w);
+                }
             }
             __syncwarp();      // the row buffer is free for the next position
-            fft4s<-1>(re[0], re[1], re[2], re[3], im[0], im[1], im[2], im[3]);
-            fft4s<-1>(re[4], re[5], re[6], re[7], im[4], im[5], im[6], im[7]);
+            fft8s<-1>(re, im);
             float2 v[8];
 #pragma unroll
             for (int c = 0; c < 8; c++) v[c] = __ffma2_rn(im[c], im[c], __fmul2_rn(re[c], re[c]));
             if (P.map) {
-                // v[4w + k2] is angle bin b + 8 kq + 32 w + 64 k2 = lane-contiguous: one 128-byte line per store instruction
-                float *mp = P.map + ((long long)cpi * Nr + n) * NA + ab + 8 * as;
+                // v[k2] is angle bin lane + 32 k2: one 128-byte line per store instruction
+                float *mp = P.map + ((long long)cpi * Nr + n) * NA + lane;
 #pragma unroll
                 for (int c = 0; c < 8; c++) {
-                    __stcs(mp + 32 * (c >> 2) + 64 * (c & 3), v[c].x);
-                    __stcs(mp + NA + 32 * (c >> 2) + 64 * (c & 3), v[c].y);
+                    __stcs(mp + 32 * c, v[c].x);
+                    __stcs(mp + NA + 32 * c, v[c].y);
                 }
             }
             const float ma = fmaxf(fmaxf(fmaxf(v[0].x, v[1].x), fmaxf(v[2].x, v[3].x)), fmaxf(fmaxf(v[4].x, v[5].x), fmaxf(v[6].x, v[7].x)));
