@@ -140,13 +140,6 @@ __global__ void __launch_bounds__(SliceGeom::THREADS, 1) k_slice256(const SliceP
     const long long n_units = (long long)P.n_cpi * units_per_cpi;
     for (long long unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
         const int cpi = (int)(unit / units_per_cpi), q0 = 2 * (int)(unit % units_per_cpi);
-        // channel estimates of this warp's first channel: in flight while the twiddle table is built
-        c32 hn[8];
-        if (warp < V) {
-            const c32 *Hp = P.H + ((long long)cpi * V + warp) * N + lane;
-#pragma unroll
-            for (int m = 0; m < 8; m++) hn[m] = __ldcg(Hp + 32 * m);
-        }
         // ---- slice twiddles of this unit ----
         for (int k = tid; k < N; k += Gm::THREADS) {
             const c32 a = __ldg(P.tw_range + (((long long)k * q0) % Nr)), b = __ldg(P.tw_range + (((long long)k * (q0 + 1)) % Nr));
@@ -163,15 +156,11 @@ __global__ void __launch_bounds__(SliceGeom::THREADS, 1) k_slice256(const SliceP
         }
         for (int p = warp; p < V; p += Gm::WARPS) {
             float4 *Y = Ys + p * PITCH;
+            const c32 *Hp = P.H + ((long long)cpi * V + p) * N + lane;
             float2 re[8], im[8];
             c32 h[8];
 #pragma unroll
-            for (int m = 0; m < 8; m++) h[m] = hn[m];
-            if (p + Gm::WARPS < V) {
-                const c32 *Hp = P.H + ((long long)cpi * V + p + Gm::WARPS) * N + lane;
-#pragma unroll
-                for (int m = 0; m < 8; m++) hn[m] = __ldcg(Hp + 32 * m);
-            }
+            for (int m = 0; m < 8; m++) h[m] = __ldcg(Hp + 32 * m);
 #pragma unroll
             for (int m = 0; m < 8; m++) {
                 const float4 s = Sl[lane + 32 * m];
@@ -219,25 +208,15 @@ __global__ void __launch_bounds__(SliceGeom::THREADS, 1) k_slice256(const SliceP
         }
         float best = -1.f, sec_t = -1.f;
         int best_row = 0;
-        float4 xn[4];                                   // inputs of the next position, loaded one iteration ahead
-        {
-            const float4 *yp = Ys + as8 * PITCH + fpad(warp);
-#pragma unroll
-            for (int mm = 0; mm < 4; mm++) xn[mm] = yp[8 * mm * PITCH];
-        }
         for (int pos = warp; pos < N; pos += Gm::WARPS) {
             const int m = (pos >> 5) | (((pos >> 2) & 7) << 3) | ((pos & 3) << 6);       // dif_freq<8>(pos)
             const int n = q0 + IR * m;
             float2 re[8], im[8];
             {
+                const float4 *yp = Ys + as8 * PITCH + fpad(pos);
                 float4 x[4];
 #pragma unroll
-                for (int mm = 0; mm < 4; mm++) x[mm] = xn[mm];
-                if (pos + Gm::WARPS < N) {
-                    const float4 *yp = Ys + as8 * PITCH + fpad(pos + Gm::WARPS);
-#pragma unroll
-                    for (int mm = 0; mm < 4; mm++) xn[mm] = yp[8 * mm * PITCH];      // 8 distinct rows per quarter warp: one wavefront each
-                }
+                for (int mm = 0; mm < 4; mm++) x[mm] = yp[8 * mm * PITCH];      // 8 distinct rows per quarter warp: one wavefront each
 #pragma unroll
                 for (int bi = 0; bi < 2; bi++) {
                     float2 *r4 = re + 4 * bi, *i4 = im + 4 * bi;
