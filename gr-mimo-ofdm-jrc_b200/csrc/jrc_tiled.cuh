@@ -415,14 +415,16 @@ __global__ void __launch_bounds__(128) k_map_finalize(const float *__restrict__ 
     extern __shared__ float s_abins[];     // angle_bins copy: the window geometry's binary search stays on chip
     __shared__ int s_istar[4], s_ncand[4];
     __shared__ double s_acc[4];
-    for (int i = threadIdx.x; i < NA; i += blockDim.x) s_abins[i] = P.angle_bins[i];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int cpi = blockIdx.x;            // one CTA per CPI: the window reads are latency bound
+    if (cpi >= n_cpi) return;
+    // the key, the runner-up and the angle axis are independent loads: one round trip
+    const unsigned long long key = __ldcg(keys + cpi);
+    const unsigned sec_bits = __ldcg(sec + cpi);
+    for (int i = tid; i < NA; i += blockDim.x) s_abins[i] = P.angle_bins[i];
     __syncthreads();
     EstParams est = P;
     est.angle_bins = s_abins;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int cpi = blockIdx.x;            // one CTA per CPI: the window reads are latency bound, 128 lanes keep 1024 in flight
-    if (cpi >= n_cpi) return;
-    const unsigned long long key = keys[cpi];
     if (key == 0ull) {   // NaN-only input: nothing can win the strict '>' scan
         if (tid == 0) {
             DetDev d; d.range_idx = -1; d.angle_idx = -1; d.peak_power = -1.f;
@@ -456,10 +458,10 @@ __global__ void __launch_bounds__(128) k_map_finalize(const float *__restrict__ 
     const int ncols = w.end_a - w.start_a, nrows = w.end_r - w.start_r;
     const int total = (ncols > 0 && nrows > 0) ? nrows * ncols : 0;
     double acc = 0.0;
-    for (int j0 = tid; j0 < total; j0 += 128 * 8) {      // 8 independent loads in flight per lane
-        float v[8];
+    for (int j0 = tid; j0 < total; j0 += 128 * 16) {     // 16 independent loads in flight per lane
+        float v[16];
 #pragma unroll
-        for (int q = 0; q < 8; q++) {
+        for (int q = 0; q < 16; q++) {
             const int j = j0 + 128 * q;
             v[q] = 0.f;
             if (j < total) {
@@ -469,7 +471,7 @@ __global__ void __launch_bounds__(128) k_map_finalize(const float *__restrict__ 
             }
         }
 #pragma unroll
-        for (int q = 0; q < 8; q++) acc += (double)v[q];
+        for (int q = 0; q < 16; q++) acc += (double)v[q];
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
@@ -483,7 +485,7 @@ __global__ void __launch_bounds__(128) k_map_finalize(const float *__restrict__ 
         d.snr_db = snr_db_fast(d.peak_power, d.noise_power);
         d.flags = (d.snr_db >= P.snr_threshold && d.peak_power >= P.power_threshold) ? DET_PASSED : 0u;
         // decisions that FFT rounding could turn are not taken here (jrc_exact.cuh)
-        if (ncand > 1 || __uint_as_float(sec[cpi]) >= thr_amb) d.flags |= DET_PENDING | DET_AMB;
+        if (ncand > 1 || __uint_as_float(sec_bits) >= thr_amb) d.flags |= DET_PENDING | DET_AMB;
         if (gate_is_marginal(d.peak_power, d.noise_power, d.snr_db, total, P.snr_threshold, P.power_threshold))
             d.flags |= DET_PENDING | DET_GATE;
         d.cpi = cpi0 + cpi;
