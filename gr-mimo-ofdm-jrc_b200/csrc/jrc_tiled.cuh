@@ -207,6 +207,66 @@ __device__ __forceinline__ void dif_passes(c32 *x, int t, const TW &T, c32 (&out
     }
 }
 
+// The passes between the first and the last one for ROWS independent rows that all threads of the CTA work on (thread t
+// of every row): the rows are walked inside each pass, so one barrier per pass serves all of them and a thread has ROWS
+// independent load -> DFT -> store chains to overlap.  x0: first row, rs: row pitch.  Ends with a barrier.
+template <int LOG2N, int DIR, int ROWS, class TW>
+__device__ __forceinline__ void dif_mid_passes_rows(c32 *x0, int rs, int t, const TW &T)
+{
+    int log2L = LOG2N - 3;
+#pragma unroll
+    for (int i = 1; i < TiledGeom<LOG2N>::NTW; i++, log2L -= 3) {
+        const int s = 1 << (log2L - 3);
+        const int j = t & (s - 1), base = ((t >> (log2L - 3)) << log2L) + j;
+#pragma unroll
+        for (int r = 0; r < ROWS; r++) {
+            c32 *xb = x0 + r * rs + fpad(base);
+            c32 u[8];
+#pragma unroll
+            for (int m = 0; m < 8; m++) u[m] = xb[fpad_step(m, s)];
+            JRC_FFT8<DIR>(u);
+#pragma unroll
+            for (int k = 1; k < 8; k++) u[k] = cmul_fma(u[k], T.get(i, k));
+#pragma unroll
+            for (int k = 0; k < 8; k++) xb[fpad_step(k, s)] = u[k];
+        }
+        __syncthreads();
+    }
+}
+
+// The last pass of one row (8 consecutive points 8t .. 8t+7 -> frequencies dif_freq(8t + c)); no synchronisation.
+template <int LOG2N, int DIR>
+__device__ __forceinline__ void dif_last_pass(const c32 *x, int t, c32 (&out)[8])
+{
+    constexpr int NTW = TiledGeom<LOG2N>::NTW;
+    constexpr int log2L = LOG2N - 3 * NTW;
+    const c32 *xb = x + 9 * t;
+#pragma unroll
+    for (int m = 0; m < 8; m++) out[m] = xb[m];
+    if (log2L == 3) {
+        JRC_FFT8<DIR>(out);
+    } else if (log2L == 2) {
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const c32 a = out[4 * h], b = out[4 * h + 1], c = out[4 * h + 2], d = out[4 * h + 3];
+            const c32 s0 = __fadd2_rn(a, c), s1 = __fadd2_rn(a, mk(-c.x, -c.y)), s2 = __fadd2_rn(b, d);
+            const c32 s3 = __fadd2_rn(b, mk(-d.x, -d.y));
+            const c32 r3 = DIR < 0 ? mk(s3.y, -s3.x) : mk(-s3.y, s3.x);
+            out[4 * h] = __fadd2_rn(s0, s2);
+            out[4 * h + 2] = __fadd2_rn(s0, mk(-s2.x, -s2.y));
+            out[4 * h + 1] = __fadd2_rn(s1, r3);
+            out[4 * h + 3] = __fadd2_rn(s1, mk(-r3.x, -r3.y));
+        }
+    } else {
+#pragma unroll
+        for (int h = 0; h < 4; h++) {
+            const c32 a = out[2 * h], b = out[2 * h + 1];
+            out[2 * h] = __fadd2_rn(a, b);
+            out[2 * h + 1] = __fadd2_rn(a, mk(-b.x, -b.y));
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------
 // range IFFT: row r reads n_in samples at in + r*in_stride (the rest of the N-point input is zero) and
 // writes N samples at out + r*N, natural order.

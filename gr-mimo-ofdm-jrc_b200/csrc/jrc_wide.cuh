@@ -206,11 +206,13 @@ __global__ void __launch_bounds__(TiledGeom<LOG2N>::THREADS, 2) k_wide_range_mag
             dif_first_full<LOG2N, 1>(rowbuf + r * RROW, t, u, Tw);
         }
         __syncthreads();
+        // the middle passes of all AB rows share their barriers; the last pass leaves the results in registers
+        dif_mid_passes_rows<LOG2N, 1, AB>(rowbuf, RROW, t, Tw);
         float v[8][AB];                        // |.|^2 at this thread's 8 range bins, all AB angle bins
 #pragma unroll
         for (int r = 0; r < AB; r++) {
             c32 o[8];
-            dif_passes<LOG2N, 1, false, true>(rowbuf + r * RROW, t, Tw, o);
+            dif_last_pass<LOG2N, 1>(rowbuf + r * RROW, t, o);
 #pragma unroll
             for (int c = 0; c < 8; c++) {
                 const c32 sq = __fmul2_rn(o[c], o[c]);
