@@ -508,7 +508,7 @@ static jrc_status launch_wide(jrc_chain *h, PortDev rx, PortDev tx, const c32 *H
     CU(cudaFuncSetAttribute(ka, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Gm::SMEM_A));
     CU(cudaFuncSetAttribute(kb, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Gm::SMEM_B));
     long long ua = (long long)n_cpi * (Gm::N / Gm::KB), ub = (long long)n_cpi * (Gm::V / Gm::AB);
-    long long ga = ua < h->sm_count ? ua : h->sm_count, gb = ub < 2LL * h->sm_count ? ub : 2LL * h->sm_count;
+    long long ga = ua < h->sm_count ? ua : h->sm_count, gb = ub < 3LL * h->sm_count ? ub : 3LL * h->sm_count;
     ka<<<(unsigned)ga, Gm::TA, Gm::SMEM_A, h->stream>>>(P);
     CU(cudaGetLastError());
     kb<<<(unsigned)gb, Gm::GR::THREADS, Gm::SMEM_B, h->stream>>>(P);
@@ -869,9 +869,11 @@ static jrc_status run_batch_impl(jrc_chain *h, jrc_port_layout rx, jrc_port_layo
         if (chunk > n_cpi) chunk = n_cpi;
         const bool slice = slice_config_ok(h);
         const bool wide = wide_config_ok(h);
-        // the wide kernels hand G (2 MiB per CPI) from one to the other through the L2: 18 CPIs = 36 MiB per round, and
-        // 18 x 16 angle-bin blocks fill the 148 SMs twice
-        const int wide_round = 18;
+        // the wide kernels hand G (2 MiB per CPI) from one to the other through the L2: 27 CPIs = 54 MiB per round, and
+        // 27 x 32 angle-bin blocks fill the 3 x 148 CTA slots of k_wide_range_mag twice (measured: 13 / 18 / 27 / 36 CPIs per
+        // round -> 264 / 265 / 305 / 295 k CPI/s)
+        static const int wide_round_env = getenv("JRC_WIDE_ROUND") ? atoi(getenv("JRC_WIDE_ROUND")) : 0;
+        const int wide_round = wide_round_env > 0 ? wide_round_env : 27;
         if (wide) {
             const bool need_h = bg || recording;
             if (need_h) ST(h->sH.need((size_t)chunk * V * N * sizeof(c32)));

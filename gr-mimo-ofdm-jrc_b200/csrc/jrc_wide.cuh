@@ -181,7 +181,7 @@ __global__ void __launch_bounds__(WideGeom<LOG2N>::TA, 1) k_wide_mac_angle(const
 // range IFFT + |.|^2 + arg-max partials, one (CPI, 8 angle bins) at a time
 // ---------------------------------------------------------------------------
 template <int LOG2N>
-__global__ void __launch_bounds__(TiledGeom<LOG2N>::THREADS, 2) k_wide_range_mag(const WideParams P)
+__global__ void __launch_bounds__(TiledGeom<LOG2N>::THREADS, 3) k_wide_range_mag(const WideParams P)
 {
     using Gm = WideGeom<LOG2N>;
     using GR = typename Gm::GR;
