@@ -97,16 +97,19 @@ struct GrowBuf {   // grow-only device / pinned-host buffer
 
 enum { JRC_STREAM_DEPTH = 4 };
 struct jrc_stream_state;
+struct jrc_fused_state;
 
 struct jrc_chain {
     jrc_chain_cfg cfg;
     jrc_stream_state *sstate = nullptr;         // jrc_chain_submit / jrc_chain_wait slots, created on first use
+    jrc_fused_state *fstate = nullptr;          // jrc_radar_estimate_fused ring, created on first use
     int V = 0, Nr = 0, Na = 0;
     int sm_count = 0;
     cudaStream_t stream = nullptr, s_h2d = nullptr, s_d2h = nullptr;
     cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
     // estimator
     bool est_set = false;
+    int est_epoch = 0;                          // bumped by every estimator / threshold change (captured graphs bake them in)
     std::vector<float> range_bins, angle_bins;
     float nd_range_m = 0, nd_angle_deg = 0, snr_thr = 0, pow_thr = 0;
     std::map<std::pair<int, int>, double2 *> dft_tabs;    // (n, forward) -> cos/sin table of k_dft_any
@@ -159,6 +162,7 @@ static jrc_status get_twiddles(jrc_chain *h, int n, int forward, const c32 **out
 
 extern "C" void jrc_chain_destroy(jrc_chain *h);
 static void stream_state_destroy(jrc_chain *h);
+static void fused_state_destroy(jrc_chain *h);
 struct GrowBuf;
 static jrc_status stream_stats(jrc_chain *h, const std::function<jrc_status(const GrowBuf &)> &add);
 
@@ -225,6 +229,7 @@ extern "C" void jrc_chain_destroy(jrc_chain *h)
     cudaSetDevice(h->cfg.device);
     cudaDeviceSynchronize();
     stream_state_destroy(h);
+    fused_state_destroy(h);
     for (auto &kv : h->twiddles) cudaFree(kv.second);
     GrowBuf *bufs[] = {&h->sH, &h->sY, &h->sC, &h->sKeys, &h->sSec, &h->sFix, &h->sExact, &h->sDet, &h->sIn[0], &h->sIn[1], &h->sMap[0], &h->sMap[1],
                        &h->sDets[0], &h->sDets[1], &h->sMisc, &h->sMisc2, &h->pin_a, &h->pin_b};
@@ -292,6 +297,7 @@ extern "C" jrc_status jrc_chain_set_estimator(jrc_chain *h, const float *range_b
     h->angle_bins.assign(angle_bins, angle_bins + n_angle);
     h->nd_range_m = noise_discard_range_m; h->nd_angle_deg = noise_discard_angle_deg;
     h->snr_thr = snr_threshold; h->pow_thr = power_threshold;
+    h->est_epoch++;
     if (h->d_angle_bins) { cudaFree(h->d_angle_bins); h->d_angle_bins = nullptr; }
     CU(cudaMalloc(&h->d_angle_bins, sizeof(float) * (size_t)n_angle));
     CU(cudaMemcpyAsync(h->d_angle_bins, angle_bins, sizeof(float) * (size_t)n_angle, cudaMemcpyHostToDevice, h->stream));
@@ -315,6 +321,7 @@ extern "C" jrc_status jrc_chain_set_thresholds(jrc_chain *h, float snr_threshold
 {
     if (!h) return fail(JRC_ERR_INVALID, "null handle");
     h->snr_thr = snr_threshold; h->pow_thr = power_threshold;
+    h->est_epoch++;
     return JRC_OK;
 }
 extern "C" jrc_status jrc_chain_set_background_record(jrc_chain *h, int32_t on)
@@ -1537,35 +1544,255 @@ struct Staging {   // maps caller pointers onto device memory for the duration o
     }
 };
 
-extern "C" jrc_status jrc_radar_estimate(jrc_chain *h, const jrc_c32 *const *tx, const jrc_c32 *const *rx,
-                                          size_t tx_skip_items, jrc_c32 *out, jrc_c32 *chan_est_host)
+// ---- fused mode for an unmodified flowgraph: ring of results keyed by CPI sequence number -------------------
+struct FusedEntry {
+    std::atomic<int64_t> seq{-1};        // -1 while the device may be writing the entry
+    cudaEvent_t done = nullptr;          // everything of the entry is on the host
+    cudaEvent_t t_done = nullptr;        // the transposed array is (the estimator's reference-order noise sum is one
+                                         // thread's work and takes longer than everything before it)
+    c32 *T = nullptr;                    // page-locked [Nr][Na]
+    DetDev *det = nullptr;               // page-locked
+    cudaGraphExec_t graph = nullptr;     // the rest of the chain into THIS entry, captured once: up to the transposed array
+    cudaGraphExec_t graph2 = nullptr;    // ... and from there to the detection record
+    int epoch = -1;
+};
+struct jrc_fused_state {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t h_ready = nullptr;
+    cudaEvent_t last_done = nullptr;     // the previous frame's continuation (it reads the estimate the next call overwrites)
+    FusedEntry e[JRC_FUSED_RING];
+    int64_t next_seq = 0;
+    GrowBuf dT, dDet;
+};
+
+static jrc_status fused_state(jrc_chain *h, jrc_fused_state **out)
+{
+    if (!h->fstate) {
+        jrc_fused_state *F = new jrc_fused_state();
+        h->fstate = F;
+        CU(cudaStreamCreateWithFlags(&F->stream, cudaStreamNonBlocking));
+        CU(cudaEventCreateWithFlags(&F->h_ready, cudaEventDisableTiming));
+        const size_t cells = (size_t)h->Nr * h->Na;
+        for (FusedEntry &e : F->e) {
+            CU(cudaEventCreateWithFlags(&e.done, cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&e.t_done, cudaEventDisableTiming));
+            CU(cudaMallocHost(&e.T, cells * sizeof(c32)));
+            CU(cudaMallocHost(&e.det, sizeof(DetDev)));
+        }
+    }
+    *out = h->fstate;
+    return JRC_OK;
+}
+
+static void fused_state_destroy(jrc_chain *h)
+{
+    jrc_fused_state *F = h->fstate;
+    if (!F) return;
+    if (F->stream) { cudaStreamSynchronize(F->stream); cudaStreamDestroy(F->stream); }
+    if (F->h_ready) cudaEventDestroy(F->h_ready);
+    for (FusedEntry &e : F->e) {
+        if (e.graph) cudaGraphExecDestroy(e.graph);
+        if (e.graph2) cudaGraphExecDestroy(e.graph2);
+        if (e.done) cudaEventDestroy(e.done);
+        if (e.t_done) cudaEventDestroy(e.t_done);
+        if (e.T) cudaFreeHost(e.T);
+        if (e.det) cudaFreeHost(e.det);
+    }
+    F->dT.release();
+    F->dDet.release();
+    delete F;
+    h->fstate = nullptr;
+}
+
+static jrc_status radar_estimate_impl(jrc_chain *h, const jrc_c32 *const *tx, const jrc_c32 *const *rx, size_t tx_skip_items,
+                                      jrc_c32 *out, jrc_c32 *chan_est_host, int64_t *cpi_seq)
 {
     if (!h || !tx || !rx || !out) return fail(JRC_ERR_INVALID, "null argument");
     CU(cudaSetDevice(h->cfg.device));
     const jrc_chain_cfg &c = h->cfg;
-    const int N = c.fft_len, V = h->V, Nr = h->Nr;
+    const int N = c.fft_len, V = h->V, Nr = h->Nr, Na = h->Na;
+    jrc_fused_state *F = nullptr;
+    FusedEntry *fused_entry_pending = nullptr;
+    int64_t fused_seq = -1;
+    if (cpi_seq) {
+        if (!h->est_set) return fail(JRC_ERR_STATE, "fused mode needs jrc_chain_set_estimator on this handle");
+        if (!is_pow2(Nr) || !is_pow2(Na) || Nr > 16384 || Na > 16384)
+            return fail(JRC_ERR_INVALID, "the FFT chain needs power-of-two Nr=%d / Na=%d <= 16384", Nr, Na);
+        ST(fused_state(h, &F));
+        if (F->last_done) CU(cudaStreamWaitEvent(h->stream, F->last_done, 0));
+    }
     const size_t frame = (size_t)(c.n_pre + c.n_sym) * N;   // items actually read per port
     Staging sg(h);
     // gather the per-port packets into one device block [T+R][frame]
     ST(h->sMisc.need((size_t)(c.n_tx + c.n_rx) * frame * sizeof(c32)));
     c32 *blk = (c32 *)h->sMisc.p;
-    for (int t = 0; t < c.n_tx; t++) {
-        const jrc_c32 *src = tx[t] + tx_skip_items * (size_t)N;    // lib/mimo_ofdm_radar_impl.cc:260
-        CU(cudaMemcpyAsync(blk + (size_t)t * frame, src, frame * sizeof(c32), cudaMemcpyDefault, h->stream));
+    const bool host_in = !ptr_is_device(tx[0]) && !ptr_is_device(rx[0]);
+    if (host_in) {
+        // stream buffers of the scheduler (pageable): one packed page-locked block instead of a driver-staged copy per
+        // port; the estimate kernel reads it in place over PCIe (27 KiB, each sample once) unless JRC_ZEROCOPY=0
+        const size_t bytes = (size_t)(c.n_tx + c.n_rx) * frame * sizeof(c32);
+        ST(h->pin_a.need(bytes));
+        c32 *pk = (c32 *)h->pin_a.p;
+        for (int t = 0; t < c.n_tx; t++)
+            memcpy(pk + (size_t)t * frame, tx[t] + tx_skip_items * (size_t)N, frame * sizeof(c32));   // lib/mimo_ofdm_radar_impl.cc:260
+        for (int r = 0; r < c.n_rx; r++) memcpy(pk + (size_t)(c.n_tx + r) * frame, rx[r], frame * sizeof(c32));
+        c32 *alias = h->zero_copy ? (c32 *)host_dev_alias(pk) : nullptr;
+        if (alias) blk = alias;
+        else CU(cudaMemcpyAsync(blk, pk, bytes, cudaMemcpyHostToDevice, h->stream));
+    } else {
+        for (int t = 0; t < c.n_tx; t++) {
+            const jrc_c32 *src = tx[t] + tx_skip_items * (size_t)N;
+            CU(cudaMemcpyAsync(blk + (size_t)t * frame, src, frame * sizeof(c32), cudaMemcpyDefault, h->stream));
+        }
+        for (int r = 0; r < c.n_rx; r++)
+            CU(cudaMemcpyAsync(blk + (size_t)(c.n_tx + r) * frame, rx[r], frame * sizeof(c32), cudaMemcpyDefault, h->stream));
     }
-    for (int r = 0; r < c.n_rx; r++)
-        CU(cudaMemcpyAsync(blk + (size_t)(c.n_tx + r) * frame, rx[r], frame * sizeof(c32), cudaMemcpyDefault, h->stream));
     PortDev dtx{blk, 0, (long long)frame}, drx{blk + (size_t)c.n_tx * frame, 0, (long long)frame};
     ST(h->sH.need((size_t)V * N * sizeof(c32)));
     c32 *dH = (c32 *)h->sH.p;
     ST(launch_chan_est(h, drx, dtx, 1, dH, c.n_pre));
+    if (F) {
+        // the rest of the chain, in the arithmetic of the separate blocks, behind this call's back: one graph launch
+        // on the second stream (eight nodes: range fft_vcc, transpose, its copy out, angle fft_vcc, estimator, record out)
+        NvtxRange nv("fused mode: range fft, transpose, angle fft, estimator");
+        const int64_t seq = F->next_seq++;
+        FusedEntry &e = F->e[seq % JRC_FUSED_RING];
+        e.seq.store(-1, std::memory_order_release);
+        if (!e.graph || e.epoch != h->est_epoch) {
+            const size_t cells = (size_t)Nr * Na;
+            ST(h->sY.need((size_t)V * Nr * sizeof(c32)));
+            ST(h->sC.need(cells * sizeof(c32)));
+            ST(F->dT.need(cells * sizeof(c32)));
+            ST(F->dDet.need(sizeof(DetDev)));
+            ST(h->sKeys.need(sizeof(unsigned long long)));
+            const c32 *tw = nullptr;
+            ST(get_twiddles(h, Nr, 0, &tw));        // (tables are built on the handle's stream, before the capture)
+            ST(get_twiddles(h, Na, 1, &tw));
+            if (e.graph) { CU(cudaGraphExecDestroy(e.graph)); e.graph = nullptr; }
+            if (e.graph2) { CU(cudaGraphExecDestroy(e.graph2)); e.graph2 = nullptr; }
+            c32 *dY = (c32 *)h->sY.p, *dT = (c32 *)F->dT.p, *dC = (c32 *)h->sC.p;
+            auto capture = [&](cudaGraphExec_t *exec, const std::function<jrc_status()> &body) -> jrc_status {
+                CU(cudaStreamBeginCapture(F->stream, cudaStreamCaptureModeThreadLocal));
+                std::swap(h->stream, F->stream);
+                jrc_status st = body();
+                std::swap(h->stream, F->stream);
+                cudaGraph_t g = nullptr;
+                cudaError_t ce = cudaStreamEndCapture(F->stream, &g);
+                if (st != JRC_OK) { if (g) cudaGraphDestroy(g); return st; }
+                CU(ce);
+                ce = cudaGraphInstantiate(exec, g, 0);
+                cudaGraphDestroy(g);
+                CU(ce);
+                return JRC_OK;
+            };
+            ST(capture(&e.graph, [&]() -> jrc_status {
+                ST(launch_fft_rows(h, dH, N, N, dY, Nr, V, 0, 0));
+                ST(launch_transpose(h, dY, dT, V, Nr, Na, 1));
+                CU(cudaMemcpyAsync(e.T, dT, cells * sizeof(c32), cudaMemcpyDeviceToHost, h->stream));
+                return JRC_OK;
+            }));
+            ST(capture(&e.graph2, [&]() -> jrc_status {
+                ST(launch_fft_rows(h, dT, Na, Na, dC, Na, Nr, 1, 1));
+                ST(launch_estimate(h, dC, Nr, Na, 1, 0, (DetDev *)F->dDet.p));
+                CU(cudaMemcpyAsync(e.det, F->dDet.p, sizeof(DetDev), cudaMemcpyDeviceToHost, h->stream));
+                return JRC_OK;
+            }));
+            e.epoch = h->est_epoch;
+        }
+        fused_entry_pending = &e;
+        fused_seq = seq;
+    }
+    if (fused_entry_pending) {
+        // (queued before this call's own outputs: the device is still busy with the transfer in and the estimate)
+        FusedEntry &e = *fused_entry_pending;
+        CU(cudaEventRecord(F->h_ready, h->stream));
+        CU(cudaStreamWaitEvent(F->stream, F->h_ready, 0));
+        CU(cudaGraphLaunch(e.graph, F->stream));
+        CU(cudaEventRecord(e.t_done, F->stream));
+        CU(cudaGraphLaunch(e.graph2, F->stream));
+        CU(cudaEventRecord(e.done, F->stream));
+        h->launches += 5;
+        F->last_done = e.done;
+        e.seq.store(fused_seq, std::memory_order_release);
+        *cpi_seq = fused_seq;
+    }
+    const size_t out_items = (size_t)V * Nr, est_items = (size_t)V * N;
+    if (!ptr_is_device(out) && !host_ptr_is_pinned(out) && h->zero_copy) {
+        // pageable output (a scheduler buffer): the pad kernel stores the packet, and the estimate behind it, into ONE
+        // page-locked block in place; two host copies after the synchronize instead of two driver-staged transfers
+        ST(h->pin_b.need((out_items + est_items) * sizeof(c32)));
+        c32 *pin = (c32 *)h->pin_b.p, *dpin = (c32 *)host_dev_alias(pin);
+        if (dpin) {
+            k_pad_rows<<<grid_for((long long)out_items, 256, h->sm_count), 256, 0, h->stream>>>(dH, dpin, V, N, Nr,
+                                                                                            chan_est_host ? dpin + out_items : nullptr);
+            CU(cudaGetLastError());
+            h->launches++;
+            CU(cudaStreamSynchronize(h->stream));
+            memcpy(out, pin, out_items * sizeof(c32));
+            if (chan_est_host) memcpy(chan_est_host, pin + out_items, est_items * sizeof(c32));
+            return JRC_OK;
+        }
+    }
     void *dout = nullptr;
-    ST(sg.out(out, (size_t)V * Nr * sizeof(c32), &dout));
-    k_pad_rows<<<grid_for((long long)V * Nr, 256, h->sm_count), 256, 0, h->stream>>>(dH, (c32 *)dout, V, N, Nr);
+    ST(sg.out(out, out_items * sizeof(c32), &dout));
+    k_pad_rows<<<grid_for((long long)out_items, 256, h->sm_count), 256, 0, h->stream>>>(dH, (c32 *)dout, V, N, Nr, nullptr);
     CU(cudaGetLastError());
     h->launches++;
-    if (chan_est_host) CU(cudaMemcpyAsync(chan_est_host, dH, (size_t)V * N * sizeof(c32), cudaMemcpyDeviceToHost, h->stream));
+    if (chan_est_host) CU(cudaMemcpyAsync(chan_est_host, dH, est_items * sizeof(c32), cudaMemcpyDeviceToHost, h->stream));
     return sg.finish();
+}
+
+extern "C" jrc_status jrc_radar_estimate(jrc_chain *h, const jrc_c32 *const *tx, const jrc_c32 *const *rx,
+                                          size_t tx_skip_items, jrc_c32 *out, jrc_c32 *chan_est_host)
+{
+    return radar_estimate_impl(h, tx, rx, tx_skip_items, out, chan_est_host, nullptr);
+}
+
+extern "C" jrc_status jrc_radar_estimate_fused(jrc_chain *h, const jrc_c32 *const *tx, const jrc_c32 *const *rx,
+                                                size_t tx_skip_items, jrc_c32 *out, jrc_c32 *chan_est_host, int64_t *cpi_seq)
+{
+    if (!cpi_seq) return fail(JRC_ERR_INVALID, "null argument");
+    return radar_estimate_impl(h, tx, rx, tx_skip_items, out, chan_est_host, cpi_seq);
+}
+
+// Both fetches run on the downstream blocks' threads while the radar block's thread keeps submitting: an entry is
+// valid for a sequence number if it carries that number before AND after the copy.
+static jrc_status fused_entry(jrc_chain *h, int64_t cpi_seq, bool transposed_only, FusedEntry **out)
+{
+    if (!h) return fail(JRC_ERR_INVALID, "null argument");
+    jrc_fused_state *F = h->fstate;
+    if (!F || cpi_seq < 0) return fail(JRC_ERR_STATE, "CPI %lld is not cached", (long long)cpi_seq);
+    FusedEntry &e = F->e[cpi_seq % JRC_FUSED_RING];
+    if (e.seq.load(std::memory_order_acquire) != cpi_seq) return fail(JRC_ERR_STATE, "CPI %lld is not cached", (long long)cpi_seq);
+    CU(cudaSetDevice(h->cfg.device));
+    CU(cudaEventSynchronize(transposed_only ? e.t_done : e.done));
+    *out = &e;
+    return JRC_OK;
+}
+
+extern "C" jrc_status jrc_fused_fetch_transposed(jrc_chain *h, int64_t cpi_seq, jrc_c32 *out)
+{
+    if (!out) return fail(JRC_ERR_INVALID, "null argument");
+    FusedEntry *e = nullptr;
+    ST(fused_entry(h, cpi_seq, true, &e));
+    memcpy(out, e->T, (size_t)h->Nr * h->Na * sizeof(c32));
+    if (e->seq.load(std::memory_order_acquire) != cpi_seq) return fail(JRC_ERR_STATE, "CPI %lld was overwritten", (long long)cpi_seq);
+    return JRC_OK;
+}
+
+extern "C" jrc_status jrc_fused_fetch_det(jrc_chain *h, int64_t cpi_seq, float snr_threshold, float power_threshold, jrc_det *det)
+{
+    if (!det) return fail(JRC_ERR_INVALID, "null argument");
+    FusedEntry *e = nullptr;
+    ST(fused_entry(h, cpi_seq, false, &e));
+    memcpy(det, e->det, sizeof(DetDev));
+    if (e->seq.load(std::memory_order_acquire) != cpi_seq) return fail(JRC_ERR_STATE, "CPI %lld was overwritten", (long long)cpi_seq);
+    if (det->range_idx >= 0) {
+        // final scalar of lib/range_angle_estimator_impl.cc:227,234 with the host libm, like jrc_estimate2d
+        det->snr_db = 10 * std::log10(det->peak_power / det->noise_power);
+        det->flags = (det->snr_db >= snr_threshold && det->peak_power >= power_threshold) ? JRC_DET_PASSED : 0u;
+    }
+    return JRC_OK;
 }
 
 extern "C" jrc_status jrc_fft_vcc(jrc_chain *h, const jrc_c32 *in, jrc_c32 *out, int32_t n, int32_t batch,

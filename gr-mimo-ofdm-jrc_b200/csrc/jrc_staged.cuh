@@ -125,14 +125,21 @@ __global__ void k_background(c32 *__restrict__ H /* [n_cpi][VN] in: raw, out: su
 }
 
 // zero-padded copy H[cpi][p][0:N] -> out[cpi][p][0:N*interp]  (:243, :312-315)
-__global__ void k_pad_rows(const c32 *__restrict__ H, c32 *__restrict__ out, long long rows, int N, int Nout)
+// (copy, optional: the unpadded rows once more, for the block's capture_radar_data -- :348-370)
+__global__ void k_pad_rows(const c32 *__restrict__ H, c32 *__restrict__ out, long long rows, int N, int Nout,
+                           c32 *__restrict__ copy)
 {
     const long long total = rows * Nout;
     for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total;
          e += (long long)gridDim.x * blockDim.x) {
         int n = (int)(e % Nout);
         long long row = e / Nout;
-        out[e] = (n < N) ? H[row * N + n] : mk(0.f, 0.f);
+        c32 v = mk(0.f, 0.f);
+        if (n < N) {
+            v = H[row * N + n];
+            if (copy) copy[row * N + n] = v;
+        }
+        out[e] = v;
     }
 }
 

@@ -13,6 +13,7 @@
 #include <fstream>
 #include <iomanip>
 #include <iostream>
+#include <memory>
 #include <sstream>
 #include <stdexcept>
 #include <string>
@@ -57,6 +58,80 @@ inline jrc_chain_cfg utility_cfg()
     c.fft_len = 64; c.n_tx = 1; c.n_rx = 1; c.n_sym = 1; c.interp_range = 1; c.interp_angle = 1;
     return c;
 }
+
+// ---- fused mode for an UNMODIFIED flowgraph (JRC_FUSED=1) ---------------------------------------
+// The make() signatures stay the reference's, so no block knows the whole chain: mimo_ofdm_radar has the frame
+// geometry and the range interpolation, matrix_transpose the angle interpolation, range_angle_estimator the bin axes
+// and the noise window.  Each of the three leaves its share here when it is constructed; on its first frame the
+// radar block puts them together, opens ONE handle for the whole chain and from then on runs
+// jrc_radar_estimate_fused(), tagging its packet with the sequence number ("jrc_cpi").  The stock fft_vcc blocks
+// between the three pass the tag along (sync blocks, TPP_ALL_TO_ALL); matrix_transpose and range_angle_estimator
+// fetch their result for that number instead of a device round trip of their own, and fall back to their
+// per-block call whenever the tag or the cached result is missing.
+class fused_session
+{
+    std::mutex d_mu;
+    bool d_have_radar = false, d_have_transpose = false, d_have_estimator = false;
+    jrc_chain_cfg d_radar{};
+    int d_tr_input_len = 0, d_tr_output_len = 0, d_tr_interp = 0;
+    int d_vlen = 0;
+    std::vector<float> d_range_bins, d_angle_bins;
+    float d_nd_range_m = 0, d_nd_angle_deg = 0, d_snr_thr = 0, d_pow_thr = 0;
+    std::weak_ptr<chain_handle> d_chain;
+
+public:
+    static fused_session &get() { static fused_session s; return s; }
+    static bool requested()
+    {
+        const char *e = std::getenv("JRC_FUSED");
+        return e && std::atoi(e) != 0;
+    }
+    static const pmt::pmt_t &tag_key() { static const pmt::pmt_t k = pmt::string_to_symbol("jrc_cpi"); return k; }
+
+    void register_radar(const jrc_chain_cfg &cfg) { std::lock_guard<std::mutex> g(d_mu); d_radar = cfg; d_have_radar = true; }
+    void register_transpose(int input_len, int output_len, int interp)
+    {
+        std::lock_guard<std::mutex> g(d_mu);
+        d_tr_input_len = input_len; d_tr_output_len = output_len; d_tr_interp = interp; d_have_transpose = true;
+    }
+    void register_estimator(int vlen, const std::vector<float> &rb, const std::vector<float> &ab, float nd_range_m,
+                            float nd_angle_deg, float snr_thr, float pow_thr)
+    {
+        std::lock_guard<std::mutex> g(d_mu);
+        d_vlen = vlen; d_range_bins = rb; d_angle_bins = ab; d_nd_range_m = nd_range_m; d_nd_angle_deg = nd_angle_deg;
+        d_snr_thr = snr_thr; d_pow_thr = pow_thr; d_have_estimator = true;
+    }
+
+    // the radar block's first frame: one handle for the whole chain, or nullptr and why
+    std::shared_ptr<chain_handle> open(const jrc_chain_cfg &radar_cfg, const char *who, std::string *why)
+    {
+        std::lock_guard<std::mutex> g(d_mu);
+        const int Nr = radar_cfg.fft_len * radar_cfg.interp_range, V = radar_cfg.n_tx * radar_cfg.n_rx;
+        if (!d_have_transpose || !d_have_estimator) { *why = "no matrix_transpose / range_angle_estimator in this process"; return nullptr; }
+        if (d_tr_input_len != Nr || d_tr_output_len != V) { *why = "matrix_transpose sizes do not continue this block's output"; return nullptr; }
+        const int Na = V * d_tr_interp;
+        if (d_vlen != Na || (int)d_range_bins.size() != Nr || (int)d_angle_bins.size() != Na) {
+            *why = "range_angle_estimator sizes do not continue matrix_transpose's output";
+            return nullptr;
+        }
+        jrc_chain_cfg full = radar_cfg;
+        full.interp_angle = d_tr_interp;
+        auto chain = std::make_shared<chain_handle>(full, who);
+        check(jrc_chain_set_estimator(chain->get(), d_range_bins.data(), Nr, d_angle_bins.data(), Na, d_nd_range_m, d_nd_angle_deg,
+                                      d_snr_thr, d_pow_thr), who);
+        d_chain = chain;
+        return chain;
+    }
+    std::shared_ptr<chain_handle> chain() { std::lock_guard<std::mutex> g(d_mu); return d_chain.lock(); }
+
+    // sequence number on the packet that starts at nitems_read(0), or -1
+    static int64_t packet_seq(gr::block &blk, int n_items)
+    {
+        std::vector<gr::tag_t> tags;
+        blk.get_tags_in_range(tags, 0, blk.nitems_read(0), blk.nitems_read(0) + (uint64_t)n_items, tag_key());
+        return tags.empty() ? -1 : (int64_t)pmt::to_long(tags[0].value);
+    }
+};
 
 // "MM-DD-YYYY HH:MM:SS" and "HH:MM:SS.mmm"
 inline std::string date_time_stamp()

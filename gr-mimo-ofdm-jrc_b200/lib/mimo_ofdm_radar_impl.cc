@@ -31,12 +31,16 @@ mimo_ofdm_radar_impl::mimo_ofdm_radar_impl(int fft_len, int N_tx, int N_rx, int 
       d_fft_len(fft_len), d_N_tx(N_tx), d_N_rx(N_rx), d_N_sym(N_sym), d_N_pre(N_pre), d_interp_factor(interp_factor),
       d_radar_chan_file(radar_chan_file), d_debug(debug), d_chan_est((size_t)N_tx * N_rx * fft_len)
 {
-    jrc_chain_cfg cfg{};
+    jrc_chain_cfg &cfg = d_cfg;
     cfg.fft_len = fft_len; cfg.n_tx = N_tx; cfg.n_rx = N_rx; cfg.n_sym = N_sym; cfg.n_pre = N_pre;
     cfg.interp_range = interp_factor; cfg.interp_angle = 1; cfg.tx_interleave = enable_tx_interleave;
     cfg.background_removal = background_removal; cfg.background_recording = background_recording;
     cfg.record_len = record_len;
-    d_chain.open(cfg, "MIMO OFDM RADAR");
+    d_chain = std::make_shared<host::chain_handle>(cfg, "MIMO OFDM RADAR");
+    if (host::fused_session::requested()) {
+        host::fused_session::get().register_radar(cfg);
+        d_fused_pending = true;
+    }
     set_tag_propagation_policy(TPP_DONT);
     set_output_multiple(N_tx * N_rx);   // one call emits all virtual channels of a frame
 }
@@ -45,7 +49,8 @@ void mimo_ofdm_radar_impl::set_background_record(bool background_recording)
 {
     std::lock_guard<std::mutex> guard(d_lock);
     std::cout << "[MIMO OFDM RADAR] Background recording set to  " << background_recording << std::endl;
-    host::check(jrc_chain_set_background_record(d_chain.get(), background_recording), "MIMO OFDM RADAR");
+    d_cfg.background_recording = background_recording;
+    host::check(jrc_chain_set_background_record(d_chain->get(), background_recording), "MIMO OFDM RADAR");
 }
 
 void mimo_ofdm_radar_impl::capture_radar_data(bool capture_sig)
@@ -93,16 +98,40 @@ int mimo_ofdm_radar_impl::general_work(int noutput_items, gr_vector_int &ninput_
     }
     if (noutput_items < V) return 0;
 
+    if (d_fused_pending) {
+        // first frame: every block of the flowgraph exists by now.  The whole-chain handle replaces this block's own
+        // (no background frame has been recorded yet).
+        d_fused_pending = false;
+        std::string why;
+        if (auto chain = host::fused_session::get().open(d_cfg, "MIMO OFDM RADAR", &why)) {
+            d_chain = chain;
+            d_fused = true;
+            std::cout << "[MIMO OFDM RADAR] JRC_FUSED: one device pass per frame for the three radar blocks" << std::endl;
+        } else {
+            std::cout << "[MIMO OFDM RADAR] JRC_FUSED ignored: " << why << std::endl;
+        }
+    }
+
     std::vector<const jrc_c32 *> tx(d_N_tx), rx(d_N_rx);
     for (int t = 0; t < d_N_tx; t++) tx[t] = static_cast<const jrc_c32 *>(input_items[t]);
     for (int r = 0; r < d_N_rx; r++) rx[r] = static_cast<const jrc_c32 *>(input_items[d_N_tx + r]);
-    host::check(jrc_radar_estimate(d_chain.get(), tx.data(), rx.data(), (size_t)plan.tx_skip_items,
-                                   static_cast<jrc_c32 *>(output_items[0]),
-                                   reinterpret_cast<jrc_c32 *>(d_chan_est.data())),
-                "MIMO OFDM RADAR");
+    int64_t seq = -1;
+    if (d_fused)
+        host::check(jrc_radar_estimate_fused(d_chain->get(), tx.data(), rx.data(), (size_t)plan.tx_skip_items,
+                                             static_cast<jrc_c32 *>(output_items[0]),
+                                             reinterpret_cast<jrc_c32 *>(d_chan_est.data()), &seq),
+                    "MIMO OFDM RADAR");
+    else
+        host::check(jrc_radar_estimate(d_chain->get(), tx.data(), rx.data(), (size_t)plan.tx_skip_items,
+                                       static_cast<jrc_c32 *>(output_items[0]),
+                                       reinterpret_cast<jrc_c32 *>(d_chan_est.data())),
+                    "MIMO OFDM RADAR");
 
     add_item_tag(0, nitems_written(0), pmt::string_to_symbol("packet_len"), pmt::from_long(V),
                  pmt::string_to_symbol(alias()));
+    if (d_fused)
+        add_item_tag(0, nitems_written(0), host::fused_session::tag_key(), pmt::from_long((long)seq),
+                     pmt::string_to_symbol(alias()));
     for (int r = 0; r < d_N_rx; r++) consume(d_N_tx + r, (int)plan.rx_packet_len);
     for (int t = 0; t < d_N_tx; t++) consume(t, (int)(plan.tx_skip_items + plan.tx_packet_len));
     if (d_debug) std::cout << "[MIMO OFDM RADAR] frame done, tx skip " << plan.tx_skip_items << std::endl;

@@ -10,7 +10,9 @@ class mimo_ofdm_radar_impl : public mimo_ofdm_radar
     const int d_fft_len, d_N_tx, d_N_rx, d_N_sym, d_N_pre, d_interp_factor;
     const std::string d_radar_chan_file;
     const bool d_debug;
-    host::chain_handle d_chain;
+    std::shared_ptr<host::chain_handle> d_chain;
+    jrc_chain_cfg d_cfg{};
+    bool d_fused_pending = false, d_fused = false;   // JRC_FUSED=1: resolved on the first frame (jrc_host.h, fused_session)
     std::vector<gr_complex> d_chan_est;   // last radar_chan_est, host copy for capture_radar_data
     std::mutex d_lock;                    // the GRC callbacks run on another thread than general_work()
 

@@ -16,6 +16,7 @@ class range_angle_estimator_impl : public range_angle_estimator
     float d_snr_threshold, d_power_threshold;
     host::stats_log d_log;
     const bool d_debug;
+    const bool d_fused;                 // JRC_FUSED=1 (jrc_host.h, fused_session)
     host::chain_handle d_chain;
 
     void push_thresholds() { host::check(jrc_chain_set_thresholds(d_chain.get(), d_snr_threshold, d_power_threshold), "RANGE-ANGLE ESTIMATOR"); }
@@ -31,8 +32,11 @@ public:
                                   gr::io_signature::make(0, 0, 0), len_key),
           d_vlen(vlen), d_range_bins(range_bins), d_angle_bins(angle_bins), d_nd_range_m(nd_range_m),
           d_nd_angle_deg(nd_angle_deg), d_snr_threshold(snr_threshold), d_power_threshold(power_threshold), d_debug(debug),
-          d_chain(host::utility_cfg(), "RANGE-ANGLE ESTIMATOR")
+          d_fused(host::fused_session::requested()), d_chain(host::utility_cfg(), "RANGE-ANGLE ESTIMATOR")
     {
+        if (d_fused)
+            host::fused_session::get().register_estimator(vlen, range_bins, angle_bins, nd_range_m, nd_angle_deg, snr_threshold,
+                                                          power_threshold);
         message_port_register_out(pmt::mp("params"));
         d_log.path = stats_path; d_log.record = stats_record;
         std::ofstream probe(stats_path, std::ofstream::app);
@@ -49,8 +53,17 @@ public:
     int work(int, gr_vector_int &ninput_items, gr_vector_const_void_star &input_items, gr_vector_void_star &) override
     {
         jrc_det det;
-        host::check(jrc_estimate2d(d_chain.get(), static_cast<const jrc_c32 *>(input_items[0]), ninput_items[0], d_vlen, &det),
-                    "RANGE-ANGLE ESTIMATOR");
+        bool served = false;
+        if (d_fused) {
+            // the record of this frame was made when the radar block ran the chain; the gate uses this block's thresholds
+            const int64_t seq = host::fused_session::packet_seq(*this, ninput_items[0]);
+            auto chain = seq >= 0 ? host::fused_session::get().chain() : nullptr;
+            served = chain && ninput_items[0] == (int)d_range_bins.size() &&
+                     jrc_fused_fetch_det(chain->get(), seq, d_snr_threshold, d_power_threshold, &det) == JRC_OK;
+        }
+        if (!served)
+            host::check(jrc_estimate2d(d_chain.get(), static_cast<const jrc_c32 *>(input_items[0]), ninput_items[0], d_vlen, &det),
+                        "RANGE-ANGLE ESTIMATOR");
         if (d_debug)
             std::cout << "[RANGE-ANGLE ESTIMATOR] peak (" << det.range_idx << ", " << det.angle_idx << ") power " << det.peak_power
                       << " noise " << det.noise_power << " snr " << det.snr_db << std::endl;

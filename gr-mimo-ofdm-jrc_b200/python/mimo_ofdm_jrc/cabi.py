@@ -55,6 +55,7 @@ EXPORTS = [
     "jrc_cp_remove", "jrc_ofdm_demod", "jrc_chain_submit", "jrc_chain_poll", "jrc_chain_wait",
     "jrc_pinned_alloc", "jrc_pinned_free", "jrc_host_register", "jrc_host_unregister", "jrc_chain_exact_stats", "jrc_scene_synth", "jrc_chain_run_burst",
     "jrc_dev_alloc", "jrc_dev_free", "jrc_dev_copy", "jrc_ipc_export", "jrc_ipc_open", "jrc_ipc_close",
+    "jrc_radar_estimate_fused", "jrc_fused_fetch_transposed", "jrc_fused_fetch_det",
 ]
 
 _lib = None
@@ -114,6 +115,9 @@ def load():
     lib.jrc_ipc_export.argtypes = [vp, vp]
     lib.jrc_ipc_open.argtypes = [vp, i32, C.POINTER(vp)]
     lib.jrc_ipc_close.argtypes = [vp]
+    lib.jrc_radar_estimate_fused.argtypes = [vp, vp, vp, sz, vp, vp, C.POINTER(i64)]
+    lib.jrc_fused_fetch_transposed.argtypes = [vp, i64, vp]
+    lib.jrc_fused_fetch_det.argtypes = [vp, i64, f32, f32, vp]
     for name in EXPORTS:
         fn = getattr(lib, name)
         if name not in ("jrc_last_error", "jrc_abi_version", "jrc_chain_destroy", "jrc_chain_stream",

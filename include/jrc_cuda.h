@@ -215,6 +215,27 @@ JRC_API jrc_status jrc_ipc_close(void *p);
 JRC_API jrc_status jrc_radar_estimate(jrc_chain *h, const jrc_c32 *const *tx, const jrc_c32 *const *rx,
                                       size_t tx_skip_items, jrc_c32 *out, jrc_c32 *chan_est_host);
 
+/* ---- fused mode for an UNMODIFIED flowgraph: in the shipped graph
+ * (examples/simulation/radar/mimo_ofdm_jrc_radar_sim.grc:2165-2232) mimo_ofdm_radar, matrix_transpose and
+ * range_angle_estimator are three blocks with two stock fft_vcc blocks between them.  On a handle that carries the
+ * WHOLE chain's configuration (interp_angle and jrc_chain_set_estimator), jrc_radar_estimate_fused() is
+ * jrc_radar_estimate() -- same outputs, same background ring -- and, without the frame leaving the device, the
+ * rest of the chain in the one-kernel-per-block arithmetic (range fft_vcc, transpose, angle fft_vcc, estimator) on
+ * a second stream.  The transposed array and the detection record land in a ring of JRC_FUSED_RING page-locked
+ * entries under *cpi_seq (0, 1, 2, ... per handle); the call returns as soon as its own output is on the host.
+ * The downstream blocks fetch by sequence number (the jrc_cpi stream tag) from their own threads instead of
+ * repeating the work: JRC_ERR_STATE if that CPI is not cached (never made, or overwritten by a newer one). */
+#define JRC_FUSED_RING 16
+JRC_API jrc_status jrc_radar_estimate_fused(jrc_chain *h, const jrc_c32 *const *tx, const jrc_c32 *const *rx,
+                                            size_t tx_skip_items, jrc_c32 *out, jrc_c32 *chan_est_host,
+                                            int64_t *cpi_seq);
+/* matrix_transpose's output for that CPI: [Nr][Na] complex, zero-padded (lib/matrix_transpose_impl.cc:91-104) */
+JRC_API jrc_status jrc_fused_fetch_transposed(jrc_chain *h, int64_t cpi_seq, jrc_c32 *out);
+/* range_angle_estimator's record for that CPI (lib/range_angle_estimator_impl.cc:141-234); the gate is evaluated
+ * with the thresholds given here (the estimator block's current ones). */
+JRC_API jrc_status jrc_fused_fetch_det(jrc_chain *h, int64_t cpi_seq, float snr_threshold, float power_threshold,
+                                       jrc_det *det);
+
 /* gr::fft::fft_vcc (GNU Radio 3.8 gr-fft; examples/simulation/radar/
  * mimo_ofdm_jrc_radar_sim.grc:940-985): batch items of length n (power of two,
  * <= 16384), rectangular window, no scaling.                                  */

@@ -321,6 +321,121 @@ static void test_fused_block()
 // capture_radar_data(): the CSV line of the drop-in block against the line the REFERENCE block wrote for the same frame
 // (tests/golden/c1_capture_line.txt, produced by tests/golden/make_golden.py from the reference's own sources;
 // lib/mimo_ofdm_radar_impl.cc:348-377).  The time stamp in front of the first ", " is the only difference allowed.
+// JRC_FUSED=1 on the unmodified five-block wiring: the radar block runs the whole chain once per frame, the two
+// downstream blocks serve what it cached under the frame's jrc_cpi tag.  Outputs, tags and messages must be the ones
+// the separate blocks give; the downstream blocks are handed ZEROED inputs here, so anything they computed themselves
+// would show.
+static void test_fused_mode()
+{
+    const int N = 64, T = 4, R = 2, S = 4, pre = 5, IR = 8, IA = 16, V = 8, Nr = N * IR, Na = V * IA, items = pre + S;
+    auto rb = range_bins(N, IR); auto ab = angle_bins(Na);
+    const float ndr = 2.4f, nda = 2 * 14.4775f;
+    setenv("JRC_FUSED", "1", 1);
+    auto radar = mimo_ofdm_radar::make(N, T, R, S, pre, true, true, 3, IR, false, "/tmp/jrc_cpp_chan.csv");
+    auto transp = matrix_transpose::make(Nr, V, IA, false);
+    auto estim = range_angle_estimator::make(Na, rb, ab, ndr, nda, -100.f, 0.f, "/tmp/jrc_cpp_log.csv", false);
+    unsetenv("JRC_FUSED");
+    orc_radar *ref = orc_radar_create(N, T, R, S, pre, 1, 1, 3, IR, 0);
+    uint64_t rd = 0, rd2 = 0, rd3 = 0;
+    const cvec zeros_y((size_t)V * Nr), zeros_cm((size_t)Nr * Na);
+    const int n_frames = JRC_FUSED_RING + 4;            // the ring of cached results wraps
+    for (int it = 0; it < n_frames; it++) {
+        frame_t f = make_frame(T, R, items, N);
+        std::vector<shim::input_t> in(T + R);
+        for (int t = 0; t < T; t++) { in[t].items = f.tx[t].data(); in[t].n_items = items; }
+        for (int r = 0; r < R; r++) { in[T + r].items = f.rx[r].data(); in[T + r].n_items = items; }
+        in[0].tags.push_back(shim::make_tag(rd, "packet_len", pmt::from_long(items)));
+        in[T].tags.push_back(shim::make_tag(rd, "packet_len", pmt::from_long(items)));
+        rd += items;
+        cvec pad((size_t)V * Nr), tr((size_t)Nr * Na);
+        auto r1 = shim::run_once(*radar, in, {{pad.data(), 64}});
+        CHECK(r1.produced == V, "fused mode: radar produced %d", r1.produced);
+        CHECK(r1.out_tags[0].size() == 2 && pmt::symbol_to_string(r1.out_tags[0][0].key) == "packet_len" &&
+                  pmt::to_long(r1.out_tags[0][0].value) == V && r1.out_tags[0][0].offset == (uint64_t)it * V &&
+                  pmt::symbol_to_string(r1.out_tags[0][1].key) == "jrc_cpi" && pmt::to_long(r1.out_tags[0][1].value) == it &&
+                  r1.out_tags[0][1].offset == (uint64_t)it * V,
+              "fused mode: radar output tags");
+        // oracle, block by block
+        std::vector<const orc_c32 *> tp, rp;
+        for (auto &v : f.tx) tp.push_back((const orc_c32 *)v.data());
+        for (auto &v : f.rx) rp.push_back((const orc_c32 *)v.data());
+        cvec opad((size_t)V * Nr), oy((size_t)V * Nr), otr((size_t)Nr * Na), ocm((size_t)Nr * Na);
+        orc_radar_work(ref, tp.data(), rp.data(), 0, (orc_c32 *)opad.data());
+        orc_fft_vcc_batch((orc_c32 *)opad.data(), (orc_c32 *)oy.data(), Nr, V, 0, 0);
+        orc_matrix_transpose((orc_c32 *)oy.data(), V, Nr, V, IA, (orc_c32 *)otr.data());
+        orc_fft_vcc_batch((orc_c32 *)otr.data(), (orc_c32 *)ocm.data(), Na, Nr, 1, 1);
+        orc_det od;
+        orc_range_angle_estimate((orc_c32 *)ocm.data(), Nr, Na, rb.data(), Nr, ab.data(), Na, ndr, nda, -100.f, 0.f, &od, nullptr);
+        CHECK(same(pad.data(), (const orc_c32 *)opad.data(), pad.size()), "fused mode: radar output differs (frame %d)", it);
+        // the stock fft_vcc between the blocks keeps the tags where they are (sync block, TPP_ALL_TO_ALL)
+        shim::input_t ti; ti.items = zeros_y.data(); ti.n_items = V;
+        ti.tags.push_back(shim::make_tag(rd2, "packet_len", pmt::from_long(V)));
+        ti.tags.push_back(shim::make_tag(rd2, "jrc_cpi", pmt::from_long(it)));
+        rd2 += V;
+        auto r2 = shim::run_once(*transp, {ti}, {{tr.data(), Nr}});
+        CHECK(r2.produced == Nr && r2.consumed[0] == V, "fused mode: transpose produced %d consumed %d", r2.produced, r2.consumed[0]);
+        CHECK(same(tr.data(), (const orc_c32 *)otr.data(), tr.size()), "fused mode: transposed array differs (frame %d)", it);
+        bool have_len = false, have_seq = false;
+        for (auto &t : r2.out_tags[0]) {
+            if (pmt::symbol_to_string(t.key) == "packet_len") have_len = pmt::to_long(t.value) == Nr && t.offset == (uint64_t)it * Nr;
+            if (pmt::symbol_to_string(t.key) == "jrc_cpi") have_seq = pmt::to_long(t.value) == it && t.offset == (uint64_t)it * Nr;
+        }
+        CHECK(have_len && have_seq && r2.out_tags[0].size() == 2, "fused mode: transpose output tags");
+        shim::input_t ei; ei.items = zeros_cm.data(); ei.n_items = Nr;
+        ei.tags.push_back(shim::make_tag(rd3, "packet_len", pmt::from_long(Nr)));
+        ei.tags.push_back(shim::make_tag(rd3, "jrc_cpi", pmt::from_long(it)));
+        rd3 += Nr;
+        auto r3 = shim::run_once(*estim, {ei}, {});
+        CHECK(r3.produced == 0 && r3.consumed[0] == Nr, "fused mode: estimator consumes the packet");
+        auto &msgs = estim->shim_published["params"];
+        CHECK((int)msgs.size() == it + 1, "fused mode: params message count %zu", msgs.size());
+        if ((int)msgs.size() == it + 1) {
+            auto m = msgs.back();
+            auto field = [&](int k) { return pmt::f32vector_elements(pmt::nth(1, pmt::nth(k, m)))[0]; };
+            CHECK(field(0) == rb[od.range_idx] && field(1) == ab[od.angle_idx] && field(2) == od.peak_power && field(3) == od.snr_db,
+                  "fused mode: message differs (frame %d): %g %g %g %g vs %g %g %g %g", it, field(0), field(1), field(2), field(3),
+                  rb[od.range_idx], ab[od.angle_idx], od.peak_power, od.snr_db);
+        }
+        if (it == 5) { radar->set_background_record(false); orc_radar_set_background_record(ref, 0); }
+    }
+    // a packet whose cached result is gone (frame 0 was overwritten by frame JRC_FUSED_RING) or that carries no
+    // jrc_cpi tag goes through the block's own device call: the input decides
+    cvec y = randvec((size_t)V * Nr), tr((size_t)Nr * Na), otr((size_t)Nr * Na);
+    orc_matrix_transpose((orc_c32 *)y.data(), V, Nr, V, IA, (orc_c32 *)otr.data());
+    for (int tagged = 0; tagged < 2; tagged++) {
+        shim::input_t ti; ti.items = y.data(); ti.n_items = V;
+        ti.tags.push_back(shim::make_tag(rd2, "packet_len", pmt::from_long(V)));
+        if (tagged) ti.tags.push_back(shim::make_tag(rd2, "jrc_cpi", pmt::from_long(0)));
+        rd2 += V;
+        auto r2 = shim::run_once(*transp, {ti}, {{tr.data(), Nr}});
+        CHECK(r2.produced == Nr && same(tr.data(), (const orc_c32 *)otr.data(), tr.size()) && r2.out_tags[0].size() == 1,
+              "fused mode: fallback of matrix_transpose (tagged %d)", tagged);
+    }
+    // the estimator's own thresholds gate a cached record
+    estim->set_snr_threshold(1000.f);
+    shim::input_t ei; ei.items = zeros_cm.data(); ei.n_items = Nr;
+    ei.tags.push_back(shim::make_tag(rd3, "packet_len", pmt::from_long(Nr)));
+    ei.tags.push_back(shim::make_tag(rd3, "jrc_cpi", pmt::from_long(n_frames - 1)));
+    const size_t before = estim->shim_published["params"].size();
+    shim::run_once(*estim, {ei}, {});
+    CHECK(estim->shim_published["params"].size() == before, "fused mode: threshold change ignored");
+    orc_radar_destroy(ref);
+
+    // blocks that do not continue each other: the radar block says so and stays on its own call
+    setenv("JRC_FUSED", "1", 1);
+    auto radar2 = mimo_ofdm_radar::make(N, T, R, S, pre, false, false, 1, 4, false, "/tmp/jrc_cpp_chan.csv");
+    unsetenv("JRC_FUSED");
+    frame_t f = make_frame(T, R, items, N);
+    std::vector<shim::input_t> in(T + R);
+    for (int t = 0; t < T; t++) { in[t].items = f.tx[t].data(); in[t].n_items = items; }
+    for (int r = 0; r < R; r++) { in[T + r].items = f.rx[r].data(); in[T + r].n_items = items; }
+    in[0].tags.push_back(shim::make_tag(0, "packet_len", pmt::from_long(items)));
+    in[T].tags.push_back(shim::make_tag(0, "packet_len", pmt::from_long(items)));
+    cvec pad((size_t)V * N * 4);
+    auto r1 = shim::run_once(*radar2, in, {{pad.data(), 64}});
+    CHECK(r1.produced == V && r1.out_tags[0].size() == 1, "fused mode: mismatching blocks must fall back");
+}
+
 static void test_capture_format(const char *golden_dir)
 {
     const int N = 64, T = 4, R = 2, S = 4, V = T * R;
@@ -357,6 +472,7 @@ int main()
     test_chain_of_blocks();
     test_peak_and_pad();
     test_fused_block();
+    test_fused_mode();
     if (g_fail) { std::printf("%d check(s) FAILED\n", g_fail); return 1; }
     std::printf("ALL BLOCK TESTS PASSED\n");
     return 0;
