@@ -122,6 +122,7 @@ struct jrc_chain {
     int ring_size = 0, ring_head = 0;
     // scratch
     GrowBuf sH, sY, sC, sKeys, sSec, sDet, sIn[2], sMap[2], sDets[2], sMisc, sMisc2, sStage[8];
+    GrowBuf sDemod;                              // jrc_chain_run_batch_time: demodulated symbols of one chunk
     GrowBuf sFix, sExact;                        // marked-CPI list (FixCtl + int[n]) and range-spectra scratch of k_est_exact
     int exact_grid = 0;
     GrowBuf pin_a, pin_b;
@@ -232,7 +233,7 @@ extern "C" void jrc_chain_destroy(jrc_chain *h)
     fused_state_destroy(h);
     for (auto &kv : h->twiddles) cudaFree(kv.second);
     GrowBuf *bufs[] = {&h->sH, &h->sY, &h->sC, &h->sKeys, &h->sSec, &h->sFix, &h->sExact, &h->sDet, &h->sIn[0], &h->sIn[1], &h->sMap[0], &h->sMap[1],
-                       &h->sDets[0], &h->sDets[1], &h->sMisc, &h->sMisc2, &h->pin_a, &h->pin_b};
+                       &h->sDets[0], &h->sDets[1], &h->sMisc, &h->sMisc2, &h->pin_a, &h->pin_b, &h->sDemod};
     for (GrowBuf *b : bufs) b->release();
     for (GrowBuf &b : h->sStage) b.release();
     for (auto &kv : h->twiddles_full) cudaFree(kv.second);
@@ -1037,6 +1038,55 @@ extern "C" jrc_status jrc_chain_run_batch(jrc_chain *h, jrc_port_layout rx, jrc_
 
 // ---------------------------------------------------------------------------
 // host-buffer chain: pinned double-buffered pipeline
+// The chain fed with the RX antennas' raw time samples: the demodulation runs in front of the chain on the same stream,
+// chunk by chunk, and hands the symbols over in a scratch small enough to stay in the L2 (4096 CPIs of configs[1]: 16 MiB).
+extern "C" jrc_status jrc_chain_run_batch_time(jrc_chain *h, jrc_port_layout rx_time, int32_t cp_len, jrc_port_layout tx,
+                                                int32_t n_cpi, int32_t cpi0, float *map, jrc_c32 *cmap, jrc_det *dets, int32_t path)
+{
+    if (!h) return fail(JRC_ERR_INVALID, "null handle");
+    if (n_cpi < 0 || cp_len < 0) return fail(JRC_ERR_INVALID, "n_cpi < 0 or cp_len < 0");
+    if (n_cpi == 0) return JRC_OK;
+    if (!rx_time.base || !tx.base) return fail(JRC_ERR_INVALID, "null input pointer");
+    CU(cudaSetDevice(h->cfg.device));
+    const jrc_chain_cfg &c = h->cfg;
+    const int N = c.fft_len, R = c.n_rx, S = c.n_sym;
+    if (!is_pow2(N) || N > 4096) return fail(JRC_ERR_INVALID, "the OFDM demodulator needs a power-of-two fft_len <= 4096");
+    if (c.background_removal || h->bg_recording.load())
+        return fail(JRC_ERR_INVALID, "background removal keeps per-frame state: demodulate with jrc_ofdm_demod and use jrc_radar_estimate");
+    NvtxRange nv("jrc_chain_run_batch_time");
+    const size_t per_cpi = (size_t)R * S * N * sizeof(c32);
+    int chunk = (int)(((size_t)32 << 20) / per_cpi);
+    if (chunk < 1) chunk = 1;
+    if (chunk > n_cpi) chunk = n_cpi;
+    ST(h->sDemod.need((size_t)chunk * per_cpi));
+    const c32 *tw = nullptr;
+    ST(get_twiddles(h, N, 1, &tw));
+    const int rpc = N >= 512 ? 1 : 512 / N;
+    const size_t smem = (size_t)rpc * N * sizeof(c32);
+    const size_t Nr = h->Nr, Na = h->Na;
+    for (int c0 = 0; c0 < n_cpi; c0 += chunk) {
+        const int nc = n_cpi - c0 < chunk ? n_cpi - c0 : chunk;
+        PortDev drx{(const c32 *)rx_time.base + (long long)c0 * rx_time.cpi_stride, rx_time.cpi_stride, rx_time.ant_stride};
+        const long long rows = (long long)nc * R * S;
+        const bool al16 = aligned16(drx.base) && rx_time.cpi_stride % 2 == 0 && rx_time.ant_stride % 2 == 0 && cp_len % 2 == 0;
+        if (N == 64 && al16)
+            k_ofdm_demod64<<<grid_for(rows * 32, 256, h->sm_count), 256, 0, h->stream>>>(drx, R, c.n_pre, S, cp_len, (c32 *)h->sDemod.p,
+                                                                                       rows, tw);
+        else
+            k_ofdm_demod_batch<<<(unsigned)((rows + rpc - 1) / rpc), 256, smem, h->stream>>>(drx, R, c.n_pre, S, cp_len,
+                                                                                          (c32 *)h->sDemod.p, N, ilog2(N), rows, rpc, tw);
+        CU(cudaGetLastError());
+        h->launches++;
+        jrc_port_layout sym{(const jrc_c32 *)h->sDemod.p, (int64_t)R * S * N, (int64_t)S * N};
+        // tx keeps its n_pre symbols in front, the demodulated rx has none: tx's base moves instead of two offsets
+        jrc_port_layout ctx = tx;
+        ctx.base = tx.base + (long long)c0 * tx.cpi_stride + (long long)c.n_pre * N;
+        ST(run_batch_impl(h, sym, ctx, nc, cpi0 + c0, map ? map + (size_t)c0 * Nr * Na : nullptr,
+                          cmap ? cmap + (size_t)c0 * Nr * Na : nullptr, dets ? dets + c0 : nullptr, path, 0, false));
+    }
+    return JRC_OK;
+}
+
 // ---------------------------------------------------------------------------
 // Pinned ranges created through jrc_pinned_alloc / jrc_host_register: looked up without a driver call (the streaming
 // path asks four times per CPI).

@@ -205,6 +205,83 @@ __global__ void k_fft_rows(const c32 *in, long long in_stride, int n_in,   // in
 }
 
 // ---------------------------------------------------------------------------
+// RX OFDM front end for a whole batch: ofdm_cyclic_prefix_remover
+// (lib/ofdm_cyclic_prefix_remover_impl.cc:92-95) + fft_vxx(forward, shift) (...radar_sim.grc:898-939) for the n_sym
+// symbols behind the n_pre preamble symbols of every RX antenna of every CPI.  Time samples
+//   rx[cpi*cpi_stride + r*ant_stride + (n_pre + s)*(n + cp) + cp + i]
+// -> DC-centred subcarrier vectors sym[((cpi*R + r)*n_sym + s)*n + k], the packed layout the chain kernels read with
+// n_pre = 0.  Same butterflies as k_fft_rows: bit-identical to jrc_ofdm_demod symbol by symbol.
+// ---------------------------------------------------------------------------
+__global__ void k_ofdm_demod_batch(PortDev rx, int R, int n_pre, int n_sym, int cp, c32 *__restrict__ sym, int n, int log2n,
+                                   long long rows, int rows_per_cta, const c32 *__restrict__ tw /* [n/2], forward */)
+{
+    extern __shared__ c32 sm[];
+    const long long row0 = (long long)blockIdx.x * rows_per_cta;
+    const int offset = (n + 1) / 2;
+    const int tot = rows_per_cta * n;
+    for (int e = threadIdx.x; e < tot; e += blockDim.x) {
+        int lr = e / n, i = e % n;
+        long long row = row0 + lr;
+        c32 v = mk(0.f, 0.f);
+        if (row < rows) {
+            const int s = (int)(row % n_sym);
+            const long long ca = row / n_sym;
+            const int r = (int)(ca % R);
+            const long long cpi = ca / R;
+            v = rx.base[cpi * rx.cpi_stride + r * rx.ant_stride + (long long)(n_pre + s) * (n + cp) + cp + i];
+        }
+        unsigned rev = (log2n == 0) ? 0u : (__brev((unsigned)i) >> (32 - log2n));
+        sm[lr * n + rev] = v;
+    }
+    __syncthreads();
+    radix2_rows(sm, n, rows_per_cta, tw);
+    for (int e = threadIdx.x; e < tot; e += blockDim.x) {
+        int lr = e / n, i = e % n;
+        long long row = row0 + lr;
+        if (row < rows) sym[row * n + i] = sm[lr * n + (i + offset) % n];      // fft_vxx shift=True: output halves swapped
+    }
+}
+
+// The 64-subcarrier case of k_ofdm_demod_batch, one WARP per symbol, no shared memory: lane l holds positions l and
+// l + 32 of the bit-reversed working array, i.e. the consecutive input samples 2*brev5(l) and 2*brev5(l) + 1 (one
+// 16-byte load).  A butterfly of the stages with half < 32 pairs lane l with lane l ^ half: the upper lane forms v*w,
+// the two exchange (u or v*w) and each forms its own output with the oracle's operations, in the oracle's order
+// (radix2_rows: u + v*w, u - v*w; w = tw[j * 64 / len]); the last stage is local to the lane.  Bit-identical to the
+// generic kernel.  Rows must start 16-byte aligned (even strides, even cp).
+__global__ void __launch_bounds__(256) k_ofdm_demod64(PortDev rx, int R, int n_pre, int n_sym, int cp, c32 *__restrict__ sym,
+                                                      long long rows, const c32 *__restrict__ tw /* [32], forward */)
+{
+    const int lane = threadIdx.x & 31;
+    const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    const int src = (int)(__brev((unsigned)lane) >> 27) * 2;
+    for (long long row = warp0; row < rows; row += nwarps) {
+        const int s = (int)(row % n_sym);
+        const long long ca = row / n_sym;
+        const int r = (int)(ca % R);
+        const long long cpi = ca / R;
+        const c32 *x = rx.base + cpi * rx.cpi_stride + r * rx.ant_stride + (long long)(n_pre + s) * (64 + cp) + cp;
+        const float4 ld = *reinterpret_cast<const float4 *>(x + src);
+        c32 a = mk(ld.x, ld.y), b = mk(ld.z, ld.w);          // positions lane, lane + 32
+#pragma unroll
+        for (int half = 1; half < 32; half <<= 1) {
+            const bool upper = (lane & half) != 0;
+            const c32 w = tw[(lane & (half - 1)) * (32 / half)];
+            const c32 ta = upper ? cmul_exact(a, w) : a, tb = upper ? cmul_exact(b, w) : b;
+            c32 oa, ob;
+            oa.x = __shfl_xor_sync(0xffffffffu, ta.x, half); oa.y = __shfl_xor_sync(0xffffffffu, ta.y, half);
+            ob.x = __shfl_xor_sync(0xffffffffu, tb.x, half); ob.y = __shfl_xor_sync(0xffffffffu, tb.y, half);
+            a = upper ? csub_exact(oa, ta) : cadd_exact(ta, oa);
+            b = upper ? csub_exact(ob, tb) : cadd_exact(tb, ob);
+        }
+        const c32 v = cmul_exact(b, tw[lane]);
+        const c32 lo = cadd_exact(a, v), hi = csub_exact(a, v);   // positions lane, lane + 32
+        sym[row * 64 + lane + 32] = lo;                           // fft_vxx shift=True: output halves swapped
+        sym[row * 64 + lane] = hi;
+    }
+}
+
+// ---------------------------------------------------------------------------
 // matrix_transpose  (lib/matrix_transpose_impl.cc:97-104), batched over mats:
 // in [mat][K][L] -> out [mat][L][W], W = output_len*interp, out[l][k] = in[k][l] for
 // k < K, zero elsewhere.  32x32 shared-memory tiles keep both sides coalesced.

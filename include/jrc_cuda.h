@@ -139,6 +139,18 @@ enum { JRC_PATH_AUTO = 0, JRC_PATH_FUSED = 1, JRC_PATH_STAGED = 2, JRC_PATH_TILE
 JRC_API jrc_status jrc_chain_run_batch(jrc_chain *h, jrc_port_layout rx, jrc_port_layout tx,
                                        int32_t n_cpi, int32_t cpi0,
                                        float *map, jrc_c32 *cmap, jrc_det *dets, int32_t path);
+/* The same chain fed with the RX antennas' raw TIME samples: in the flowgraph
+ * ofdm_cyclic_prefix_remover (lib/ofdm_cyclic_prefix_remover_impl.cc:62-99) and fft_vxx(forward, shift)
+ * (...radar_sim.grc:898-939) sit between the receiver and the radar block's rx ports.  Sample i of symbol s of
+ * antenna a of a CPI lives at
+ *     rx_time.base + cpi*cpi_stride + a*ant_stride + s*(fft_len + cp_len) + i,   s < n_pre + n_sym
+ * (strides in complex samples; the n_pre preamble symbols are skipped, not transformed).  tx stays in the frequency
+ * domain, as in the flowgraph's TX branch.  The demodulation runs in front of the chain on the same stream, in
+ * chunks whose symbols stay in the L2, and is bit-identical to jrc_ofdm_demod symbol by symbol; everything else as
+ * jrc_chain_run_batch.  Not for handles with background removal (per-frame state).                           */
+JRC_API jrc_status jrc_chain_run_batch_time(jrc_chain *h, jrc_port_layout rx_time, int32_t cp_len,
+                                            jrc_port_layout tx, int32_t n_cpi, int32_t cpi0,
+                                            float *map, jrc_c32 *cmap, jrc_det *dets, int32_t path);
 /* Range-Doppler-angle cube of a burst of n_burst consecutive CPIs (power of two): the complex range-angle maps of the
  * burst (one-kernel-per-block path, bit-identical to the CPU restatement) followed by a forward, fftshifted FFT along
  * slow time for every (range, angle) cell and |.|^2.  Device pointers, asynchronous on the handle's stream.

@@ -629,3 +629,50 @@ def test_range_doppler_angle_cube(jrc, orc):
     assert np.abs(got - ref).max() <= 2e-5 * ref.max(), np.abs(got - ref).max() / ref.max()
     n, i, d = np.unravel_index(np.argmax(got), got.shape)
     assert d == nb // 2 + int(round(fd / prf * nb)) and (n, i) == synth.expected_peak(20.0, 15.0, 64, 4, 8, 4)
+
+
+@pytest.mark.parametrize("name,pre,n", [("C2", 5, 300), ("C1", 0, 64), ("C3s", 2, 12), ("C5", 1, 3)])
+def test_chain_from_raw_time_samples(jrc, orc, name, pre, n):
+    """SURVEY.md 8(f) rank 1 for whole batches (jrc_chain_run_batch_time): cyclic-prefix removal + the RX OFDM FFT in
+    front of the chain, on the device.  The demodulated symbols are bit-identical to the oracle's cp_remove + fft_vcc, so
+    map and records equal, bit for bit, the ones of jrc_chain_run_batch on the oracle-demodulated symbols; and the
+    detection lists equal the oracle chain's."""
+    import torch
+    cfg = CFGS[name]
+    N, T, R, S = cfg["N"], cfg["T"], cfg["R"], cfg["S"]
+    cp = N // 4
+    est = est_for(cfg)
+    rx, tx, _ = scene(cfg, n, seed=17, n_targets=2, amp_db_span=6.0)
+    rng = np.random.default_rng(5)
+    sym_all = np.empty((n, R, pre + S, N), np.complex64)           # what the antennas' demodulators should deliver
+    sym_all[:, :, :pre] = (rng.standard_normal((n, R, pre, N)) + 1j * rng.standard_normal((n, R, pre, N))).astype(np.complex64)
+    sym_all[:, :, pre:] = rx
+    td = np.fft.ifft(np.fft.ifftshift(sym_all.astype(np.complex128), axes=-1), axis=-1)
+    td = np.concatenate([td[..., N - cp:], td], axis=-1).astype(np.complex64)      # [n][R][pre+S][cp+N]
+    tx_all = np.concatenate([np.ones((T, pre, N), np.complex64), tx], axis=1)      # TX packets carry the preamble too
+    # the oracle's front end, antenna row by antenna row
+    dem = np.empty_like(sym_all)
+    for c in range(n):
+        for r in range(R):
+            dem[c, r] = orc.fft_vcc(orc.cp_remove(td[c, r].ravel(), pre + S, N, cp), True, True)
+    ch = jrc.Chain(N, T, R, S, pre, cfg["IR"], cfg["IA"])
+    ch.set_estimator(**est)
+    Nr, Na = ch.Nr, ch.Na
+    dtd, dtx, ddem = torch.from_numpy(td).cuda(), torch.from_numpy(tx_all).cuda(), torch.from_numpy(dem).cuda()
+    m1 = torch.empty((n, Nr, Na), dtype=torch.float32, device="cuda")
+    m2 = torch.empty_like(m1)
+    d1 = torch.zeros((n, 32), dtype=torch.uint8, device="cuda")
+    d2 = torch.zeros_like(d1)
+    torch.cuda.synchronize()
+    row_t, row_f = (pre + S) * (N + cp), (pre + S) * N
+    ch.run_batch_time_ptr(dtd.data_ptr(), R * row_t, row_t, cp, dtx.data_ptr(), 0, row_f, n, 0, m1.data_ptr(), None, d1.data_ptr())
+    path = ch.last_path
+    ch.run_batch_ptr(ddem.data_ptr(), R * row_f, row_f, dtx.data_ptr(), 0, row_f, n, 0, m2.data_ptr(), None, d2.data_ptr())
+    ch.sync()
+    assert ch.last_path == path == (jrc.PATH_FUSED if name in ("C1", "C2") else jrc.PATH_TILED)
+    assert torch.equal(m1, m2)
+    assert torch.equal(d1, d2)
+    mo, _, do = oracle(orc, np.ascontiguousarray(dem[:, :, pre:]), tx, cfg, est)
+    err = np.abs(m1.cpu().numpy() - mo).reshape(n, -1).max(axis=1) / mo.reshape(n, -1).max(axis=1)
+    assert err.max() <= 5e-6, err.max()
+    check_detections(jrc, jrc.radar_chain.dets_to_numpy(d1), do, f"time samples {name}")
