@@ -515,8 +515,8 @@ static jrc_status launch_wide(jrc_chain *h, PortDev rx, PortDev tx, const c32 *H
     auto kb = k_wide_range_mag<11>;
     CU(cudaFuncSetAttribute(ka, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Gm::SMEM_A));
     CU(cudaFuncSetAttribute(kb, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Gm::SMEM_B));
-    long long ua = (long long)n_cpi * (Gm::N / Gm::KB), ub = (long long)n_cpi * (Gm::V / Gm::AB);
-    long long ga = ua < h->sm_count ? ua : h->sm_count, gb = ub < 3LL * h->sm_count ? ub : 3LL * h->sm_count;
+    long long ua = (long long)n_cpi * (Gm::N / Gm::KB), ub = (long long)n_cpi * (Gm::V / Gm::UB);
+    long long ga = ua < h->sm_count ? ua : h->sm_count, gb = ub < 2LL * h->sm_count ? ub : 2LL * h->sm_count;
     ka<<<(unsigned)ga, Gm::TA, Gm::SMEM_A, h->stream>>>(P);
     CU(cudaGetLastError());
     kb<<<(unsigned)gb, Gm::GR::THREADS, Gm::SMEM_B, h->stream>>>(P);
@@ -877,15 +877,18 @@ static jrc_status run_batch_impl(jrc_chain *h, jrc_port_layout rx, jrc_port_layo
         if (chunk > n_cpi) chunk = n_cpi;
         const bool slice = slice_config_ok(h);
         const bool wide = wide_config_ok(h);
-        // the wide kernels hand G (2 MiB per CPI) from one to the other through the L2: 27 CPIs = 54 MiB per round, and
-        // 27 x 32 angle-bin blocks fill the 3 x 148 CTA slots of k_wide_range_mag twice (measured: 13 / 18 / 27 / 36 CPIs per
-        // round -> 264 / 265 / 305 / 295 k CPI/s)
+        // the wide kernels hand G (2 MiB per CPI) from one to the other in rounds of CPIs.  Measured (n = 148): rounds of
+        // 37 / 74 / 148 CPIs -> 350 / 371 / 384 k CPI/s, and 228 k at 8, although only rounds of <= 8 CPIs keep all of G in
+        // the L2 (ncu, caches left alone: no write-back of G at 8, 100 % at 27; an access-policy window over G with the
+        // persisting carve-out changed neither the traffic nor the time): the kernels are latency- and issue-bound, not
+        // bandwidth-bound, and what a round costs is its partial last wave.  37 k CPIs fill both grids exactly
+        // (64 x 37 = 16 x 148 units, 16 x 37 = 2 x 296 units).
         static const int wide_round_env = getenv("JRC_WIDE_ROUND") ? atoi(getenv("JRC_WIDE_ROUND")) : 0;
-        const int wide_round = wide_round_env > 0 ? wide_round_env : 27;
+        const int wide_round = wide_round_env > 0 ? wide_round_env : 148;
         if (wide) {
             const bool need_h = bg || recording;
             if (need_h) ST(h->sH.need((size_t)chunk * V * N * sizeof(c32)));
-            ST(h->sY.need((size_t)wide_round * V * N * sizeof(c32)));
+            ST(h->sY.need((size_t)(chunk < wide_round ? chunk : wide_round) * V * N * sizeof(c32)));
             if (!map) ST(h->sC.need((size_t)chunk * Nr * Na * sizeof(float)));
             if (dets) {
                 ST(h->sKeys.need(sizeof(unsigned long long) * (size_t)chunk));

@@ -10,10 +10,10 @@
 //                      channels (register tiled: 4 RX x 2 TX per thread), angle FFT + fftshift across the channels for each
 //                      subcarrier (matrix_transpose + fft_vcc #B, lib/matrix_transpose_impl.cc:97-104,
 //                      ...radar_sim.grc:963-985), result G[cpi][angle bin][k] written as whole 128-byte lines.
-//   k_wide_range_mag   per (CPI, block of 4 angle bins): range IFFT over k of 4 rows of G (fft_vcc #A,
-//                      ...radar_sim.grc:940-962), |.|^2 (:637-652); a thread ends up with the same range bins of all four
-//                      rows, so map[n][a0..a0+3] leaves as 16-byte stores straight from registers (the 32 blocks of a CPI
-//                      run side by side: the L2 merges them into whole lines), arg-max partials as in k_angle_mag.
+//   k_wide_range_mag   per (CPI, block of 8 angle bins): range IFFT over k of 2 x 4 rows of G (fft_vcc #A,
+//                      ...radar_sim.grc:940-962), |.|^2 (:637-652); a thread ends up with the same range bins of all eight
+//                      rows, so map[n][a0..a0+7] leaves as one 32-byte store (a whole sector) straight from registers,
+//                      arg-max partials as in k_angle_mag.
 //
 // G (2 MiB per CPI) is produced and consumed chunk by chunk of CPIs small enough to stay in the 126 MB L2.
 // HBM per CPI: 3 MiB symbols + 1 MiB map (+ what the L2 spills of G) against 12 MiB for chan_est -> range -> angle.
@@ -42,7 +42,8 @@ template <int LOG2N>
 struct WideGeom {
     static constexpr int N = 1 << LOG2N, V = 128, KB = 32;           // subcarriers per k_wide_mac_angle unit
     static constexpr int TA = 16 * KB;                                // threads of k_wide_mac_angle: 16 per subcarrier
-    static constexpr int AB = 4;                                      // angle bins per k_wide_range_mag unit
+    static constexpr int AB = 4;                                      // rows per pass of k_wide_range_mag
+    static constexpr int UB = 8;                                      // angle bins per unit (two passes): one 32-byte sector of the map
     using GA = TiledGeom<7>;                                          // angle FFT rows: 16 threads per row, 16 rows per CTA
     using GR = TiledGeom<LOG2N>;
     static constexpr int MAX_ANT = 24, MAX_S = 8;
@@ -181,7 +182,7 @@ __global__ void __launch_bounds__(WideGeom<LOG2N>::TA, 1) k_wide_mac_angle(const
 // range IFFT + |.|^2 + arg-max partials, one (CPI, 8 angle bins) at a time
 // ---------------------------------------------------------------------------
 template <int LOG2N>
-__global__ void __launch_bounds__(TiledGeom<LOG2N>::THREADS, 3) k_wide_range_mag(const WideParams P)
+__global__ void __launch_bounds__(TiledGeom<LOG2N>::THREADS, 2) k_wide_range_mag(const WideParams P)
 {
     using Gm = WideGeom<LOG2N>;
     using GR = typename Gm::GR;
@@ -192,46 +193,61 @@ __global__ void __launch_bounds__(TiledGeom<LOG2N>::THREADS, 3) k_wide_range_mag
     const int tid = threadIdx.x, lane = tid & 31, t = tid % TPR;
     DifTw<LOG2N> Tw;
     Tw.load(P.tw_r, t, t);
-    const int units_per_cpi = V / AB;
+    constexpr int UB = Gm::UB, HALVES = UB / AB;
+    const int units_per_cpi = V / UB;
     const long long n_units = (long long)P.n_cpi * units_per_cpi;
     for (long long unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
-        const int cpi = (int)(unit / units_per_cpi), a0 = (int)(unit % units_per_cpi) * AB;
-        const c32 *Gu = P.G + ((long long)cpi * V + a0) * N;
-        // first pass of all AB rows straight from global memory (L2): 8 loads in flight per row and thread
+        const int cpi = (int)(unit / units_per_cpi), a0 = (int)(unit % units_per_cpi) * UB;
+        // |.|^2 at this thread's 8 range bins for all UB angle bins: the AB rows of one pass at a time through the row
+        // buffer, the values of the earlier pass waiting in registers -- the thread then owns whole 32-byte sectors of the
+        // map (a 16-byte store leaves half a sector, which the L2 completes by READING the other half from HBM:
+        // measured 2 MiB of fill reads per CPI for the 1 MiB map)
+        float v[8][UB];
 #pragma unroll
-        for (int r = 0; r < AB; r++) {
-            c32 u[8];
+        for (int hf = 0; hf < HALVES; hf++) {
+            const c32 *Gu = P.G + ((long long)cpi * V + a0 + hf * AB) * N;
+            if (hf) __syncthreads();           // the rows of the previous pass have been read
+            // first pass of the AB rows straight from global memory (L2): 8 loads in flight per row and thread
 #pragma unroll
-            for (int m = 0; m < 8; m++) u[m] = __ldcg(Gu + (long long)r * N + t + m * TPR);
-            dif_first_full<LOG2N, 1>(rowbuf + r * RROW, t, u, Tw);
-        }
-        __syncthreads();
-        // the middle passes of all AB rows share their barriers; the last pass leaves the results in registers
-        dif_mid_passes_rows<LOG2N, 1, AB>(rowbuf, RROW, t, Tw);
-        float v[8][AB];                        // |.|^2 at this thread's 8 range bins, all AB angle bins
+            for (int r = 0; r < AB; r++) {
+                c32 u[8];
 #pragma unroll
-        for (int r = 0; r < AB; r++) {
-            c32 o[8];
-            dif_last_pass<LOG2N, 1>(rowbuf + r * RROW, t, o);
+                for (int m = 0; m < 8; m++) u[m] = __ldcg(Gu + (long long)r * N + t + m * TPR);
+                dif_first_full<LOG2N, 1>(rowbuf + r * RROW, t, u, Tw);
+            }
+            __syncthreads();
+            // the middle passes of all AB rows share their barriers; the last pass leaves the results in registers
+            dif_mid_passes_rows<LOG2N, 1, AB>(rowbuf, RROW, t, Tw);
 #pragma unroll
-            for (int c = 0; c < 8; c++) {
-                const c32 sq = __fmul2_rn(o[c], o[c]);
-                v[c][r] = __fadd_rn(sq.x, sq.y);
+            for (int r = 0; r < AB; r++) {
+                c32 o[8];
+                dif_last_pass<LOG2N, 1>(rowbuf + r * RROW, t, o);
+#pragma unroll
+                for (int c = 0; c < 8; c++) {
+                    const c32 sq = __fmul2_rn(o[c], o[c]);
+                    v[c][hf * AB + r] = __fadd_rn(sq.x, sq.y);
+                }
             }
         }
-        // map[cpi][n][a0 .. a0+3] straight from registers; running maximum per range bin
+        // map[cpi][n][a0 .. a0+7] straight from registers, one 32-byte store per range bin; running maximum per range bin
         float best = -1.f, sec_t = -1.f;
         int best_row = 0;
         float *mp = P.map ? P.map + (long long)cpi * N * V + a0 : nullptr;
 #pragma unroll
         for (int c = 0; c < 8; c++) {
             const int n = dif_freq<LOG2N>(8 * t) + dif_freq<LOG2N>(c);
-            if (mp) __stcs(reinterpret_cast<float4 *>(mp + (long long)n * V), make_float4(v[c][0], v[c][1], v[c][2], v[c][3]));
-            const float hi = fmaxf(fmaxf(v[c][0], v[c][1]), fmaxf(v[c][2], v[c][3]));
-            // runner-up: the second largest of the four, and whatever loses against the running maximum
-            const float lo01 = fminf(v[c][0], v[c][1]), hi01 = fmaxf(v[c][0], v[c][1]);
-            const float lo23 = fminf(v[c][2], v[c][3]), hi23 = fmaxf(v[c][2], v[c][3]);
-            sec_t = fmaxf(sec_t, fmaxf(fminf(hi01, hi23), fmaxf(lo01, lo23)));
+            if (mp)
+                asm volatile("st.global.cs.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(mp + (long long)n * V), "f"(v[c][0]),
+                             "f"(v[c][1]), "f"(v[c][2]), "f"(v[c][3]), "f"(v[c][4]), "f"(v[c][5]), "f"(v[c][6]), "f"(v[c][7])
+                             : "memory");
+            // largest and runner-up of the eight, then whatever loses against the running maximum
+            float hi = v[c][0], lo = -1.f;
+#pragma unroll
+            for (int j = 1; j < UB; j++) {
+                lo = fmaxf(lo, fminf(hi, v[c][j]));
+                hi = fmaxf(hi, v[c][j]);
+            }
+            sec_t = fmaxf(sec_t, lo);
             sec_t = fmaxf(sec_t, fminf(hi, best));
             if (hi > best || (hi == best && n < best_row)) { best = hi; best_row = n; }
         }
