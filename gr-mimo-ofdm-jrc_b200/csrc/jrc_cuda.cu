@@ -683,21 +683,26 @@ static jrc_status launch_exact(jrc_chain *h, PortDev rx, PortDev tx, const c32 *
     const int big = h->Nr > h->Na ? h->Nr : h->Na;
     P.buf_elems = big > 8192 ? big : 8192;
     const size_t smem = (size_t)P.buf_elems * sizeof(c32);
+    // large maps: eight CTAs per marked CPI (a thread-block cluster), sixteen clusters; small ones: one CTA each
+    const int cl = ((size_t)h->V * h->Nr * sizeof(c32) >= ((size_t)256 << 10)) ? 8 : 1;
     if (!h->exact_grid) {
         CU(cudaFuncSetAttribute(k_est_exact, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        h->exact_grid = 32;
+        h->exact_grid = cl > 1 ? 16 * cl : 32;
     }
-    ST(h->sExact.need((size_t)h->exact_grid * h->V * h->Nr * sizeof(c32)));
+    P.scratch_stride = (size_t)h->V * h->Nr + EXACT_WCAP / 2;
+    ST(h->sExact.need((size_t)(h->exact_grid / cl) * P.scratch_stride * sizeof(c32)));
     P.scratch = (c32 *)h->sExact.p;
     // programmatic dependent launch: the grid is staged while the kernel in front of it drains (it waits for that
     // kernel's memory with griddepcontrol.wait), so an empty marked-CPI list costs no launch gap
     cudaLaunchConfig_t lc;
     memset(&lc, 0, sizeof(lc));
     lc.gridDim = dim3((unsigned)h->exact_grid); lc.blockDim = dim3(256); lc.dynamicSmemBytes = smem; lc.stream = h->stream;
-    cudaLaunchAttribute at[1];
+    cudaLaunchAttribute at[2];
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[0].val.programmaticStreamSerializationAllowed = 1;
-    lc.attrs = at; lc.numAttrs = 1;
+    at[1].id = cudaLaunchAttributeClusterDimension;
+    at[1].val.clusterDim.x = (unsigned)cl; at[1].val.clusterDim.y = 1; at[1].val.clusterDim.z = 1;
+    lc.attrs = at; lc.numAttrs = 2;
     CU(cudaLaunchKernelEx(&lc, k_est_exact, P));
     h->launches++;
     return JRC_OK;

@@ -14,11 +14,11 @@
 //                candidates (taken from the fast |.|^2 map when there is one, else from a full scan)
 //   DET_GATE     snr_db / peak_power lie within the error bound of the fast noise estimate of a threshold:
 //                the window sum is redone in the reference's order
-// One CTA per marked CPI; the marked CPIs of a batch come as a device list (FixCtl).  Rare by construction
-// (~1e-4 of the CPIs of a random scene), so clarity beats speed here.
+// One cluster of CTAs per marked CPI; the marked CPIs of a batch come as a device list (FixCtl).
 #pragma once
 #include "jrc_common.cuh"
 #include "jrc_staged.cuh"
+#include <cooperative_groups.h>
 
 namespace jrc {
 
@@ -106,24 +106,44 @@ struct ExactParams {
     int cpi0;
     const int *list;
     FixCtl *ctl;
-    c32 *scratch;            // [gridDim.x][V][Nr] range spectra
+    c32 *scratch;            // per cluster: [V][Nr] range spectra, then EXACT_WCAP floats of window samples
+    size_t scratch_stride;   // in c32
     int buf_elems;           // dynamic shared memory, in c32 (>= max(Nr, Na))
 };
 
 constexpr int EXACT_MAX_CAND = 64;
+constexpr int EXACT_WCAP = 1 << 16;          // window samples a cluster exchanges at a time (floats)
+
+// One CLUSTER of CTAs per marked CPI (cluster size 1 for the small maps, 8 for the large ones: a 4096 x 256 map with 32
+// channels is ~1 M exact butterflies, 0.95 ms on one CTA).  The CTAs of a cluster split every stage by rank and meet at
+// cluster barriers; rank 0 owns the candidate list and the per-CTA arg-max keys (the other ranks write them through
+// distributed shared memory) and does the one thing that cannot be split, the sequential window sum.  All decisions that
+// steer control flow are read from rank 0 after a barrier, so the barriers are cluster-uniform.
+struct ExactShared {
+    int ncand;
+    int cand[EXACT_MAX_CAND];
+    unsigned long long keys[16];
+};
 
 __global__ void __launch_bounds__(256) k_est_exact(const ExactParams P)
 {
+    namespace cg = cooperative_groups;
     extern __shared__ c32 sm[];
     __shared__ float chunk[1024];
     __shared__ unsigned long long s_red[8];
-    __shared__ int s_cand[EXACT_MAX_CAND], s_ncand, s_rows[EXACT_MAX_CAND], s_wrows[EXACT_MAX_CAND];
+    __shared__ ExactShared S;
+    __shared__ int s_rows[EXACT_MAX_CAND], s_wrows[EXACT_MAX_CAND];
     __shared__ float s_noise;
+    cg::cluster_group cl = cg::this_cluster();
+    const int CL = (int)cl.num_blocks(), rank = (int)cl.block_rank();
+    const int cid = (int)blockIdx.x / CL, ncl = (int)gridDim.x / CL;
+    ExactShared *S0 = cl.map_shared_rank(&S, 0);          // rank 0's copy (== &S on rank 0)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     asm volatile("griddepcontrol.wait;" ::: "memory");     // launched programmatically behind the kernel that fills the list
     const int count = *reinterpret_cast<volatile int *>(&P.ctl->count);
     const int N = P.N, V = P.V, Nr = P.Nr, Na = P.Na;
-    c32 *Y = P.scratch + (size_t)blockIdx.x * V * Nr;
+    c32 *Y = P.scratch + (size_t)cid * P.scratch_stride;
+    float *W = reinterpret_cast<float *>(Y + (size_t)V * Nr);      // [EXACT_WCAP] window samples, reference order
 
     auto block_max = [&](unsigned long long key) {
 #pragma unroll
@@ -153,12 +173,14 @@ __global__ void __launch_bounds__(256) k_est_exact(const ExactParams P)
     };
     auto ang = [&](int lr, int i) { return sm[lr * Na + ((i + (Na + 1) / 2) % Na)]; };
 
-    for (int it = blockIdx.x; it < count; it += gridDim.x) {
+    for (int it = cid; it < count; it += ncl) {
         const int c = P.list[it];
-        const DetDev d0 = P.dets[c];
+        const DetDev d0 = P.dets[c];             // (rank 0 rewrites it only behind the barriers below)
+        if (rank == 0 && tid == 0) S.ncand = 0;
         // ---- range spectra of all channels, staged arithmetic: conj-MAC (:250-274), zero-pad, fft_vcc #A ----
         const int rp = max(1, min(V, P.buf_elems / Nr));
-        for (int p0 = 0; p0 < V; p0 += rp) {
+        for (int p0 = 0, q = 0; p0 < V; p0 += rp, q++) {
+            if (q % CL != rank) continue;
             const int np = min(rp, V - p0);
             for (int e = tid; e < np * Nr; e += 256) {
                 const int lr = e / Nr, i = e % Nr, p = p0 + lr;
@@ -183,33 +205,42 @@ __global__ void __launch_bounds__(256) k_est_exact(const ExactParams P)
             for (int e = tid; e < np * Nr; e += 256) Y[(size_t)(p0 + e / Nr) * Nr + e % Nr] = sm[e];
             __syncthreads();
         }
+        __threadfence();
+        cl.sync();                               // Y complete, S.ncand reset
         const int rpa = max(1, P.buf_elems / Na);
 
         // ---- arg-max (:137-151): first maximum of (float)pow(abs(z),2) in row-major order ----
         unsigned long long key = 0ull;
-        if (tid == 0) s_ncand = 0;
-        __syncthreads();
         bool full_scan = (d0.flags & DET_AMB) && (P.map == nullptr || d0.range_idx < 0);
         if ((d0.flags & DET_AMB) && !full_scan) {
-            // candidates: every element of the fast map within 2*EPS_AMB of its maximum
+            // candidates: every element of the fast map within 2*EPS_AMB of its maximum; every rank scans its share
             const float *mc = P.map + (size_t)c * Nr * Na;
             const float thr = __fmul_rn(mc[(size_t)d0.range_idx * Na + d0.angle_idx], 1.f - 2.f * EPS_AMB);
-            const long long tot = (long long)Nr * Na;
-            for (long long e = (long long)tid * 4; e < tot; e += 256 * 4) {
-                const float4 v = __ldcs(reinterpret_cast<const float4 *>(mc + e));
-                const float vv[4] = {v.x, v.y, v.z, v.w};
+            const long long tot4 = ((long long)Nr * Na) >> 2;
+            const long long q0 = tot4 * rank / CL, q1 = tot4 * (rank + 1) / CL;
+            for (long long q = q0 + tid; q < q1; q += 256 * 4) {
+                float4 v4[4];
 #pragma unroll
-                for (int k = 0; k < 4; k++)
-                    if (vv[k] >= thr) {
-                        const int slot = atomicAdd(&s_ncand, 1);
-                        if (slot < EXACT_MAX_CAND) s_cand[slot] = (int)(e + k);
-                    }
+                for (int u = 0; u < 4; u++)
+                    v4[u] = (q + 256 * u < q1) ? __ldcs(reinterpret_cast<const float4 *>(mc) + q + 256 * u) : make_float4(-1.f, -1.f, -1.f, -1.f);
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const float vv[4] = {v4[u].x, v4[u].y, v4[u].z, v4[u].w};
+#pragma unroll
+                    for (int k = 0; k < 4; k++)
+                        if (vv[k] >= thr) {
+                            const int slot = atomicAdd(&S0->ncand, 1);
+                            if (slot < EXACT_MAX_CAND) S0->cand[slot] = (int)((q + 256 * u) * 4 + k);
+                        }
+                }
             }
-            __syncthreads();
-            if (s_ncand > EXACT_MAX_CAND || s_ncand == 0) full_scan = true;      // block-uniform
+            cl.sync();
+            const int ncand = S0->ncand;
+            if (ncand > EXACT_MAX_CAND || ncand == 0) full_scan = true;      // cluster-uniform
         }
         if (full_scan) {
-            for (int n0 = 0; n0 < Nr; n0 += rpa) {
+            for (int n0 = 0, q = 0; n0 < Nr; n0 += rpa, q++) {
+                if (q % CL != rank) continue;
                 const int nr = min(rpa, Nr - n0);
                 angle_rows(nullptr, n0, nr, true);
                 for (int e = tid; e < nr * Na; e += 256) {
@@ -222,16 +253,16 @@ __global__ void __launch_bounds__(256) k_est_exact(const ExactParams P)
                 }
                 __syncthreads();
             }
-        } else {
+        } else if (rank == 0) {
             // one row per candidate (the unmarked arg-max is a single candidate: the fast path's own peak)
-            const int nc = (d0.flags & DET_AMB) ? s_ncand : 1;
-            for (int c0 = 0; c0 < nc; c0 += rpa) {
-                const int nr = min(rpa, nc - c0);
-                if (tid < nr) s_rows[tid] = ((d0.flags & DET_AMB) ? s_cand[c0 + tid] : d0.range_idx * Na + d0.angle_idx) / Na;
+            const int nc = (d0.flags & DET_AMB) ? S.ncand : 1;
+            for (int c0 = 0; c0 < nc; c0 += min(rpa, EXACT_MAX_CAND)) {
+                const int nr = min(min(rpa, EXACT_MAX_CAND), nc - c0);
+                if (tid < nr) s_rows[tid] = ((d0.flags & DET_AMB) ? S.cand[c0 + tid] : d0.range_idx * Na + d0.angle_idx) / Na;
                 __syncthreads();
                 angle_rows(s_rows, 0, nr, false);
                 if (tid < nr) {
-                    const int lin = (d0.flags & DET_AMB) ? s_cand[c0 + tid] : d0.range_idx * Na + d0.angle_idx;
+                    const int lin = (d0.flags & DET_AMB) ? S.cand[c0 + tid] : d0.range_idx * Na + d0.angle_idx;
                     const float pw = (float)ref_pow_abs2(ang(tid, lin % Na));
                     if (pw == pw) key = pack_key(pw, (unsigned)lin);
                 }
@@ -239,13 +270,18 @@ __global__ void __launch_bounds__(256) k_est_exact(const ExactParams P)
             }
         }
         key = block_max(key);
+        if (tid == 0) S0->keys[rank] = key;
+        cl.sync();
+        key = S0->keys[0];
+        for (int r = 1; r < CL; r++) { const unsigned long long k2 = S0->keys[r]; key = k2 > key ? k2 : key; }
         if (key == 0ull) {       // NaN-only map: nothing wins the strict '>' scan
-            if (tid == 0) {
+            if (rank == 0 && tid == 0) {
                 DetDev d; d.range_idx = -1; d.angle_idx = -1; d.peak_power = -1.f;
                 d.noise_power = __int_as_float(0x7fc00000); d.snr_db = d.noise_power;
                 d.n_noise = 0; d.flags = DET_EXACT; d.cpi = P.cpi0 + c;
                 P.dets[c] = d;
             }
+            cl.sync();           // rank 0's shared state is reused by the next marked CPI
             continue;
         }
         const unsigned lin = 0xFFFFFFFFu - (unsigned)(key & 0xFFFFFFFFull);
@@ -253,7 +289,8 @@ __global__ void __launch_bounds__(256) k_est_exact(const ExactParams P)
         const float peak = __uint_as_float((unsigned)(key >> 32));
         if (!(d0.flags & DET_GATE) && nstar == d0.range_idx && istar == d0.angle_idx) {
             // the candidates' order is the fast path's: its window, noise estimate and (safe) gate decision stand
-            if (tid == 0) P.dets[c].flags = d0.flags & DET_PASSED;
+            if (rank == 0 && tid == 0) P.dets[c].flags = d0.flags & DET_PASSED;
+            cl.sync();
             continue;
         }
 
@@ -263,9 +300,49 @@ __global__ void __launch_bounds__(256) k_est_exact(const ExactParams P)
         const int total = (ncols > 0 && nrows > 0) ? nrows * ncols : 0;
         if (tid == 0) s_noise = 0.f;
         __syncthreads();
-        if (total > 0) {
-            for (int r0 = 0; r0 < nrows; r0 += min(rpa, EXACT_MAX_CAND)) {
-                const int nr = min(min(rpa, EXACT_MAX_CAND), nrows - r0);
+        const int rb = min(rpa, EXACT_MAX_CAND);             // rows per angle_rows call
+        if (total > 0 && CL > 1 && ncols <= EXACT_WCAP) {
+            // the ranks fill W with the window's sqrt-power samples, rows_seg rows at a time; rank 0 adds them up in order
+            const int rows_seg = max(1, EXACT_WCAP / ncols);
+            for (int s0 = 0; s0 < nrows; s0 += rows_seg) {
+                const int ns = min(rows_seg, nrows - s0);
+                for (int r0 = 0, q = 0; r0 < ns; r0 += rb, q++) {
+                    if (q % CL != rank) continue;
+                    const int nr = min(rb, ns - r0);
+                    if (tid < nr) { const int ir = w.start_r + s0 + r0 + tid; s_wrows[tid] = ((ir % Nr) + Nr) % Nr; }
+                    __syncthreads();
+                    angle_rows(s_wrows, 0, nr, false);
+                    for (int e = tid; e < nr * ncols; e += 256) {
+                        const int lr = e / ncols, j = e % ncols;
+                        const int ia = w.start_a + j, a_idx = ((ia % Na) + Na) % Na;
+                        W[(size_t)(r0 + lr) * ncols + j] = ref_abs(ang(lr, a_idx));
+                    }
+                    __syncthreads();
+                }
+                __threadfence();
+                cl.sync();
+                if (rank == 0) {
+                    const int cells = ns * ncols;
+                    for (int cb = 0; cb < cells; cb += 1024) {
+                        const int cnt = min(1024, cells - cb);
+                        for (int j = tid; j < cnt; j += 256) chunk[j] = __ldcg(W + cb + j);
+                        __syncthreads();
+                        if (tid == 0) {
+                            float acc = s_noise;
+                            for (int j = 0; j < cnt; j++) {
+                                const double a = (double)chunk[j];
+                                acc = (float)((double)acc + a * a);          // :217 float += double
+                            }
+                            s_noise = acc;
+                        }
+                        __syncthreads();
+                    }
+                }
+                if (s0 + rows_seg < nrows) cl.sync();        // W is rewritten by the next segment
+            }
+        } else if (total > 0 && rank == 0) {
+            for (int r0 = 0; r0 < nrows; r0 += rb) {
+                const int nr = min(rb, nrows - r0);
                 if (tid < nr) { const int ir = w.start_r + r0 + tid; s_wrows[tid] = ((ir % Nr) + Nr) % Nr; }
                 __syncthreads();
                 angle_rows(s_wrows, 0, nr, false);
@@ -289,7 +366,7 @@ __global__ void __launch_bounds__(256) k_est_exact(const ExactParams P)
                     }
             }
         }
-        if (tid == 0) {
+        if (rank == 0 && tid == 0) {
             DetDev d;
             d.range_idx = nstar; d.angle_idx = istar; d.peak_power = peak; d.n_noise = total;
             d.noise_power = __fdiv_rn(s_noise, (float)total);                                   // :226
@@ -299,7 +376,7 @@ __global__ void __launch_bounds__(256) k_est_exact(const ExactParams P)
             P.dets[c] = d;
             atomicAdd(&P.ctl->n_redone, 1);
         }
-        __syncthreads();
+        cl.sync();               // rank 0's shared state and W are reused by the next marked CPI
     }
     // the last CTA to finish re-arms the list for the next batch
     __shared__ bool s_last;
@@ -309,6 +386,7 @@ __global__ void __launch_bounds__(256) k_est_exact(const ExactParams P)
     }
     __syncthreads();
     if (s_last && tid == 0) { P.ctl->count = 0; P.ctl->done = 0; __threadfence(); }
+    cl.sync();                   // no CTA leaves while its shared memory may still be read by another rank
 }
 
 }  // namespace jrc
