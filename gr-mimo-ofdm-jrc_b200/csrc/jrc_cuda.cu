@@ -500,6 +500,37 @@ static bool wide_config_ok(const jrc_chain *h)
            c.n_rx % 4 == 0 && c.n_tx <= 8 && c.n_rx <= 16 && c.n_sym <= 8;
 }
 
+// 4-D tensor map over the packets of one port: (float index within a symbol, symbol, antenna, CPI); a tile is
+// [n_ant][n_sym][KB subcarriers].  The encoder comes from the driver at run time (no link dependency on libcuda).
+typedef CUresult (*tmap_encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                   const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static tmap_encode_fn tmap_encoder()
+{
+    static tmap_encode_fn fn = []() -> tmap_encode_fn {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) {
+            cudaGetLastError();
+            return nullptr;
+        }
+        return (tmap_encode_fn)p;
+    }();
+    return fn;
+}
+static bool port_tensor_map(CUtensorMap *tm, const PortDev &port, int n_pre, int N, int n_sym, int n_ant, int n_cpi, int KB)
+{
+    tmap_encode_fn enc = tmap_encoder();
+    const long long cs = port.cpi_stride ? port.cpi_stride : (long long)n_ant * port.ant_stride;    // shared frame: one "CPI"
+    if (!enc || ((uintptr_t)port.base & 15u) || (port.ant_stride & 1) || (cs & 1) || port.ant_stride <= 0 || cs <= 0) return false;
+    const cuuint64_t dims[4] = {(cuuint64_t)2 * N, (cuuint64_t)n_sym, (cuuint64_t)n_ant, (cuuint64_t)(port.cpi_stride ? n_cpi : 1)};
+    const cuuint64_t strides[3] = {(cuuint64_t)N * sizeof(c32), (cuuint64_t)port.ant_stride * sizeof(c32), (cuuint64_t)cs * sizeof(c32)};
+    const cuuint32_t box[4] = {(cuuint32_t)2 * KB, (cuuint32_t)n_sym, (cuuint32_t)n_ant, 1}, es[4] = {1, 1, 1, 1};
+    return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void *)(port.base + (long long)n_pre * N), dims, strides, box, es,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 static jrc_status launch_wide(jrc_chain *h, PortDev rx, PortDev tx, const c32 *H, int n_pre, int n_cpi, c32 *G, float *map,
                               unsigned long long *keys, unsigned *sec)
 {
@@ -511,13 +542,19 @@ static jrc_status launch_wide(jrc_chain *h, PortDev rx, PortDev tx, const c32 *H
     P.n_cpi = n_cpi; P.G = G; P.map = map; P.keys = keys; P.sec = sec;
     ST(get_twiddles_full(h, 128, 1, &P.tw_a));
     ST(get_twiddles_full(h, 2048, 0, &P.tw_r));
+    static const bool tma_off = getenv("JRC_WIDE_TMA") && atoi(getenv("JRC_WIDE_TMA")) == 0;      // A/B switch
+    CUtensorMap tm_rx, tm_tx;
+    memset(&tm_rx, 0, sizeof(tm_rx));
+    memset(&tm_tx, 0, sizeof(tm_tx));
+    P.use_tma = !tma_off && !H && port_tensor_map(&tm_rx, rx, n_pre, Gm::N, c.n_sym, c.n_rx, n_cpi, Gm::KB) &&
+                port_tensor_map(&tm_tx, tx, n_pre, Gm::N, c.n_sym, c.n_tx, n_cpi, Gm::KB);
     auto ka = c.n_sym == 8 ? k_wide_mac_angle<11, 8> : (c.n_sym == 4 ? k_wide_mac_angle<11, 4> : k_wide_mac_angle<11, 0>);
     auto kb = k_wide_range_mag<11>;
     CU(cudaFuncSetAttribute(ka, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Gm::SMEM_A));
     CU(cudaFuncSetAttribute(kb, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Gm::SMEM_B));
     long long ua = (long long)n_cpi * (Gm::N / Gm::KB), ub = (long long)n_cpi * (Gm::V / Gm::UB);
     long long ga = ua < h->sm_count ? ua : h->sm_count, gb = ub < 2LL * h->sm_count ? ub : 2LL * h->sm_count;
-    ka<<<(unsigned)ga, Gm::TA, Gm::SMEM_A, h->stream>>>(P);
+    ka<<<(unsigned)ga, Gm::TA, Gm::SMEM_A, h->stream>>>(P, tm_rx, tm_tx);
     CU(cudaGetLastError());
     kb<<<(unsigned)gb, Gm::GR::THREADS, Gm::SMEM_B, h->stream>>>(P);
     CU(cudaGetLastError());

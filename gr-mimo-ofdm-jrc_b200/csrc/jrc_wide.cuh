@@ -20,6 +20,7 @@
 // Float32 arithmetic of the same class as the oracle's radix-2 FFTs, not its rounding or order: the criterion is 1e-4 of
 // the map peak; detection decisions are settled by jrc_exact.cuh.
 #pragma once
+#include <cuda.h>             // CUtensorMap (types only: the encoder is looked up at run time, no libcuda link)
 #include "jrc_common.cuh"
 #include "jrc_tiled.cuh"
 #include "jrc_fused.cuh"      // cp_async16
@@ -36,7 +37,37 @@ struct WideParams {
     unsigned *sec;
     const c32 *tw_a;            // [128] w_128^i (forward)
     const c32 *tw_r;            // [N]   W_N^i  (inverse)
+    int use_tma;                // symbols arrive as two TMA tiles per unit (tensor maps passed next to this struct)
 };
+
+// ---- TMA + mbarrier (sm_100a): the symbol tiles of a unit are two bulk tensor copies issued by one thread ----
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// tile of a 4-D tensor (coordinates innermost first) -> shared memory, completion counted in bytes on the mbarrier
+__device__ __forceinline__ void tma_load_4d(void *dst, const CUtensorMap *tm, unsigned long long *bar, int c0, int c1, int c2, int c3)
+{
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                 ::"r"(smem_u32(dst)), "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
 
 template <int LOG2N>
 struct WideGeom {
@@ -59,12 +90,13 @@ struct WideGeom {
 // conj-MAC + angle FFT, one (CPI, 16-subcarrier block) at a time
 // ---------------------------------------------------------------------------
 template <int LOG2N, int S_CT>      // S_CT: number of LTF symbols when known at compile time (0: run-time)
-__global__ void __launch_bounds__(WideGeom<LOG2N>::TA, 1) k_wide_mac_angle(const WideParams P)
+__global__ void __launch_bounds__(WideGeom<LOG2N>::TA, 1) k_wide_mac_angle(const WideParams P, const __grid_constant__ CUtensorMap tm_rx,
+                                                                            const __grid_constant__ CUtensorMap tm_tx)
 {
     using Gm = WideGeom<LOG2N>;
     using GA = typename Gm::GA;
     constexpr int N = Gm::N, V = Gm::V, KB = Gm::KB, RS = GA::RS, TA = Gm::TA, CPR = KB / 2;   // CPR: 16-byte chunks per row
-    extern __shared__ __align__(16) unsigned char smem_wide[];
+    extern __shared__ __align__(128) unsigned char smem_wide[];
     c32 *sym = reinterpret_cast<c32 *>(smem_wide);                        // [2][(T+R)*S][KB]
     c32 *rows = sym + 2 * Gm::MAX_ANT * Gm::MAX_S * KB;                   // [KB][RS]: H[.][k] then its angle transform
     c32 *stg = rows + KB * RS;                                            // [V][KB+1]: G block, angle bin major
@@ -80,25 +112,48 @@ __global__ void __launch_bounds__(WideGeom<LOG2N>::TA, 1) k_wide_mac_angle(const
     // conj-MAC thread mapping: subcarrier kk, RX block of 4, TX block of 2 (T = 8: 4 blocks) -> 8 channels x S products
     const int kk = tid % KB, rb = (tid / KB) & 3, tb = tid / (4 * KB);
 
-    // cp.async plan of this thread, fixed for the whole kernel: chunk i = 16 bytes (two subcarriers) of antenna-symbol
-    // row tid / CPR + (TA / CPR) i; only the CPI and the subcarrier block change from unit to unit
+    // Symbols of a unit -> shared memory.  TMA form: the tile [T][S][KB] of the TX packets and the tile [R][S][KB] of the RX
+    // packets are one cp.async.bulk.tensor each (4-D tensor maps over (subcarrier, symbol, antenna, CPI), built by the host
+    // for this call), issued by thread 0 and counted in bytes on the buffer's mbarrier.  cp.async form (odd strides,
+    // JRC_WIDE_TMA=0): chunk i of this thread = 16 bytes (two subcarriers) of antenna-symbol row tid / CPR + (TA / CPR) i,
+    // a plan fixed for the whole kernel; only the CPI and the subcarrier block change from unit to unit.
+    __shared__ __align__(8) unsigned long long bar[2];
+    const bool tma = P.use_tma != 0;
     constexpr int MAXCH = Gm::MAX_ANT * Gm::MAX_S * CPR / TA, RSTEP = TA / CPR;
     const c32 *src0[MAXCH];
     unsigned is_tx = 0;
+    if (tma) {
+        if (tid == 0) {
+            mbar_init(&bar[0], 1);
+            mbar_init(&bar[1], 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+    } else {
 #pragma unroll
-    for (int i = 0; i < MAXCH; i++) {
-        const int row = tid / CPR + RSTEP * i, ch = tid % CPR, ant = row / S, sy = row - ant * S;
-        src0[i] = nullptr;
-        if (row < per) {
-            const bool txr = ant < T;
-            src0[i] = (txr ? P.tx.base + (long long)ant * P.tx.ant_stride : P.rx.base + (long long)(ant - T) * P.rx.ant_stride) +
-                      (long long)(P.n_pre + sy) * N + 2 * ch;
-            is_tx |= txr ? (1u << i) : 0u;
+        for (int i = 0; i < MAXCH; i++) {
+            const int row = tid / CPR + RSTEP * i, ch = tid % CPR, ant = row / S, sy = row - ant * S;
+            src0[i] = nullptr;
+            if (row < per) {
+                const bool txr = ant < T;
+                src0[i] = (txr ? P.tx.base + (long long)ant * P.tx.ant_stride : P.rx.base + (long long)(ant - T) * P.rx.ant_stride) +
+                          (long long)(P.n_pre + sy) * N + 2 * ch;
+                is_tx |= txr ? (1u << i) : 0u;
+            }
         }
     }
     auto prefetch = [&](long long unit, int buf) {
         const long long cpi = unit / blocks_per_cpi;
         const int k0 = (int)(unit % blocks_per_cpi) * KB;
+        if (tma) {
+            if (tid == 0) {
+                c32 *dst = sym + (size_t)buf * per * KB;
+                mbar_expect_tx(&bar[buf], (unsigned)(per * KB * sizeof(c32)));
+                tma_load_4d(dst, &tm_tx, &bar[buf], 2 * k0, 0, 0, P.tx.cpi_stride ? (int)cpi : 0);
+                tma_load_4d(dst + T * S * KB, &tm_rx, &bar[buf], 2 * k0, 0, 0, (int)cpi);
+            }
+            return;
+        }
         const long long otx = cpi * P.tx.cpi_stride + k0, orx = cpi * P.rx.cpi_stride + k0;
         c32 *dst = sym + ((size_t)buf * per + tid / CPR) * KB + 2 * (tid % CPR);
 #pragma unroll
@@ -106,6 +161,7 @@ __global__ void __launch_bounds__(WideGeom<LOG2N>::TA, 1) k_wide_mac_angle(const
             if (src0[i]) cp_async16(dst + RSTEP * i * KB, src0[i] + ((is_tx >> i) & 1 ? otx : orx));
         cp_async_commit();
     };
+    unsigned phase = 0;          // bit b: parity the next wait on bar[b] expects
 
     long long unit = blockIdx.x;
     int buf = 0;
@@ -113,7 +169,12 @@ __global__ void __launch_bounds__(WideGeom<LOG2N>::TA, 1) k_wide_mac_angle(const
     for (; unit < n_units; unit += gridDim.x, buf ^= 1) {
         const int cpi = (int)(unit / blocks_per_cpi), k0 = (int)(unit % blocks_per_cpi) * KB;
         if (!P.H) {
-            cp_async_wait_all();
+            if (tma) {
+                mbar_wait(&bar[buf], (phase >> buf) & 1u);
+                phase ^= 1u << buf;
+            } else {
+                cp_async_wait_all();
+            }
             __syncthreads();                                  // symbols of this unit visible; previous unit's stores done
             if (unit + gridDim.x < n_units) prefetch(unit + gridDim.x, buf ^ 1);
             // ---- conj-MAC: H[p][k0 + kk] for r in 4 rb .. +3, t in 2 tb .. +1 ----
@@ -188,7 +249,7 @@ __global__ void __launch_bounds__(TiledGeom<LOG2N>::THREADS, 2) k_wide_range_mag
     using GR = typename Gm::GR;
     constexpr int N = Gm::N, V = Gm::V, AB = Gm::AB, RROW = Gm::RROW, TPR = GR::TPR;
     static_assert(GR::RPC == 1, "one transform per pass of the CTA");
-    extern __shared__ __align__(16) unsigned char smem_wide[];
+    extern __shared__ __align__(128) unsigned char smem_wide[];
     c32 *rowbuf = reinterpret_cast<c32 *>(smem_wide);                     // [AB][RROW]
     const int tid = threadIdx.x, lane = tid & 31, t = tid % TPR;
     DifTw<LOG2N> Tw;
