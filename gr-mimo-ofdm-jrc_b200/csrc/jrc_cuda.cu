@@ -548,13 +548,25 @@ static jrc_status launch_wide(jrc_chain *h, PortDev rx, PortDev tx, const c32 *H
     memset(&tm_tx, 0, sizeof(tm_tx));
     P.use_tma = !tma_off && !H && port_tensor_map(&tm_rx, rx, n_pre, Gm::N, c.n_sym, c.n_rx, n_cpi, Gm::KB) &&
                 port_tensor_map(&tm_tx, tx, n_pre, Gm::N, c.n_sym, c.n_tx, n_cpi, Gm::KB);
+    // G [n_cpi][128][N] as (float index within a row, angle bin, CPI); a store tile is [128][16 subcarriers], 128-byte swizzle
+    CUtensorMap tm_g;
+    memset(&tm_g, 0, sizeof(tm_g));
+    static const bool tmas_off = getenv("JRC_WIDE_TMA_STORE") && atoi(getenv("JRC_WIDE_TMA_STORE")) == 0;
+    if (!tma_off && !tmas_off && tmap_encoder() && !((uintptr_t)G & 127u)) {
+        const cuuint64_t dims[3] = {(cuuint64_t)2 * Gm::N, (cuuint64_t)Gm::V, (cuuint64_t)n_cpi};
+        const cuuint64_t strides[2] = {(cuuint64_t)Gm::N * sizeof(c32), (cuuint64_t)Gm::V * Gm::N * sizeof(c32)};
+        const cuuint32_t box[3] = {32, (cuuint32_t)Gm::V, 1}, es[3] = {1, 1, 1};
+        P.use_tma_store = tmap_encoder()(&tm_g, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void *)G, dims, strides, box, es,
+                                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+    }
     auto ka = c.n_sym == 8 ? k_wide_mac_angle<11, 8> : (c.n_sym == 4 ? k_wide_mac_angle<11, 4> : k_wide_mac_angle<11, 0>);
     auto kb = k_wide_range_mag<11>;
     CU(cudaFuncSetAttribute(ka, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Gm::SMEM_A));
     CU(cudaFuncSetAttribute(kb, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Gm::SMEM_B));
     long long ua = (long long)n_cpi * (Gm::N / Gm::KB), ub = (long long)n_cpi * (Gm::V / Gm::UB);
     long long ga = ua < h->sm_count ? ua : h->sm_count, gb = ub < 2LL * h->sm_count ? ub : 2LL * h->sm_count;
-    ka<<<(unsigned)ga, Gm::TA, Gm::SMEM_A, h->stream>>>(P, tm_rx, tm_tx);
+    ka<<<(unsigned)ga, Gm::TA, Gm::SMEM_A, h->stream>>>(P, tm_rx, tm_tx, tm_g);
     CU(cudaGetLastError());
     kb<<<(unsigned)gb, Gm::GR::THREADS, Gm::SMEM_B, h->stream>>>(P);
     CU(cudaGetLastError());

@@ -38,6 +38,7 @@ struct WideParams {
     const c32 *tw_a;            // [128] w_128^i (forward)
     const c32 *tw_r;            // [N]   W_N^i  (inverse)
     int use_tma;                // symbols arrive as two TMA tiles per unit (tensor maps passed next to this struct)
+    int use_tma_store;          // G leaves as two TMA tiles per unit
 };
 
 // ---- TMA + mbarrier (sm_100a): the symbol tiles of a unit are two bulk tensor copies issued by one thread ----
@@ -62,6 +63,12 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned pari
         "DONE_%=:\n"
         "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
+// shared-memory tile -> tile of a 3-D tensor, tracked by the thread's bulk async-group
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap *tm, const void *src, int c0, int c1, int c2)
+{
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+                 ::"l"(tm), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
 // tile of a 4-D tensor (coordinates innermost first) -> shared memory, completion counted in bytes on the mbarrier
 __device__ __forceinline__ void tma_load_4d(void *dst, const CUtensorMap *tm, unsigned long long *bar, int c0, int c1, int c2, int c3)
 {
@@ -79,8 +86,9 @@ struct WideGeom {
     using GR = TiledGeom<LOG2N>;
     static constexpr int MAX_ANT = 24, MAX_S = 8;
     // k_wide_mac_angle: two symbol buffers [(T+R)][S][KB] + H/FFT rows [KB][RS] (the staging of G reuses the rows)
-    static constexpr size_t SMEM_A = (size_t)2 * MAX_ANT * MAX_S * KB * sizeof(c32) + (size_t)KB * GA::RS * sizeof(c32) +
-                                     (size_t)V * (KB + 1) * sizeof(c32);
+    // (the staging tiles start on a 1024-byte boundary: TMA's 128-byte swizzle is anchored there)
+    static constexpr size_t STG_OFF = (((size_t)2 * MAX_ANT * MAX_S * KB * sizeof(c32) + (size_t)KB * GA::RS * sizeof(c32)) + 1023) / 1024 * 1024;
+    static constexpr size_t SMEM_A = STG_OFF + (size_t)V * (KB + 1) * sizeof(c32);
     // k_wide_range_mag: AB rows of the transform
     static constexpr int RROW = fpad(N - 1) + 1 + 8;
     static constexpr size_t SMEM_B = (size_t)AB * RROW * sizeof(c32);
@@ -91,15 +99,19 @@ struct WideGeom {
 // ---------------------------------------------------------------------------
 template <int LOG2N, int S_CT>      // S_CT: number of LTF symbols when known at compile time (0: run-time)
 __global__ void __launch_bounds__(WideGeom<LOG2N>::TA, 1) k_wide_mac_angle(const WideParams P, const __grid_constant__ CUtensorMap tm_rx,
-                                                                            const __grid_constant__ CUtensorMap tm_tx)
+                                                                            const __grid_constant__ CUtensorMap tm_tx,
+                                                                            const __grid_constant__ CUtensorMap tm_g)
 {
     using Gm = WideGeom<LOG2N>;
     using GA = typename Gm::GA;
     constexpr int N = Gm::N, V = Gm::V, KB = Gm::KB, RS = GA::RS, TA = Gm::TA, CPR = KB / 2;   // CPR: 16-byte chunks per row
-    extern __shared__ __align__(128) unsigned char smem_wide[];
+    extern __shared__ __align__(1024) unsigned char smem_wide[];     // (the swizzle of the staging tiles is a function of the address)
     c32 *sym = reinterpret_cast<c32 *>(smem_wide);                        // [2][(T+R)*S][KB]
     c32 *rows = sym + 2 * Gm::MAX_ANT * Gm::MAX_S * KB;                   // [KB][RS]: H[.][k] then its angle transform
-    c32 *stg = rows + KB * RS;                                            // [V][KB+1]: G block, angle bin major
+    // G block, angle bin major.  TMA-store form: two tiles [V][16 subcarriers] of 128-byte rows in the 128-byte swizzle
+    // (16-byte chunk j of row a sits at chunk j ^ (a & 7)): the column writes of the angle FFT spread over the banks as
+    // with a padded pitch, and the block leaves as two bulk tensor stores.  Otherwise [V][KB+1].
+    c32 *stg = reinterpret_cast<c32 *>(smem_wide + Gm::STG_OFF);
     const int tid = threadIdx.x;
     const int T = P.T, R = P.R, S = S_CT ? S_CT : P.S, per = (T + R) * S;  // antenna-symbol rows of KB subcarriers each
     constexpr int blocks_per_cpi = N / KB;
@@ -215,6 +227,8 @@ __global__ void __launch_bounds__(WideGeom<LOG2N>::TA, 1) k_wide_mac_angle(const
                 rows[k * RS + fpad(p)] = P.H[((long long)cpi * V + p) * N + k0 + k];
             }
         }
+        // (the previous unit's two stores have read the staging tiles by now: they had the whole conj-MAC phase)
+        if (P.use_tma_store && tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
         __syncthreads();
         // ---- angle FFT across the 128 channels of subcarrier lr_t (radix 8.8.2, fftshift folded in) ----
         {
@@ -226,16 +240,35 @@ __global__ void __launch_bounds__(WideGeom<LOG2N>::TA, 1) k_wide_mac_angle(const
             __syncthreads();
             c32 o[8];
             dif_passes<7, -1, GA::WARP_SYNC, true>(xrow, t, Tw, o);
+            if (P.use_tma_store) {
+                const int half = lr_t >> 4, kc = (lr_t & 15) >> 1, ko = lr_t & 1;
 #pragma unroll
-            for (int c = 0; c < 8; c++) stg[dif_freq<7>(8 * t + c) * (KB + 1) + lr_t] = o[c];
+                for (int c = 0; c < 8; c++) {
+                    const int a = dif_freq<7>(8 * t + c);
+                    stg[half * (V * 16) + a * 16 + (((kc ^ (a & 7)) << 1) | ko)] = o[c];
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic writes -> the async proxy's reads
+            } else {
+#pragma unroll
+                for (int c = 0; c < 8; c++) stg[dif_freq<7>(8 * t + c) * (KB + 1) + lr_t] = o[c];
+            }
         }
         __syncthreads();
-        // ---- G[cpi][a][k0 .. k0+15]: one 128-byte line per angle bin ----
-        for (int e = tid; e < V * KB; e += TA) {
-            const int a = e / KB, k = e % KB;
-            P.G[((long long)cpi * V + a) * N + k0 + k] = stg[a * (KB + 1) + k];
+        if (P.use_tma_store) {
+            if (tid == 0) {
+                tma_store_3d(&tm_g, stg, 2 * k0, 0, cpi);
+                tma_store_3d(&tm_g, stg + V * 16, 2 * (k0 + 16), 0, cpi);
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+        } else {
+            // ---- G[cpi][a][k0 .. k0+31]: two 128-byte lines per angle bin ----
+            for (int e = tid; e < V * KB; e += TA) {
+                const int a = e / KB, k = e % KB;
+                P.G[((long long)cpi * V + a) * N + k0 + k] = stg[a * (KB + 1) + k];
+            }
         }
     }
+    if (P.use_tma_store && tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     cp_async_wait_all();
 }
 
@@ -249,7 +282,7 @@ __global__ void __launch_bounds__(TiledGeom<LOG2N>::THREADS, 2) k_wide_range_mag
     using GR = typename Gm::GR;
     constexpr int N = Gm::N, V = Gm::V, AB = Gm::AB, RROW = Gm::RROW, TPR = GR::TPR;
     static_assert(GR::RPC == 1, "one transform per pass of the CTA");
-    extern __shared__ __align__(128) unsigned char smem_wide[];
+    extern __shared__ __align__(1024) unsigned char smem_wide[];
     c32 *rowbuf = reinterpret_cast<c32 *>(smem_wide);                     // [AB][RROW]
     const int tid = threadIdx.x, lane = tid & 31, t = tid % TPR;
     DifTw<LOG2N> Tw;
