@@ -60,7 +60,7 @@ def config_dict(batch, world):
     Nr, Na = CFG["N"] * CFG["IR"], CFG["T"] * CFG["R"] * CFG["IA"]
     return {"workload": WORKLOAD, "batch_per_gpu": batch, "map": [Nr, Na],
             "l2": "per-step working set (1.0 GiB map + 48 MiB symbols) exceeds the 126 MB L2; no flush needed",
-            "parallelism": f"cpi-shard x{world}, detection records land on rank 0 over NVLink (peer stores; NCCL for the IPC handle and barriers)" if world > 1 else "single GPU"}
+            "parallelism": f"cpi-shard x{world}, detection records land on rank 0 over NVLink (one peer copy per rank at the drain into a CUDA-IPC mapped table; NCCL for the IPC handle and barriers)" if world > 1 else "single GPU"}
 
 
 def make_inputs(batch, seed, cfg=CFG, targets=2, span=10.0):
@@ -412,14 +412,21 @@ def run_ours(args):
     ext = torch.cuda.ExternalStream(rc.chain.stream, device=dev)
     torch.cuda.synchronize()
 
+    # JRC_BENCH_PEER_STORES=1: the kernels store their records into the table themselves (1.6 % slower steps on the
+    # writing ranks: a kernel waits for its NVLink stores when it ends); default: local records, one peer copy at the drain
+    peer_stores = table is not None and bool(os.environ.get("JRC_BENCH_PEER_STORES"))
+
     def step(k):
-        if table is not None:
+        if peer_stores:
             rc.run(rx, tx, map_out=dmap, dets_ptr=table.ptr((k % K) * B), path=jrc.PATH_FUSED, sync_inputs=False)
         else:
             rc.run(rx, tx, map_out=dmap, dets_out=ddet_all[k % K], path=jrc.PATH_FUSED, sync_inputs=False)
 
     def gather_all():
-        if world > 1 and table is None:
+        if table is not None:
+            if not peer_stores:
+                table.push(rc.chain, ddet_all.view(K * B, 32))
+        elif world > 1:
             shard.gather_detections(ddet_all.view(K * B, 32), dst=0, counts=[K * B] * world, out=gath)
 
     with torch.cuda.stream(ext):

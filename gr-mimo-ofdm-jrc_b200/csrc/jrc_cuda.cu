@@ -1428,6 +1428,13 @@ extern "C" jrc_status jrc_dev_copy(void *dst, const void *src, size_t bytes)
     CU(cudaMemcpy(dst, src, bytes, cudaMemcpyDefault));
     return JRC_OK;
 }
+extern "C" jrc_status jrc_chain_copy_async(jrc_chain *h, void *dst, const void *src, size_t bytes)
+{
+    if (!h || !dst || !src) return fail(JRC_ERR_INVALID, "null argument");
+    CU(cudaSetDevice(h->cfg.device));
+    CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, h->stream));
+    return JRC_OK;
+}
 extern "C" jrc_status jrc_ipc_export(void *dev_ptr, void *handle64)
 {
     if (!dev_ptr || !handle64) return fail(JRC_ERR_INVALID, "null argument");

@@ -56,6 +56,7 @@ EXPORTS = [
     "jrc_pinned_alloc", "jrc_pinned_free", "jrc_host_register", "jrc_host_unregister", "jrc_chain_exact_stats", "jrc_scene_synth", "jrc_chain_run_burst",
     "jrc_dev_alloc", "jrc_dev_free", "jrc_dev_copy", "jrc_ipc_export", "jrc_ipc_open", "jrc_ipc_close",
     "jrc_radar_estimate_fused", "jrc_fused_fetch_transposed", "jrc_fused_fetch_det", "jrc_chain_run_batch_time",
+    "jrc_chain_copy_async",
 ]
 
 _lib = None
@@ -116,6 +117,7 @@ def load():
     lib.jrc_ipc_open.argtypes = [vp, i32, C.POINTER(vp)]
     lib.jrc_ipc_close.argtypes = [vp]
     lib.jrc_chain_run_batch_time.argtypes = [vp, PortLayout, i32, PortLayout, i32, i32, vp, vp, vp, i32]
+    lib.jrc_chain_copy_async.argtypes = [vp, vp, vp, sz]
     lib.jrc_radar_estimate_fused.argtypes = [vp, vp, vp, sz, vp, vp, C.POINTER(i64)]
     lib.jrc_fused_fetch_transposed.argtypes = [vp, i64, vp]
     lib.jrc_fused_fetch_det.argtypes = [vp, i64, f32, f32, vp]
@@ -210,6 +212,10 @@ class Chain:
         rx = PortLayout(rx_ptr, rx_cpi_stride, rx_ant_stride)
         tx = PortLayout(tx_ptr, tx_cpi_stride, tx_ant_stride)
         check(load().jrc_chain_run_batch_time(self._h, rx, cp_len, tx, n_cpi, cpi0, map_ptr, cmap_ptr, dets_ptr, path))
+
+    def copy_async(self, dst_ptr, src_ptr, nbytes):
+        """Device/peer copy queued on the handle's stream."""
+        check(load().jrc_chain_copy_async(self._h, dst_ptr, src_ptr, nbytes))
 
     def run_burst_ptr(self, rx_ptr, rx_cpi_stride, rx_ant_stride, tx_ptr, tx_cpi_stride, tx_ant_stride, n_burst, cube_ptr):
         """Range-Doppler-angle cube [Nr][Na][n_burst] of a burst of CPIs (device pointers)."""

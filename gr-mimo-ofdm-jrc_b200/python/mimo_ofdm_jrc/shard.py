@@ -100,6 +100,14 @@ class PeerRecordTable:
     def ptr(self, i=0):
         return self._base.value + (self.rank * self.n + i) * 32
 
+    def push(self, chain, dets, i=0):
+        """Queues ONE peer copy of this rank's records `dets` ([n][32] uint8, device) to slot i.. of its slice on the chain's
+        stream: the drain-time alternative to handing `ptr()` to the kernels."""
+        n = int(dets.shape[0])
+        if i < 0 or i + n > self.n:
+            raise ValueError("records do not fit this rank's slice")
+        chain.copy_async(self.ptr(i), dets.data_ptr(), n * 32)
+
     def complete(self):
         self._dist.barrier(group=self._group)
 
