@@ -40,3 +40,19 @@ tk = [ch.submit_ptr(jrc.cabi.np_ptr(np.ascontiguousarray(rx[i:i + 1])), jrc.cabi
 for t in tk:
     ch.wait(t)
 print("submit/wait", [int(x["range_idx"][0]) for x in dets])
+# raw time samples in front of the chain (k_ofdm_demod64 / k_ofdm_demod_batch)
+import torch
+for (T, R, S, N, IR, IA, n) in ((4, 2, 4, 64, 16, 8, 64), (4, 8, 4, 256, 4, 2, 4)):
+    rx, tx = scene(T, R, S, N, n)
+    cp = N // 4
+    td = np.fft.ifft(np.fft.ifftshift(rx.astype(np.complex128), axes=-1), axis=-1)
+    td = np.concatenate([td[..., N - cp:], td], axis=-1).astype(np.complex64)
+    ch = jrc.Chain(N, T, R, S, 0, IR, IA)
+    ch.set_estimator(**synth.default_estimator_params(N, T * R, IR, IA))
+    dtd, dtx = torch.from_numpy(td).cuda(), torch.from_numpy(tx).cuda()
+    m = torch.empty((n, ch.Nr, ch.Na), dtype=torch.float32, device="cuda")
+    d = torch.zeros((n, 32), dtype=torch.uint8, device="cuda")
+    torch.cuda.synchronize()
+    ch.run_batch_time_ptr(dtd.data_ptr(), R * S * (N + cp), S * (N + cp), cp, dtx.data_ptr(), 0, S * N, n, 0, m.data_ptr(), None, d.data_ptr())
+    ch.sync()
+    print("time samples", (N, T * R), "path", ch.last_path, float(m.max()))
