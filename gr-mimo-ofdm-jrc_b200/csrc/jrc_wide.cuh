@@ -301,6 +301,16 @@ __global__ void __launch_bounds__(TiledGeom<LOG2N>::THREADS, 2) k_wide_range_mag
         for (int hf = 0; hf < HALVES; hf++) {
             const c32 *Gu = P.G + ((long long)cpi * V + a0 + hf * AB) * N;
             if (hf) __syncthreads();           // the rows of the previous pass have been read
+            {
+                // the rows of the NEXT pass (this unit's other half, or the first half of this CTA's next unit) on their way
+                // from HBM into the L2 while this pass computes: one 128-byte line per lane and row covers the row's 16 KiB
+                const long long nu = unit + gridDim.x;
+                const c32 *Gn = hf + 1 < HALVES ? Gu + (long long)AB * N
+                                                : (nu < n_units ? P.G + ((nu / units_per_cpi) * V + (nu % units_per_cpi) * UB) * (long long)N : nullptr);
+                if (Gn && tid < 128)
+#pragma unroll
+                    for (int r = 0; r < AB; r++) asm volatile("prefetch.global.L2 [%0];" ::"l"(Gn + (long long)r * N + tid * 16));
+            }
             // first pass of the AB rows straight from global memory (L2): 8 loads in flight per row and thread
 #pragma unroll
             for (int r = 0; r < AB; r++) {
