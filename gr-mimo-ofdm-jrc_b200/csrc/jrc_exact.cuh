@@ -76,6 +76,33 @@ __device__ __forceinline__ c32 dit_bin8(const c32 (&x)[8], int log2n, const c32 
     return dit_level(B[0], B[1], tw, log2n, l0 + 2, o);
 }
 
+// 32 * 2^lm inputs, one warp, any power-of-two transform length >= the input count: lane holds the 2^lm consecutive leaves
+// A[(lane << lm) + idx] = x[rev(...)] (fetched through load(), which returns zero beyond the real inputs: zeros in front of
+// the copy levels go through the same u +- w*0 the transform performs), reduces them with a binary-counter stack, then
+// five levels across the lanes.  Result in lane 0.
+template <class F>
+__device__ __forceinline__ c32 dit_bin_warp(F load, int log2_in, int log2n, const c32 *__restrict__ tw, int o, int lane)
+{
+    const int l0 = log2n - log2_in, lm = log2_in - 5;
+    c32 stack[8];
+    for (int idx = 0; idx < (1 << lm); idx++) {
+        const unsigned g = ((unsigned)lane << lm) + (unsigned)idx;
+        c32 val = load((int)(__brev(g) >> (32 - log2_in)));
+        int lev = 0;
+        for (int k = idx; k & 1; k >>= 1) { val = dit_level(stack[lev], val, tw, log2n, l0 + lev, o); lev++; }
+        stack[lev] = val;
+    }
+    c32 val = stack[lm];
+#pragma unroll
+    for (int s = 0; s < 5; s++) {
+        c32 other;
+        other.x = __shfl_down_sync(0xffffffffu, val.x, 1 << s);
+        other.y = __shfl_down_sync(0xffffffffu, val.y, 1 << s);
+        val = dit_level(val, other, tw, log2n, l0 + lm + s, o);
+    }
+    return val;
+}
+
 // Is the gate decision (:234) safe on the fast path's values?  noise carries the error of the fast window sum against
 // the reference's sequential float accumulation (<= n_noise * 2^-24 relative, the worst case of recursive summation of
 // positive terms), the FFT rounding of the window samples (each within 3e-7 of the map PEAK amplitude) and of the peak.
@@ -173,41 +200,54 @@ __global__ void __launch_bounds__(256) k_est_exact(const ExactParams P)
     };
     auto ang = [&](int lr, int i) { return sm[lr * Na + ((i + (Na + 1) / 2) % Na)]; };
 
+    if (rank == 0 && tid == 0) S.ncand = 0;
+    cl.sync();
+    // single-bin evaluation of candidates (no transform): needs at least a warp's worth of points on either axis
+    const int log2N = 31 - __clz(N);
+    int log2V = 5;
+    while ((1 << log2V) < V) log2V++;
+    const bool single_bin_ok = P.map && (1 << log2N) == N && N >= 32 && Nr >= N && Na >= (1 << log2V) && V <= 256;
+    __shared__ c32 s_y[256];
+
     for (int it = cid; it < count; it += ncl) {
         const int c = P.list[it];
         const DetDev d0 = P.dets[c];             // (rank 0 rewrites it only behind the barriers below)
-        if (rank == 0 && tid == 0) S.ncand = 0;
-        // ---- range spectra of all channels, staged arithmetic: conj-MAC (:250-274), zero-pad, fft_vcc #A ----
-        const int rp = max(1, min(V, P.buf_elems / Nr));
-        for (int p0 = 0, q = 0; p0 < V; p0 += rp, q++) {
-            if (q % CL != rank) continue;
-            const int np = min(rp, V - p0);
-            for (int e = tid; e < np * Nr; e += 256) {
-                const int lr = e / Nr, i = e % Nr, p = p0 + lr;
-                c32 v = mk(0.f, 0.f);
-                if (i < N) {
-                    if (P.H) v = P.H[((size_t)c * V + p) * N + i];
-                    else {
-                        int r, t;
-                        if (P.tx_interleave) { t = p / P.R; r = p % P.R; } else { r = p / P.T; t = p % P.T; }
-                        const c32 *prx = P.rx.base + c * P.rx.cpi_stride + r * P.rx.ant_stride + (long long)P.n_pre * N + i;
-                        const c32 *ptx = P.tx.base + c * P.tx.cpi_stride + t * P.tx.ant_stride + (long long)P.n_pre * N + i;
-                        for (int s = 0; s < P.S; s++) {
-                            const c32 a = prx[(long long)s * N], b = ptx[(long long)s * N];
-                            v = cadd_exact(v, cmul_exact(a, mk(b.x, -b.y)));
-                        }
-                    }
-                }
-                sm[lr * Nr + (__brev((unsigned)i) >> (32 - P.log2Nr))] = v;
-            }
-            __syncthreads();
-            radix2_rows(sm, Nr, np, P.tw_r);
-            for (int e = tid; e < np * Nr; e += 256) Y[(size_t)(p0 + e / Nr) * Nr + e % Nr] = sm[e];
-            __syncthreads();
-        }
-        __threadfence();
-        cl.sync();                               // Y complete, S.ncand reset
         const int rpa = max(1, P.buf_elems / Na);
+        // exact conj-MAC (:250-274) of channel p, subcarrier i
+        auto chan_est = [&](int p, int i) {
+            if (P.H) return P.H[((size_t)c * V + p) * N + i];
+            int r, t;
+            if (P.tx_interleave) { t = p / P.R; r = p % P.R; } else { r = p / P.T; t = p % P.T; }
+            const c32 *prx = P.rx.base + c * P.rx.cpi_stride + r * P.rx.ant_stride + (long long)P.n_pre * N + i;
+            const c32 *ptx = P.tx.base + c * P.tx.cpi_stride + t * P.tx.ant_stride + (long long)P.n_pre * N + i;
+            c32 v = mk(0.f, 0.f);
+            for (int s = 0; s < P.S; s++) {
+                const c32 a = prx[(long long)s * N], b = ptx[(long long)s * N];
+                v = cadd_exact(v, cmul_exact(a, mk(b.x, -b.y)));
+            }
+            return v;
+        };
+        // ---- range spectra of all channels, staged arithmetic: conj-MAC, zero-pad, fft_vcc #A (made when first needed) ----
+        bool have_Y = false;
+        auto range_spectra = [&]() {
+            if (have_Y) return;
+            have_Y = true;
+            const int rp = max(1, min(V, P.buf_elems / Nr));
+            for (int p0 = 0, q = 0; p0 < V; p0 += rp, q++) {
+                if (q % CL != rank) continue;
+                const int np = min(rp, V - p0);
+                for (int e = tid; e < np * Nr; e += 256) {
+                    const int lr = e / Nr, i = e % Nr;
+                    sm[lr * Nr + (__brev((unsigned)i) >> (32 - P.log2Nr))] = i < N ? chan_est(p0 + lr, i) : mk(0.f, 0.f);
+                }
+                __syncthreads();
+                radix2_rows(sm, Nr, np, P.tw_r);
+                for (int e = tid; e < np * Nr; e += 256) Y[(size_t)(p0 + e / Nr) * Nr + e % Nr] = sm[e];
+                __syncthreads();
+            }
+            __threadfence();
+            cl.sync();                           // Y complete
+        };
 
         // ---- arg-max (:137-151): first maximum of (float)pow(abs(z),2) in row-major order ----
         unsigned long long key = 0ull;
@@ -218,13 +258,13 @@ __global__ void __launch_bounds__(256) k_est_exact(const ExactParams P)
             const float thr = __fmul_rn(mc[(size_t)d0.range_idx * Na + d0.angle_idx], 1.f - 2.f * EPS_AMB);
             const long long tot4 = ((long long)Nr * Na) >> 2;
             const long long q0 = tot4 * rank / CL, q1 = tot4 * (rank + 1) / CL;
-            for (long long q = q0 + tid; q < q1; q += 256 * 4) {
-                float4 v4[4];
+            for (long long q = q0 + tid; q < q1; q += 256 * 8) {
+                float4 v4[8];
 #pragma unroll
-                for (int u = 0; u < 4; u++)
+                for (int u = 0; u < 8; u++)
                     v4[u] = (q + 256 * u < q1) ? __ldcs(reinterpret_cast<const float4 *>(mc) + q + 256 * u) : make_float4(-1.f, -1.f, -1.f, -1.f);
 #pragma unroll
-                for (int u = 0; u < 4; u++) {
+                for (int u = 0; u < 8; u++) {
                     const float vv[4] = {v4[u].x, v4[u].y, v4[u].z, v4[u].w};
 #pragma unroll
                     for (int k = 0; k < 4; k++)
@@ -239,6 +279,7 @@ __global__ void __launch_bounds__(256) k_est_exact(const ExactParams P)
             if (ncand > EXACT_MAX_CAND || ncand == 0) full_scan = true;      // cluster-uniform
         }
         if (full_scan) {
+            range_spectra();
             for (int n0 = 0, q = 0; n0 < Nr; n0 += rpa, q++) {
                 if (q % CL != rank) continue;
                 const int nr = min(rpa, Nr - n0);
@@ -253,20 +294,49 @@ __global__ void __launch_bounds__(256) k_est_exact(const ExactParams P)
                 }
                 __syncthreads();
             }
-        } else if (rank == 0) {
-            // one row per candidate (the unmarked arg-max is a single candidate: the fast path's own peak)
-            const int nc = (d0.flags & DET_AMB) ? S.ncand : 1;
-            for (int c0 = 0; c0 < nc; c0 += min(rpa, EXACT_MAX_CAND)) {
-                const int nr = min(min(rpa, EXACT_MAX_CAND), nc - c0);
-                if (tid < nr) s_rows[tid] = ((d0.flags & DET_AMB) ? S.cand[c0 + tid] : d0.range_idx * Na + d0.angle_idx) / Na;
-                __syncthreads();
-                angle_rows(s_rows, 0, nr, false);
-                if (tid < nr) {
-                    const int lin = (d0.flags & DET_AMB) ? S.cand[c0 + tid] : d0.range_idx * Na + d0.angle_idx;
-                    const float pw = (float)ref_pow_abs2(ang(tid, lin % Na));
-                    if (pw == pw) key = pack_key(pw, (unsigned)lin);
+        } else if (single_bin_ok) {
+            // every candidate cell in the staged arithmetic WITHOUT the transforms (dit_bin_warp): per channel one bin of the
+            // zero-padded range IFFT (a warp each), then one bin of the angle FFT over the channels.  The candidates are
+            // dealt round the ranks.  (The unmarked arg-max is a single candidate: the fast path's own peak.)
+            const int nc = (d0.flags & DET_AMB) ? S0->ncand : 1;
+            for (int j = rank; j < nc; j += CL) {
+                const int lin = (d0.flags & DET_AMB) ? S0->cand[j] : d0.range_idx * Na + d0.angle_idx;
+                const int nn = lin / Na, ii = lin % Na;
+                for (int p = warp; p < V; p += 8) {
+                    const c32 y = dit_bin_warp([&](int i) { return chan_est(p, i); }, log2N, P.log2Nr, P.tw_r, nn, lane);
+                    if (lane == 0) s_y[p] = y;
                 }
                 __syncthreads();
+                if (warp == 0) {
+                    const c32 z = dit_bin_warp([&](int i) { return i < V ? s_y[i] : mk(0.f, 0.f); }, log2V, P.log2Na, P.tw_a,
+                                               (ii + (Na + 1) / 2) % Na, lane);
+                    if (lane == 0) {
+                        const float pw = (float)ref_pow_abs2(z);
+                        if (pw == pw) {
+                            const unsigned long long k2 = pack_key(pw, (unsigned)lin);
+                            key = k2 > key ? k2 : key;
+                        }
+                    }
+                }
+                __syncthreads();
+            }
+        } else {
+            range_spectra();
+            if (rank == 0) {
+                // one row per candidate
+                const int nc = (d0.flags & DET_AMB) ? S.ncand : 1;
+                for (int c0 = 0; c0 < nc; c0 += min(rpa, EXACT_MAX_CAND)) {
+                    const int nr = min(min(rpa, EXACT_MAX_CAND), nc - c0);
+                    if (tid < nr) s_rows[tid] = ((d0.flags & DET_AMB) ? S.cand[c0 + tid] : d0.range_idx * Na + d0.angle_idx) / Na;
+                    __syncthreads();
+                    angle_rows(s_rows, 0, nr, false);
+                    if (tid < nr) {
+                        const int lin = (d0.flags & DET_AMB) ? S.cand[c0 + tid] : d0.range_idx * Na + d0.angle_idx;
+                        const float pw = (float)ref_pow_abs2(ang(tid, lin % Na));
+                        if (pw == pw) key = pack_key(pw, (unsigned)lin);
+                    }
+                    __syncthreads();
+                }
             }
         }
         key = block_max(key);
@@ -280,6 +350,7 @@ __global__ void __launch_bounds__(256) k_est_exact(const ExactParams P)
                 d.noise_power = __int_as_float(0x7fc00000); d.snr_db = d.noise_power;
                 d.n_noise = 0; d.flags = DET_EXACT; d.cpi = P.cpi0 + c;
                 P.dets[c] = d;
+                S.ncand = 0;
             }
             cl.sync();           // rank 0's shared state is reused by the next marked CPI
             continue;
@@ -289,10 +360,11 @@ __global__ void __launch_bounds__(256) k_est_exact(const ExactParams P)
         const float peak = __uint_as_float((unsigned)(key >> 32));
         if (!(d0.flags & DET_GATE) && nstar == d0.range_idx && istar == d0.angle_idx) {
             // the candidates' order is the fast path's: its window, noise estimate and (safe) gate decision stand
-            if (rank == 0 && tid == 0) P.dets[c].flags = d0.flags & DET_PASSED;
+            if (rank == 0 && tid == 0) { P.dets[c].flags = d0.flags & DET_PASSED; S.ncand = 0; }
             cl.sync();
             continue;
         }
+        range_spectra();         // (a no-op when the arg-max already needed them)
 
         // ---- noise window (:152-227) in the reference's order ----
         const NoiseWin w = noise_window(P.est, nstar, istar);
@@ -375,6 +447,7 @@ __global__ void __launch_bounds__(256) k_est_exact(const ExactParams P)
             d.cpi = P.cpi0 + c;
             P.dets[c] = d;
             atomicAdd(&P.ctl->n_redone, 1);
+            S.ncand = 0;
         }
         cl.sync();               // rank 0's shared state and W are reused by the next marked CPI
     }

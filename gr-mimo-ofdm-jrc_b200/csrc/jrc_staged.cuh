@@ -156,14 +156,17 @@ __global__ void k_pad_rows(const c32 *__restrict__ H, c32 *__restrict__ out, lon
 // float operation order below IS the oracle's.
 __device__ __forceinline__ void radix2_rows(c32 *sm, int n, int rows, const c32 *__restrict__ tw)
 {
-    const int nbf = rows * (n >> 1);
-    for (int len = 2; len <= n; len <<= 1) {
-        const int half = len >> 1, step = n / len;
+    // n is a power of two: every index below is a shift or a mask (integer divisions were 40 % of this loop's instructions)
+    const int log2n = __ffs(n) - 1, hmask = (n >> 1) - 1;
+    if (log2n == 0) return;
+    const int nbf = rows << (log2n - 1);
+    for (int lh = 0; lh < log2n; lh++) {                 // len = 2 << lh, half = 1 << lh, step = n / len
+        const int half = 1 << lh, tshift = log2n - lh - 1;
         for (int b = threadIdx.x; b < nbf; b += blockDim.x) {
-            int lr = b / (n >> 1), bb = b % (n >> 1);
-            int grp = bb / half, j = bb % half;
-            int i0 = lr * n + grp * len + j, i1 = i0 + half;
-            c32 w = tw[j * step];
+            const int lr = b >> (log2n - 1), bb = b & hmask;
+            const int grp = bb >> lh, j = bb & (half - 1);
+            const int i0 = (lr << log2n) + (grp << (lh + 1)) + j, i1 = i0 + half;
+            c32 w = tw[j << tshift];
             c32 u = sm[i0];
             c32 v = cmul_exact(sm[i1], w);
             sm[i0] = cadd_exact(u, v);
