@@ -416,23 +416,34 @@ def test_gate_decision_at_the_threshold(jrc, orc):
 
 
 def test_exact_ties_in_the_map(jrc, orc):
-    """Two targets whose echoes are mirror images give (near-)equal map maxima: the arg-max is taken in the reference's
-    order on the candidates, first maximum in row-major order wins, on both the fused and the tiled path."""
-    for name in ("C2", "C3s"):
+    """Two echoes half the unambiguous range apart, same angle, same amplitude, no noise: the second is the first times
+    (-1)^k (the carrier phase of the extra delay is a whole number of turns), so the map repeats after Nr/2 rows and every
+    CPI has two maxima that are equal up to rounding.  The arg-max is then taken in the reference's order on the
+    candidates -- first maximum in row-major order wins -- on the fused path (inside k_fused64x8) and on the tiled paths
+    (k_est_exact's cluster: the candidate cells bin by bin, with 8, 8 and 64 range inputs and 1, 1 and 4 channels per
+    lane for C3s, C3 and C5).  The second half of the CPIs has amplitudes 1e-6 apart."""
+    for name, n in (("C2", 12), ("C3s", 12), ("C3", 6), ("C5", 4)):
         cfg = CFGS[name]
         est = est_for(cfg)
         tx = synth.tx_symbols(cfg["T"], cfg["S"], cfg["N"])
-        n = 12
         rng = np.random.default_rng(5)
-        r = np.stack([rng.uniform(5, 30, n), rng.uniform(40, 60, n)], axis=1)
-        a = np.stack([rng.uniform(-40, 40, n), rng.uniform(-40, 40, n)], axis=1)
+        half_range = synth.C_LIGHT / (2 * 125e6) * (cfg["N"] / 2)
+        r1 = rng.uniform(0.05, 0.4, n) * 2 * half_range
+        r = np.stack([r1, r1 + half_range], axis=1)
+        az = rng.uniform(-40, 40, n)
+        a = np.stack([az, az], axis=1)
         amp = np.ones((n, 2))
         amp[n // 2:, 1] = 1.0 + 1e-6 * rng.standard_normal(n - n // 2)       # equal and almost equal heights
         rx = synth.rx_symbols(tx, cfg["R"], r, a, amp)
         ch = gpu_chain(jrc, cfg, est)
         _, d = ch.run_host(rx, tx)
-        _, _, do = oracle(orc, rx, tx, cfg, est)
+        mo, _, do = oracle(orc, rx, tx, cfg, est)
+        top = np.sort(mo.reshape(n, -1), axis=1)[:, -2:]
+        assert ((top[:, 1] - top[:, 0]) <= 4e-6 * top[:, 1]).sum() >= n // 2      # the scene does what it says
         check_detections(jrc, d, do, f"ties {name}", rtol_peak=1e-5)
+        st = ch.exact_stats()
+        print(f"[ties {name}] {st}")
+        assert st["marked"] + st["ties_in_kernel"] >= n // 2, st          # and those CPIs went through the candidate logic
 
 
 @pytest.mark.parametrize("n", [1040, 1024, 250])
