@@ -1671,8 +1671,9 @@ struct FusedEntry {
     int epoch = -1;
 };
 struct jrc_fused_state {
-    cudaStream_t stream = nullptr;
-    cudaEvent_t h_ready = nullptr;
+    cudaStream_t stream = nullptr, stream2 = nullptr;
+    cudaEvent_t h_ready = nullptr, t_ready = nullptr;
+    cudaEvent_t last_t_done = nullptr;   // the previous frame's copy of the transposed array out of dT
     cudaEvent_t last_done = nullptr;     // the previous frame's continuation (it reads the estimate the next call overwrites)
     FusedEntry e[JRC_FUSED_RING];
     int64_t next_seq = 0;
@@ -1685,7 +1686,9 @@ static jrc_status fused_state(jrc_chain *h, jrc_fused_state **out)
         jrc_fused_state *F = new jrc_fused_state();
         h->fstate = F;
         CU(cudaStreamCreateWithFlags(&F->stream, cudaStreamNonBlocking));
+        CU(cudaStreamCreateWithFlags(&F->stream2, cudaStreamNonBlocking));
         CU(cudaEventCreateWithFlags(&F->h_ready, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&F->t_ready, cudaEventDisableTiming));
         const size_t cells = (size_t)h->Nr * h->Na;
         for (FusedEntry &e : F->e) {
             CU(cudaEventCreateWithFlags(&e.done, cudaEventDisableTiming));
@@ -1703,6 +1706,8 @@ static void fused_state_destroy(jrc_chain *h)
     jrc_fused_state *F = h->fstate;
     if (!F) return;
     if (F->stream) { cudaStreamSynchronize(F->stream); cudaStreamDestroy(F->stream); }
+    if (F->stream2) { cudaStreamSynchronize(F->stream2); cudaStreamDestroy(F->stream2); }
+    if (F->t_ready) cudaEventDestroy(F->t_ready);
     if (F->h_ready) cudaEventDestroy(F->h_ready);
     for (FusedEntry &e : F->e) {
         if (e.graph) cudaGraphExecDestroy(e.graph);
@@ -1802,7 +1807,6 @@ static jrc_status radar_estimate_impl(jrc_chain *h, const jrc_c32 *const *tx, co
             ST(capture(&e.graph, [&]() -> jrc_status {
                 ST(launch_fft_rows(h, dH, N, N, dY, Nr, V, 0, 0));
                 ST(launch_transpose(h, dY, dT, V, Nr, Na, 1));
-                CU(cudaMemcpyAsync(e.T, dT, cells * sizeof(c32), cudaMemcpyDeviceToHost, h->stream));
                 return JRC_OK;
             }));
             ST(capture(&e.graph2, [&]() -> jrc_status {
@@ -1821,12 +1825,18 @@ static jrc_status radar_estimate_impl(jrc_chain *h, const jrc_c32 *const *tx, co
         FusedEntry &e = *fused_entry_pending;
         CU(cudaEventRecord(F->h_ready, h->stream));
         CU(cudaStreamWaitEvent(F->stream, F->h_ready, 0));
+        if (F->last_t_done) CU(cudaStreamWaitEvent(F->stream, F->last_t_done, 0));   // the previous frame's copy out of dT
         CU(cudaGraphLaunch(e.graph, F->stream));
-        CU(cudaEventRecord(e.t_done, F->stream));
+        // the transposed array goes out on a stream of its own while the angle transform and the estimator carry on
+        CU(cudaEventRecord(F->t_ready, F->stream));
+        CU(cudaStreamWaitEvent(F->stream2, F->t_ready, 0));
+        CU(cudaMemcpyAsync(e.T, F->dT.p, (size_t)Nr * Na * sizeof(c32), cudaMemcpyDeviceToHost, F->stream2));
+        CU(cudaEventRecord(e.t_done, F->stream2));
         CU(cudaGraphLaunch(e.graph2, F->stream));
         CU(cudaEventRecord(e.done, F->stream));
         h->launches += 5;
         F->last_done = e.done;
+        F->last_t_done = e.t_done;
         e.seq.store(fused_seq, std::memory_order_release);
         *cpi_seq = fused_seq;
     }
