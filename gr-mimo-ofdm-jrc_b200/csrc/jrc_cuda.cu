@@ -565,7 +565,8 @@ static jrc_status launch_wide(jrc_chain *h, PortDev rx, PortDev tx, const c32 *H
     CU(cudaFuncSetAttribute(ka, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Gm::SMEM_A));
     CU(cudaFuncSetAttribute(kb, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Gm::SMEM_B));
     long long ua = (long long)n_cpi * (Gm::N / Gm::KB), ub = (long long)n_cpi * (Gm::V / Gm::UB);
-    long long ga = ua < h->sm_count ? ua : h->sm_count, gb = ub < 2LL * h->sm_count ? ub : 2LL * h->sm_count;
+    const long long cap_a = (long long)Gm::CTAS_A * h->sm_count;
+    long long ga = ua < cap_a ? ua : cap_a, gb = ub < 2LL * h->sm_count ? ub : 2LL * h->sm_count;
     ka<<<(unsigned)ga, Gm::TA, Gm::SMEM_A, h->stream>>>(P, tm_rx, tm_tx, tm_g);
     CU(cudaGetLastError());
     kb<<<(unsigned)gb, Gm::GR::THREADS, Gm::SMEM_B, h->stream>>>(P);

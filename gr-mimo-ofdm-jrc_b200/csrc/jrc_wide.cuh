@@ -78,7 +78,11 @@ __device__ __forceinline__ void tma_load_4d(void *dst, const CUtensorMap *tm, un
 
 template <int LOG2N>
 struct WideGeom {
-    static constexpr int N = 1 << LOG2N, V = 128, KB = 32;           // subcarriers per k_wide_mac_angle unit
+#ifndef JRC_WIDE_KB
+#define JRC_WIDE_KB 16      // subcarriers per k_wide_mac_angle unit: 16 (256 threads, two CTAs per SM) or 32 (512 threads, one)
+#endif
+    static constexpr int N = 1 << LOG2N, V = 128, KB = JRC_WIDE_KB;
+    static constexpr int CTAS_A = KB == 16 ? 2 : 1;                   // resident CTAs per SM of k_wide_mac_angle
     static constexpr int TA = 16 * KB;                                // threads of k_wide_mac_angle: 16 per subcarrier
     static constexpr int AB = 4;                                      // rows per pass of k_wide_range_mag
     static constexpr int UB = 8;                                      // angle bins per unit (two passes): one 32-byte sector of the map
@@ -98,7 +102,7 @@ struct WideGeom {
 // conj-MAC + angle FFT, one (CPI, 16-subcarrier block) at a time
 // ---------------------------------------------------------------------------
 template <int LOG2N, int S_CT>      // S_CT: number of LTF symbols when known at compile time (0: run-time)
-__global__ void __launch_bounds__(WideGeom<LOG2N>::TA, 1) k_wide_mac_angle(const WideParams P, const __grid_constant__ CUtensorMap tm_rx,
+__global__ void __launch_bounds__(WideGeom<LOG2N>::TA, WideGeom<LOG2N>::CTAS_A) k_wide_mac_angle(const WideParams P, const __grid_constant__ CUtensorMap tm_rx,
                                                                             const __grid_constant__ CUtensorMap tm_tx,
                                                                             const __grid_constant__ CUtensorMap tm_g)
 {
@@ -241,7 +245,7 @@ __global__ void __launch_bounds__(WideGeom<LOG2N>::TA, 1) k_wide_mac_angle(const
             c32 o[8];
             dif_passes<7, -1, GA::WARP_SYNC, true>(xrow, t, Tw, o);
             if (P.use_tma_store) {
-                const int half = lr_t >> 4, kc = (lr_t & 15) >> 1, ko = lr_t & 1;
+                const int half = lr_t >> 4, kc = (lr_t & 15) >> 1, ko = lr_t & 1;      // (KB = 16: one tile, half == 0)
 #pragma unroll
                 for (int c = 0; c < 8; c++) {
                     const int a = dif_freq<7>(8 * t + c);
@@ -257,7 +261,7 @@ __global__ void __launch_bounds__(WideGeom<LOG2N>::TA, 1) k_wide_mac_angle(const
         if (P.use_tma_store) {
             if (tid == 0) {
                 tma_store_3d(&tm_g, stg, 2 * k0, 0, cpi);
-                tma_store_3d(&tm_g, stg + V * 16, 2 * (k0 + 16), 0, cpi);
+                if (KB > 16) tma_store_3d(&tm_g, stg + V * 16, 2 * (k0 + 16), 0, cpi);
                 asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             }
         } else {
