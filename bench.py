@@ -45,7 +45,7 @@ OTHER_CONFIGS = {
                                                              kernels=["k_fused64x8<8,16>", "k_est_exact"]),
     "configs[2] 4x8, 256 sc, 4096x256, 5 targets": dict(T=4, R=8, S=4, N=256, IR=16, IA=8, n=592, targets=5,
                                                         kernels=["k_chan_est_tile<4,4>", "k_slice256", "k_map_finalize", "k_est_exact"]),
-    "configs[4] 8x16, 2048 sc, 2048x128": dict(T=8, R=16, S=8, N=2048, IR=1, IA=1, n=148, targets=3,
+    "configs[4] 8x16, 2048 sc, 2048x128": dict(T=8, R=16, S=8, N=2048, IR=1, IA=1, n=222, targets=3,
                                                kernels=["k_wide_mac_angle<11,8>", "k_wide_range_mag<11>", "k_map_finalize", "k_est_exact"]),
 }
 
@@ -566,13 +566,13 @@ def run_ours(args):
         cfg5 = {k: c5[k] for k in ("T", "R", "S", "N", "IR", "IA")}
         total = 65536
         lo, hi = shard.shard_range(total, rank, world)
-        nblk = 148                                  # one round of the two wide kernels: both grids filled exactly
+        nblk = 222                                  # one round of the two wide kernels: both grids filled exactly
         from mimo_ofdm_jrc import synth
         rx5_h, tx5_h, est5 = make_inputs(nblk, seed=7 + rank, cfg=cfg5, targets=3, span=15.0)
         rc5 = jrc.radar_chain(cfg5["N"], cfg5["T"], cfg5["R"], cfg5["S"], cfg5["IR"], cfg5["IA"], device=local, estimator=est5)
         rx5, tx5 = torch.from_numpy(rx5_h).to(dev), torch.from_numpy(tx5_h).to(dev)
-        # every block of 148 CPIs is a NEW scene, synthesised on the device right before it is processed (jrc_scene_synth:
-        # the 128 GiB of RX symbols of the sweep exist 296 MiB at a time); noise level as in make_inputs (20 dB)
+        # every block of 222 CPIs is a NEW scene, synthesised on the device right before it is processed (jrc_scene_synth:
+        # the 128 GiB of RX symbols of the sweep exist 444 MiB at a time); noise level as in make_inputs (20 dB)
         sigma5 = float(np.sqrt(np.mean(np.abs(rx5_h[:4]) ** 2)) * 10 ** (-20.0 / 20.0) / np.sqrt(2) / np.sqrt(1.01))
         rng5 = np.random.default_rng(1000 + rank)
         m5 = torch.empty((nblk, rc5.Nr, rc5.Na), dtype=torch.float32, device=dev)
@@ -613,7 +613,7 @@ def run_ours(args):
         assert (d5n["flags"] & 1).mean() > 0.9 and np.array_equal(d5n["cpi"], np.arange(lo, hi))
         ms5 = max_over_ranks(chain_ms)
         sweep = {"workload": "configs[4]: 2048 subcarriers, 8 x 16 virtual array, 65536 CPIs sharded over the ranks, detection records "
-                             "gathered to rank 0 over NCCL; every block of 148 CPIs is a new 3-target scene synthesised on the device "
+                             "gathered to rank 0 over NCCL; every block of 222 CPIs is a new 3-target scene synthesised on the device "
                              "(jrc_scene_synth) right before it is processed; ms = chain time (CUDA events around every chain call + "
                              "the gather, max over ranks), wall_s includes the scene synthesis",
                  "n_gpus": world, "cpis": total, "ms": ms5, "wall_s": wall5, "cpi_per_s": total / (ms5 * 1e-3),

@@ -552,7 +552,8 @@ static jrc_status launch_wide(jrc_chain *h, PortDev rx, PortDev tx, const c32 *H
     CUtensorMap tm_g;
     memset(&tm_g, 0, sizeof(tm_g));
     static const bool tmas_off = getenv("JRC_WIDE_TMA_STORE") && atoi(getenv("JRC_WIDE_TMA_STORE")) == 0;
-    if (!tma_off && !tmas_off && tmap_encoder() && !((uintptr_t)G & 127u)) {
+    // (only with TMA loads or no loads at all: a cp.async prefetch by all threads could not wait for the store's reads)
+    if (!tma_off && !tmas_off && (P.use_tma || H) && tmap_encoder() && !((uintptr_t)G & 127u)) {
         const cuuint64_t dims[3] = {(cuuint64_t)2 * Gm::N, (cuuint64_t)Gm::V, (cuuint64_t)n_cpi};
         const cuuint64_t strides[2] = {(cuuint64_t)Gm::N * sizeof(c32), (cuuint64_t)Gm::V * Gm::N * sizeof(c32)};
         const cuuint32_t box[3] = {32, (cuuint32_t)Gm::V, 1}, es[3] = {1, 1, 1};
@@ -937,9 +938,9 @@ static jrc_status run_batch_impl(jrc_chain *h, jrc_port_layout rx, jrc_port_layo
         // the L2 (ncu, caches left alone: no write-back of G at 8, 100 % at 27; an access-policy window over G with the
         // persisting carve-out changed neither the traffic nor the time): the kernels are latency- and issue-bound, not
         // bandwidth-bound, and what a round costs is its partial last wave.  37 k CPIs fill both grids exactly
-        // (64 x 37 = 16 x 148 units, 16 x 37 = 2 x 296 units).
+        // (128 x 37 = 16 x 296 units of the first kernel, 16 x 37 = 2 x 296 units of the second); 222 CPIs per round.
         static const int wide_round_env = getenv("JRC_WIDE_ROUND") ? atoi(getenv("JRC_WIDE_ROUND")) : 0;
-        const int wide_round = wide_round_env > 0 ? wide_round_env : 148;
+        const int wide_round = wide_round_env > 0 ? wide_round_env : 222;
         if (wide) {
             const bool need_h = bg || recording;
             if (need_h) ST(h->sH.need((size_t)chunk * V * N * sizeof(c32)));

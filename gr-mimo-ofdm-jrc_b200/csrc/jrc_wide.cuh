@@ -89,10 +89,11 @@ struct WideGeom {
     using GA = TiledGeom<7>;                                          // angle FFT rows: 16 threads per row, 16 rows per CTA
     using GR = TiledGeom<LOG2N>;
     static constexpr int MAX_ANT = 24, MAX_S = 8;
-    // k_wide_mac_angle: two symbol buffers [(T+R)][S][KB] + H/FFT rows [KB][RS] (the staging of G reuses the rows)
-    // (the staging tiles start on a 1024-byte boundary: TMA's 128-byte swizzle is anchored there)
-    static constexpr size_t STG_OFF = (((size_t)2 * MAX_ANT * MAX_S * KB * sizeof(c32) + (size_t)KB * GA::RS * sizeof(c32)) + 1023) / 1024 * 1024;
-    static constexpr size_t SMEM_A = STG_OFF + (size_t)V * (KB + 1) * sizeof(c32);
+    // k_wide_mac_angle: two symbol buffers [(T+R)][S][KB] + H/FFT rows [KB][RS].  The staging tile of G lives in the symbol
+    // buffer the conj-MAC has just consumed (the next prefetch into it waits for the tile's TMA store to have read it).
+    static constexpr int BUF = MAX_ANT * MAX_S * KB;                  // c32 per symbol buffer (1024-byte multiple)
+    static constexpr size_t SMEM_A = (size_t)2 * BUF * sizeof(c32) + (size_t)KB * GA::RS * sizeof(c32);
+    static_assert((size_t)V * (KB + 1) * sizeof(c32) <= (size_t)BUF * sizeof(c32), "staging tile fits a symbol buffer");
     // k_wide_range_mag: AB rows of the transform
     static constexpr int RROW = fpad(N - 1) + 1 + 8;
     static constexpr size_t SMEM_B = (size_t)AB * RROW * sizeof(c32);
@@ -111,11 +112,11 @@ __global__ void __launch_bounds__(WideGeom<LOG2N>::TA, WideGeom<LOG2N>::CTAS_A) 
     constexpr int N = Gm::N, V = Gm::V, KB = Gm::KB, RS = GA::RS, TA = Gm::TA, CPR = KB / 2;   // CPR: 16-byte chunks per row
     extern __shared__ __align__(1024) unsigned char smem_wide[];     // (the swizzle of the staging tiles is a function of the address)
     c32 *sym = reinterpret_cast<c32 *>(smem_wide);                        // [2][(T+R)*S][KB]
-    c32 *rows = sym + 2 * Gm::MAX_ANT * Gm::MAX_S * KB;                   // [KB][RS]: H[.][k] then its angle transform
+    c32 *rows = sym + 2 * Gm::BUF;                                        // [KB][RS]: H[.][k] then its angle transform
     // G block, angle bin major.  TMA-store form: two tiles [V][16 subcarriers] of 128-byte rows in the 128-byte swizzle
     // (16-byte chunk j of row a sits at chunk j ^ (a & 7)): the column writes of the angle FFT spread over the banks as
     // with a padded pitch, and the block leaves as two bulk tensor stores.  Otherwise [V][KB+1].
-    c32 *stg = reinterpret_cast<c32 *>(smem_wide + Gm::STG_OFF);
+    // (the tile of a unit is the symbol buffer of that unit: stg below)
     const int tid = threadIdx.x;
     const int T = P.T, R = P.R, S = S_CT ? S_CT : P.S, per = (T + R) * S;  // antenna-symbol rows of KB subcarriers each
     constexpr int blocks_per_cpi = N / KB;
@@ -163,7 +164,9 @@ __global__ void __launch_bounds__(WideGeom<LOG2N>::TA, WideGeom<LOG2N>::CTAS_A) 
         const int k0 = (int)(unit % blocks_per_cpi) * KB;
         if (tma) {
             if (tid == 0) {
-                c32 *dst = sym + (size_t)buf * per * KB;
+                c32 *dst = sym + (size_t)buf * Gm::BUF;
+                // (the G tile staged in this buffer two units ago has been read by its store)
+                if (P.use_tma_store) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
                 mbar_expect_tx(&bar[buf], (unsigned)(per * KB * sizeof(c32)));
                 tma_load_4d(dst, &tm_tx, &bar[buf], 2 * k0, 0, 0, P.tx.cpi_stride ? (int)cpi : 0);
                 tma_load_4d(dst + T * S * KB, &tm_rx, &bar[buf], 2 * k0, 0, 0, (int)cpi);
@@ -171,7 +174,7 @@ __global__ void __launch_bounds__(WideGeom<LOG2N>::TA, WideGeom<LOG2N>::CTAS_A) 
             return;
         }
         const long long otx = cpi * P.tx.cpi_stride + k0, orx = cpi * P.rx.cpi_stride + k0;
-        c32 *dst = sym + ((size_t)buf * per + tid / CPR) * KB + 2 * (tid % CPR);
+        c32 *dst = sym + (size_t)buf * Gm::BUF + (size_t)(tid / CPR) * KB + 2 * (tid % CPR);
 #pragma unroll
         for (int i = 0; i < MAXCH; i++)
             if (src0[i]) cp_async16(dst + RSTEP * i * KB, src0[i] + ((is_tx >> i) & 1 ? otx : orx));
@@ -194,7 +197,7 @@ __global__ void __launch_bounds__(WideGeom<LOG2N>::TA, WideGeom<LOG2N>::CTAS_A) 
             __syncthreads();                                  // symbols of this unit visible; previous unit's stores done
             if (unit + gridDim.x < n_units) prefetch(unit + gridDim.x, buf ^ 1);
             // ---- conj-MAC: H[p][k0 + kk] for r in 4 rb .. +3, t in 2 tb .. +1 ----
-            const c32 *sb = sym + (size_t)buf * per * KB + kk;
+            const c32 *sb = sym + (size_t)buf * Gm::BUF + kk;
             for (int r0 = 4 * rb; r0 < R; r0 += 16)
                 for (int t0 = 2 * tb; t0 < T; t0 += 8) {
                     c32 acc[4][2];
@@ -231,9 +234,8 @@ __global__ void __launch_bounds__(WideGeom<LOG2N>::TA, WideGeom<LOG2N>::CTAS_A) 
                 rows[k * RS + fpad(p)] = P.H[((long long)cpi * V + p) * N + k0 + k];
             }
         }
-        // (the previous unit's two stores have read the staging tiles by now: they had the whole conj-MAC phase)
-        if (P.use_tma_store && tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
         __syncthreads();
+        c32 *stg = sym + (size_t)buf * Gm::BUF;              // this unit's symbols are consumed: its G tile is staged in their place
         // ---- angle FFT across the 128 channels of subcarrier lr_t (radix 8.8.2, fftshift folded in) ----
         {
             c32 *xrow = rows + lr_t * RS;
