@@ -43,7 +43,7 @@ METRIC, UNIT = "range-angle CPIs/s", "CPI/s"
 OTHER_CONFIGS = {
     "configs[0] shipped flowgraph 4x2, 64 sc, 512x128": dict(T=4, R=2, S=4, N=64, IR=8, IA=16, n=4096, targets=1,
                                                              kernels=["k_fused64x8<8,16>", "k_est_exact"]),
-    "configs[2] 4x8, 256 sc, 4096x256, 5 targets": dict(T=4, R=8, S=4, N=256, IR=16, IA=8, n=592, targets=5,
+    "configs[2] 4x8, 256 sc, 4096x256, 5 targets": dict(T=4, R=8, S=4, N=256, IR=16, IA=8, n=888, targets=5,
                                                         kernels=["k_chan_est_tile<4,4>", "k_slice256", "k_map_finalize", "k_est_exact"]),
     "configs[4] 8x16, 2048 sc, 2048x128": dict(T=8, R=16, S=8, N=2048, IR=1, IA=1, n=222, targets=3,
                                                kernels=["k_wide_mac_angle<11,8>", "k_wide_range_mag<11>", "k_map_finalize", "k_est_exact"]),

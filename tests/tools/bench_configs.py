@@ -12,7 +12,7 @@ from oracle import orc
 CONFIGS = {
     "configs[0] shipped sim 4x2, 64 sc, 512x128": dict(T=4, R=2, S=4, N=64, IR=8, IA=16, n=4096, targets=1),
     "configs[1] 64 sc, 8 ch, 1024x64": dict(T=4, R=2, S=4, N=64, IR=16, IA=8, n=4096, targets=2),
-    "configs[2] 4x8, 256 sc, 4096x256, multi-target": dict(T=4, R=8, S=4, N=256, IR=16, IA=8, n=592, targets=5),
+    "configs[2] 4x8, 256 sc, 4096x256, multi-target": dict(T=4, R=8, S=4, N=256, IR=16, IA=8, n=888, targets=5),
     "configs[4] 8x16, 2048 sc, 2048x128": dict(T=8, R=16, S=8, N=2048, IR=1, IA=1, n=222, targets=3),
 }
 
