@@ -527,6 +527,34 @@ def test_tiled_path_with_background_removal_and_requests(jrc, orc):
         rc2.run(torch.from_numpy(rx2).cuda(), torch.from_numpy(tx2).cuda(), path=jrc.PATH_TILED)   # Na = 16 < 64
 
 
+@pytest.mark.parametrize("name", ["C3", "C5"])
+def test_shape_specific_paths_with_background_removal_and_per_cpi_tx(jrc, orc, name):
+    """k_slice256 (configs[2]) and the k_wide_* pair (configs[4]) behind the background ring (channel estimates instead of
+    symbols as their input) and with per-CPI TX frames (the TX tensor map of the TMA loads then has a CPI axis)."""
+    cfg = CFGS[name]
+    est = est_for(cfg)
+    n = 5
+    rx, tx, _ = scene(cfg, n, seed=31, n_targets=2, amp_db_span=6.0, tx_per_cpi=True)
+    V = cfg["T"] * cfg["R"]
+    # per-CPI TX frames, no background: against the oracle chain
+    ch0 = gpu_chain(jrc, cfg, est)
+    m0, d0 = ch0.run_host(rx, tx)
+    assert ch0.last_path == jrc.PATH_TILED
+    mo, _, do = oracle(orc, rx, tx, cfg, est)
+    err = np.abs(m0 - mo).reshape(n, -1).max(axis=1) / mo.reshape(n, -1).max(axis=1)
+    assert err.max() <= 5e-6, err.max()
+    check_detections(jrc, d0, do, f"per-CPI TX {name}")
+    # background removal + recording: block by block against the oracle's radar block
+    ch = gpu_chain(jrc, cfg, est, background_removal=True, background_recording=True, record_len=3)
+    m, d = ch.run_host(rx, tx)
+    assert ch.last_path == jrc.PATH_TILED
+    rad = orc.Radar(cfg["N"], cfg["T"], cfg["R"], cfg["S"], 0, True, True, 3, cfg["IR"], False)
+    for c in range(n):
+        pad = rad.work(list(tx[c].reshape(cfg["T"], -1)), list(rx[c].reshape(cfg["R"], -1)))
+        mo_c = orc.mag_squared(orc.fft_vcc(orc.matrix_transpose(orc.fft_vcc(pad, False, False), V, cfg["IA"]), True, True))
+        assert np.abs(m[c] - mo_c).max() <= 1e-5 * mo_c.max() + 1e-3, c
+
+
 def test_tiled_path_chunks_long_batches(jrc, orc):
     """A batch whose scratch (range spectra + map) exceeds the 1 GiB budget runs in chunks: records of CPIs on both
     sides of the chunk borders equal the oracle's, the CPI ids are continuous."""
