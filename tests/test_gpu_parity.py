@@ -670,8 +670,9 @@ def test_range_doppler_angle_cube(jrc, orc):
     assert d == nb // 2 + int(round(fd / prf * nb)) and (n, i) == synth.expected_peak(20.0, 15.0, 64, 4, 8, 4)
 
 
-@pytest.mark.parametrize("name,pre,n", [("C2", 5, 300), ("C1", 0, 64), ("C3s", 2, 12), ("C5", 1, 3)])
-def test_chain_from_raw_time_samples(jrc, orc, name, pre, n):
+@pytest.mark.parametrize("name,pre,n,cp", [("C2", 5, 300, 16), ("C1", 0, 64, 16), ("C3s", 2, 12, 64), ("C5", 1, 3, 512),
+                                            ("C2", 1, 40, 15)])       # (odd prefix: rows not 16-byte aligned, generic kernel)
+def test_chain_from_raw_time_samples(jrc, orc, name, pre, n, cp):
     """SURVEY.md 8(f) rank 1 for whole batches (jrc_chain_run_batch_time): cyclic-prefix removal + the RX OFDM FFT in
     front of the chain, on the device.  The demodulated symbols are bit-identical to the oracle's cp_remove + fft_vcc, so
     map and records equal, bit for bit, the ones of jrc_chain_run_batch on the oracle-demodulated symbols; and the
@@ -679,7 +680,6 @@ def test_chain_from_raw_time_samples(jrc, orc, name, pre, n):
     import torch
     cfg = CFGS[name]
     N, T, R, S = cfg["N"], cfg["T"], cfg["R"], cfg["S"]
-    cp = N // 4
     est = est_for(cfg)
     rx, tx, _ = scene(cfg, n, seed=17, n_targets=2, amp_db_span=6.0)
     rng = np.random.default_rng(5)
