@@ -6,17 +6,19 @@
 // 2-D transform of H[p][k], so they may run in either order.  The channel estimate is local in k -- H[.][k] only needs
 // the 24 antennas' symbols at subcarrier k (lib/mimo_ofdm_radar_impl.cc:250-274) -- hence:
 //
-//   k_wide_mac_angle   per (CPI, block of 16 subcarriers): symbols -> shared memory (cp.async), conj-MAC of all 128
-//                      channels (register tiled: 4 RX x 2 TX per thread), angle FFT + fftshift across the channels for each
-//                      subcarrier (matrix_transpose + fft_vcc #B, lib/matrix_transpose_impl.cc:97-104,
-//                      ...radar_sim.grc:963-985), result G[cpi][angle bin][k] written as whole 128-byte lines.
+//   k_wide_mac_angle   per (CPI, block of 16 subcarriers): symbols -> shared memory (two TMA tensor tiles on an mbarrier,
+//                      double buffered; cp.async when a layout has no tensor map), conj-MAC of all 128 channels (register
+//                      tiled: 4 RX x 2 TX per thread), angle FFT + fftshift across the channels for each subcarrier
+//                      (matrix_transpose + fft_vcc #B, lib/matrix_transpose_impl.cc:97-104, ...radar_sim.grc:963-985),
+//                      result G[cpi][angle bin][k] leaves as one TMA tensor store of whole 128-byte lines.
 //   k_wide_range_mag   per (CPI, block of 8 angle bins): range IFFT over k of 2 x 4 rows of G (fft_vcc #A,
 //                      ...radar_sim.grc:940-962), |.|^2 (:637-652); a thread ends up with the same range bins of all eight
 //                      rows, so map[n][a0..a0+7] leaves as one 32-byte store (a whole sector) straight from registers,
 //                      arg-max partials as in k_angle_mag.
 //
-// G (2 MiB per CPI) is produced and consumed chunk by chunk of CPIs small enough to stay in the 126 MB L2.
-// HBM per CPI: 3 MiB symbols + 1 MiB map (+ what the L2 spills of G) against 12 MiB for chan_est -> range -> angle.
+// G (2 MiB per CPI) is produced and consumed in rounds of CPIs (222: both grids filled exactly).  Measured, it does not
+// stay in the L2 at that size and the pair is not bandwidth-bound: HBM per CPI is 2 MiB symbols + 2 x 2 MiB
+// G + 1 MiB map against 12 MiB for chan_est -> range -> angle.
 // Float32 arithmetic of the same class as the oracle's radix-2 FFTs, not its rounding or order: the criterion is 1e-4 of
 // the map peak; detection decisions are settled by jrc_exact.cuh.
 #pragma once
