@@ -10,6 +10,11 @@
 #include <cstdlib>
 #include <cstring>
 #include <random>
+#include <atomic>
+#include <condition_variable>
+#include <deque>
+#include <mutex>
+#include <thread>
 
 #include <mimo_ofdm_jrc/fft_peak_detect.h>
 #include <mimo_ofdm_jrc/matrix_transpose.h>
@@ -436,6 +441,100 @@ static void test_fused_mode()
     CHECK(r1.produced == V && r1.out_tags[0].size() == 1, "fused mode: mismatching blocks must fall back");
 }
 
+// JRC_FUSED=1 with the blocks on their own threads, as under the GNU Radio scheduler: the radar block runs ahead on one
+// thread (far enough at times that the ring of cached results wraps over frames the consumers have not fetched yet), the
+// two downstream blocks follow on another.  Every packet carries the RIGHT input as well, so a fetch that finds its frame
+// overwritten falls back to the block's own call and the outputs must still equal the oracle's, frame by frame.
+static void test_fused_mode_threads()
+{
+    const int N = 64, T = 4, R = 2, S = 4, pre = 5, IR = 16, IA = 8, V = 8, Nr = N * IR, Na = V * IA, items = pre + S;
+    auto rb = range_bins(N, IR); auto ab = angle_bins(Na);
+    const float ndr = 2.4f, nda = 2 * 14.4775f;
+    setenv("JRC_FUSED", "1", 1);
+    auto radar = mimo_ofdm_radar::make(N, T, R, S, pre, false, false, 1, IR, false, "/tmp/jrc_cpp_chan.csv");
+    auto transp = matrix_transpose::make(Nr, V, IA, false);
+    auto estim = range_angle_estimator::make(Na, rb, ab, ndr, nda, -100.f, 0.f, "/tmp/jrc_cpp_log.csv", false);
+    unsetenv("JRC_FUSED");
+    const int n_frames = 120;
+    struct job_t { int it; cvec y, cm; };               // what the stock fft_vcc blocks would hand on
+    std::deque<job_t> queue;
+    std::mutex mu;
+    std::condition_variable cv;
+    std::vector<cvec> want_tr(n_frames);
+    std::vector<orc_det> want_det(n_frames);
+    std::atomic<int> bad_tr{0}, bad_msg{0}, served{0};
+    std::thread consumer([&]() {
+        uint64_t rd2 = 0, rd3 = 0;
+        for (int done = 0; done < n_frames; done++) {
+            job_t j;
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                cv.wait(lk, [&] { return !queue.empty(); });
+                j = std::move(queue.front());
+                queue.pop_front();
+            }
+            cvec tr((size_t)Nr * Na);
+            shim::input_t ti; ti.items = j.y.data(); ti.n_items = V;
+            ti.tags.push_back(shim::make_tag(rd2, "packet_len", pmt::from_long(V)));
+            ti.tags.push_back(shim::make_tag(rd2, "jrc_cpi", pmt::from_long(j.it)));
+            rd2 += V;
+            auto r2 = shim::run_once(*transp, {ti}, {{tr.data(), Nr}});
+            if (r2.produced != Nr || !same(tr.data(), (const orc_c32 *)want_tr[j.it].data(), tr.size())) bad_tr++;
+            if (r2.out_tags[0].size() == 2) served++;
+            shim::input_t ei; ei.items = j.cm.data(); ei.n_items = Nr;
+            ei.tags.push_back(shim::make_tag(rd3, "packet_len", pmt::from_long(Nr)));
+            ei.tags.push_back(shim::make_tag(rd3, "jrc_cpi", pmt::from_long(j.it)));
+            rd3 += Nr;
+            shim::run_once(*estim, {ei}, {});
+            auto &msgs = estim->shim_published["params"];
+            const orc_det &od = want_det[j.it];
+            if (msgs.size() != 1) { bad_msg++; msgs.clear(); continue; }
+            auto field = [&](int k) { return pmt::f32vector_elements(pmt::nth(1, pmt::nth(k, msgs[0])))[0]; };
+            if (!(field(0) == rb[od.range_idx] && field(1) == ab[od.angle_idx] && field(2) == od.peak_power && field(3) == od.snr_db)) bad_msg++;
+            msgs.clear();
+        }
+    });
+    orc_radar *ref = orc_radar_create(N, T, R, S, pre, 0, 0, 1, IR, 0);
+    uint64_t rd = 0;
+    int bad_pad = 0;
+    for (int it = 0; it < n_frames; it++) {
+        frame_t f = make_frame(T, R, items, N);
+        std::vector<const orc_c32 *> tp, rp;
+        for (auto &v : f.tx) tp.push_back((const orc_c32 *)v.data());
+        for (auto &v : f.rx) rp.push_back((const orc_c32 *)v.data());
+        cvec opad((size_t)V * Nr), oy((size_t)V * Nr), otr((size_t)Nr * Na), ocm((size_t)Nr * Na);
+        orc_radar_work(ref, tp.data(), rp.data(), 0, (orc_c32 *)opad.data());
+        orc_fft_vcc_batch((orc_c32 *)opad.data(), (orc_c32 *)oy.data(), Nr, V, 0, 0);
+        orc_matrix_transpose((orc_c32 *)oy.data(), V, Nr, V, IA, (orc_c32 *)otr.data());
+        orc_fft_vcc_batch((orc_c32 *)otr.data(), (orc_c32 *)ocm.data(), Na, Nr, 1, 1);
+        orc_range_angle_estimate((orc_c32 *)ocm.data(), Nr, Na, rb.data(), Nr, ab.data(), Na, ndr, nda, -100.f, 0.f, &want_det[it], nullptr);
+        want_tr[it] = otr;
+        std::vector<shim::input_t> in(T + R);
+        for (int t = 0; t < T; t++) { in[t].items = f.tx[t].data(); in[t].n_items = items; }
+        for (int r = 0; r < R; r++) { in[T + r].items = f.rx[r].data(); in[T + r].n_items = items; }
+        in[0].tags.push_back(shim::make_tag(rd, "packet_len", pmt::from_long(items)));
+        in[T].tags.push_back(shim::make_tag(rd, "packet_len", pmt::from_long(items)));
+        rd += items;
+        cvec pad((size_t)V * Nr);
+        auto r1 = shim::run_once(*radar, in, {{pad.data(), 64}});
+        if (r1.produced != V || !same(pad.data(), (const orc_c32 *)opad.data(), pad.size())) bad_pad++;
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            queue.push_back(job_t{it, std::move(oy), std::move(ocm)});
+        }
+        // hand the frames over in bursts: the radar block gets up to 40 frames ahead of the consumers
+        if (it % 40 == 39 || it == n_frames - 1) cv.notify_one();
+    }
+    cv.notify_one();
+    consumer.join();
+    orc_radar_destroy(ref);
+    CHECK(bad_pad == 0 && bad_tr.load() == 0 && bad_msg.load() == 0, "fused mode on two threads: %d radar outputs, %d transposed arrays, %d messages differ",
+          bad_pad, bad_tr.load(), bad_msg.load());
+    CHECK(served.load() > 0 && served.load() < n_frames, "fused mode on two threads: %d of %d frames served from the cache (expected some of each kind)",
+          served.load(), n_frames);
+    std::printf("fused mode on two threads: %d of %d frames served from the cache, the rest through the blocks' own calls\n", served.load(), n_frames);
+}
+
 static void test_capture_format(const char *golden_dir)
 {
     const int N = 64, T = 4, R = 2, S = 4, V = T * R;
@@ -473,6 +572,7 @@ int main()
     test_peak_and_pad();
     test_fused_block();
     test_fused_mode();
+    test_fused_mode_threads();
     if (g_fail) { std::printf("%d check(s) FAILED\n", g_fail); return 1; }
     std::printf("ALL BLOCK TESTS PASSED\n");
     return 0;
