@@ -231,6 +231,50 @@ __device__ __forceinline__ float snr_db_fast(float peak, float noise)
     return __fmul_rn(10.f, log10f(__fdiv_rn(peak, noise)));
 }
 
+// acc <- (float)((double)acc + (double)v * (double)v) for v = chunk[0 .. cnt) in order: the reference's `float += double`
+// (lib/range_angle_estimator_impl.cc:217), a serial chain of convert, add, convert per window cell (~35 cycles).  One warp
+// runs it speculatively 32 cells at a time.  With p = v*v = ph + pl (ph = RN(v*v), pl = fma(v, v, -ph), exact) and
+// t = RN(acc + ph), e = its exact rounding error (TwoSum), the exact sum is t + (e + pl): whenever |e + pl| stays clear of
+// half an ulp of t and t is not a power of two, the reference's result IS t -- rounding the exact sum to double first
+// moves it by 2^-53 relative, 2^-29 of that ulp.  So every lane carries the same chain t <- RN(t + ph_k) (one FADD per
+// cell, the ph_k by shuffle), lane k keeps the two values of ITS step and checks it afterwards, off the chain; a block with a
+// step inside the margin (or a start from zero, a power of two, NaN, Inf, tiny values) is redone with the reference's own
+// expression.  ~2.5e-4 of the steps of a noise sum are; NumPy model against the expression, midpoints included:
+// tests/test_oracle_kat.py::test_speculative_sequential_sum.  All 32 lanes call it with the same arguments.
+__device__ __forceinline__ float seq_sum_sq_warp(float acc, const float *chunk, int cnt, int lane)
+{
+    for (int j0 = 0; j0 < cnt; j0 += 32) {
+        const int n = min(32, cnt - j0);
+        const float a = lane < n ? chunk[j0 + lane] : 0.f;
+        const float ph = __fmul_rn(a, a), pl = __fmaf_rn(a, a, -ph);
+        float t = acc, my_s = 0.f, my_t = 0.f;
+#pragma unroll 8
+        for (int k = 0; k < n; k++) {
+            const float phk = __shfl_sync(0xffffffffu, ph, k);
+            const float tn = __fadd_rn(t, phk);
+            if (lane == k) { my_s = t; my_t = tn; }
+            t = tn;
+        }
+        bool safe = true;
+        if (lane < n) {
+            const float bv = __fsub_rn(my_t, my_s);
+            const float e = __fadd_rn(__fsub_rn(my_s, __fsub_rn(my_t, bv)), __fsub_rn(ph, bv));
+            const float d = __fadd_rn(e, pl);
+            const unsigned tb = __float_as_uint(my_t), ex = (tb >> 23) & 0xffu;
+            const float ul = __uint_as_float((tb & 0x7f800000u) - (23u << 23));
+            safe = (fabsf(d) <= __fmul_rn(0.49999f, ul)) && (tb & 0x007fffffu) != 0u && ex > 30u && ex < 250u;
+        }
+        if (__all_sync(0xffffffffu, safe)) { acc = t; continue; }
+        float s = acc;
+        for (int k = 0; k < n; k++) {
+            const double ak = (double)__shfl_sync(0xffffffffu, a, k);
+            s = (float)((double)s + ak * ak);
+        }
+        acc = s;
+    }
+    return acc;
+}
+
 __device__ __forceinline__ unsigned long long pack_key(float v, unsigned idx)
 {
     // v >= 0 and not NaN: float bits are monotonic; ties -> the smaller index wins

@@ -399,13 +399,9 @@ __global__ void __launch_bounds__(256) k_est_exact(const ExactParams P)
                         const int cnt = min(1024, cells - cb);
                         for (int j = tid; j < cnt; j += 256) chunk[j] = __ldcg(W + cb + j);
                         __syncthreads();
-                        if (tid == 0) {
-                            float acc = s_noise;
-                            for (int j = 0; j < cnt; j++) {
-                                const double a = (double)chunk[j];
-                                acc = (float)((double)acc + a * a);          // :217 float += double
-                            }
-                            s_noise = acc;
+                        if (tid < 32) {
+                            const float acc = seq_sum_sq_warp(s_noise, chunk, cnt, tid);        // :217 float += double
+                            if (tid == 0) s_noise = acc;
                         }
                         __syncthreads();
                     }
@@ -426,13 +422,9 @@ __global__ void __launch_bounds__(256) k_est_exact(const ExactParams P)
                             chunk[j] = ref_abs(ang(lr, a_idx));
                         }
                         __syncthreads();
-                        if (tid == 0) {
-                            float acc = s_noise;
-                            for (int j = 0; j < cnt; j++) {
-                                const double a = (double)chunk[j];
-                                acc = (float)((double)acc + a * a);          // :217 float += double
-                            }
-                            s_noise = acc;
+                        if (tid < 32) {
+                            const float acc = seq_sum_sq_warp(s_noise, chunk, cnt, tid);        // :217 float += double
+                            if (tid == 0) s_noise = acc;
                         }
                         __syncthreads();
                     }

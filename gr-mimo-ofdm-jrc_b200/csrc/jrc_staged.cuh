@@ -616,13 +616,9 @@ __global__ void k_est_finalize(const c32 *__restrict__ map, long long per_mat, i
             chunk[j] = ref_abs(m[a_idx + (long long)vlen * r_idx]);
         }
         __syncthreads();
-        if (threadIdx.x == 0) {
-            float acc = s_noise;
-            for (int j = 0; j < cnt; j++) {
-                double a = (double)chunk[j];
-                acc = (float)((double)acc + a * a);                      // :217 float += double
-            }
-            s_noise = acc;
+        if (threadIdx.x < 32) {
+            const float acc = seq_sum_sq_warp(s_noise, chunk, cnt, threadIdx.x);      // :217 float += double
+            if (threadIdx.x == 0) s_noise = acc;
         }
         __syncthreads();
     }

@@ -241,3 +241,60 @@ def test_single_bin_dit(orc):
         for i in range(0, n, 1 if n <= 128 else 7):
             o = (i + n // 2) % n if fwd else i
             assert dit_bin(x, n, tw, o).view(np.uint64) == ref[i].view(np.uint64), (n_in, n, i)
+
+
+def test_speculative_sequential_sum():
+    """The device's noise-window sum (jrc_common.cuh seq_sum_sq_warp) takes t = RN32(acc + RN32(v*v)) as the result of the
+    reference's acc = (float)((double)acc + (double)v*v) (lib/range_angle_estimator_impl.cc:217) whenever the exact remainder
+    stays clear of half an ulp of t, and redoes the step with the expression itself otherwise.  NumPy model of that test:
+    no accepted step may differ from the expression -- random operands over 12 decades, sums placed ON and next to float
+    midpoints -- and a noise-like accumulation must accept nearly every step."""
+    f32 = np.float32
+
+    def ulp_of(t):
+        return ((t.view(np.uint32) & np.uint32(0x7f800000)) - np.uint32(23 << 23)).view(np.float32)
+
+    def fast_step(s, a):
+        ph = a * a
+        pl = (a.astype(np.float64) * a.astype(np.float64) - ph.astype(np.float64)).astype(f32)     # = fma(a, a, -ph), exact
+        t = s + ph
+        bv = t - s
+        e = (s - (t - bv)) + (ph - bv)
+        d = e + pl
+        tb = t.view(np.uint32)
+        ex = (tb >> 23) & 0xff
+        safe = (np.abs(d) <= f32(0.49999) * ulp_of(t)) & ((tb & np.uint32(0x007fffff)) != 0) & (ex > 30) & (ex < 250)
+        return t, safe
+
+    def ref_step(s, a):
+        return (s.astype(np.float64) + a.astype(np.float64) * a.astype(np.float64)).astype(f32)
+
+    rng = np.random.default_rng(1)
+    n_safe = 0
+    with np.errstate(all="ignore"):
+        for scale_s in (1e-3, 1.0, 37.0, 1e4, 3e7):
+            for scale_a in (1e-4, 1e-2, 0.3, 1.0, 20.0, 3e3):
+                s = (np.abs(rng.standard_normal(100000)) * scale_s).astype(f32)
+                a = (rng.standard_normal(100000) * scale_a).astype(f32)
+                t, safe = fast_step(s, a)
+                assert not (safe & (t != ref_step(s, a))).any()
+                n_safe += int(safe.sum())
+        s = (np.abs(rng.standard_normal(500000)) * 8).astype(f32)
+        mid = s.astype(np.float64) + ulp_of(s).astype(np.float64) * (rng.integers(0, 64, s.size) + 0.5)
+        a0 = np.sqrt(mid - s.astype(np.float64)).astype(f32)
+        for a in (np.nextafter(a0, f32(0)), a0, np.nextafter(a0, f32(np.inf))):
+            t, safe = fast_step(s, a)
+            assert not (safe & (t != ref_step(s, a))).any()
+            n_safe += int(safe.sum())
+    assert n_safe > 2_000_000
+    a = (rng.standard_normal(5000) * 3e-2).astype(f32)
+    acc, unsafe = f32(0), 0
+    for v in a:
+        t, safe = fast_step(np.array([acc], f32), np.array([v], f32))
+        r = ref_step(np.array([acc], f32), np.array([v], f32))[0]
+        if safe[0]:
+            assert t[0] == r
+        else:
+            unsafe += 1
+        acc = r
+    assert unsafe <= 25, unsafe
