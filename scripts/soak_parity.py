@@ -2,7 +2,7 @@
 many records sit near the 15 dB gate, plus tie scenes whose map repeats after Nr/2 rows) through the fast paths and the
 one-kernel-per-block path on the GPU; range_idx / angle_idx / n_noise / gate flag must be equal on EVERY CPI and every
 record redone in the reference's order equal in every bit (tests/test_gpu_parity.py::check_detections).
-    python scripts/soak_parity.py [seconds] -> one JSON line"""
+    python scripts/soak_parity.py [seconds] [gate] -> one JSON line"""
 import json, os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "gr-mimo-ofdm-jrc_b200", "python")); sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -12,6 +12,7 @@ from mimo_ofdm_jrc import synth
 from test_gpu_parity import check_detections, CFGS
 
 budget = float(sys.argv[1]) if len(sys.argv) > 1 else 60.0
+gate_mode = len(sys.argv) > 2 and sys.argv[2] == "gate"       # every scene gets a threshold on one of its own SNRs
 plans = [("C2", 2048), ("C1", 2048), ("C3s", 256), ("C3", 24), ("C5", 12), ("sq8", 1024)]
 chains = {}
 tot = {k: dict(cpis=0, exact=0, marked=0, ties_in_kernel=0, near_gate=0) for k, _ in plans}
@@ -39,6 +40,13 @@ while time.time() < t_end:
         if name not in chains:
             chains[name] = jrc.radar_chain(cfg["N"], cfg["T"], cfg["R"], cfg["S"], cfg["IR"], cfg["IA"], estimator=est)
         rc = chains[name]
+        if gate_mode:
+            # gate threshold on a record's own SNR (first pass), so that records land inside the gate margin
+            _, dq = rc.run(torch.from_numpy(rx).cuda(), torch.from_numpy(tx).cuda(), want_map=True)
+            rc.sync()
+            snr = rc.dets_to_numpy(dq)["snr_db"]
+            est = dict(est, snr_threshold=float(np.float32(snr[int(rng.integers(0, n))]) + np.float32(rng.choice([0.0, 1e-5, -1e-5, 3e-4]))))
+            rc.chain.set_thresholds(est["snr_threshold"], est["power_threshold"])
         drx, dtx = torch.from_numpy(rx).cuda(), torch.from_numpy(tx).cuda()
         _, d1 = rc.run(drx, dtx, want_map=True)
         rc.sync()
@@ -51,4 +59,4 @@ while time.time() < t_end:
 for name, rc in chains.items():
     st = rc.chain.exact_stats()
     tot[name]["marked"], tot[name]["ties_in_kernel"] = st["marked"], st["ties_in_kernel"]
-print(json.dumps({"seconds": budget, "scenes": seed, "detection_lists_identical": True, "per_config": tot}))
+print(json.dumps({"seconds": budget, "gate_mode": gate_mode, "scenes": seed, "detection_lists_identical": True, "per_config": tot}))
