@@ -1668,14 +1668,12 @@ struct FusedEntry {
                                          // thread's work and takes longer than everything before it)
     c32 *T = nullptr;                    // page-locked [Nr][Na]
     DetDev *det = nullptr;               // page-locked
-    cudaGraphExec_t graph = nullptr;     // the rest of the chain into THIS entry, captured once: up to the transposed array
-    cudaGraphExec_t graph2 = nullptr;    // ... and from there to the detection record
+    cudaGraphExec_t graph = nullptr;     // the rest of the chain into THIS entry, captured once
     int epoch = -1;
 };
 struct jrc_fused_state {
     cudaStream_t stream = nullptr, stream2 = nullptr;
-    cudaEvent_t h_ready = nullptr, t_ready = nullptr;
-    cudaEvent_t last_t_done = nullptr;   // the previous frame's copy of the transposed array out of dT
+    cudaEvent_t h_ready = nullptr, t_ready = nullptr, t_join = nullptr;   // (t_ready / t_join: fork and join inside the captured graph)
     cudaEvent_t last_done = nullptr;     // the previous frame's continuation (it reads the estimate the next call overwrites)
     FusedEntry e[JRC_FUSED_RING];
     int64_t next_seq = 0;
@@ -1691,6 +1689,7 @@ static jrc_status fused_state(jrc_chain *h, jrc_fused_state **out)
         CU(cudaStreamCreateWithFlags(&F->stream2, cudaStreamNonBlocking));
         CU(cudaEventCreateWithFlags(&F->h_ready, cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&F->t_ready, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&F->t_join, cudaEventDisableTiming));
         const size_t cells = (size_t)h->Nr * h->Na;
         for (FusedEntry &e : F->e) {
             CU(cudaEventCreateWithFlags(&e.done, cudaEventDisableTiming));
@@ -1710,10 +1709,10 @@ static void fused_state_destroy(jrc_chain *h)
     if (F->stream) { cudaStreamSynchronize(F->stream); cudaStreamDestroy(F->stream); }
     if (F->stream2) { cudaStreamSynchronize(F->stream2); cudaStreamDestroy(F->stream2); }
     if (F->t_ready) cudaEventDestroy(F->t_ready);
+    if (F->t_join) cudaEventDestroy(F->t_join);
     if (F->h_ready) cudaEventDestroy(F->h_ready);
     for (FusedEntry &e : F->e) {
         if (e.graph) cudaGraphExecDestroy(e.graph);
-        if (e.graph2) cudaGraphExecDestroy(e.graph2);
         if (e.done) cudaEventDestroy(e.done);
         if (e.t_done) cudaEventDestroy(e.t_done);
         if (e.T) cudaFreeHost(e.T);
@@ -1790,33 +1789,34 @@ static jrc_status radar_estimate_impl(jrc_chain *h, const jrc_c32 *const *tx, co
             ST(get_twiddles(h, Nr, 0, &tw));        // (tables are built on the handle's stream, before the capture)
             ST(get_twiddles(h, Na, 1, &tw));
             if (e.graph) { CU(cudaGraphExecDestroy(e.graph)); e.graph = nullptr; }
-            if (e.graph2) { CU(cudaGraphExecDestroy(e.graph2)); e.graph2 = nullptr; }
             c32 *dY = (c32 *)h->sY.p, *dT = (c32 *)F->dT.p, *dC = (c32 *)h->sC.p;
-            auto capture = [&](cudaGraphExec_t *exec, const std::function<jrc_status()> &body) -> jrc_status {
-                CU(cudaStreamBeginCapture(F->stream, cudaStreamCaptureModeThreadLocal));
-                std::swap(h->stream, F->stream);
-                jrc_status st = body();
-                std::swap(h->stream, F->stream);
-                cudaGraph_t g = nullptr;
-                cudaError_t ce = cudaStreamEndCapture(F->stream, &g);
-                if (st != JRC_OK) { if (g) cudaGraphDestroy(g); return st; }
-                CU(ce);
-                ce = cudaGraphInstantiate(exec, g, 0);
-                cudaGraphDestroy(g);
-                CU(ce);
-                return JRC_OK;
-            };
-            ST(capture(&e.graph, [&]() -> jrc_status {
+            // ONE graph: range fft_vcc, transpose, then two branches -- the transposed array's copy out with the entry's
+            // t_done recorded behind it (an external event-record node: pending from the graph launch on, fired when the
+            // copy is through), and angle fft_vcc, estimator, record out -- joined at the end.
+            CU(cudaStreamBeginCapture(F->stream, cudaStreamCaptureModeThreadLocal));
+            std::swap(h->stream, F->stream);
+            jrc_status st = [&]() -> jrc_status {
                 ST(launch_fft_rows(h, dH, N, N, dY, Nr, V, 0, 0));
                 ST(launch_transpose(h, dY, dT, V, Nr, Na, 1));
-                return JRC_OK;
-            }));
-            ST(capture(&e.graph2, [&]() -> jrc_status {
+                CU(cudaEventRecord(F->t_ready, h->stream));
+                CU(cudaStreamWaitEvent(F->stream2, F->t_ready, 0));
+                CU(cudaMemcpyAsync(e.T, dT, cells * sizeof(c32), cudaMemcpyDeviceToHost, F->stream2));
+                CU(cudaEventRecordWithFlags(e.t_done, F->stream2, cudaEventRecordExternal));
+                CU(cudaEventRecord(F->t_join, F->stream2));
                 ST(launch_fft_rows(h, dT, Na, Na, dC, Na, Nr, 1, 1));
                 ST(launch_estimate(h, dC, Nr, Na, 1, 0, (DetDev *)F->dDet.p));
                 CU(cudaMemcpyAsync(e.det, F->dDet.p, sizeof(DetDev), cudaMemcpyDeviceToHost, h->stream));
+                CU(cudaStreamWaitEvent(h->stream, F->t_join, 0));
                 return JRC_OK;
-            }));
+            }();
+            std::swap(h->stream, F->stream);
+            cudaGraph_t g = nullptr;
+            cudaError_t ce = cudaStreamEndCapture(F->stream, &g);
+            if (st != JRC_OK) { if (g) cudaGraphDestroy(g); return st; }
+            CU(ce);
+            ce = cudaGraphInstantiate(&e.graph, g, 0);
+            cudaGraphDestroy(g);
+            CU(ce);
             e.epoch = h->est_epoch;
         }
         fused_entry_pending = &e;
@@ -1827,18 +1827,10 @@ static jrc_status radar_estimate_impl(jrc_chain *h, const jrc_c32 *const *tx, co
         FusedEntry &e = *fused_entry_pending;
         CU(cudaEventRecord(F->h_ready, h->stream));
         CU(cudaStreamWaitEvent(F->stream, F->h_ready, 0));
-        if (F->last_t_done) CU(cudaStreamWaitEvent(F->stream, F->last_t_done, 0));   // the previous frame's copy out of dT
         CU(cudaGraphLaunch(e.graph, F->stream));
-        // the transposed array goes out on a stream of its own while the angle transform and the estimator carry on
-        CU(cudaEventRecord(F->t_ready, F->stream));
-        CU(cudaStreamWaitEvent(F->stream2, F->t_ready, 0));
-        CU(cudaMemcpyAsync(e.T, F->dT.p, (size_t)Nr * Na * sizeof(c32), cudaMemcpyDeviceToHost, F->stream2));
-        CU(cudaEventRecord(e.t_done, F->stream2));
-        CU(cudaGraphLaunch(e.graph2, F->stream));
         CU(cudaEventRecord(e.done, F->stream));
         h->launches += 5;
         F->last_done = e.done;
-        F->last_t_done = e.t_done;
         e.seq.store(fused_seq, std::memory_order_release);
         *cpi_seq = fused_seq;
     }
