@@ -368,7 +368,7 @@ static int grid_for(long long n, int threads, int sm_count)
 // staged kernels: launch helpers (all on h->stream)
 // ---------------------------------------------------------------------------
 static jrc_status launch_fft_rows(jrc_chain *h, const c32 *in, long long in_stride, int n_in, c32 *out, int n,
-                                  long long rows, int forward, int shift)
+                                  long long rows, int forward, int shift, int tr_w = 0, unsigned long long *keys = nullptr)
 {
     if (!is_pow2(n) || n > 16384) return fail(JRC_ERR_INVALID, "FFT length %d unsupported (power of two <= 16384)", n);
     if (rows <= 0) return JRC_OK;
@@ -381,7 +381,7 @@ static jrc_status launch_fft_rows(jrc_chain *h, const c32 *in, long long in_stri
         CU(cudaFuncSetAttribute(k_fft_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     long long ctas = (rows + rpc - 1) / rpc;
     if (ctas > 0x7fffffffLL) return fail(JRC_ERR_INVALID, "too many FFT rows");
-    k_fft_rows<<<(unsigned)ctas, threads, smem, h->stream>>>(in, in_stride, n_in, out, n, ilog2(n), rows, rpc, forward, shift, tw);
+    k_fft_rows<<<(unsigned)ctas, threads, smem, h->stream>>>(in, in_stride, n_in, out, n, ilog2(n), rows, rpc, forward, shift, tw, tr_w, keys);
     CU(cudaGetLastError());
     h->launches++;
     return JRC_OK;
@@ -601,24 +601,28 @@ static jrc_status launch_angle_mag(jrc_chain *h, const c32 *Y, int V, int Nr, in
     return fail(JRC_ERR_INVALID, "angle FFT length %d unsupported by the tiled path", Na);
 }
 
-static jrc_status launch_estimate(jrc_chain *h, const c32 *cmap, int n_inputs, int vlen, int mats, int cpi0, DetDev *dets)
+// ready_keys: the arg-max keys are already there (k_fft_rows' epilogue, a buffer of the caller's); k_est_finalize zeroes
+// them again for the next frame (the caller zeroed them once, before the first)
+static jrc_status launch_estimate(jrc_chain *h, const c32 *cmap, int n_inputs, int vlen, int mats, int cpi0, DetDev *dets,
+                                  unsigned long long *ready_keys = nullptr)
 {
     EstParams P;
     ST(est_params(h, n_inputs, vlen, &P));
-    ST(h->sKeys.need(sizeof(unsigned long long) * (size_t)mats));
-    unsigned long long *keys = (unsigned long long *)h->sKeys.p;
-    CU(cudaMemsetAsync(keys, 0, sizeof(unsigned long long) * (size_t)mats, h->stream));
+    const bool have_keys = ready_keys != nullptr;
+    if (!have_keys) ST(h->sKeys.need(sizeof(unsigned long long) * (size_t)mats));
+    unsigned long long *keys = have_keys ? ready_keys : (unsigned long long *)h->sKeys.p;
+    if (!have_keys) CU(cudaMemsetAsync(keys, 0, sizeof(unsigned long long) * (size_t)mats, h->stream));
     long long per = (long long)n_inputs * vlen;
     int bx = (int)((per + 256 * 8 - 1) / (256 * 8));
     if (bx < 1) bx = 1;
     if (bx > 256) bx = 256;
-    for (int m0 = 0; m0 < mats; m0 += 65535) {
+    for (int m0 = 0; m0 < mats && !have_keys; m0 += 65535) {
         int mc = mats - m0 < 65535 ? mats - m0 : 65535;
         k_est_argmax<<<dim3(bx, mc), 256, 0, h->stream>>>(cmap + (long long)m0 * per, per, keys + m0);
         CU(cudaGetLastError());
         h->launches++;
     }
-    k_est_finalize<<<mats, 256, 0, h->stream>>>(cmap, per, n_inputs, vlen, keys, P, dets, cpi0);
+    k_est_finalize<<<mats, 256, 0, h->stream>>>(cmap, per, n_inputs, vlen, keys, P, dets, cpi0, have_keys ? 1 : 0);
     CU(cudaGetLastError());
     h->launches++;
     return JRC_OK;
@@ -1661,23 +1665,33 @@ struct Staging {   // maps caller pointers onto device memory for the duration o
 };
 
 // ---- fused mode for an unmodified flowgraph: ring of results keyed by CPI sequence number -------------------
+#define JRC_FUSED_MAX_CHUNKS 8
 struct FusedEntry {
     std::atomic<int64_t> seq{-1};        // -1 while the device may be writing the entry
     cudaEvent_t done = nullptr;          // everything of the entry is on the host
-    cudaEvent_t t_done = nullptr;        // the transposed array is (the estimator's reference-order noise sum is one
-                                         // thread's work and takes longer than everything before it)
+    cudaEvent_t t_done[JRC_FUSED_MAX_CHUNKS] = {};   // piece i of the transposed array is (the array leaves in pieces so
+                                         // that the consumer's copy into the scheduler's buffer runs behind the transfer)
+    cudaEvent_t t_dev = nullptr;         // the transposed array is complete on the device (dT)
     c32 *T = nullptr;                    // page-locked [Nr][Na]
+    c32 *dT = nullptr;                   // the same array on the device: a consumer whose buffer is page-locked takes it from
+                                         // here in one transfer (no copy through T)
+    std::atomic<int> direct{-1};         // the graph was captured without (1) / with (0) the copy into T
     DetDev *det = nullptr;               // page-locked
     cudaGraphExec_t graph = nullptr;     // the rest of the chain into THIS entry, captured once
     int epoch = -1;
 };
 struct jrc_fused_state {
+    std::atomic<int> direct{0};          // set by the first fetch into a page-locked buffer: frames from then on skip T
+    cudaStream_t stream3 = nullptr;      // the consumer's transfers out of dT
+    int chunks = 4;                      // pieces of the transposed array's copy out (JRC_FUSED_CHUNKS=1..8)
+    bool short_chain = true;             // transpose and arg-max as epilogues of the two fft_vcc kernels (JRC_FUSED_SHORT=0: own kernels)
+    bool pad_first = true;               // the radar block's own output is queued before the continuation (JRC_FUSED_PAD_FIRST=0: after)
     cudaStream_t stream = nullptr, stream2 = nullptr;
     cudaEvent_t h_ready = nullptr, t_ready = nullptr, t_join = nullptr;   // (t_ready / t_join: fork and join inside the captured graph)
     cudaEvent_t last_done = nullptr;     // the previous frame's continuation (it reads the estimate the next call overwrites)
     FusedEntry e[JRC_FUSED_RING];
     int64_t next_seq = 0;
-    GrowBuf dT, dDet;
+    GrowBuf dDet, dKeys;                 // (dKeys: zero between frames)
 };
 
 static jrc_status fused_state(jrc_chain *h, jrc_fused_state **out)
@@ -1685,15 +1699,22 @@ static jrc_status fused_state(jrc_chain *h, jrc_fused_state **out)
     if (!h->fstate) {
         jrc_fused_state *F = new jrc_fused_state();
         h->fstate = F;
+        if (const char *e = std::getenv("JRC_FUSED_CHUNKS")) F->chunks = std::min(std::max(std::atoi(e), 1), JRC_FUSED_MAX_CHUNKS);
+        if (const char *e = std::getenv("JRC_FUSED_PAD_FIRST")) F->pad_first = std::atoi(e) != 0;
+        if (const char *e = std::getenv("JRC_FUSED_SHORT")) F->short_chain = std::atoi(e) != 0;
         CU(cudaStreamCreateWithFlags(&F->stream, cudaStreamNonBlocking));
         CU(cudaStreamCreateWithFlags(&F->stream2, cudaStreamNonBlocking));
+        CU(cudaStreamCreateWithFlags(&F->stream3, cudaStreamNonBlocking));
         CU(cudaEventCreateWithFlags(&F->h_ready, cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&F->t_ready, cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&F->t_join, cudaEventDisableTiming));
         const size_t cells = (size_t)h->Nr * h->Na;
         for (FusedEntry &e : F->e) {
             CU(cudaEventCreateWithFlags(&e.done, cudaEventDisableTiming));
-            CU(cudaEventCreateWithFlags(&e.t_done, cudaEventDisableTiming));
+            for (cudaEvent_t &ev : e.t_done) CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&e.t_dev, cudaEventDisableTiming));
+            CU(cudaMalloc(&e.dT, cells * sizeof(c32)));
+            CU(cudaMemset(e.dT, 0, cells * sizeof(c32)));      // (the short chain only ever writes the V data columns)
             CU(cudaMallocHost(&e.T, cells * sizeof(c32)));
             CU(cudaMallocHost(&e.det, sizeof(DetDev)));
         }
@@ -1708,18 +1729,22 @@ static void fused_state_destroy(jrc_chain *h)
     if (!F) return;
     if (F->stream) { cudaStreamSynchronize(F->stream); cudaStreamDestroy(F->stream); }
     if (F->stream2) { cudaStreamSynchronize(F->stream2); cudaStreamDestroy(F->stream2); }
+    if (F->stream3) { cudaStreamSynchronize(F->stream3); cudaStreamDestroy(F->stream3); }
     if (F->t_ready) cudaEventDestroy(F->t_ready);
     if (F->t_join) cudaEventDestroy(F->t_join);
     if (F->h_ready) cudaEventDestroy(F->h_ready);
     for (FusedEntry &e : F->e) {
         if (e.graph) cudaGraphExecDestroy(e.graph);
         if (e.done) cudaEventDestroy(e.done);
-        if (e.t_done) cudaEventDestroy(e.t_done);
+        for (cudaEvent_t ev : e.t_done)
+            if (ev) cudaEventDestroy(ev);
+        if (e.t_dev) cudaEventDestroy(e.t_dev);
+        if (e.dT) cudaFree(e.dT);
         if (e.T) cudaFreeHost(e.T);
         if (e.det) cudaFreeHost(e.det);
     }
-    F->dT.release();
     F->dDet.release();
+    F->dKeys.release();
     delete F;
     h->fstate = nullptr;
 }
@@ -1778,35 +1803,58 @@ static jrc_status radar_estimate_impl(jrc_chain *h, const jrc_c32 *const *tx, co
         const int64_t seq = F->next_seq++;
         FusedEntry &e = F->e[seq % JRC_FUSED_RING];
         e.seq.store(-1, std::memory_order_release);
-        if (!e.graph || e.epoch != h->est_epoch) {
+        const int direct = F->direct.load(std::memory_order_acquire);
+        if (!e.graph || e.epoch != h->est_epoch || e.direct.load(std::memory_order_relaxed) != direct) {
             const size_t cells = (size_t)Nr * Na;
             ST(h->sY.need((size_t)V * Nr * sizeof(c32)));
             ST(h->sC.need(cells * sizeof(c32)));
-            ST(F->dT.need(cells * sizeof(c32)));
             ST(F->dDet.need(sizeof(DetDev)));
             ST(h->sKeys.need(sizeof(unsigned long long)));
+            if (!F->dKeys.p) {
+                ST(F->dKeys.need(sizeof(unsigned long long)));
+                CU(cudaMemsetAsync(F->dKeys.p, 0, sizeof(unsigned long long), h->stream));   // (ordered before the graph by h_ready)
+            }
             const c32 *tw = nullptr;
             ST(get_twiddles(h, Nr, 0, &tw));        // (tables are built on the handle's stream, before the capture)
             ST(get_twiddles(h, Na, 1, &tw));
             if (e.graph) { CU(cudaGraphExecDestroy(e.graph)); e.graph = nullptr; }
-            c32 *dY = (c32 *)h->sY.p, *dT = (c32 *)F->dT.p, *dC = (c32 *)h->sC.p;
+            c32 *dY = (c32 *)h->sY.p, *dT = e.dT, *dC = (c32 *)h->sC.p;
             // ONE graph: range fft_vcc, transpose, then two branches -- the transposed array's copy out with the entry's
             // t_done recorded behind it (an external event-record node: pending from the graph launch on, fired when the
             // copy is through), and angle fft_vcc, estimator, record out -- joined at the end.
             CU(cudaStreamBeginCapture(F->stream, cudaStreamCaptureModeThreadLocal));
             std::swap(h->stream, F->stream);
             jrc_status st = [&]() -> jrc_status {
-                ST(launch_fft_rows(h, dH, N, N, dY, Nr, V, 0, 0));
-                ST(launch_transpose(h, dY, dT, V, Nr, Na, 1));
-                CU(cudaEventRecord(F->t_ready, h->stream));
-                CU(cudaStreamWaitEvent(F->stream2, F->t_ready, 0));
-                CU(cudaMemcpyAsync(e.T, dT, cells * sizeof(c32), cudaMemcpyDeviceToHost, F->stream2));
-                CU(cudaEventRecordWithFlags(e.t_done, F->stream2, cudaEventRecordExternal));
-                CU(cudaEventRecord(F->t_join, F->stream2));
-                ST(launch_fft_rows(h, dT, Na, Na, dC, Na, Nr, 1, 1));
-                ST(launch_estimate(h, dC, Nr, Na, 1, 0, (DetDev *)F->dDet.p));
-                CU(cudaMemcpyAsync(e.det, F->dDet.p, sizeof(DetDev), cudaMemcpyDeviceToHost, h->stream));
-                CU(cudaStreamWaitEvent(h->stream, F->t_join, 0));
+                if (F->short_chain) {
+                    ST(launch_fft_rows(h, dH, N, N, dT, Nr, V, 0, 0, Na));
+                } else {
+                    ST(launch_fft_rows(h, dH, N, N, dY, Nr, V, 0, 0));
+                    ST(launch_transpose(h, dY, dT, V, Nr, Na, 1));
+                }
+                if (direct) CU(cudaEventRecordWithFlags(e.t_dev, h->stream, cudaEventRecordExternal));
+                if (!direct) {
+                    CU(cudaEventRecord(F->t_ready, h->stream));
+                    CU(cudaStreamWaitEvent(F->stream2, F->t_ready, 0));
+                    for (int i = 0; i < F->chunks; i++) {
+                        const size_t lo = cells * i / F->chunks, hi = cells * (i + 1) / F->chunks;
+                        CU(cudaMemcpyAsync(e.T + lo, dT + lo, (hi - lo) * sizeof(c32), cudaMemcpyDeviceToHost, F->stream2));
+                        CU(cudaEventRecordWithFlags(e.t_done[i], F->stream2, cudaEventRecordExternal));
+                    }
+                    CU(cudaEventRecord(F->t_join, F->stream2));
+                }
+                if (F->short_chain) {
+                    // the record goes straight into the entry's page-locked slot (one 32-byte store over PCIe, no copy node)
+                    DetDev *det_alias = (DetDev *)host_dev_alias(e.det);
+                    unsigned long long *keys = (unsigned long long *)F->dKeys.p;
+                    ST(launch_fft_rows(h, dT, Na, Na, dC, Na, Nr, 1, 1, 0, keys));
+                    ST(launch_estimate(h, dC, Nr, Na, 1, 0, det_alias ? det_alias : (DetDev *)F->dDet.p, keys));
+                    if (!det_alias) CU(cudaMemcpyAsync(e.det, F->dDet.p, sizeof(DetDev), cudaMemcpyDeviceToHost, h->stream));
+                } else {
+                    ST(launch_fft_rows(h, dT, Na, Na, dC, Na, Nr, 1, 1));
+                    ST(launch_estimate(h, dC, Nr, Na, 1, 0, (DetDev *)F->dDet.p));
+                    CU(cudaMemcpyAsync(e.det, F->dDet.p, sizeof(DetDev), cudaMemcpyDeviceToHost, h->stream));
+                }
+                if (!direct) CU(cudaStreamWaitEvent(h->stream, F->t_join, 0));
                 return JRC_OK;
             }();
             std::swap(h->stream, F->stream);
@@ -1818,14 +1866,19 @@ static jrc_status radar_estimate_impl(jrc_chain *h, const jrc_c32 *const *tx, co
             cudaGraphDestroy(g);
             CU(ce);
             e.epoch = h->est_epoch;
+            e.direct.store(direct, std::memory_order_relaxed);
         }
         fused_entry_pending = &e;
         fused_seq = seq;
     }
-    if (fused_entry_pending) {
-        // (queued before this call's own outputs: the device is still busy with the transfer in and the estimate)
+    // The continuation depends on the estimate only (h_ready is recorded here).  Its launch is the longest host-side step
+    // of the call: with pad_first this call's own small output kernel is queued first and completes while the host is busy
+    // with the graph launch, so the synchronize below returns at once; otherwise the graph is queued first.
+    if (fused_entry_pending) CU(cudaEventRecord(F->h_ready, h->stream));
+    auto launch_continuation = [&]() -> jrc_status {
+        if (!fused_entry_pending) return JRC_OK;
         FusedEntry &e = *fused_entry_pending;
-        CU(cudaEventRecord(F->h_ready, h->stream));
+        fused_entry_pending = nullptr;
         CU(cudaStreamWaitEvent(F->stream, F->h_ready, 0));
         CU(cudaGraphLaunch(e.graph, F->stream));
         CU(cudaEventRecord(e.done, F->stream));
@@ -1833,24 +1886,31 @@ static jrc_status radar_estimate_impl(jrc_chain *h, const jrc_c32 *const *tx, co
         F->last_done = e.done;
         e.seq.store(fused_seq, std::memory_order_release);
         *cpi_seq = fused_seq;
-    }
+        return JRC_OK;
+    };
+    if (F && !F->pad_first) ST(launch_continuation());
     const size_t out_items = (size_t)V * Nr, est_items = (size_t)V * N;
     if (!ptr_is_device(out) && !host_ptr_is_pinned(out) && h->zero_copy) {
-        // pageable output (a scheduler buffer): the pad kernel stores the packet, and the estimate behind it, into ONE
-        // page-locked block in place; two host copies after the synchronize instead of two driver-staged transfers
-        ST(h->pin_b.need((out_items + est_items) * sizeof(c32)));
+        // pageable output (a scheduler buffer): only the estimate crosses the bus (V*N samples stored in place into a
+        // page-locked block: the packet is the estimate's rows followed by zeros, lib/mimo_ofdm_radar_impl.cc:300-312), the
+        // range zero-padding is written by the host straight into the caller's buffer
+        ST(h->pin_b.need(est_items * sizeof(c32)));
         c32 *pin = (c32 *)h->pin_b.p, *dpin = (c32 *)host_dev_alias(pin);
         if (dpin) {
-            k_pad_rows<<<grid_for((long long)out_items, 256, h->sm_count), 256, 0, h->stream>>>(dH, dpin, V, N, Nr,
-                                                                                            chan_est_host ? dpin + out_items : nullptr);
+            k_pad_rows<<<grid_for((long long)est_items, 256, h->sm_count), 256, 0, h->stream>>>(dH, dpin, V, N, N, nullptr);
             CU(cudaGetLastError());
             h->launches++;
+            ST(launch_continuation());
             CU(cudaStreamSynchronize(h->stream));
-            memcpy(out, pin, out_items * sizeof(c32));
-            if (chan_est_host) memcpy(chan_est_host, pin + out_items, est_items * sizeof(c32));
+            for (int v = 0; v < V; v++) {
+                memcpy(out + (size_t)v * Nr, pin + (size_t)v * N, (size_t)N * sizeof(c32));
+                memset(out + (size_t)v * Nr + N, 0, (size_t)(Nr - N) * sizeof(c32));
+            }
+            if (chan_est_host) memcpy(chan_est_host, pin, est_items * sizeof(c32));
             return JRC_OK;
         }
     }
+    ST(launch_continuation());
     void *dout = nullptr;
     ST(sg.out(out, out_items * sizeof(c32), &dout));
     k_pad_rows<<<grid_for((long long)out_items, 256, h->sm_count), 256, 0, h->stream>>>(dH, (c32 *)dout, V, N, Nr, nullptr);
@@ -1883,7 +1943,7 @@ static jrc_status fused_entry(jrc_chain *h, int64_t cpi_seq, bool transposed_onl
     FusedEntry &e = F->e[cpi_seq % JRC_FUSED_RING];
     if (e.seq.load(std::memory_order_acquire) != cpi_seq) return fail(JRC_ERR_STATE, "CPI %lld is not cached", (long long)cpi_seq);
     CU(cudaSetDevice(h->cfg.device));
-    CU(cudaEventSynchronize(transposed_only ? e.t_done : e.done));
+    if (!transposed_only) CU(cudaEventSynchronize(e.done));
     *out = &e;
     return JRC_OK;
 }
@@ -1893,7 +1953,28 @@ extern "C" jrc_status jrc_fused_fetch_transposed(jrc_chain *h, int64_t cpi_seq, 
     if (!out) return fail(JRC_ERR_INVALID, "null argument");
     FusedEntry *e = nullptr;
     ST(fused_entry(h, cpi_seq, true, &e));
-    memcpy(out, e->T, (size_t)h->Nr * h->Na * sizeof(c32));
+    // piece by piece behind the transfer: the copy into the caller's (pageable) buffer is the longer of the two
+    const size_t cells = (size_t)h->Nr * h->Na;
+    jrc_fused_state *F = h->fstate;
+    const bool pinned_out = host_ptr_is_pinned(out);
+    if (pinned_out || e->direct.load(std::memory_order_relaxed) == 1) {
+        // a page-locked destination (the block registered its stream buffer, jrc_host_register): one transfer from the
+        // device copy of the array, nothing passes through T -- and later frames stop producing T at all.  (A pageable
+        // destination after that switch still gets its array, through the driver's staging.)
+        if (pinned_out) F->direct.store(1, std::memory_order_release);
+        const bool entry_direct = e->direct.load(std::memory_order_relaxed) == 1;
+        CU(cudaStreamWaitEvent(F->stream3, entry_direct ? e->t_dev : e->t_done[F->chunks - 1], 0));
+        CU(cudaMemcpyAsync(out, e->dT, cells * sizeof(c32), cudaMemcpyDeviceToHost, F->stream3));
+        CU(cudaStreamSynchronize(F->stream3));
+        if (e->seq.load(std::memory_order_acquire) != cpi_seq) return fail(JRC_ERR_STATE, "CPI %lld was overwritten", (long long)cpi_seq);
+        return JRC_OK;
+    }
+    const int chunks = F->chunks;
+    for (int i = 0; i < chunks; i++) {
+        const size_t lo = cells * i / chunks, hi = cells * (i + 1) / chunks;
+        CU(cudaEventSynchronize(e->t_done[i]));
+        memcpy(out + lo, e->T + lo, (hi - lo) * sizeof(c32));
+    }
     if (e->seq.load(std::memory_order_acquire) != cpi_seq) return fail(JRC_ERR_STATE, "CPI %lld was overwritten", (long long)cpi_seq);
     return JRC_OK;
 }

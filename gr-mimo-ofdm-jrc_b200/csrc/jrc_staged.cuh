@@ -176,9 +176,15 @@ __device__ __forceinline__ void radix2_rows(c32 *sm, int n, int rows, const c32 
     }
 }
 
+// Two optional epilogues for the one-frame chain of the fused mode (same values, fewer launches on its critical path):
+//   tr_w > 0: the spectra leave transposed, out[i * tr_w + row] -- matrix_transpose (lib/matrix_transpose_impl.cc:97-104)
+//             into an array whose padding columns the caller zeroed once;
+//   keys:     the rows are ONE map: arg-max key of (float)pow(abs(z),2) over the outputs, exactly k_est_argmax's
+//             (lib/range_angle_estimator_impl.cc:137-151); *keys zeroed by the caller.
 __global__ void k_fft_rows(const c32 *in, long long in_stride, int n_in,   // in may alias out (in place)
                            c32 *out, int n, int log2n, long long rows, int rows_per_cta,
-                           int forward, int shift, const c32 *__restrict__ tw /* [n/2] */)
+                           int forward, int shift, const c32 *__restrict__ tw /* [n/2] */,
+                           int tr_w, unsigned long long *keys)
 {
     extern __shared__ c32 sm[];
     const long long row0 = (long long)blockIdx.x * rows_per_cta;
@@ -197,12 +203,39 @@ __global__ void k_fft_rows(const c32 *in, long long in_stride, int n_in,   // in
     }
     __syncthreads();
     radix2_rows(sm, n, rows_per_cta, tw);
+    unsigned long long best = 0ull;
     for (int e = threadIdx.x; e < tot; e += blockDim.x) {
         int lr = e / n, i = e % n;
         long long row = row0 + lr;
         if (row < rows) {
             int src = (forward && shift) ? (i + offset) % n : i;    // swap output halves
-            out[row * n + i] = sm[lr * n + src];
+            const c32 v = sm[lr * n + src];
+            if (tr_w) out[(long long)i * tr_w + row] = v;
+            else out[row * n + i] = v;
+            if (keys) {
+                const float p = (float)ref_pow_abs2(v);
+                if (p == p) {
+                    const unsigned long long key = pack_key(p, (unsigned)(row * n + i));
+                    best = key > best ? key : best;
+                }
+            }
+        }
+    }
+    if (keys) {
+        for (int o = 16; o > 0; o >>= 1) {
+            unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
+            best = other > best ? other : best;
+        }
+        __shared__ unsigned long long wbest[32];
+        if ((threadIdx.x & 31) == 0) wbest[threadIdx.x >> 5] = best;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            best = threadIdx.x < (blockDim.x >> 5) ? wbest[threadIdx.x] : 0ull;
+            for (int o = 16; o > 0; o >>= 1) {
+                unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
+                best = other > best ? other : best;
+            }
+            if (threadIdx.x == 0 && best) atomicMax(keys, best);
         }
     }
 }
@@ -576,8 +609,8 @@ __global__ void k_est_tables(EstParams P, int2 *__restrict__ win, double2 *__res
 // noise power is bit-identical.  snr/flags are finalised here (snr_db_of: log10 in double, rounded once);
 // host-side callers that need the host libm's bit pattern recompute them.
 __global__ void k_est_finalize(const c32 *__restrict__ map, long long per_mat, int n_inputs, int vlen,
-                               const unsigned long long *__restrict__ keys, EstParams P,
-                               DetDev *__restrict__ dets, int cpi0)
+                               unsigned long long *keys, EstParams P,
+                               DetDev *__restrict__ dets, int cpi0, int reset_keys)   // reset_keys: leave keys[] zeroed for the next frame
 {
     const long long mat = blockIdx.x;
     const c32 *m = map + mat * per_mat;
@@ -632,6 +665,7 @@ __global__ void k_est_finalize(const c32 *__restrict__ map, long long per_mat, i
         d.flags = (d.snr_db >= P.snr_threshold && d.peak_power >= P.power_threshold) ? 1u : 0u;   // :234
         d.cpi = cpi0 + (int)mat;
         dets[mat] = d;
+        if (reset_keys) keys[mat] = 0ull;
     }
 }
 
