@@ -1665,33 +1665,24 @@ struct Staging {   // maps caller pointers onto device memory for the duration o
 };
 
 // ---- fused mode for an unmodified flowgraph: ring of results keyed by CPI sequence number -------------------
-#define JRC_FUSED_MAX_CHUNKS 8
 struct FusedEntry {
     std::atomic<int64_t> seq{-1};        // -1 while the device may be writing the entry
     cudaEvent_t done = nullptr;          // everything of the entry is on the host
-    cudaEvent_t t_done[JRC_FUSED_MAX_CHUNKS] = {};   // piece i of the transposed array is (the array leaves in pieces so
-                                         // that the consumer's copy into the scheduler's buffer runs behind the transfer)
-    cudaEvent_t t_dev = nullptr;         // the transposed array is complete on the device (dT)
-    c32 *T = nullptr;                    // page-locked [Nr][Na]
-    c32 *dT = nullptr;                   // the same array on the device: a consumer whose buffer is page-locked takes it from
-                                         // here in one transfer (no copy through T)
-    std::atomic<int> direct{-1};         // the graph was captured without (1) / with (0) the copy into T
+    cudaEvent_t t_done = nullptr;        // the transposed spectra are (an external event-record node of the entry's graph)
+    c32 *T = nullptr;                    // page-locked [Nr][V]: the V data columns of matrix_transpose's [Nr][Na] output.  The
+                                         // other Na - V columns are zeros (lib/matrix_transpose_impl.cc:91-104): they never
+                                         // cross the bus, the consumer's fetch writes them into its buffer itself
     DetDev *det = nullptr;               // page-locked
     cudaGraphExec_t graph = nullptr;     // the rest of the chain into THIS entry, captured once
     int epoch = -1;
 };
 struct jrc_fused_state {
-    std::atomic<int> direct{0};          // set by the first fetch into a page-locked buffer: frames from then on skip T
-    cudaStream_t stream3 = nullptr;      // the consumer's transfers out of dT
-    int chunks = 4;                      // pieces of the transposed array's copy out (JRC_FUSED_CHUNKS=1..8)
-    bool short_chain = true;             // transpose and arg-max as epilogues of the two fft_vcc kernels (JRC_FUSED_SHORT=0: own kernels)
-    bool pad_first = true;               // the radar block's own output is queued before the continuation (JRC_FUSED_PAD_FIRST=0: after)
     cudaStream_t stream = nullptr, stream2 = nullptr;
     cudaEvent_t h_ready = nullptr, t_ready = nullptr, t_join = nullptr;   // (t_ready / t_join: fork and join inside the captured graph)
     cudaEvent_t last_done = nullptr;     // the previous frame's continuation (it reads the estimate the next call overwrites)
     FusedEntry e[JRC_FUSED_RING];
     int64_t next_seq = 0;
-    GrowBuf dDet, dKeys;                 // (dKeys: zero between frames)
+    GrowBuf dT, dDet, dKeys;             // dT: [Nr][V] on the device; dKeys: zero between frames
 };
 
 static jrc_status fused_state(jrc_chain *h, jrc_fused_state **out)
@@ -1699,23 +1690,15 @@ static jrc_status fused_state(jrc_chain *h, jrc_fused_state **out)
     if (!h->fstate) {
         jrc_fused_state *F = new jrc_fused_state();
         h->fstate = F;
-        if (const char *e = std::getenv("JRC_FUSED_CHUNKS")) F->chunks = std::min(std::max(std::atoi(e), 1), JRC_FUSED_MAX_CHUNKS);
-        if (const char *e = std::getenv("JRC_FUSED_PAD_FIRST")) F->pad_first = std::atoi(e) != 0;
-        if (const char *e = std::getenv("JRC_FUSED_SHORT")) F->short_chain = std::atoi(e) != 0;
         CU(cudaStreamCreateWithFlags(&F->stream, cudaStreamNonBlocking));
         CU(cudaStreamCreateWithFlags(&F->stream2, cudaStreamNonBlocking));
-        CU(cudaStreamCreateWithFlags(&F->stream3, cudaStreamNonBlocking));
         CU(cudaEventCreateWithFlags(&F->h_ready, cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&F->t_ready, cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&F->t_join, cudaEventDisableTiming));
-        const size_t cells = (size_t)h->Nr * h->Na;
         for (FusedEntry &e : F->e) {
             CU(cudaEventCreateWithFlags(&e.done, cudaEventDisableTiming));
-            for (cudaEvent_t &ev : e.t_done) CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-            CU(cudaEventCreateWithFlags(&e.t_dev, cudaEventDisableTiming));
-            CU(cudaMalloc(&e.dT, cells * sizeof(c32)));
-            CU(cudaMemset(e.dT, 0, cells * sizeof(c32)));      // (the short chain only ever writes the V data columns)
-            CU(cudaMallocHost(&e.T, cells * sizeof(c32)));
+            CU(cudaEventCreateWithFlags(&e.t_done, cudaEventDisableTiming));
+            CU(cudaMallocHost(&e.T, (size_t)h->Nr * h->V * sizeof(c32)));
             CU(cudaMallocHost(&e.det, sizeof(DetDev)));
         }
     }
@@ -1729,20 +1712,17 @@ static void fused_state_destroy(jrc_chain *h)
     if (!F) return;
     if (F->stream) { cudaStreamSynchronize(F->stream); cudaStreamDestroy(F->stream); }
     if (F->stream2) { cudaStreamSynchronize(F->stream2); cudaStreamDestroy(F->stream2); }
-    if (F->stream3) { cudaStreamSynchronize(F->stream3); cudaStreamDestroy(F->stream3); }
     if (F->t_ready) cudaEventDestroy(F->t_ready);
     if (F->t_join) cudaEventDestroy(F->t_join);
     if (F->h_ready) cudaEventDestroy(F->h_ready);
     for (FusedEntry &e : F->e) {
         if (e.graph) cudaGraphExecDestroy(e.graph);
         if (e.done) cudaEventDestroy(e.done);
-        for (cudaEvent_t ev : e.t_done)
-            if (ev) cudaEventDestroy(ev);
-        if (e.t_dev) cudaEventDestroy(e.t_dev);
-        if (e.dT) cudaFree(e.dT);
+        if (e.t_done) cudaEventDestroy(e.t_done);
         if (e.T) cudaFreeHost(e.T);
         if (e.det) cudaFreeHost(e.det);
     }
+    F->dT.release();
     F->dDet.release();
     F->dKeys.release();
     delete F;
@@ -1797,19 +1777,18 @@ static jrc_status radar_estimate_impl(jrc_chain *h, const jrc_c32 *const *tx, co
     c32 *dH = (c32 *)h->sH.p;
     ST(launch_chan_est(h, drx, dtx, 1, dH, c.n_pre));
     if (F) {
-        // the rest of the chain, in the arithmetic of the separate blocks, behind this call's back: one graph launch
-        // on the second stream (eight nodes: range fft_vcc, transpose, its copy out, angle fft_vcc, estimator, record out)
+        // the rest of the chain, in the arithmetic of the separate blocks, behind this call's back: one graph launch on
+        // the second stream -- three kernels (range fft_vcc storing its spectra transposed, angle fft_vcc with the arg-max
+        // scan as its epilogue, k_est_finalize storing the record into its page-locked slot), one 32 KiB copy, one event
         NvtxRange nv("fused mode: range fft, transpose, angle fft, estimator");
         const int64_t seq = F->next_seq++;
         FusedEntry &e = F->e[seq % JRC_FUSED_RING];
         e.seq.store(-1, std::memory_order_release);
-        const int direct = F->direct.load(std::memory_order_acquire);
-        if (!e.graph || e.epoch != h->est_epoch || e.direct.load(std::memory_order_relaxed) != direct) {
-            const size_t cells = (size_t)Nr * Na;
-            ST(h->sY.need((size_t)V * Nr * sizeof(c32)));
+        if (!e.graph || e.epoch != h->est_epoch) {
+            const size_t cells = (size_t)Nr * Na, tcells = (size_t)Nr * V;
             ST(h->sC.need(cells * sizeof(c32)));
+            ST(F->dT.need(tcells * sizeof(c32)));
             ST(F->dDet.need(sizeof(DetDev)));
-            ST(h->sKeys.need(sizeof(unsigned long long)));
             if (!F->dKeys.p) {
                 ST(F->dKeys.need(sizeof(unsigned long long)));
                 CU(cudaMemsetAsync(F->dKeys.p, 0, sizeof(unsigned long long), h->stream));   // (ordered before the graph by h_ready)
@@ -1818,43 +1797,25 @@ static jrc_status radar_estimate_impl(jrc_chain *h, const jrc_c32 *const *tx, co
             ST(get_twiddles(h, Nr, 0, &tw));        // (tables are built on the handle's stream, before the capture)
             ST(get_twiddles(h, Na, 1, &tw));
             if (e.graph) { CU(cudaGraphExecDestroy(e.graph)); e.graph = nullptr; }
-            c32 *dY = (c32 *)h->sY.p, *dT = e.dT, *dC = (c32 *)h->sC.p;
-            // ONE graph: range fft_vcc, transpose, then two branches -- the transposed array's copy out with the entry's
-            // t_done recorded behind it (an external event-record node: pending from the graph launch on, fired when the
-            // copy is through), and angle fft_vcc, estimator, record out -- joined at the end.
+            c32 *dT = (c32 *)F->dT.p, *dC = (c32 *)h->sC.p;
+            unsigned long long *keys = (unsigned long long *)F->dKeys.p;
+            DetDev *det_alias = (DetDev *)host_dev_alias(e.det);
+            // Two branches behind the range transform: the spectra's copy out with the entry's t_done recorded behind it
+            // (an external event-record node: pending from the graph launch on, fired when the copy is through), and angle
+            // fft_vcc (it zero-pads its V-sample rows itself, as it does for the separate block) + estimator; joined at the end.
             CU(cudaStreamBeginCapture(F->stream, cudaStreamCaptureModeThreadLocal));
             std::swap(h->stream, F->stream);
             jrc_status st = [&]() -> jrc_status {
-                if (F->short_chain) {
-                    ST(launch_fft_rows(h, dH, N, N, dT, Nr, V, 0, 0, Na));
-                } else {
-                    ST(launch_fft_rows(h, dH, N, N, dY, Nr, V, 0, 0));
-                    ST(launch_transpose(h, dY, dT, V, Nr, Na, 1));
-                }
-                if (direct) CU(cudaEventRecordWithFlags(e.t_dev, h->stream, cudaEventRecordExternal));
-                if (!direct) {
-                    CU(cudaEventRecord(F->t_ready, h->stream));
-                    CU(cudaStreamWaitEvent(F->stream2, F->t_ready, 0));
-                    for (int i = 0; i < F->chunks; i++) {
-                        const size_t lo = cells * i / F->chunks, hi = cells * (i + 1) / F->chunks;
-                        CU(cudaMemcpyAsync(e.T + lo, dT + lo, (hi - lo) * sizeof(c32), cudaMemcpyDeviceToHost, F->stream2));
-                        CU(cudaEventRecordWithFlags(e.t_done[i], F->stream2, cudaEventRecordExternal));
-                    }
-                    CU(cudaEventRecord(F->t_join, F->stream2));
-                }
-                if (F->short_chain) {
-                    // the record goes straight into the entry's page-locked slot (one 32-byte store over PCIe, no copy node)
-                    DetDev *det_alias = (DetDev *)host_dev_alias(e.det);
-                    unsigned long long *keys = (unsigned long long *)F->dKeys.p;
-                    ST(launch_fft_rows(h, dT, Na, Na, dC, Na, Nr, 1, 1, 0, keys));
-                    ST(launch_estimate(h, dC, Nr, Na, 1, 0, det_alias ? det_alias : (DetDev *)F->dDet.p, keys));
-                    if (!det_alias) CU(cudaMemcpyAsync(e.det, F->dDet.p, sizeof(DetDev), cudaMemcpyDeviceToHost, h->stream));
-                } else {
-                    ST(launch_fft_rows(h, dT, Na, Na, dC, Na, Nr, 1, 1));
-                    ST(launch_estimate(h, dC, Nr, Na, 1, 0, (DetDev *)F->dDet.p));
-                    CU(cudaMemcpyAsync(e.det, F->dDet.p, sizeof(DetDev), cudaMemcpyDeviceToHost, h->stream));
-                }
-                if (!direct) CU(cudaStreamWaitEvent(h->stream, F->t_join, 0));
+                ST(launch_fft_rows(h, dH, N, N, dT, Nr, V, 0, 0, V));                      // dT[n][v] = spectrum of channel v at bin n
+                CU(cudaEventRecord(F->t_ready, h->stream));
+                CU(cudaStreamWaitEvent(F->stream2, F->t_ready, 0));
+                CU(cudaMemcpyAsync(e.T, dT, tcells * sizeof(c32), cudaMemcpyDeviceToHost, F->stream2));
+                CU(cudaEventRecordWithFlags(e.t_done, F->stream2, cudaEventRecordExternal));
+                CU(cudaEventRecord(F->t_join, F->stream2));
+                ST(launch_fft_rows(h, dT, V, V, dC, Na, Nr, 1, 1, 0, keys));
+                ST(launch_estimate(h, dC, Nr, Na, 1, 0, det_alias ? det_alias : (DetDev *)F->dDet.p, keys));
+                if (!det_alias) CU(cudaMemcpyAsync(e.det, F->dDet.p, sizeof(DetDev), cudaMemcpyDeviceToHost, h->stream));
+                CU(cudaStreamWaitEvent(h->stream, F->t_join, 0));
                 return JRC_OK;
             }();
             std::swap(h->stream, F->stream);
@@ -1866,14 +1827,13 @@ static jrc_status radar_estimate_impl(jrc_chain *h, const jrc_c32 *const *tx, co
             cudaGraphDestroy(g);
             CU(ce);
             e.epoch = h->est_epoch;
-            e.direct.store(direct, std::memory_order_relaxed);
         }
         fused_entry_pending = &e;
         fused_seq = seq;
     }
     // The continuation depends on the estimate only (h_ready is recorded here).  Its launch is the longest host-side step
-    // of the call: with pad_first this call's own small output kernel is queued first and completes while the host is busy
-    // with the graph launch, so the synchronize below returns at once; otherwise the graph is queued first.
+    // of the call: this call's own small output kernel is queued first and completes while the host is busy with the graph
+    // launch, so the synchronize below returns at once.
     if (fused_entry_pending) CU(cudaEventRecord(F->h_ready, h->stream));
     auto launch_continuation = [&]() -> jrc_status {
         if (!fused_entry_pending) return JRC_OK;
@@ -1888,7 +1848,6 @@ static jrc_status radar_estimate_impl(jrc_chain *h, const jrc_c32 *const *tx, co
         *cpi_seq = fused_seq;
         return JRC_OK;
     };
-    if (F && !F->pad_first) ST(launch_continuation());
     const size_t out_items = (size_t)V * Nr, est_items = (size_t)V * N;
     if (!ptr_is_device(out) && !host_ptr_is_pinned(out) && h->zero_copy) {
         // pageable output (a scheduler buffer): only the estimate crosses the bus (V*N samples stored in place into a
@@ -1953,28 +1912,18 @@ extern "C" jrc_status jrc_fused_fetch_transposed(jrc_chain *h, int64_t cpi_seq, 
     if (!out) return fail(JRC_ERR_INVALID, "null argument");
     FusedEntry *e = nullptr;
     ST(fused_entry(h, cpi_seq, true, &e));
-    // piece by piece behind the transfer: the copy into the caller's (pageable) buffer is the longer of the two
-    const size_t cells = (size_t)h->Nr * h->Na;
-    jrc_fused_state *F = h->fstate;
-    const bool pinned_out = host_ptr_is_pinned(out);
-    if (pinned_out || e->direct.load(std::memory_order_relaxed) == 1) {
-        // a page-locked destination (the block registered its stream buffer, jrc_host_register): one transfer from the
-        // device copy of the array, nothing passes through T -- and later frames stop producing T at all.  (A pageable
-        // destination after that switch still gets its array, through the driver's staging.)
-        if (pinned_out) F->direct.store(1, std::memory_order_release);
-        const bool entry_direct = e->direct.load(std::memory_order_relaxed) == 1;
-        CU(cudaStreamWaitEvent(F->stream3, entry_direct ? e->t_dev : e->t_done[F->chunks - 1], 0));
-        CU(cudaMemcpyAsync(out, e->dT, cells * sizeof(c32), cudaMemcpyDeviceToHost, F->stream3));
-        CU(cudaStreamSynchronize(F->stream3));
-        if (e->seq.load(std::memory_order_acquire) != cpi_seq) return fail(JRC_ERR_STATE, "CPI %lld was overwritten", (long long)cpi_seq);
-        return JRC_OK;
-    }
-    const int chunks = F->chunks;
-    for (int i = 0; i < chunks; i++) {
-        const size_t lo = cells * i / chunks, hi = cells * (i + 1) / chunks;
-        CU(cudaEventSynchronize(e->t_done[i]));
-        memcpy(out + lo, e->T + lo, (hi - lo) * sizeof(c32));
-    }
+    // row n of the [Nr][Na] array: the V spectra samples, then zeros (lib/matrix_transpose_impl.cc:91-104) -- 1/interp_angle
+    // of the array is read (from the entry), the rest is stores into the caller's buffer
+    const int V = h->V, Na = h->Na, Nr = h->Nr;
+    // The zeros do not depend on the frame: they are written while the spectra are still on their way (the range transform
+    // starts when the radar block's estimate is there, i.e. about when that block returns), one memset of the whole array;
+    // then the wait, then the short data runs.
+    c32 *o = (c32 *)out;
+    const c32 *t = e->T;
+    if (Na > V) memset(o, 0, (size_t)Nr * Na * sizeof(c32));
+    CU(cudaEventSynchronize(e->t_done));
+    for (int n = 0; n < Nr; n++, o += Na, t += V)
+        for (int v = 0; v < V; v++) o[v] = t[v];
     if (e->seq.load(std::memory_order_acquire) != cpi_seq) return fail(JRC_ERR_STATE, "CPI %lld was overwritten", (long long)cpi_seq);
     return JRC_OK;
 }

@@ -614,7 +614,7 @@ __global__ void k_est_finalize(const c32 *__restrict__ map, long long per_mat, i
 {
     const long long mat = blockIdx.x;
     const c32 *m = map + mat * per_mat;
-    __shared__ float chunk[1024];
+    __shared__ float chunk[2][1024];
     __shared__ NoiseWin win;
     __shared__ int s_peak_r, s_peak_a;
     __shared__ float s_noise;
@@ -639,22 +639,28 @@ __global__ void k_est_finalize(const c32 *__restrict__ map, long long per_mat, i
     const int ncols = win.end_a - win.start_a;
     const int nrows = win.end_r - win.start_r;
     const long long total = (ncols > 0 && nrows > 0) ? (long long)nrows * ncols : 0;
-    for (long long base = 0; base < total; base += 1024) {
-        int cnt = (int)((total - base) < 1024 ? (total - base) : 1024);
-        for (int j = threadIdx.x; j < cnt; j += blockDim.x) {
+    // 1024 cells at a time: warp 0 runs the chain over one block of values while the other warps evaluate the next one
+    auto eval_chunk = [&](long long base, float *dst, int t0, int nt) {
+        const int cnt = (int)((total - base) < 1024 ? (total - base) : 1024);
+        for (int j = t0; j < cnt; j += nt) {
             long long s = base + j;
             int ir = win.start_r + (int)(s / ncols), ia = win.start_a + (int)(s % ncols);
             int r_idx = ((ir % n_inputs) + n_inputs) % n_inputs;
             int a_idx = ((ia % vlen) + vlen) % vlen;
-            chunk[j] = ref_abs(m[a_idx + (long long)vlen * r_idx]);
+            dst[j] = ref_abs(m[a_idx + (long long)vlen * r_idx]);
         }
-        __syncthreads();
-        if (threadIdx.x < 32) {
-            const float acc = seq_sum_sq_warp(s_noise, chunk, cnt, threadIdx.x);      // :217 float += double
-            if (threadIdx.x == 0) s_noise = acc;
-        }
+    };
+    if (total > 0) eval_chunk(0, chunk[0], threadIdx.x, blockDim.x);
+    __syncthreads();
+    float acc = 0.f;
+    int b = 0;
+    for (long long base = 0; base < total; base += 1024, b ^= 1) {
+        const int cnt = (int)((total - base) < 1024 ? (total - base) : 1024);
+        if (threadIdx.x < 32) acc = seq_sum_sq_warp(acc, chunk[b], cnt, threadIdx.x);      // :217 float += double
+        else if (base + 1024 < total) eval_chunk(base + 1024, chunk[b ^ 1], threadIdx.x - 32, blockDim.x - 32);
         __syncthreads();
     }
+    if (threadIdx.x == 0) s_noise = acc;
     if (threadIdx.x == 0) {
         DetDev d;
         d.range_idx = s_peak_r; d.angle_idx = s_peak_a;

@@ -105,10 +105,6 @@ int main(int argc, char **argv)
             jrc_chain_destroy(util);
             std::sort(us5.begin(), us5.end());
         }
-        // (locked = 1: matrix_transpose's output buffer is page-locked, as a block does with jrc_host_register on its
-        //  stream buffer: the transposed array then arrives in one transfer from the device, no page-locked intermediate)
-        std::string fused_json;
-        for (int locked = 0; locked < 2; locked++) {
         std::vector<double> us3, us3_radar, us3_transp, us3_estim;
         {
             setenv("JRC_FUSED", "1", 1);
@@ -117,7 +113,6 @@ int main(int argc, char **argv)
             auto estim = range_angle_estimator::make(Na, rb, ab, 2.4f, 28.955f, 15.f, 0.f, "/tmp/jrc_lat_log.csv", false);
             unsetenv("JRC_FUSED");
             cvec pad((size_t)V * Nr), tr((size_t)Nr * Na);
-            if (locked && jrc_host_register(tr.data(), tr.size() * sizeof(gr_complex)) != JRC_OK) { std::fprintf(stderr, "%s\n", jrc_last_error()); return 1; }
             uint64_t r1 = 0, r2 = 0, r3 = 0;
             const int n3 = n_calls / 4 + 50;
             for (int it = 0; it < n3; it++) {
@@ -155,13 +150,6 @@ int main(int argc, char **argv)
                 estim->shim_published["params"].clear();
             }
             for (auto *v : {&us3, &us3_radar, &us3_transp, &us3_estim}) std::sort(v->begin(), v->end());
-            if (locked) jrc_host_unregister(tr.data());
-        }
-        std::snprintf(line, sizeof(line), "\"five-block wiring %dx%d with JRC_FUSED=1%s, the three radar blocks, 1 CPI\": {\"calls\": %zu, \"p50_us\": %.1f, \"p99_us\": %.1f, "
-                    "\"p50_us_mimo_ofdm_radar\": %.1f, \"p50_us_matrix_transpose\": %.1f, \"p50_us_range_angle_estimator\": %.1f}, ",
-                    Nr, Na, locked ? " and matrix_transpose's output buffer page-locked" : "", us3.size(), us3[us3.size() / 2], us3[(size_t)(us3.size() * 0.99)],
-                    us3_radar[us3_radar.size() / 2], us3_transp[us3_transp.size() / 2], us3_estim[us3_estim.size() / 2]);
-        fused_json += line;
         }
         // ---- pipelined: up to 4 frames in flight, page-locked output ring ----
         std::vector<double> lat;
@@ -214,7 +202,11 @@ int main(int argc, char **argv)
         std::snprintf(line, sizeof(line), "%s\"five separate blocks %dx%d, 1 CPI\": {\"calls\": %zu, \"p50_us\": %.1f, \"p99_us\": %.1f}, ", ci ? ", " : "", Nr, Na,
                     us5.size(), us5[us5.size() / 2], us5[(size_t)(us5.size() * 0.99)]);
         json += line;
-        json += fused_json;
+        std::snprintf(line, sizeof(line), "\"five-block wiring %dx%d with JRC_FUSED=1, the three radar blocks, 1 CPI\": {\"calls\": %zu, \"p50_us\": %.1f, \"p99_us\": %.1f, "
+                    "\"p50_us_mimo_ofdm_radar\": %.1f, \"p50_us_matrix_transpose\": %.1f, \"p50_us_range_angle_estimator\": %.1f}, ",
+                    Nr, Na, us3.size(), us3[us3.size() / 2], us3[(size_t)(us3.size() * 0.99)], us3_radar[us3_radar.size() / 2],
+                    us3_transp[us3_transp.size() / 2], us3_estim[us3_estim.size() / 2]);
+        json += line;
         std::snprintf(line, sizeof(line), "\"radar_chain block %dx%d, 1 CPI per work(), pageable buffers\": {\"calls\": %d, \"p50_us\": %.2f, \"p99_us\": %.2f, \"mean_us\": %.2f}, ",
                     Nr, Na, n_calls, us[us.size() / 2], us[(size_t)(us.size() * 0.99)],
                     std::accumulate(us.begin(), us.end(), 0.0) / us.size());

@@ -330,14 +330,9 @@ static void test_fused_block()
 // downstream blocks serve what it cached under the frame's jrc_cpi tag.  Outputs, tags and messages must be the ones
 // the separate blocks give; the downstream blocks are handed ZEROED inputs here, so anything they computed themselves
 // would show.
-// pinned_out: matrix_transpose's output buffer is page-locked (jrc_host_register on the stream buffer) on
-// two frames of three -- the array then comes straight from the device copy, frames after the first such fetch are
-// produced without the page-locked intermediate, and the pageable third still gets its array.
-static void test_fused_mode(bool pinned_out)
+static void test_fused_mode()
 {
     const int N = 64, T = 4, R = 2, S = 4, pre = 5, IR = 8, IA = 16, V = 8, Nr = N * IR, Na = V * IA, items = pre + S;
-    cvec tr_locked((size_t)Nr * Na);
-    if (pinned_out) CHECK(jrc_host_register(tr_locked.data(), tr_locked.size() * sizeof(gr_complex)) == JRC_OK, "jrc_host_register: %s", jrc_last_error());
     auto rb = range_bins(N, IR); auto ab = angle_bins(Na);
     const float ndr = 2.4f, nda = 2 * 14.4775f;
     setenv("JRC_FUSED", "1", 1);
@@ -357,9 +352,7 @@ static void test_fused_mode(bool pinned_out)
         in[0].tags.push_back(shim::make_tag(rd, "packet_len", pmt::from_long(items)));
         in[T].tags.push_back(shim::make_tag(rd, "packet_len", pmt::from_long(items)));
         rd += items;
-        cvec pad((size_t)V * Nr), tr_pageable((size_t)Nr * Na);
-        cvec &tr = pinned_out && it % 3 != 2 ? tr_locked : tr_pageable;
-        std::fill(tr.begin(), tr.end(), gr_complex(0, 0));
+        cvec pad((size_t)V * Nr), tr((size_t)Nr * Na);
         auto r1 = shim::run_once(*radar, in, {{pad.data(), 64}});
         CHECK(r1.produced == V, "fused mode: radar produced %d", r1.produced);
         CHECK(r1.out_tags[0].size() == 2 && pmt::symbol_to_string(r1.out_tags[0][0].key) == "packet_len" &&
@@ -432,10 +425,6 @@ static void test_fused_mode(bool pinned_out)
     shim::run_once(*estim, {ei}, {});
     CHECK(estim->shim_published["params"].size() == before, "fused mode: threshold change ignored");
     orc_radar_destroy(ref);
-    if (pinned_out) {
-        CHECK(jrc_host_unregister(tr_locked.data()) == JRC_OK, "jrc_host_unregister: %s", jrc_last_error());
-        return;
-    }
 
     // blocks that do not continue each other: the radar block says so and stays on its own call
     setenv("JRC_FUSED", "1", 1);
@@ -582,8 +571,7 @@ int main()
     test_chain_of_blocks();
     test_peak_and_pad();
     test_fused_block();
-    test_fused_mode(false);
-    test_fused_mode(true);
+    test_fused_mode();
     test_fused_mode_threads();
     if (g_fail) { std::printf("%d check(s) FAILED\n", g_fail); return 1; }
     std::printf("ALL BLOCK TESTS PASSED\n");
