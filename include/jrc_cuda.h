@@ -239,8 +239,8 @@ JRC_API jrc_status jrc_radar_estimate(jrc_chain *h, const jrc_c32 *const *tx, co
  * rest of the chain in the one-kernel-per-block arithmetic (range fft_vcc, transpose, angle fft_vcc, estimator) on
  * a second stream.  The transposed array and the detection record land in a ring of JRC_FUSED_RING
  * entries under *cpi_seq (0, 1, 2, ... per handle); the call returns as soon as its own output is on the host.
- * jrc_fused_fetch_transposed into a page-locked buffer (jrc_host_register) is one transfer from the entry's device copy;
- * into a pageable one it is a host copy out of the entry's page-locked copy.
+ * Of the transposed array only the V data columns are kept (the rest is matrix_transpose's zero padding):
+ * jrc_fused_fetch_transposed writes the zeros into the caller's buffer itself.
  * The downstream blocks fetch by sequence number (the jrc_cpi stream tag) from their own threads instead of
  * repeating the work: JRC_ERR_STATE if that CPI is not cached (never made, or overwritten by a newer one). */
 #define JRC_FUSED_RING 16
