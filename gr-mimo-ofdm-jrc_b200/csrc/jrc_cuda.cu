@@ -1313,7 +1313,7 @@ extern "C" jrc_status jrc_chain_submit(jrc_chain *h, const jrc_c32 *rx_host, con
     const bool bgp = c.background_removal || h->bg_recording.load();
     if (bgp)
         for (StreamSlot &o : S->slot)
-            if (o.busy) CU(cudaEventSynchronize(o.done));
+            if (o.busy) CU(cudaStreamSynchronize(o.stream));
     const size_t rx_cpi = (size_t)c.n_rx * c.n_sym * c.fft_len, tx_cpi = (size_t)c.n_tx * c.n_sym * c.fft_len;
     const size_t map_cpi = (size_t)h->Nr * h->Na;
     const size_t txn = tx_shared ? tx_cpi : (size_t)n_cpi * tx_cpi;
@@ -1373,7 +1373,7 @@ extern "C" jrc_status jrc_chain_submit(jrc_chain *h, const jrc_c32 *rx_host, con
         if (st == JRC_OK && dets_host) CU(cudaMemcpyAsync(dst_dets, d_dets, det_bytes, cudaMemcpyDeviceToHost, sl.stream));
     }
     if (st != JRC_OK) return st;
-    CU(cudaEventRecord(sl.done, sl.stream));
+    // (no event: the slot's stream carries this submission and nothing else until it is waited for)
     sl.busy = true;
     sl.ticket = S->next_ticket++;
     *ticket = sl.ticket;
@@ -1476,8 +1476,8 @@ extern "C" jrc_status jrc_chain_poll(jrc_chain *h, int64_t ticket, int32_t *done
     if (!h || !done) return fail(JRC_ERR_INVALID, "null argument");
     StreamSlot *sl = find_ticket(h, ticket);
     if (!sl) return fail(JRC_ERR_INVALID, "unknown ticket %lld", (long long)ticket);
-    cudaError_t e = cudaEventQuery(sl->done);
-    if (e != cudaSuccess && e != cudaErrorNotReady) return fail(JRC_ERR_CUDA, "cudaEventQuery: %s", cudaGetErrorString(e));
+    cudaError_t e = cudaStreamQuery(sl->stream);
+    if (e != cudaSuccess && e != cudaErrorNotReady) return fail(JRC_ERR_CUDA, "cudaStreamQuery: %s", cudaGetErrorString(e));
     *done = e == cudaSuccess;
     return JRC_OK;
 }
@@ -1491,7 +1491,7 @@ extern "C" jrc_status jrc_chain_wait(jrc_chain *h, int64_t ticket)
     CU(cudaSetDevice(h->cfg.device));
     NvtxRange nv("jrc_chain_wait");
     sl.busy = false;                       // whatever happens below, the slot is free again
-    CU(cudaEventSynchronize(sl.done));
+    CU(cudaStreamSynchronize(sl.stream));
     const jrc_chain_cfg &c = h->cfg;
     if (sl.dets_final) {
         if (sl.deferred) {

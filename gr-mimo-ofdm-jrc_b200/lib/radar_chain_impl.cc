@@ -23,6 +23,7 @@ class radar_chain_impl : public radar_chain
     float d_snr_threshold, d_power_threshold;
     host::stats_log d_log;
     const bool d_debug;
+    pmt::pmt_t d_srcid;                 // alias() as a symbol, made on first use (the alias is final once the block is in a graph)
     host::chain_handle d_chain;
     std::mutex d_lock;                      // the GRC callbacks run on another thread than general_work()
     int d_depth = 1;
@@ -40,7 +41,8 @@ class radar_chain_impl : public radar_chain
     {
         if (!(det.flags & JRC_DET_PASSED)) return;
         const float range_val = d_range_bins[det.range_idx], angle_val = d_angle_bins[det.angle_idx];
-        message_port_pub(pmt::mp("params"), host::params_message(range_val, angle_val, det.peak_power, det.snr_db));
+        static const pmt::pmt_t port = pmt::mp("params");
+        message_port_pub(port, host::params_message(range_val, angle_val, det.peak_power, det.snr_db));
         if (d_log.record && !d_log.append(det.peak_power, det.snr_db, range_val, angle_val))
             throw std::runtime_error("[RADAR CHAIN] Could not open file!!");
     }
@@ -51,7 +53,9 @@ class radar_chain_impl : public radar_chain
         const inflight_t f = d_q.front();
         host::check(jrc_chain_wait(d_chain.get(), f.ticket), "RADAR CHAIN");
         d_q.pop_front();
-        add_item_tag(0, nitems_written(0), pmt::string_to_symbol("packet_len"), pmt::from_long(d_Nr), pmt::string_to_symbol(alias()));
+        static const pmt::pmt_t len_key = pmt::string_to_symbol("packet_len");
+        if (!d_srcid) d_srcid = pmt::string_to_symbol(alias());
+        add_item_tag(0, nitems_written(0), len_key, pmt::from_long(d_Nr), d_srcid);
         publish(*d_slot[f.slot].det);
         return d_Nr;
     }
