@@ -330,9 +330,11 @@ static void test_fused_block()
 // downstream blocks serve what it cached under the frame's jrc_cpi tag.  Outputs, tags and messages must be the ones
 // the separate blocks give; the downstream blocks are handed ZEROED inputs here, so anything they computed themselves
 // would show.
-static void test_fused_mode()
+// (IR, IA) = (8, 16): the shipped 512x128 map; (16, 8): 1024x64; (4, 1): no angle zero-padding at all -- of the transposed
+// array only the data columns are cached, the zero columns are written by the fetch.
+static void test_fused_mode(const int IR, const int IA)
 {
-    const int N = 64, T = 4, R = 2, S = 4, pre = 5, IR = 8, IA = 16, V = 8, Nr = N * IR, Na = V * IA, items = pre + S;
+    const int N = 64, T = 4, R = 2, S = 4, pre = 5, V = 8, Nr = N * IR, Na = V * IA, items = pre + S;
     auto rb = range_bins(N, IR); auto ab = angle_bins(Na);
     const float ndr = 2.4f, nda = 2 * 14.4775f;
     setenv("JRC_FUSED", "1", 1);
@@ -428,7 +430,8 @@ static void test_fused_mode()
 
     // blocks that do not continue each other: the radar block says so and stays on its own call
     setenv("JRC_FUSED", "1", 1);
-    auto radar2 = mimo_ofdm_radar::make(N, T, R, S, pre, false, false, 1, 4, false, "/tmp/jrc_cpp_chan.csv");
+    const int IR2 = IR == 4 ? 2 : 4;
+    auto radar2 = mimo_ofdm_radar::make(N, T, R, S, pre, false, false, 1, IR2, false, "/tmp/jrc_cpp_chan.csv");
     unsetenv("JRC_FUSED");
     frame_t f = make_frame(T, R, items, N);
     std::vector<shim::input_t> in(T + R);
@@ -436,7 +439,7 @@ static void test_fused_mode()
     for (int r = 0; r < R; r++) { in[T + r].items = f.rx[r].data(); in[T + r].n_items = items; }
     in[0].tags.push_back(shim::make_tag(0, "packet_len", pmt::from_long(items)));
     in[T].tags.push_back(shim::make_tag(0, "packet_len", pmt::from_long(items)));
-    cvec pad((size_t)V * N * 4);
+    cvec pad((size_t)V * N * IR2);
     auto r1 = shim::run_once(*radar2, in, {{pad.data(), 64}});
     CHECK(r1.produced == V && r1.out_tags[0].size() == 1, "fused mode: mismatching blocks must fall back");
 }
@@ -571,7 +574,9 @@ int main()
     test_chain_of_blocks();
     test_peak_and_pad();
     test_fused_block();
-    test_fused_mode();
+    test_fused_mode(8, 16);
+    test_fused_mode(16, 8);
+    test_fused_mode(4, 1);
     test_fused_mode_threads();
     if (g_fail) { std::printf("%d check(s) FAILED\n", g_fail); return 1; }
     std::printf("ALL BLOCK TESTS PASSED\n");
